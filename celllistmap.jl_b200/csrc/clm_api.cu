@@ -1,0 +1,418 @@
+// C ABI of libclm_b200.so (include/clm_b200.h) and the non-map members of Engine<T>:
+// box construction, position upload, cell-list build (UpdateCellList! equivalent), result staging.
+#include <cstring>
+#include <cmath>
+#include <limits>
+#include <new>
+#include "clm_engine.cuh"
+
+namespace clm {
+
+static thread_local std::string g_create_error;
+
+template <class T> int Engine<T>::init(int dim_, int device_) {
+    dim = dim_; device = device_; dtype = (sizeof(T) == 4) ? CLM_F32 : CLM_F64;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(CLM_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(CLM_ERR_ARGUMENT, "device ordinal out of range");
+    CLM_CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CLM_CK(cudaGetDeviceProperties(&prop, device));
+    n_sm = prop.multiProcessorCount;
+    CLM_CK(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+    stream = own_stream;
+    CLM_CK(cudaEventCreate(&ev0));
+    CLM_CK(cudaEventCreate(&ev1));
+    CLM_CK(dscal.ensure(DS_COUNT));
+    CLM_CK(d_res.ensure(1));
+    CLM_CK(d_minres.ensure(2));
+    CLM_CK(cudaMallocHost((void**)&h_dscal, DS_COUNT * sizeof(int)));
+    CLM_CK(cudaMallocHost((void**)&h_res, sizeof(ResultBlock) + 2 * sizeof(MinResult)));
+    std::memset(&stats, 0, sizeof(stats));
+    stats.n_sm = n_sm;
+    return CLM_OK;
+}
+
+template <class T> Engine<T>::~Engine() {
+    cudaSetDevice(device);
+    if (own_stream) cudaStreamSynchronize(own_stream);
+    for (auto& s : sets) { s.pos.release(); s.rec.release(); s.cell_start.release(); s.cell_count.release(); s.cell_nreal.release(); s.aux.release(); }
+    dscal.release(); scan_partial.release(); row_ntiles.release(); row_range.release(); tiles.release(); d_res.release();
+    d_hcount.release(); nl.release(); d_hsum.release(); d_rbins.release(); d_forces.release(); d_minmax.release(); d_minpart.release(); d_minres.release();
+    if (h_dscal) cudaFreeHost(h_dscal);
+    if (h_res) cudaFreeHost(h_res);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    if (own_stream) cudaStreamDestroy(own_stream);
+}
+
+// Box(...) dispatch: sides -> orthorhombic matrix (Box.jl:330-335), matrix (Box.jl:191-203), Limits deferred (Box.jl:374-377)
+template <class T> int Engine<T>::set_box(int cell_type, const void* uc, int is_matrix, const void* cutoff, int lcell) {
+    if (!cutoff) return fail(CLM_ERR_ARGUMENT, "cutoff pointer is NULL");
+    if (lcell < 1) return fail(CLM_ERR_ARGUMENT, "lcell must be greater or equal to 1");
+    const T rc = *(const T*)cutoff;
+    dirty = true;
+    if (cell_type == CLM_NONPERIODIC) {
+        nonperiodic = true; np_cutoff = rc; np_lcell = lcell; box_set = false;
+        return CLM_OK;
+    }
+    if (cell_type != CLM_ORTHORHOMBIC && cell_type != CLM_TRICLINIC) return fail(CLM_ERR_ARGUMENT, "unknown cell type");
+    if (!uc) return fail(CLM_ERR_ARGUMENT, "unit cell pointer is NULL");
+    nonperiodic = false;
+    T cell[3][3];
+    geo::eye(cell);
+    const T* c = (const T*)uc;
+    if (is_matrix) { for (int col = 0; col < dim; ++col) for (int r = 0; r < dim; ++r) cell[r][col] = c[r + dim * col]; }
+    else { for (int k = 0; k < dim; ++k) cell[k][k] = c[k]; }
+    if (dim == 2) { cell[2][2] = T(1); }
+    const T origin[3] = {T(0), T(0), T(0)};
+    box_set = false;
+    int rcode = make_box(box, dim, cell_type, cell, rc, lcell, origin, err);
+    if (rcode != CLM_OK) return rcode;
+    box_set = true;
+    return CLM_OK;
+}
+
+template <class T> int Engine<T>::get_box(clm_box_info* o) {
+    if (!o) return fail(CLM_ERR_ARGUMENT, "output pointer is NULL");
+    if (!box_set) return fail(CLM_ERR_STATE, "box not set (non-periodic boxes exist after clm_build)");
+    std::memset(o, 0, sizeof(*o));
+    o->dim = dim; o->dtype = dtype; o->cell_type = box.cell_type; o->lcell = box.lcell;
+    o->cutoff = box.cutoff; o->cutoff_sqr = box.cutoff_sqr;
+    for (int k = 0; k < 3; ++k) o->nc[k] = (k < dim) ? box.nc[k] : 1;
+    for (int col = 0; col < dim; ++col)
+        for (int r = 0; r < dim; ++r) {
+            o->input_unit_cell[r + dim * col] = box.in[r][col]; o->aligned_unit_cell[r + dim * col] = box.al[r][col];
+            o->rotation[r + dim * col] = box.rot[r][col]; o->inv_rotation[r + dim * col] = box.irot[r][col];
+        }
+    for (int k = 0; k < dim; ++k) { o->computing_box_min[k] = box.cb_min[k]; o->computing_box_max[k] = box.cb_max[k]; o->cell_size[k] = box.cs[k]; o->origin[k] = box.origin[k]; }
+    return CLM_OK;
+}
+
+template <class T> int Engine<T>::set_positions(int set, const void* xyz, int64_t n, int on_device) {
+    if (set != 0 && set != 1) return fail(CLM_ERR_ARGUMENT, "set must be 0 (x) or 1 (y)");
+    if (n < 0) return fail(CLM_ERR_ARGUMENT, "negative particle count");
+    if (n > 0 && !xyz) return fail(CLM_ERR_ARGUMENT, "positions pointer is NULL");
+    if (n > (int64_t)(TagT<float>::MASK)) return fail(CLM_ERR_UNSUPPORTED, "more than 2^30 particles in one set");
+    CLM_CK(cudaSetDevice(device));
+    DevSet<T>& s = sets[set];
+    CLM_CK(s.pos.ensure((size_t)n * dim));
+    if (n) CLM_CK(cudaMemcpyAsync(s.pos.p, xyz, (size_t)n * dim * sizeof(T), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+    s.n = n;
+    if (set == 1) two_sets = (n > 0) || (xyz != nullptr);   // (NULL, 0) removes the second set; an empty y set gives no pairs
+    dirty = true;
+    return CLM_OK;
+}
+
+template <class T> int Engine<T>::scan(const int* in, int* out, int n, int* total_slot, int* out_end) {
+    const int nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    CLM_CK(scan_partial.ensure((size_t)std::max(nb, 1)));
+    k_scan_local<<<nb, SCAN_THREADS, 0, stream>>>(in, out, n, scan_partial.p);
+    k_scan_partials<<<1, SCAN_THREADS, 0, stream>>>(scan_partial.p, nb, total_slot, out_end);
+    k_scan_add<<<nb, SCAN_THREADS, 0, stream>>>(out, n, scan_partial.p);
+    CLM_CK(cudaGetLastError());
+    stats.launches += 3;
+    return CLM_OK;
+}
+
+// UpdateCellList! (CellLists.jl:727-927; non-periodic NonPeriodicCells.jl:93-230)
+template <class T> int Engine<T>::build() {
+    if (!dirty) return CLM_OK;
+    CLM_CK(cudaSetDevice(device));
+    const int nsets = two_sets ? 2 : 1;
+    for (int s = 0; s < nsets; ++s)
+        if (sets[s].n > 0x7fffffffLL / 28) return fail(CLM_ERR_UNSUPPORTED, "too many particles for 32-bit record indices");
+    CLM_CK(cudaEventRecord(ev0, stream));
+    // device scalars
+    for (int k = 0; k < DS_COUNT; ++k) h_dscal[k] = 0;
+    h_dscal[DS_NAN] = h_dscal[DS_OOB] = h_dscal[DS_SET_STRIDE + DS_NAN] = h_dscal[DS_SET_STRIDE + DS_OOB] = IDX_NONE;
+    CLM_CK(cudaMemcpyAsync(dscal.p, h_dscal, DS_COUNT * sizeof(int), cudaMemcpyHostToDevice, stream));
+    if (nonperiodic) {
+        // Box(limits(x[,y]), cutoff): sides = extent + 2.1*cutoff, origin = minimum coordinates
+        // (CellOperations.jl:290-324, Box.jl:38, :374-377); limits by a device reduction
+        T lo[3], hi[3];
+        for (int k = 0; k < 3; ++k) { lo[k] = std::numeric_limits<T>::max(); hi[k] = std::numeric_limits<T>::lowest(); }
+        for (int s = 0; s < nsets; ++s) {
+            const int64_t n = sets[s].n;
+            T slo[3] = {T(0), T(0), T(0)}, shi[3] = {T(0), T(0), T(0)};   // empty set: zero limits (_minmax, CellOperations.jl:263-265)
+            if (n > 0) {
+                const int nb = (int)std::min<int64_t>(1024, (n + 255) / 256);
+                CLM_CK(d_minmax.ensure((size_t)nb * 6));
+                if (dim == 3) k_minmax<T, 3><<<nb, 256, 0, stream>>>(sets[s].pos.p, (int)n, d_minmax.p, dscal.p + s * DS_SET_STRIDE);
+                else k_minmax<T, 2><<<nb, 256, 0, stream>>>(sets[s].pos.p, (int)n, d_minmax.p, dscal.p + s * DS_SET_STRIDE);
+                CLM_CK(cudaGetLastError());
+                stats.launches += 1;
+                std::vector<T> h((size_t)nb * 6);
+                CLM_CK(cudaMemcpyAsync(h.data(), d_minmax.p, h.size() * sizeof(T), cudaMemcpyDeviceToHost, stream));
+                CLM_CK(cudaStreamSynchronize(stream));
+                for (int k = 0; k < 3; ++k) { slo[k] = std::numeric_limits<T>::max(); shi[k] = std::numeric_limits<T>::lowest(); }
+                for (int b = 0; b < nb; ++b)
+                    for (int k = 0; k < dim; ++k) { slo[k] = std::min(slo[k], h[(size_t)b * 6 + k]); shi[k] = std::max(shi[k], h[(size_t)b * 6 + 3 + k]); }
+            }
+            for (int k = 0; k < dim; ++k) { lo[k] = std::min(lo[k], slo[k]); hi[k] = std::max(hi[k], shi[k]); }
+        }
+        T cell[3][3], origin[3] = {T(0), T(0), T(0)};
+        geo::eye(cell);
+        const T pad = T(210) * np_cutoff / T(100);
+        for (int k = 0; k < dim; ++k) { cell[k][k] = (hi[k] - lo[k]) + pad; origin[k] = lo[k]; }
+        box_set = false;
+        // a NaN coordinate poisons the limits: report it as the reference does (validation runs first there)
+        CLM_CK(cudaMemcpyAsync(h_dscal, dscal.p, DS_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CLM_CK(cudaStreamSynchronize(stream));
+        for (int s = 0; s < nsets; ++s)
+            if (h_dscal[s * DS_SET_STRIDE + DS_NAN] != IDX_NONE)
+                return fail(CLM_ERR_INVALID_COORDINATES, "Invalid coordinates found (NaN) for particle of index " + std::to_string(h_dscal[s * DS_SET_STRIDE + DS_NAN] + 1) + (s ? " of the second set" : ""));
+        int rcode = make_box(box, dim, CLM_NONPERIODIC, cell, np_cutoff, np_lcell, origin, err);
+        if (rcode != CLM_OK) return rcode;
+        box_set = true;
+    }
+    if (!box_set) return fail(CLM_ERR_STATE, "clm_set_box must be called before clm_build");
+    fill_geom(box, geom);
+    double nc_total = 1;
+    for (int k = 0; k < dim; ++k) nc_total *= (double)box.nc[k];
+    if (nc_total > 2.0e9) return fail(CLM_ERR_UNSUPPORTED, "more than 2e9 computing cells: increase the cutoff or use lcell = 1");
+    for (int k = 0; k < dim; ++k) if (box.nc[k] > 32767) return fail(CLM_ERR_UNSUPPORTED, "more than 32767 cells along one dimension");
+    ncells = (int64_t)nc_total;
+    // device row = cells along the LAST reference dimension (see cell_of)
+    nfast = (int)box.nc[dim - 1]; nmid = (int)((dim == 3) ? box.nc[1] : box.nc[0]); nslow = (int)((dim == 3) ? box.nc[0] : 1);
+    nrows = ncells / nfast;
+    for (int s = 0; s < nsets; ++s) {
+        DevSet<T>& S = sets[s];
+        CLM_CK(S.cell_start.ensure((size_t)ncells + 1));
+        CLM_CK(S.cell_count.ensure((size_t)ncells));
+        CLM_CK(S.cell_nreal.ensure((size_t)ncells));
+        CLM_CK(cudaMemsetAsync(S.cell_count.p, 0, (size_t)ncells * sizeof(int), stream));
+        CLM_CK(cudaMemsetAsync(S.cell_nreal.p, 0, (size_t)ncells * sizeof(int), stream));
+        int* ds = dscal.p + s * DS_SET_STRIDE;
+        if (S.n > 0) {
+            const int nb = (int)((S.n + 255) / 256);
+            if (dim == 3) k_bin<T, 3, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count.p, S.cell_nreal.p, nullptr, nullptr, ds);
+            else k_bin<T, 2, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count.p, S.cell_nreal.p, nullptr, nullptr, ds);
+            CLM_CK(cudaGetLastError());
+            stats.launches += 1;
+        }
+        if (int rc = scan(S.cell_count.p, S.cell_start.p, (int)ncells, ds + DS_NTOT, S.cell_start.p + ncells)) return rc;
+    }
+    CLM_CK(cudaMemcpyAsync(h_dscal, dscal.p, DS_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CLM_CK(cudaStreamSynchronize(stream));
+    for (int s = 0; s < nsets; ++s) {
+        const int* hs = h_dscal + s * DS_SET_STRIDE;
+        if (hs[DS_NAN] != IDX_NONE)
+            return fail(CLM_ERR_INVALID_COORDINATES, "Invalid coordinates found (NaN) for particle of index " + std::to_string(hs[DS_NAN] + 1) + (s ? " of the second set" : ""));
+        if (hs[DS_OOB] != IDX_NONE)
+            return fail(CLM_ERR_INVALID_COORDINATES, "Invalid coordinates found: particle of index " + std::to_string(hs[DS_OOB] + 1) + " falls outside the computing grid (non-finite coordinate?)");
+        sets[s].n_tot = hs[DS_NTOT];
+    }
+    for (int s = 0; s < nsets; ++s) {
+        DevSet<T>& S = sets[s];
+        CLM_CK(S.rec.ensure((size_t)std::max<int64_t>(S.n_tot, 1)));
+        CLM_CK(cudaMemsetAsync(S.cell_count.p, 0, (size_t)ncells * sizeof(int), stream));
+        if (S.n > 0) {
+            const int nb = (int)((S.n + 255) / 256);
+            int* ds = dscal.p + s * DS_SET_STRIDE;
+            if (dim == 3) k_bin<T, 3, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count.p, S.cell_nreal.p, S.cell_start.p, S.rec.p, ds);
+            else k_bin<T, 2, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count.p, S.cell_nreal.p, S.cell_start.p, S.rec.p, ds);
+            CLM_CK(cudaGetLastError());
+            stats.launches += 1;
+        }
+    }
+    // tile size: particles per warp tile; small tiles (more j-slices) when cells hold few particles
+    {
+        double inner = 1;
+        for (int k = 0; k < dim; ++k) inner *= (double)std::max<int64_t>(1, box.nc[k] - 2 * box.lcell - 1);
+        const double per_cell = (double)sets[0].n / inner;
+        tile_i = opt_tile_i ? opt_tile_i : (per_cell >= 20.0 ? 32 : (per_cell >= 6.0 ? 16 : 8));
+        log2ti = (tile_i == 32) ? 5 : (tile_i == 16 ? 4 : 3);
+    }
+    CLM_CK(row_ntiles.ensure((size_t)nrows + 1));
+    CLM_CK(row_range.ensure((size_t)nrows));
+    tiles_upper = sets[0].n_tot / tile_i + nrows + 1;
+    CLM_CK(tiles.ensure((size_t)tiles_upper));
+    {
+        const int nb = (int)((nrows * 32 + 255) / 256);
+        k_rows<<<nb, 256, 0, stream>>>(sets[0].cell_nreal.p, sets[0].cell_start.p, nfast, (int)nrows, tile_i, row_ntiles.p, row_range.p, dscal.p);
+        stats.launches += 1;
+        if (two_sets) {
+            k_rows<<<nb, 256, 0, stream>>>(sets[1].cell_nreal.p, sets[1].cell_start.p, nfast, (int)nrows, tile_i, nullptr, nullptr, dscal.p + DS_SET_STRIDE);
+            stats.launches += 1;
+        }
+        CLM_CK(cudaGetLastError());
+        if (int rc = scan(row_ntiles.p, row_ntiles.p, (int)nrows, dscal.p + DS_NTILES, nullptr)) return rc;
+        const int nbt = (int)((tiles_upper + 255) / 256);
+        k_tiles<<<nbt, 256, 0, stream>>>(row_ntiles.p, row_range.p, sets[0].cell_start.p, nfast, (int)nrows, tile_i, dscal.p, tiles.p);
+        CLM_CK(cudaGetLastError());
+        stats.launches += 1;
+    }
+    CLM_CK(cudaEventRecord(ev1, stream));
+    CLM_CK(cudaMemcpyAsync(h_dscal, dscal.p, DS_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CLM_CK(cudaStreamSynchronize(stream));
+    float ms = 0;
+    CLM_CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    stats.build_ms = ms;
+    stats.n_cells = ncells;
+    stats.n_tiles = h_dscal[DS_NTILES];
+    for (int s = 0; s < 2; ++s) {
+        stats.n_real[s] = (s < nsets) ? sets[s].n : 0;
+        stats.n_total[s] = (s < nsets) ? sets[s].n_tot : 0;
+        stats.n_cells_real[s] = (s < nsets) ? h_dscal[s * DS_SET_STRIDE + DS_NCELLS_REAL] : 0;
+    }
+    dirty = false;
+    return CLM_OK;
+}
+
+template <class T> int Engine<T>::prepare_map(int flags) {
+    CLM_CK(cudaSetDevice(device));
+    if (int rc = build()) return rc;
+    if (flags & CLM_PROFILE) CLM_CK(cudaEventRecord(ev0, stream));
+    CLM_CK(cudaMemsetAsync(d_res.p, 0, sizeof(ResultBlock), stream));
+    CLM_CK(cudaMemsetAsync(dscal.p + DS_WORK, 0, sizeof(int), stream));
+    return CLM_OK;
+}
+template <class T> int Engine<T>::finish_map(int flags) {
+    if (flags & CLM_PROFILE) {
+        CLM_CK(cudaEventRecord(ev1, stream));
+        CLM_CK(cudaEventSynchronize(ev1));
+        float ms = 0;
+        CLM_CK(cudaEventElapsedTime(&ms, ev0, ev1));
+        stats.map_ms = ms;
+    }
+    return CLM_OK;
+}
+template <class T> int Engine<T>::fetch_results() {
+    CLM_CK(cudaMemcpyAsync(h_res, d_res.p, sizeof(ResultBlock), cudaMemcpyDeviceToHost, stream));
+    CLM_CK(cudaStreamSynchronize(stream));
+    return CLM_OK;
+}
+
+// per-particle auxiliary input (weights / velocities) -> record order of `set`
+template <class T> int Engine<T>::gather_aux(int set, const T* aux, int ncomp, bool rotate, bool on_device) {
+    DevSet<T>& S = sets[set];
+    const size_t out_n = (size_t)std::max<int64_t>(S.n_tot, 1) * (ncomp == 1 ? 1 : 4);
+    const size_t in_n = (size_t)S.n * ncomp;
+    CLM_CK(S.aux.ensure(out_n + in_n + 4));
+    T* staged = S.aux.p + out_n;
+    if (S.n == 0) return CLM_OK;
+    CLM_CK(cudaMemcpyAsync(staged, aux, in_n * sizeof(T), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+    const int nb = (int)((S.n_tot + 255) / 256);
+    if (nb) k_gather_aux<T><<<nb, 256, 0, stream>>>(S.rec.p, (int)S.n_tot, staged, ncomp, geom, rotate ? 1 : 0, S.aux.p);
+    CLM_CK(cudaGetLastError());
+    stats.launches += 1;
+    return CLM_OK;
+}
+
+// scalar / small-vector real outputs: out = (reset ? 0 : out) + scale * accumulator
+template <class T> int Engine<T>::store_real(void* out, const double* dev_src, const double* host_src, int n, double scale, int flags) {
+    if (!out) return CLM_OK;
+    if (flags & CLM_OUT_DEVICE) {
+        k_store_real<T><<<(n + 127) / 128, 128, 0, stream>>>((T*)out, dev_src, n, scale, (flags & CLM_RESET) ? 0 : 1);
+        CLM_CK(cudaGetLastError());
+        stats.launches += 1;
+    } else {
+        T* o = (T*)out;
+        for (int k = 0; k < n; ++k) o[k] = (T)(((flags & CLM_RESET) ? 0.0 : (double)o[k]) + scale * host_src[k]);
+    }
+    return CLM_OK;
+}
+template <class T> int Engine<T>::store_i64(int64_t* out, const unsigned long long* dev_src, const unsigned long long* host_src, int n, int flags) {
+    if (!out) return CLM_OK;
+    if (flags & CLM_OUT_DEVICE) {
+        k_store_i64<<<(n + 127) / 128, 128, 0, stream>>>((long long*)out, dev_src, n, (flags & CLM_RESET) ? 0 : 1);
+        CLM_CK(cudaGetLastError());
+        stats.launches += 1;
+    } else {
+        for (int k = 0; k < n; ++k) out[k] = ((flags & CLM_RESET) ? 0 : out[k]) + (int64_t)host_src[k];
+    }
+    return CLM_OK;
+}
+
+// forces: the sweep stores each real particle's force exactly once.  Device outputs are written (or
+// accumulated) in place; host outputs go through a device staging buffer and are added on the host.
+template <class T> int Engine<T>::forces_begin(void* forces_out, int flags, ForceOut<T>& fo) {
+    fo.dim = dim; fo.rotated = geom.rotated;
+    for (int k = 0; k < 9; ++k) fo.inv_rot[k] = geom.inv_rot[k];
+    if (flags & CLM_OUT_DEVICE) { fo.forces = (T*)forces_out; fo.accumulate = (flags & CLM_RESET) ? 0 : 1; return CLM_OK; }
+    CLM_CK(d_forces.ensure((size_t)std::max<int64_t>(sets[0].n, 1) * dim));
+    fo.forces = d_forces.p; fo.accumulate = 0;
+    return CLM_OK;
+}
+template <class T> int Engine<T>::forces_end(void* forces_out, int flags) {
+    if (flags & CLM_OUT_DEVICE) return CLM_OK;
+    const size_t cnt = (size_t)sets[0].n * dim;
+    if (cnt == 0) return CLM_OK;
+    if (flags & CLM_RESET) {
+        CLM_CK(cudaMemcpyAsync(forces_out, d_forces.p, cnt * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        CLM_CK(cudaStreamSynchronize(stream));
+    } else {
+        h_stage.resize(cnt * sizeof(T));
+        CLM_CK(cudaMemcpyAsync(h_stage.data(), d_forces.p, cnt * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        CLM_CK(cudaStreamSynchronize(stream));
+        T* o = (T*)forces_out;
+        const T* a = (const T*)h_stage.data();
+        for (size_t k = 0; k < cnt; ++k) o[k] += a[k];
+    }
+    return CLM_OK;
+}
+
+template <class T> int Engine<T>::get_stats(clm_stats* out) {
+    if (!out) return fail(CLM_ERR_ARGUMENT, "output pointer is NULL");
+    *out = stats;
+    return CLM_OK;
+}
+template <class T> int Engine<T>::set_option(const char* name, int64_t v) {
+    if (!name) return fail(CLM_ERR_ARGUMENT, "option name is NULL");
+    const std::string s(name);
+    if (s == "tile_i") {
+        if (v != 0 && v != 8 && v != 16 && v != 32) return fail(CLM_ERR_ARGUMENT, "tile_i must be 0, 8, 16 or 32");
+        opt_tile_i = (int)v; dirty = true; return CLM_OK;
+    }
+    if (s == "blocks_per_sm") { if (v < 0) return fail(CLM_ERR_ARGUMENT, "blocks_per_sm must be >= 0"); opt_bps = (int)v; return CLM_OK; }
+    return fail(CLM_ERR_ARGUMENT, "unknown option " + s);
+}
+
+template struct Engine<float>;
+template struct Engine<double>;
+
+}  // namespace clm
+
+// ===================================================================================================
+using clm::EngineBase;
+struct clm_handle { EngineBase* e; };
+
+extern "C" {
+int clm_version(void) { return 100; }
+const char* clm_last_error(clm_handle* h) { return h ? h->e->err.c_str() : clm::g_create_error.c_str(); }
+
+int clm_create(clm_handle** out, int dim, int dtype, int device, int ngpus) {
+    if (!out) { clm::g_create_error = "handle output pointer is NULL"; return CLM_ERR_ARGUMENT; }
+    *out = nullptr;
+    if (dim != 2 && dim != 3) { clm::g_create_error = "Dimension must be 2 or 3."; return CLM_ERR_DIMENSION; }
+    if (dtype != CLM_F32 && dtype != CLM_F64) { clm::g_create_error = "dtype must be CLM_F32 or CLM_F64"; return CLM_ERR_ARGUMENT; }
+    if (ngpus != 1) { clm::g_create_error = "one handle drives one GPU; multi-GPU slabs use one handle per rank (clm_slab_*)"; return CLM_ERR_UNSUPPORTED; }
+    EngineBase* e = nullptr;
+    int rc;
+    if (dtype == CLM_F32) { auto* p = new (std::nothrow) clm::Engine<float>(); e = p; rc = p ? p->init(dim, device) : CLM_ERR_CUDA; }
+    else { auto* p = new (std::nothrow) clm::Engine<double>(); e = p; rc = p ? p->init(dim, device) : CLM_ERR_CUDA; }
+    if (rc != CLM_OK) { clm::g_create_error = e ? e->err : "out of memory"; delete e; return rc; }
+    *out = new clm_handle{e};
+    return CLM_OK;
+}
+int clm_destroy(clm_handle* h) { if (h) { delete h->e; delete h; } return CLM_OK; }
+#define H_OR_FAIL if (!h) return CLM_ERR_ARGUMENT
+int clm_set_stream(clm_handle* h, void* s) { H_OR_FAIL; return h->e->set_stream(s); }
+int clm_synchronize(clm_handle* h) { H_OR_FAIL; return h->e->synchronize(); }
+int clm_set_box(clm_handle* h, int ct, const void* uc, int is_matrix, const void* cutoff, int lcell) { H_OR_FAIL; return h->e->set_box(ct, uc, is_matrix, cutoff, lcell); }
+int clm_get_box(clm_handle* h, clm_box_info* o) { H_OR_FAIL; return h->e->get_box(o); }
+int clm_set_positions(clm_handle* h, int set, const void* xyz, int64_t n, int on_device) { H_OR_FAIL; return h->e->set_positions(set, xyz, n, on_device); }
+int clm_build(clm_handle* h) { H_OR_FAIL; return h->e->build(); }
+int clm_map_lj(clm_handle* h, const void* p, int flags, void* e, void* f) { H_OR_FAIL; return h->e->map_lj(p, flags, e, f); }
+int clm_map_coulomb(clm_handle* h, const void* wx, const void* wy, const void* k, int flags, void* e, void* f) { H_OR_FAIL; return h->e->map_coulomb(wx, wy, k, flags, e, f); }
+int clm_map_dist_hist(clm_handle* h, const void* width, int nbins, int flags, int64_t* counts) { H_OR_FAIL; return h->e->map_dist_hist(width, nbins, flags, counts); }
+int clm_map_pairvel(clm_handle* h, const void* vx, const void* vy, const void* rbins, int nbins, int flags, int64_t* counts, void* sums) { H_OR_FAIL; return h->e->map_pairvel(vx, vy, rbins, nbins, flags, counts, sums); }
+int clm_map_mindist(clm_handle* h, int flags, int64_t* i, int64_t* j, void* d) { H_OR_FAIL; return h->e->map_mindist(flags, i, j, d); }
+int clm_map_sum_d_d2(clm_handle* h, int flags, void* sd, void* sd2, int64_t* np) { H_OR_FAIL; return h->e->map_sum(flags, sd, sd2, np); }
+int clm_neighborlist(clm_handle* h, int flags, int64_t* n) { H_OR_FAIL; return h->e->neighborlist(flags, n); }
+int clm_neighborlist_copy(clm_handle* h, void* rec, int64_t cap, int on_device) { H_OR_FAIL; return h->e->neighborlist_copy(rec, cap, on_device); }
+int clm_get_stats(clm_handle* h, clm_stats* o) { H_OR_FAIL; return h->e->get_stats(o); }
+int clm_set_option(clm_handle* h, const char* name, int64_t v) { H_OR_FAIL; return h->e->set_option(name, v); }
+}

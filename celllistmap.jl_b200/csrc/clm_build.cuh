@@ -1,0 +1,298 @@
+// Cell-list construction kernels (the B200 replacement of UpdateCellList!,
+// src/internals/CellLists.jl:727-927 / add_particles! :940-950 / add_particle_to_celllist! :983-1057,
+// non-periodic src/internals/NonPeriodicCells.jl:63-70, :93-230).
+//
+// The reference builds an array of heap-allocated per-cell vectors; here the list is ONE
+// counting sort into a cell-sorted packed record array:
+//   k_bin_count   : wrap + rotate each particle, enumerate its 3^N-1 lattice images, keep those inside
+//                   the computing box, histogram real+image particles per cell (global atomics)
+//   scan          : exclusive prefix over cells (3 small kernels, reduce-then-scan)
+//   k_bin_scatter : same traversal, records scattered to cell_start[c] + atomic cursor
+//   k_rows/k_tiles: row-aligned work items for the sweep
+// All of it is HBM/latency bound integer + a few dozen flops per particle: no tensor cores.
+// Algorithmic bytes per particle: read N*sizeof(T) twice, write (1+g)*sizeof(Rec),
+// plus 8*n_cells for the histogram/prefix arrays, g = image fraction.
+#pragma once
+#include "clm_common.cuh"
+
+namespace clm {
+
+constexpr int IDX_NONE = 0x7fffffff;
+// device scalar block (ints)
+enum { DS_NAN = 0, DS_OOB = 1, DS_NTOT = 2, DS_NTILES = 3, DS_WORK = 4, DS_NCELLS_REAL = 5, DS_COUNT = 16 };
+
+// p = rotation * (M * frac(M \ x)), every operation rounded separately in T
+// (CellLists.jl:944-945; CellOperations.jl:56-66, :91-94).  Non-periodic: coordinates are used as given.
+template <class T, int DIM> __device__ __forceinline__ void place_particle(const GeomT<T>& g, const T* x, T p[3]) {
+    p[2] = T(0);
+    if (g.cell_type == CLM_NONPERIODIC_CT) {
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) p[k] = x[k];
+        return;
+    }
+    T f[DIM];
+    if (DIM == 3) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            f[k] = xdiv(xadd(xadd(xmul(g.cof[3 * k], x[0]), xmul(g.cof[3 * k + 1], x[1])), xmul(g.cof[3 * k + 2], x[2])), g.det);
+    } else {
+        f[0] = xdiv(xsub(xmul(g.cof[0], x[0]), xmul(g.cof[1], x[1])), g.det);
+        f[1] = xdiv(xsub(xmul(g.cof[3], x[1]), xmul(g.cof[4], x[0])), g.det);
+    }
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        f[k] = xsub(f[k], floor(f[k]));
+        if (f[k] == T(1)) f[k] = T(0);
+    }
+    T w[DIM];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        T s = xmul(g.m[3 * k], f[0]);
+#pragma unroll
+        for (int c = 1; c < DIM; ++c) s = xadd(s, xmul(g.m[3 * k + c], f[c]));
+        w[k] = s;
+    }
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        T s = xmul(g.rot[3 * k], w[0]);
+#pragma unroll
+        for (int c = 1; c < DIM; ++c) s = xadd(s, xmul(g.rot[3 * k + c], w[c]));
+        p[k] = s;
+    }
+}
+
+// 0-based linear cell of a point; real particles get the reference's border nudge
+// (particle_cell Box.jl:499-508, real_particle_border_case CellLists.jl:956-967).  -1 = outside the grid.
+//
+// DEVICE linearisation: the LAST reference dimension runs fastest (lin = c[N-1] + nc[N-1]*(c[N-2] + ...)),
+// the transpose of the reference's column-major cell_linear_index (CellOperations.jl:256-257).  With it
+// the reference's forward stencil (Box.jl:436-457: d1 > 0 | d1 == 0, d2 > 0 | d1 == d2 == 0, d3 > 0)
+// is "later cells of the own row + every row with a larger row index within l", so the sweep visits
+// each cell pair from the SAME home cell as the reference and therefore evaluates the same periodic
+// image of every pair (bit-identical d2).
+template <class T, int DIM> __device__ __forceinline__ int cell_of(const GeomT<T>& g, const T p[3], bool real) {
+    int lin = 0;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) {
+        const T q = floor(xdiv(xsub(p[k], g.cb_min[k]), g.cs[k]));
+        if (!(q >= T(-1) && q <= T(g.nc[k]))) return -1;  // also rejects NaN / Inf
+        int c = (int)q;
+        if (real) {
+            if (c == g.lcell - 1) c += 1;
+            if (c == g.nc[k] - g.lcell) c -= 1;
+        }
+        if (c < 0 || c >= g.nc[k]) return -1;
+        lin = lin * g.nc[k] + c;
+    }
+    return lin;
+}
+
+template <class T, int DIM, bool SCATTER>
+static __global__ void __launch_bounds__(256)
+k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, int n, int* __restrict__ cell_count,
+      int* __restrict__ cell_nreal, const int* __restrict__ cell_start, RecT<T>* __restrict__ rec, int* __restrict__ dscal) {
+    typedef TagT<T> TG;
+    const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= n) return;
+    T x[DIM];
+    bool bad = false;
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) { x[k] = pos[(size_t)ip * DIM + k]; bad |= (x[k] != x[k]); }
+    if (bad) { if (!SCATTER) atomicMin(&dscal[DS_NAN], ip); return; }   // _validate_coordinates, CellOperations.jl:6-21
+    T p[3];
+    place_particle<T, DIM>(g, x, p);
+    const int lin = cell_of<T, DIM>(g, p, true);
+    if (lin < 0) { if (!SCATTER) atomicMin(&dscal[DS_OOB], ip); return; }
+    if (!SCATTER) {
+        atomicAdd(&cell_count[lin], 1);
+        atomicAdd(&cell_nreal[lin], 1);
+    } else {
+        const int slot = cell_start[lin] + atomicAdd(&cell_count[lin], 1);
+        strec(&rec[slot], p[0], p[1], p[2], (typename TG::type)ip | TG::HOME);
+    }
+    if (g.cell_type == CLM_NONPERIODIC_CT) return;
+    // replicate_particle! (Box.jl:556-566): images x + aligned_cell*idx, idx in {-1,0,1}^N \ {0}, kept iff
+    // inside the computing box [cb_min, cb_max)
+    constexpr int NIMG = (DIM == 3) ? 27 : 9;
+    constexpr int CENTER = (DIM == 3) ? 13 : 4;
+#pragma unroll 1
+    for (int img = 0; img < NIMG; ++img) {
+        if (img == CENTER) continue;
+        T q[3] = {T(0), T(0), T(0)};
+        bool in = true;
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) {
+            q[k] = xadd(p[k], g.shift[img][k]);
+            in = in && (g.cb_min[k] <= q[k]) && (q[k] < g.cb_max[k]);
+        }
+        if (!in) continue;
+        const int lq = cell_of<T, DIM>(g, q, false);
+        if (lq < 0) continue;
+        if (!SCATTER) {
+            atomicAdd(&cell_count[lq], 1);
+        } else {
+            const int slot = cell_start[lq] + atomicAdd(&cell_count[lq], 1);
+            const typename TG::type home = (cell_nreal[lq] > 0) ? TG::HOME : (typename TG::type)0;
+            strec(&rec[slot], q[0], q[1], q[2], (typename TG::type)ip | TG::GHOST | home);
+        }
+    }
+}
+
+// ---- exclusive scan of int32 (reduce-then-scan, 4096 items per block) -------------------------------
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 16, SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int block_exclusive_scan_256(int v, int* total) {
+    __shared__ int wsum[8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    int woff = 0, tot = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { int s = wsum[k]; if (k < w) woff += s; tot += s; }
+    *total = tot;
+    __syncthreads();
+    return woff + inc - v;
+}
+
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_local(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ partial) {
+    const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? in[base + k] : 0; s += v[k]; }
+    int total;
+    int off = block_exclusive_scan_256(s, &total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) out[base + k] = off; off += v[k]; }
+    if (threadIdx.x == 0) partial[blockIdx.x] = total;
+}
+// one block: exclusive scan of the per-block totals (any count), grand total to *total_out and out_end
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_partials(int* __restrict__ partial, int nb, int* __restrict__ total_out, int* __restrict__ out_end) {
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nb; b0 += SCAN_THREADS) {
+        const int i = b0 + threadIdx.x;
+        const int v = (i < nb) ? partial[i] : 0;
+        int total;
+        const int ex = block_exclusive_scan_256(v, &total);
+        const int carry = carry_s;
+        if (i < nb) partial[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { *total_out = carry_s; if (out_end) *out_end = carry_s; }
+}
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(int* __restrict__ out, int n, const int* __restrict__ partial) {
+    const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+    const int add = partial[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) if (base + k < n) out[base + k] += add;
+}
+
+// ---- rows and tiles -----------------------------------------------------------------------------------
+// one warp per (y,z) row of cells: first/last cell holding a real particle -> the record range
+// [cell_start[first], cell_start[last+1]) whose entries act as particle i, and its tile count.
+static __global__ void __launch_bounds__(256)
+k_rows(const int* __restrict__ cell_nreal, const int* __restrict__ cell_start, int nx, int nrows, int tile_i,
+       int* __restrict__ row_ntiles, int2* __restrict__ row_range, int* __restrict__ dscal) {
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    const int base = row * nx;
+    int first = IDX_NONE, last = -1, nreal_cells = 0;
+    for (int c = lane; c < nx; c += 32)
+        if (cell_nreal[base + c] > 0) { first = min(first, c); last = max(last, c); ++nreal_cells; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+        nreal_cells += __shfl_xor_sync(0xffffffffu, nreal_cells, o);
+    }
+    if (lane == 0) {
+        int a = 0, b = 0;
+        if (last >= 0) { a = cell_start[base + first]; b = cell_start[base + last + 1]; }
+        if (row_range) {
+            row_range[row] = make_int2(a, b);
+            row_ntiles[row] = (b - a + tile_i - 1) / tile_i;
+        }
+        if (nreal_cells) atomicAdd(&dscal[DS_NCELLS_REAL], nreal_cells);
+    }
+}
+
+static __global__ void __launch_bounds__(256)
+k_tiles(const int* __restrict__ row_tile_start, const int2* __restrict__ row_range, const int* __restrict__ cell_start,
+        int nx, int nrows, int tile_i, const int* __restrict__ dscal, Tile* __restrict__ tiles) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= dscal[DS_NTILES]) return;
+    // row = last r with row_tile_start[r] <= t
+    int lo = 0, hi = nrows - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (row_tile_start[mid] <= t) lo = mid; else hi = mid - 1; }
+    const int row = lo;
+    const int2 rr = row_range[row];
+    const int k0 = rr.x + (t - row_tile_start[row]) * tile_i;
+    const int cnt = min(tile_i, rr.y - k0);
+    const int* cs = cell_start + (size_t)row * nx;   // cs[c] <= k < cs[c+1]  <=>  record k lives in cell c
+    auto cell_x = [&](int k) { int a = 0, b = nx - 1; while (a < b) { const int mid = (a + b + 1) >> 1; if (cs[mid] <= k) a = mid; else b = mid - 1; } return a; };
+    Tile tl;
+    tl.k0 = k0; tl.cnt = cnt; tl.row = row;
+    tl.cx = cell_x(k0) | (cell_x(k0 + cnt - 1) << 16);
+    tiles[t] = tl;
+}
+
+// per-block min/max of the coordinates (limits(), CellOperations.jl:262-324): out[b][0..2] = min, [3..5] = max
+template <class T, int DIM>
+__global__ void __launch_bounds__(256) k_minmax(const T* __restrict__ pos, int n, T* __restrict__ out, int* __restrict__ dscal) {
+    __shared__ T smin[8][3], smax[8][3];
+    T lo[3], hi[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { lo[k] = CUDART_INF_T<T>(); hi[k] = -CUDART_INF_T<T>(); }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) {
+            const T v = pos[(size_t)i * DIM + k];
+            if (v != v) atomicMin(&dscal[DS_NAN], i);
+            lo[k] = fmin(lo[k], v); hi[k] = fmax(hi[k], v);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo[k] = fmin(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o)); hi[k] = fmax(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o)); }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) for (int k = 0; k < 3; ++k) { smin[w][k] = lo[k]; smax[w][k] = hi[k]; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int k = threadIdx.x;
+        T a = smin[0][k], b = smax[0][k];
+        for (int q = 1; q < 8; ++q) { a = fmin(a, smin[q][k]); b = fmax(b, smax[q][k]); }
+        out[blockIdx.x * 6 + k] = a; out[blockIdx.x * 6 + 3 + k] = b;
+    }
+}
+
+// gather per-particle auxiliary data (weights, velocities) into record order so that the sweep reads
+// it with the same broadcast/coalesced pattern as the records; velocities are rotated into the
+// aligned frame (dot(v, R^-1 d) == dot(R v, d)).
+template <class T>
+static __global__ void __launch_bounds__(256)
+k_gather_aux(const RecT<T>* __restrict__ rec, int n_tot, const T* __restrict__ aux, int ncomp, const __grid_constant__ GeomT<T> g,
+             int rotate, T* __restrict__ out) {
+    typedef TagT<T> TG;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_tot) return;
+    const size_t idx = (size_t)(rec[k].tag & TG::MASK);
+    if (ncomp == 1) { out[k] = aux[idx]; return; }
+    T v[3] = {T(0), T(0), T(0)};
+    for (int c = 0; c < ncomp; ++c) v[c] = aux[idx * ncomp + c];
+    if (rotate) {
+        T r[3];
+        for (int a = 0; a < 3; ++a) r[a] = g.rot[3 * a] * v[0] + g.rot[3 * a + 1] * v[1] + g.rot[3 * a + 2] * v[2];
+        for (int a = 0; a < 3; ++a) v[a] = r[a];
+    }
+    // stored as 4 components per record (x, y, z, 0): one 128-bit (F32) / two 128-bit (F64) loads
+    out[(size_t)k * 4 + 0] = v[0]; out[(size_t)k * 4 + 1] = v[1]; out[(size_t)k * 4 + 2] = v[2]; out[(size_t)k * 4 + 3] = T(0);
+}
+
+}  // namespace clm

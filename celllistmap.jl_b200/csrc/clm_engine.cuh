@@ -1,0 +1,164 @@
+// Engine<T>: one particle system on one B200 (the object behind a clm_handle).
+// Host-side orchestration only: buffers, launch configuration, result staging.  No CPU compute path.
+#pragma once
+#include <cstdio>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include "clm_common.cuh"
+#include "clm_geometry.hpp"
+#include "clm_build.cuh"
+#include "clm_sweep.cuh"
+
+namespace clm {
+
+constexpr int DS_SET_STRIDE = 6;   // dscal block of set y starts at dscal + 6
+
+struct EngineBase {
+    std::string err;
+    int dim = 3, dtype = 0, device = 0, n_sm = 148;
+    clm_stats stats{};
+    virtual ~EngineBase() {}
+    int fail(int code, const std::string& m) { err = m; return code; }
+    virtual int set_stream(void* s) = 0;
+    virtual int synchronize() = 0;
+    virtual int set_box(int cell_type, const void* uc, int is_matrix, const void* cutoff, int lcell) = 0;
+    virtual int get_box(clm_box_info* out) = 0;
+    virtual int set_positions(int set, const void* xyz, int64_t n, int on_device) = 0;
+    virtual int build() = 0;
+    virtual int map_lj(const void* p, int flags, void* e, void* f) = 0;
+    virtual int map_coulomb(const void* wx, const void* wy, const void* k, int flags, void* e, void* f) = 0;
+    virtual int map_dist_hist(const void* width, int nbins, int flags, int64_t* counts) = 0;
+    virtual int map_pairvel(const void* vx, const void* vy, const void* rbins, int nbins, int flags, int64_t* counts, void* sums) = 0;
+    virtual int map_mindist(int flags, int64_t* i, int64_t* j, void* d) = 0;
+    virtual int map_sum(int flags, void* sd, void* sd2, int64_t* np) = 0;
+    virtual int neighborlist(int flags, int64_t* n) = 0;
+    virtual int neighborlist_copy(void* rec, int64_t cap, int on_device) = 0;
+    virtual int get_stats(clm_stats* out) = 0;
+    virtual int set_option(const char* name, int64_t v) = 0;
+};
+
+#define CLM_CK(call)                                                                                          \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) return this->fail(CLM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+template <class U> struct DBuf {
+    U* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n, bool keep = false, cudaStream_t st = 0) {
+        if (n <= cap) return cudaSuccess;
+        size_t ncap = std::max(n, cap + cap / 4);
+        U* q = nullptr;
+        cudaError_t e = cudaMalloc((void**)&q, std::max<size_t>(ncap, 1) * sizeof(U));
+        if (e != cudaSuccess) return e;
+        if (keep && p && cap) cudaMemcpyAsync(q, p, cap * sizeof(U), cudaMemcpyDeviceToDevice, st);
+        if (p) { cudaStreamSynchronize(st); cudaFree(p); }
+        p = q; cap = ncap;
+        return cudaSuccess;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <class T> struct DevSet {
+    DBuf<T> pos;             // caller's coordinates, AoS n x dim (owning copy, like ParticleSystemPositions)
+    int64_t n = 0;
+    DBuf<RecT<T>> rec;       // cell-sorted records, real + image particles
+    int64_t n_tot = 0, n_cells_real = 0;
+    DBuf<int> cell_start, cell_count, cell_nreal;
+    DBuf<T> aux;             // per-record auxiliary data gathered for the map in flight
+};
+
+template <class T> struct Engine : EngineBase {
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    HostBox<T> box;
+    GeomT<T> geom;
+    bool box_set = false, nonperiodic = false, two_sets = false, dirty = true;
+    T np_cutoff = 0;
+    int np_lcell = 1;
+    DevSet<T> sets[2];
+    DBuf<int> dscal, scan_partial, row_ntiles;
+    DBuf<int2> row_range;
+    DBuf<Tile> tiles;
+    int* h_dscal = nullptr;          // pinned
+    DBuf<ResultBlock> d_res;
+    ResultBlock* h_res = nullptr;    // pinned
+    DBuf<unsigned long long> d_hcount, nl;
+    DBuf<double> d_hsum;
+    DBuf<T> d_rbins, d_forces, d_minmax;
+    DBuf<MinPartial> d_minpart;
+    DBuf<MinResult> d_minres;
+    std::vector<unsigned char> h_stage;   // host staging for accumulate-on-host paths
+    int64_t nl_count = 0;
+    int64_t ncells = 0, nrows = 0, tiles_upper = 0;
+    int nfast = 1, nmid = 1, nslow = 1;   // device cell grid: lin = fast + nfast*(mid + nmid*slow); fast = last reference dim
+    int tile_i = 32, log2ti = 5, opt_tile_i = 0, opt_bps = 0;
+
+    int init(int dim_, int device_);
+    ~Engine() override;
+    int set_stream(void* s) override { stream = s ? (cudaStream_t)s : own_stream; return CLM_OK; }
+    int synchronize() override { CLM_CK(cudaStreamSynchronize(stream)); return CLM_OK; }
+    int set_box(int cell_type, const void* uc, int is_matrix, const void* cutoff, int lcell) override;
+    int get_box(clm_box_info* out) override;
+    int set_positions(int set, const void* xyz, int64_t n, int on_device) override;
+    int build() override;
+    int map_lj(const void* p, int flags, void* e, void* f) override;
+    int map_coulomb(const void* wx, const void* wy, const void* k, int flags, void* e, void* f) override;
+    int map_dist_hist(const void* width, int nbins, int flags, int64_t* counts) override;
+    int map_pairvel(const void* vx, const void* vy, const void* rbins, int nbins, int flags, int64_t* counts, void* sums) override;
+    int map_mindist(int flags, int64_t* i, int64_t* j, void* d) override;
+    int map_sum(int flags, void* sd, void* sd2, int64_t* np) override;
+    int neighborlist(int flags, int64_t* n) override;
+    int neighborlist_copy(void* rec, int64_t cap, int on_device) override;
+    int get_stats(clm_stats* out) override;
+    int set_option(const char* name, int64_t v) override;
+
+    // ---- helpers shared by the map translation units ----
+    int scan(const int* in, int* out, int n, int* total_slot, int* out_end);
+    int sweep_mode() const { return two_sets ? MODE_ALL : (box.cell_type == CLM_TRICLINIC ? MODE_TRI : MODE_HALF); }
+    int prepare_map(int flags);                       // build if needed, zero the result block and the work counter
+    int finish_map(int flags);                        // CLM_PROFILE timing
+    int fetch_results();                              // result block -> h_res (synchronises)
+    int gather_aux(int set, const T* aux_host_or_dev, int ncomp, bool rotate, bool on_device);
+    int store_real(void* out, const double* dev_src, const double* host_src, int n, double scale, int flags);
+    int store_i64(int64_t* out, const unsigned long long* dev_src, const unsigned long long* host_src, int n, int flags);
+    int forces_begin(void* forces_out, int flags, ForceOut<T>& fo);
+    int forces_end(void* forces_out, int flags);
+
+    SweepArgs<T> make_args() const {
+        SweepArgs<T> a;
+        const DevSet<T>& tg = sets[two_sets ? 1 : 0];
+        a.rec_i = sets[0].rec.p; a.rec_j = tg.rec.p; a.cell_start_j = tg.cell_start.p;
+        a.tiles = tiles.p; a.dscal = dscal.p; a.res = d_res.p;
+        a.nx = nfast; a.ny = nmid; a.nz = nslow; a.lcell = geom.lcell; a.log2ti = log2ti; a.self = two_sets ? 0 : 1;
+        a.rc2 = geom.cutoff_sqr;
+        return a;
+    }
+    template <int MODE, class F> int launch(const F& f, size_t smem) {
+        auto kern = k_sweep<T, MODE, F>;
+        int bps = 0;
+        CLM_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SWEEP_THREADS, smem));
+        if (bps < 1) return fail(CLM_ERR_CUDA, "sweep kernel does not fit on an SM");
+        if (opt_bps > 0) bps = std::min(bps, opt_bps);
+        int64_t grid = (int64_t)n_sm * bps;
+        grid = std::max<int64_t>(1, std::min<int64_t>(grid, (tiles_upper + (SWEEP_THREADS / 32) - 1) / (SWEEP_THREADS / 32)));
+        kern<<<(unsigned)grid, SWEEP_THREADS, smem, stream>>>(make_args(), f);
+        CLM_CK(cudaGetLastError());
+        stats.launches += 1;
+        last_grid = (int)grid;
+        return CLM_OK;
+    }
+    // reduction-type functors run in the reference's own exactly-once mode for the system type
+    template <class F> int launch_reduce(const F& f, size_t smem) {
+        switch (sweep_mode()) {
+            case MODE_HALF: return launch<MODE_HALF>(f, smem);
+            case MODE_TRI: return launch<MODE_TRI>(f, smem);
+            default: return launch<MODE_ALL>(f, smem);
+        }
+    }
+    int last_grid = 0;
+};
+
+}  // namespace clm

@@ -1,0 +1,67 @@
+// clm_map_dist_hist / clm_map_pairvel: histogram maps of the catalogue.
+#include "clm_engine.cuh"
+
+namespace clm {
+
+static inline size_t hist_smem(int nbins, bool priv, size_t sum_bytes) {
+    const size_t slots = (size_t)nbins * (priv ? SWEEP_THREADS : 1);
+    return ((slots * 4 + 15) / 16) * 16 + slots * sum_bytes;
+}
+
+template <class T> int Engine<T>::map_dist_hist(const void* width, int nbins, int flags, int64_t* counts) {
+    if (!width || !counts) return fail(CLM_ERR_ARGUMENT, "width / counts pointer is NULL");
+    if (nbins < 1 || nbins > 2048) return fail(CLM_ERR_ARGUMENT, "nbins must be in 1..2048");
+    if (int rc = prepare_map(flags)) return rc;
+    CLM_CK(d_hcount.ensure((size_t)nbins));
+    CLM_CK(cudaMemsetAsync(d_hcount.p, 0, (size_t)nbins * sizeof(unsigned long long), stream));
+    FHist<T> fn;
+    fn.width = *(const T*)width;
+    fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = nullptr;
+    if (int rc = launch_reduce(fn, hist_smem(nbins, fn.hb.priv != 0, 0))) return rc;
+    std::vector<unsigned long long> hc;
+    if (!(flags & CLM_OUT_DEVICE)) {
+        hc.resize((size_t)nbins);
+        CLM_CK(cudaMemcpyAsync(hc.data(), d_hcount.p, hc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CLM_CK(cudaStreamSynchronize(stream));
+    }
+    if (int rc = store_i64(counts, d_hcount.p, hc.data(), nbins, flags)) return rc;
+    return finish_map(flags);
+}
+
+template <class T> int Engine<T>::map_pairvel(const void* vx, const void* vy, const void* rbins, int nbins, int flags, int64_t* counts, void* sums) {
+    if (!vx || !rbins || !counts || !sums) return fail(CLM_ERR_ARGUMENT, "velocity / rbins / output pointer is NULL");
+    if (two_sets && !vy) return fail(CLM_ERR_ARGUMENT, "velocities of the second set are required for a two-set system");
+    if (nbins < 1 || nbins > 1024) return fail(CLM_ERR_ARGUMENT, "nbins must be in 1..1024");
+    if (int rc = prepare_map(flags)) return rc;
+    const bool dev = (flags & CLM_OUT_DEVICE) != 0;
+    if (int rc = gather_aux(0, (const T*)vx, dim, geom.rotated != 0, dev)) return rc;
+    if (two_sets) { if (int rc = gather_aux(1, (const T*)vy, dim, geom.rotated != 0, dev)) return rc; }
+    CLM_CK(d_hcount.ensure((size_t)nbins));
+    CLM_CK(d_hsum.ensure((size_t)nbins));
+    CLM_CK(d_rbins.ensure((size_t)nbins + 1));
+    CLM_CK(cudaMemsetAsync(d_hcount.p, 0, (size_t)nbins * sizeof(unsigned long long), stream));
+    CLM_CK(cudaMemsetAsync(d_hsum.p, 0, (size_t)nbins * sizeof(double), stream));
+    CLM_CK(cudaMemcpyAsync(d_rbins.p, rbins, ((size_t)nbins + 1) * sizeof(T), cudaMemcpyHostToDevice, stream));
+    FVel<T> fn;
+    fn.v_i = sets[0].aux.p; fn.v_j = sets[two_sets ? 1 : 0].aux.p; fn.rbins = d_rbins.p;
+    fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = d_hsum.p;
+    if (int rc = launch_reduce(fn, hist_smem(nbins, fn.hb.priv != 0, sizeof(T)))) return rc;
+    std::vector<unsigned long long> hc;
+    std::vector<double> hs;
+    if (!dev) {
+        hc.resize((size_t)nbins); hs.resize((size_t)nbins);
+        CLM_CK(cudaMemcpyAsync(hc.data(), d_hcount.p, hc.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CLM_CK(cudaMemcpyAsync(hs.data(), d_hsum.p, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, stream));
+        CLM_CK(cudaStreamSynchronize(stream));
+    }
+    if (int rc = store_i64(counts, d_hcount.p, hc.data(), nbins, flags)) return rc;
+    if (int rc = store_real(sums, d_hsum.p, hs.data(), nbins, 1.0, flags)) return rc;
+    return finish_map(flags);
+}
+
+template int Engine<float>::map_dist_hist(const void*, int, int, int64_t*);
+template int Engine<double>::map_dist_hist(const void*, int, int, int64_t*);
+template int Engine<float>::map_pairvel(const void*, const void*, const void*, int, int, int64_t*, void*);
+template int Engine<double>::map_pairvel(const void*, const void*, const void*, int, int, int64_t*, void*);
+
+}  // namespace clm

@@ -1,0 +1,64 @@
+// clm_map_lj / clm_map_coulomb: energy (+ forces) maps of the catalogue.
+#include "clm_engine.cuh"
+
+namespace clm {
+
+template <class T> int Engine<T>::map_lj(const void* p, int flags, void* e, void* f) {
+    if (!p) return fail(CLM_ERR_ARGUMENT, "LJ parameter pointer is NULL");
+    if (int rc = prepare_map(flags)) return rc;
+    const T* c = (const T*)p;
+    double scale = 1.0;
+    if (f) {
+        // full-shell sweep: every ordered pair (i real, j any image) adds to f_i only -> one plain store per
+        // particle, no atomics, no per-batch force copies; the energy is visited twice in self-set systems
+        FLJ<T, true> fn;
+        fn.c6 = c[0]; fn.c12 = c[1];
+        if (int rc = forces_begin(f, flags, fn.fo)) return rc;
+        if (int rc = launch<MODE_ALL>(fn, 0)) return rc;
+        scale = two_sets ? 1.0 : 0.5;
+    } else {
+        FLJ<T, false> fn;
+        fn.c6 = c[0]; fn.c12 = c[1];
+        std::memset(&fn.fo, 0, sizeof(fn.fo));
+        if (int rc = launch_reduce(fn, 0)) return rc;
+    }
+    if (!(flags & CLM_OUT_DEVICE)) { if (int rc = fetch_results()) return rc; }
+    if (int rc = store_real(e, &d_res.p->f[RB_ENERGY], &h_res->f[RB_ENERGY], 1, scale, flags)) return rc;
+    if (f) { if (int rc = forces_end(f, flags)) return rc; }
+    return finish_map(flags);
+}
+
+template <class T> int Engine<T>::map_coulomb(const void* wx, const void* wy, const void* k, int flags, void* e, void* f) {
+    if (!wx || !k) return fail(CLM_ERR_ARGUMENT, "weights / k pointer is NULL");
+    if (two_sets && !wy) return fail(CLM_ERR_ARGUMENT, "weights of the second set are required for a two-set system");
+    if (int rc = prepare_map(flags)) return rc;
+    const bool dev = (flags & CLM_OUT_DEVICE) != 0;
+    if (int rc = gather_aux(0, (const T*)wx, 1, false, dev)) return rc;
+    if (two_sets) { if (int rc = gather_aux(1, (const T*)wy, 1, false, dev)) return rc; }
+    const T* wi = sets[0].aux.p;
+    const T* wj = sets[two_sets ? 1 : 0].aux.p;
+    double scale = 1.0;
+    if (f) {
+        FCoul<T, true> fn;
+        fn.k = *(const T*)k; fn.w_i = wi; fn.w_j = wj;
+        if (int rc = forces_begin(f, flags, fn.fo)) return rc;
+        if (int rc = launch<MODE_ALL>(fn, 0)) return rc;
+        scale = two_sets ? 1.0 : 0.5;
+    } else {
+        FCoul<T, false> fn;
+        fn.k = *(const T*)k; fn.w_i = wi; fn.w_j = wj;
+        std::memset(&fn.fo, 0, sizeof(fn.fo));
+        if (int rc = launch_reduce(fn, 0)) return rc;
+    }
+    if (!dev) { if (int rc = fetch_results()) return rc; }
+    if (int rc = store_real(e, &d_res.p->f[RB_ENERGY], &h_res->f[RB_ENERGY], 1, scale, flags)) return rc;
+    if (f) { if (int rc = forces_end(f, flags)) return rc; }
+    return finish_map(flags);
+}
+
+template int Engine<float>::map_lj(const void*, int, void*, void*);
+template int Engine<double>::map_lj(const void*, int, void*, void*);
+template int Engine<float>::map_coulomb(const void*, const void*, const void*, int, void*, void*);
+template int Engine<double>::map_coulomb(const void*, const void*, const void*, int, void*, void*);
+
+}  // namespace clm

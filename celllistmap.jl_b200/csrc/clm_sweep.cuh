@@ -1,0 +1,453 @@
+// Pair sweep: the B200 replacement of _pairwise! (src/internals/self.jl:28-184, cross.jl:8-129,
+// vicinal_cells.jl:4-75, NonPeriodicCells.jl:281-352) for the compiled-in functor catalogue.
+//
+// Work decomposition (B200-first, not the reference's cell-by-cell task batches):
+//   * a work item ("tile") is TI consecutive records of one (y,z) row of the cell-sorted array; one warp
+//     owns a tile: lane -> (i-slot = lane % TI, j-slice = lane / TI).  Particle i lives in registers.
+//   * for every stencil row (dy,dz) the candidate partners are ONE contiguous record range
+//     [cell_start[x_first-l], cell_start[x_last+l+1]) because cells are linearised with x fastest;
+//     all lanes of a j-slice read the same record (128-bit broadcast load, L1-resident), so the loop
+//     is ~25 FP32 instructions per candidate and has no shared-memory traffic at all.
+//   * warps fetch tiles from a global atomic counter (persistent grid = SMs x resident CTAs).
+//   * exactly-once rules are the reference's: MODE_HALF (orthorhombic / non-periodic self: later
+//     records of the own row + forward rows, real_i | real_j, self.jl:143-161, vicinal_cells.jl:33),
+//     MODE_TRI (triclinic self: full stencil, i real, index_i < index_j, self.jl:164-184,
+//     vicinal_cells.jl:53-65), MODE_ALL (two-set: full stencil, i real, cross.jl:111-129; also the
+//     full-shell force sweep, where each ordered pair contributes to f_i only so that per-particle
+//     outputs need no atomics and no per-batch output copies (the reference's A16)).
+//   * the distance test is bit-identical to the oracle's: d2 = (dx*dx + dy*dy) + dz*dz, unfused, <=.
+#pragma once
+#include "clm_common.cuh"
+#include "clm_build.cuh"
+
+namespace clm {
+
+enum { MODE_HALF = 0, MODE_TRI = 1, MODE_ALL = 2 };
+constexpr int SWEEP_THREADS = 128;
+constexpr int NB_PRIV_MAX = 16;  // histograms with <= this many bins use per-thread private shared-memory bins
+
+// result block: accumulators every map kernel adds into (zeroed before the launch)
+enum { RB_ENERGY = 0, RB_SUM_D = 1, RB_SUM_D2 = 2, RB_F64_COUNT = 8 };
+enum { RC_NPAIRS = 0, RC_NBAND = 1, RC_NLIST = 2, RC_I64_COUNT = 8 };
+struct ResultBlock {
+    double f[RB_F64_COUNT];
+    unsigned long long c[RC_I64_COUNT];
+};
+
+template <class T> struct SweepArgs {
+    const RecT<T>* rec_i;
+    const RecT<T>* rec_j;
+    const int* cell_start_j;
+    const Tile* tiles;
+    int* dscal;          // DS_NTILES (read), DS_WORK (atomic tile counter)
+    ResultBlock* res;
+    int nx, ny, nz;      // cells along the device's fast / middle / slow axis = reference dims (3,2,1) in 3-D, (2,1,-) in 2-D
+    int lcell, log2ti, self;
+    T rc2;
+};
+
+template <class T> struct Ctx {   // what a functor sees for the tile in flight
+    int ki;          // record index of particle i
+    int lane, islot, slice, log2ti;
+    bool active;     // this lane holds a particle that may act as i
+    RecT<T> ri;
+};
+
+template <class T> __device__ __forceinline__ T block_sum(T v, T* smem /* >= 4 */) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) smem[w] = v;
+    __syncthreads();
+    T r = T(0);
+    if (threadIdx.x == 0) for (int k = 0; k < SWEEP_THREADS / 32; ++k) r += smem[k];
+    return r;  // valid on thread 0
+}
+
+// ===================================================================================================
+// functor catalogue.  Every functor: Acc (per thread, whole kernel), IAcc (per
+// particle i, one tile), init / begin / pair / end / finish.  pair() is called by all 32 lanes with a
+// `hit` predicate so that warp collectives inside it are legal.
+// ===================================================================================================
+
+// f1/f2 test functor (test/modules/Testing.jl:23-26) + pair count + 1-ulp cutoff band count
+template <class T> struct FSum {
+    T rc2_lo, rc2_hi;   // prevfloat/nextfloat of cutoff^2
+    struct Acc { double sd, sd2; unsigned long long n, band; };
+    struct IAcc {};
+    static constexpr bool NEEDS_BAND = true;
+    __device__ void init(Acc& a) const { a.sd = 0; a.sd2 = 0; a.n = 0; a.band = 0; }
+    __device__ void begin(IAcc&, const Ctx<T>&) const {}
+    __device__ void pair(Acc& a, IAcc&, const Ctx<T>&, bool hit, bool ok, const RecT<T>&, int, T, T, T, T d2) const {
+        if (hit) { a.sd += (double)xsqrt(d2); a.sd2 += (double)d2; a.n += 1; }
+        if (ok && d2 >= rc2_lo && d2 <= rc2_hi) a.band += 1;
+    }
+    __device__ void end(IAcc&, const Ctx<T>&) const {}
+    __device__ void finish(Acc& a, ResultBlock* res) const {
+        __shared__ double sm[4];
+        __shared__ unsigned long long smc[4];
+        double sd = block_sum(a.sd, sm), sd2 = block_sum(a.sd2, sm);
+        unsigned long long n = block_sum(a.n, smc), band = block_sum(a.band, smc);
+        if (threadIdx.x == 0) {
+            atomicAdd(&res->f[RB_SUM_D], sd); atomicAdd(&res->f[RB_SUM_D2], sd2);
+            atomicAdd(&res->c[RC_NPAIRS], n); atomicAdd(&res->c[RC_NBAND], band);
+        }
+    }
+};
+
+template <class T> __device__ __forceinline__ T fast_rcp(T x);
+template <> __device__ __forceinline__ float fast_rcp<float>(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+template <> __device__ __forceinline__ double fast_rcp<double>(double x) { return 1.0 / x; }
+template <class T> __device__ __forceinline__ T xfma(T a, T b, T c);
+template <> __device__ __forceinline__ float xfma<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <> __device__ __forceinline__ double xfma<double>(double a, double b, double c) { return fma(a, b, c); }
+
+// write per-particle force accumulators: combine the j-slices, rotate back to the input frame
+// (pair.x/pair.y are inv_rotation * coordinates, self.jl:171-178), store once per real particle.
+template <class T> struct ForceOut {
+    T* forces;        // n x dim, AoS
+    int dim, accumulate, rotated;
+    T inv_rot[9];
+    __device__ __forceinline__ void store(const Ctx<T>& c, T fx, T fy, T fz) const {
+        for (int o = 1 << c.log2ti; o < 32; o <<= 1) {
+            fx += __shfl_xor_sync(0xffffffffu, fx, o); fy += __shfl_xor_sync(0xffffffffu, fy, o); fz += __shfl_xor_sync(0xffffffffu, fz, o);
+        }
+        if (!c.active || c.slice != 0) return;
+        if (rotated) {
+            const T a = inv_rot[0] * fx + inv_rot[1] * fy + inv_rot[2] * fz;
+            const T b = inv_rot[3] * fx + inv_rot[4] * fy + inv_rot[5] * fz;
+            const T d = inv_rot[6] * fx + inv_rot[7] * fy + inv_rot[8] * fz;
+            fx = a; fy = b; fz = d;
+        }
+        T* f = forces + (size_t)(c.ri.tag & TagT<T>::MASK) * dim;
+        if (accumulate) { f[0] += fx; f[1] += fy; if (dim == 3) f[2] += fz; }
+        else { f[0] = fx; f[1] = fy; if (dim == 3) f[2] = fz; }
+    }
+};
+
+// Lennard-Jones c12/d2^6 - c6/d2^3 (test/applications/gromacs/compare_with_gromacs.jl:9-13), optional forces
+template <class T, bool FORCES> struct FLJ {
+    T c6, c12;
+    ForceOut<T> fo;
+    struct Acc { T e; };
+    struct IAcc { T fx, fy, fz; };
+    static constexpr bool NEEDS_BAND = false;
+    __device__ void init(Acc& a) const { a.e = T(0); }
+    __device__ void begin(IAcc& p, const Ctx<T>&) const { p.fx = p.fy = p.fz = T(0); }
+    __device__ __forceinline__ void pair(Acc& a, IAcc& p, const Ctx<T>&, bool hit, bool, const RecT<T>&, int, T dx, T dy, T dz, T d2) const {
+        const T inv = hit ? fast_rcp<T>(d2) : T(0);
+        const T r6 = inv * inv * inv;
+        a.e = xfma(r6, xfma(c12, r6, -c6), a.e);
+        if (FORCES) {
+            const T fs = inv * r6 * xfma(T(12) * c12, r6, T(-6) * c6);
+            p.fx = xfma(fs, dx, p.fx); p.fy = xfma(fs, dy, p.fy); p.fz = xfma(fs, dz, p.fz);
+        }
+    }
+    __device__ void end(IAcc& p, const Ctx<T>& c) const { if (FORCES) fo.store(c, p.fx, p.fy, p.fz); }
+    __device__ void finish(Acc& a, ResultBlock* res) const {
+        __shared__ double sm[4];
+        double e = block_sum((double)a.e, sm);
+        if (threadIdx.x == 0) atomicAdd(&res->f[RB_ENERGY], e);
+    }
+};
+
+// Coulomb-like k*w_i*w_j/d (test/examples/gravitational_potential.jl:30-34, gravitational_force.jl:38-44)
+template <class T, bool FORCES> struct FCoul {
+    T k;
+    const T* w_i;   // weights gathered into record order of set i / set j
+    const T* w_j;
+    ForceOut<T> fo;
+    struct Acc { T e; };
+    struct IAcc { T fx, fy, fz, wi; };
+    static constexpr bool NEEDS_BAND = false;
+    __device__ void init(Acc& a) const { a.e = T(0); }
+    __device__ void begin(IAcc& p, const Ctx<T>& c) const { p.fx = p.fy = p.fz = T(0); p.wi = c.active ? k * w_i[c.ki] : T(0); }
+    __device__ __forceinline__ void pair(Acc& a, IAcc& p, const Ctx<T>&, bool hit, bool, const RecT<T>&, int j, T dx, T dy, T dz, T d2) const {
+        const T wj = __ldg(w_j + j);
+        const T invd = hit ? rsqrt(d2) : T(0);
+        const T q = p.wi * wj * invd;     // k w_i w_j / d
+        a.e += q;
+        if (FORCES) {
+            const T g = q * invd * invd;  // k w_i w_j / d^3
+            p.fx = xfma(g, dx, p.fx); p.fy = xfma(g, dy, p.fy); p.fz = xfma(g, dz, p.fz);
+        }
+    }
+    __device__ void end(IAcc& p, const Ctx<T>& c) const { if (FORCES) fo.store(c, p.fx, p.fy, p.fz); }
+    __device__ void finish(Acc& a, ResultBlock* res) const {
+        __shared__ double sm[4];
+        double e = block_sum((double)a.e, sm);
+        if (threadIdx.x == 0) atomicAdd(&res->f[RB_ENERGY], e);
+    }
+};
+
+// histogram storage shared by the two histogram functors: per-thread private bins in shared memory
+// (bank = thread, conflict free, no atomics) when nbins <= NB_PRIV_MAX, block-shared atomics otherwise
+template <class T, bool SUMS> struct HistBins {
+    int nbins, priv;
+    unsigned long long* g_counts;   // [nbins] global accumulators
+    double* g_sums;                 // [nbins]
+    __device__ __forceinline__ unsigned int* cnt() const { extern __shared__ __align__(16) unsigned char dsm[]; return reinterpret_cast<unsigned int*>(dsm); }
+    __device__ __forceinline__ T* sum() const {
+        extern __shared__ __align__(16) unsigned char dsm[];
+        const size_t nslots = (size_t)nbins * (priv ? SWEEP_THREADS : 1);
+        return reinterpret_cast<T*>(dsm + ((nslots * 4 + 15) / 16) * 16);
+    }
+    __device__ void init() const {
+        const int nslots = nbins * (priv ? SWEEP_THREADS : 1);
+        for (int k = threadIdx.x; k < nslots; k += SWEEP_THREADS) { cnt()[k] = 0u; if (SUMS) sum()[k] = T(0); }
+        __syncthreads();
+    }
+    __device__ __forceinline__ void add(int b, T v) const {
+        if (priv) {
+            const int s = b * SWEEP_THREADS + threadIdx.x;
+            cnt()[s] += 1u;
+            if (SUMS) sum()[s] += v;
+        } else {
+            atomicAdd(&cnt()[b], 1u);
+            if (SUMS) atomicAdd(&sum()[b], v);
+        }
+    }
+    __device__ void flush() const {
+        __syncthreads();
+        if (priv) {
+            const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+            for (int b = w; b < nbins; b += SWEEP_THREADS / 32) {
+                unsigned long long c = 0; double s = 0;
+                for (int t = lane; t < SWEEP_THREADS; t += 32) { c += cnt()[b * SWEEP_THREADS + t]; if (SUMS) s += (double)sum()[b * SWEEP_THREADS + t]; }
+                c = warp_sum(c);
+                if (SUMS) s = warp_sum(s);
+                if (lane == 0 && c) { atomicAdd(&g_counts[b], c); if (SUMS) atomicAdd(&g_sums[b], s); }
+            }
+        } else {
+            for (int b = threadIdx.x; b < nbins; b += SWEEP_THREADS)
+                if (cnt()[b]) { atomicAdd(&g_counts[b], (unsigned long long)cnt()[b]); if (SUMS) atomicAdd(&g_sums[b], (double)sum()[b]); }
+        }
+    }
+};
+
+// distance histogram: counts[floor(d/width)] += 1 (test/examples/distance_histogram.jl:22-26)
+template <class T> struct FHist {
+    T width;
+    HistBins<T, false> hb;
+    struct Acc {};
+    struct IAcc {};
+    static constexpr bool NEEDS_BAND = false;
+    __device__ void init(Acc&) const { hb.init(); }
+    __device__ void begin(IAcc&, const Ctx<T>&) const {}
+    __device__ __forceinline__ void pair(Acc&, IAcc&, const Ctx<T>&, bool hit, bool, const RecT<T>&, int, T, T, T, T d2) const {
+        if (hit) {
+            const T q = floor(xdiv(xsqrt(d2), width));
+            if (q >= T(0) && q < T(hb.nbins)) hb.add((int)q, T(0));
+        }
+    }
+    __device__ void end(IAcc&, const Ctx<T>&) const {}
+    __device__ void finish(Acc&, ResultBlock*) const { hb.flush(); }
+};
+
+// halotools-style mean pairwise velocity (test/examples/pairwise_velocities.jl:17-24)
+template <class T> struct Vec4T;
+template <> struct Vec4T<float> { typedef float4 type; };
+template <> struct Vec4T<double> { typedef double4 type; };
+template <class T> struct FVel {
+    const T* v_i;     // velocities gathered into record order, 4 components per record, aligned frame
+    const T* v_j;
+    const T* rbins;   // nbins+1 ascending edges (device)
+    HistBins<T, true> hb;
+    struct Acc {};
+    struct IAcc { T vx, vy, vz; };
+    static constexpr bool NEEDS_BAND = false;
+    __device__ void init(Acc&) const { hb.init(); }
+    __device__ void begin(IAcc& p, const Ctx<T>& c) const {
+        p.vx = p.vy = p.vz = T(0);
+        if (c.active) { p.vx = v_i[(size_t)c.ki * 4]; p.vy = v_i[(size_t)c.ki * 4 + 1]; p.vz = v_i[(size_t)c.ki * 4 + 2]; }
+    }
+    __device__ __forceinline__ void pair(Acc&, IAcc& p, const Ctx<T>&, bool hit, bool, const RecT<T>&, int j, T dx, T dy, T dz, T d2) const {
+        if (hit) {
+            const T r = xsqrt(d2);
+            int first = 0;   // searchsortedfirst(rbins, r): number of edges < r
+            for (int e = 0; e <= hb.nbins; ++e) first += (__ldg(rbins + e) < r) ? 1 : 0;
+            const int b = first - 1;
+            if (b >= 0 && b < hb.nbins) {
+                const T ux = p.vx - __ldg(v_j + (size_t)j * 4), uy = p.vy - __ldg(v_j + (size_t)j * 4 + 1), uz = p.vz - __ldg(v_j + (size_t)j * 4 + 2);
+                hb.add(b, ((ux * dx + uy * dy) + uz * dz) / r);
+            }
+        }
+    }
+    __device__ void end(IAcc&, const Ctx<T>&) const {}
+    __device__ void finish(Acc&, ResultBlock*) const { hb.flush(); }
+};
+
+// minimum distance (test/examples/nearest_neighbor.jl:9-16): smallest d2, ties broken by (i, j)
+struct MinPartial { double d2; long long i, j; long long pad; };
+template <class T> struct FMin {
+    MinPartial* partial;   // [gridDim.x]
+    struct Acc { T d2; long long i, j; };
+    struct IAcc {};
+    static constexpr bool NEEDS_BAND = false;
+    __device__ void init(Acc& a) const { a.d2 = CUDART_INF_T<T>(); a.i = 0; a.j = 0; }
+    __device__ void begin(IAcc&, const Ctx<T>&) const {}
+    __device__ static __forceinline__ bool better(T d2, long long i, long long j, T e2, long long ei, long long ej) {
+        return (d2 < e2) || (d2 == e2 && (i < ei || (i == ei && j < ej)));
+    }
+    __device__ __forceinline__ void pair(Acc& a, IAcc&, const Ctx<T>& c, bool hit, bool, const RecT<T>& rj, int, T, T, T, T d2) const {
+        if (hit && d2 <= a.d2) {
+            const long long i = (long long)(c.ri.tag & TagT<T>::MASK) + 1, j = (long long)(rj.tag & TagT<T>::MASK) + 1;
+            if (better(d2, i, j, a.d2, a.i, a.j)) { a.d2 = d2; a.i = i; a.j = j; }
+        }
+    }
+    __device__ void end(IAcc&, const Ctx<T>&) const {}
+    __device__ void finish(Acc& a, ResultBlock*) const {
+        __shared__ MinPartial sm[SWEEP_THREADS / 32];
+        T d2 = a.d2; long long i = a.i, j = a.j;
+        for (int o = 16; o > 0; o >>= 1) {
+            const T e2 = __shfl_xor_sync(0xffffffffu, d2, o);
+            const long long ei = __shfl_xor_sync(0xffffffffu, i, o), ej = __shfl_xor_sync(0xffffffffu, j, o);
+            if (better(e2, ei, ej, d2, i, j)) { d2 = e2; i = ei; j = ej; }
+        }
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) { sm[w].d2 = (double)d2; sm[w].i = i; sm[w].j = j; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            MinPartial b = sm[0];
+            for (int k = 1; k < SWEEP_THREADS / 32; ++k)
+                if ((sm[k].d2 < b.d2) || (sm[k].d2 == b.d2 && (sm[k].i < b.i || (sm[k].i == b.i && sm[k].j < b.j)))) b = sm[k];
+            partial[blockIdx.x] = b;
+        }
+    }
+};
+
+// neighbour-list emission: push_pair! (internals/neighborlist.jl:67-76) as a warp-ballot compaction;
+// records are Julia's Tuple{Int,Int,T}: {int64 i; int64 j; T d (+pad)} = 24 bytes
+template <class T> struct FList {
+    unsigned long long* out;        // capacity * 3 words
+    unsigned long long capacity;
+    struct Acc {};
+    struct IAcc {};
+    static constexpr bool NEEDS_BAND = false;
+    __device__ void init(Acc&) const {}
+    __device__ void begin(IAcc&, const Ctx<T>&) const {}
+    __device__ static __forceinline__ unsigned long long dbits(float d) { return (unsigned long long)__float_as_uint(d); }
+    __device__ static __forceinline__ unsigned long long dbits(double d) { return (unsigned long long)__double_as_longlong(d); }
+    __device__ __forceinline__ void pair(Acc&, IAcc&, const Ctx<T>& c, bool hit, bool, const RecT<T>& rj, int, T, T, T, T d2, ResultBlock* res) const {
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (m == 0u) return;
+        const int leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if (c.lane == leader) base = atomicAdd(&res->c[RC_NLIST], (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (hit) {
+            const unsigned long long pos = base + (unsigned long long)__popc(m & ((1u << c.lane) - 1u));
+            if (pos < capacity) {
+                unsigned long long* r = out + pos * 3ull;
+                r[0] = (unsigned long long)(c.ri.tag & TagT<T>::MASK) + 1ull;
+                r[1] = (unsigned long long)(rj.tag & TagT<T>::MASK) + 1ull;
+                r[2] = dbits(xsqrt(d2));
+            }
+        }
+    }
+    __device__ void end(IAcc&, const Ctx<T>&) const {}
+    __device__ void finish(Acc&, ResultBlock*) const {}
+};
+template <class F> struct IsList { static constexpr bool value = false; };
+template <class T> struct IsList<FList<T>> { static constexpr bool value = true; };
+
+// ===================================================================================================
+// the sweep kernel
+// ===================================================================================================
+template <class T, int MODE, class F>
+__global__ void __launch_bounds__(SWEEP_THREADS)
+k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
+    typedef TagT<T> TG;
+    const int lane = threadIdx.x & 31;
+    const int ti = 1 << a.log2ti, nslice = 32 >> a.log2ti;
+    const int l = a.lcell;
+    typename F::Acc acc;
+    f.init(acc);
+    const int ntiles = a.dscal[DS_NTILES];
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&a.dscal[DS_WORK], 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= ntiles) break;
+        const Tile tl = a.tiles[t];
+        Ctx<T> c;
+        c.lane = lane; c.log2ti = a.log2ti; c.islot = lane & (ti - 1); c.slice = lane >> a.log2ti;
+        const bool valid = c.islot < tl.cnt;
+        c.ki = tl.k0 + (valid ? c.islot : 0);
+        c.ri = ldrec(a.rec_i + c.ki);
+        const bool real_i = (c.ri.tag & TG::GHOST) == 0;
+        c.active = valid && ((MODE == MODE_HALF) ? ((c.ri.tag & TG::HOME) != 0) : real_i);
+        const typename TG::type idx_i = c.ri.tag & TG::MASK;
+        typename F::IAcc ia;
+        f.begin(ia, c);
+        const int iy = tl.row % a.ny, iz = tl.row / a.ny;
+        const int xa = max((tl.cx & 0xffff) - l, 0), xb = min((tl.cx >> 16) + l, a.nx - 1);
+        const int dz0 = (MODE == MODE_HALF || a.nz == 1) ? 0 : -l, dz1 = (a.nz == 1) ? 0 : l;
+        for (int dz = dz0; dz <= dz1; ++dz) {
+            const int z2 = iz + dz;
+            if (z2 < 0 || z2 >= a.nz) continue;
+            const int dy0 = (MODE == MODE_HALF && dz == 0) ? 0 : -l;
+            for (int dy = dy0; dy <= l; ++dy) {
+                const int y2 = iy + dy;
+                if (y2 < 0 || y2 >= a.ny) continue;
+                const bool own = (dy == 0 && dz == 0);
+                const int base = (z2 * a.ny + y2) * a.nx;
+                int j0 = a.cell_start_j[base + xa];
+                const int j1 = a.cell_start_j[base + xb + 1];
+                if (MODE == MODE_HALF && own) j0 = max(j0, tl.k0 + 1);   // only later records of the own row
+#pragma unroll 2
+                for (int jb = j0; jb < j1; jb += nslice) {
+                    const int j = jb + c.slice;
+                    const bool inb = j < j1;
+                    const int jc = inb ? j : (j1 - 1);
+                    const RecT<T> rj = ldrec(a.rec_j + jc);
+                    bool ok = c.active && inb;
+                    if (MODE == MODE_HALF) ok = ok && (!own || jc > c.ki) && (((c.ri.tag & rj.tag) & TG::GHOST) == 0);
+                    else if (MODE == MODE_TRI) ok = ok && (idx_i < (rj.tag & TG::MASK));
+                    else ok = ok && !(a.self && own && jc == c.ki);
+                    const T dx = xsub(c.ri.x, rj.x), dy_ = xsub(c.ri.y, rj.y), dz_ = xsub(c.ri.z, rj.z);
+                    const T d2 = xadd(xadd(xmul(dx, dx), xmul(dy_, dy_)), xmul(dz_, dz_));
+                    const bool hit = ok && (d2 <= a.rc2);
+                    if constexpr (IsList<F>::value) f.pair(acc, ia, c, hit, ok, rj, jc, dx, dy_, dz_, d2, a.res);
+                    else f.pair(acc, ia, c, hit, ok, rj, jc, dx, dy_, dz_, d2);
+                }
+            }
+        }
+        f.end(ia, c);
+    }
+    f.finish(acc, a.res);
+}
+
+// ---- small epilogue kernels ---------------------------------------------------------------------------
+struct MinResult { double d2; long long i, j; long long pad; };
+static __global__ void k_min_final(const MinPartial* __restrict__ p, int n, MinResult* __restrict__ out) {
+    __shared__ MinPartial sm[256];
+    auto better = [](const MinPartial& q, const MinPartial& b) { return (q.d2 < b.d2) || (q.d2 == b.d2 && (q.i < b.i || (q.i == b.i && q.j < b.j))); };
+    MinPartial b; b.d2 = CUDART_INF_T<double>(); b.i = 0; b.j = 0; b.pad = 0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) { const MinPartial q = p[k]; if (q.i != 0 && better(q, b)) b = q; }
+    sm[threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < blockDim.x; ++k) { const MinPartial q = sm[k]; if (q.i != 0 && (b.i == 0 || better(q, b))) b = q; }
+        out->d2 = b.d2; out->i = b.i; out->j = b.j; out->pad = 0;
+    }
+}
+// device-resident (i, j, d) output of the minimum-distance map; reset = false keeps an existing smaller d
+template <class T> __global__ void k_min_store(const MinResult* __restrict__ r, long long* i_out, long long* j_out, T* d_out, int accumulate) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const T d = (r->i != 0) ? xsqrt((T)r->d2) : CUDART_INF_T<T>();
+    if (accumulate && !(d < *d_out)) return;
+    *i_out = r->i; *j_out = r->j; *d_out = d;
+}
+
+// out[k] = (accumulate ? out[k] : 0) + scale * src[k]   (device-resident outputs, CLM_OUT_DEVICE)
+template <class T> __global__ void k_store_real(T* __restrict__ out, const double* __restrict__ src, int n, double scale, int accumulate) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = (T)((accumulate ? (double)out[k] : 0.0) + scale * src[k]);
+}
+static __global__ void k_store_i64(long long* __restrict__ out, const unsigned long long* __restrict__ src, int n, int accumulate) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = (accumulate ? out[k] : 0ll) + (long long)src[k];
+}
+
+}  // namespace clm

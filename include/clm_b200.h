@@ -1,0 +1,167 @@
+/*
+ * clm_b200.h -- C ABI of the B200-native cutoff-pair engine (libclm_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of m3g/CellListMap.jl v0.10.4-DEV.  The
+ * reference has no FFI of its own (it is pure Julia): the seam these entry points replace is
+ * the pair of internal generic functions reached from the two public entry points
+ *
+ *   UpdateCellList!(x, [y,] box, cl, aux; parallel, validate_coordinates)
+ *        src/internals/CellLists.jl:727-734, :1180-1188; src/internals/NonPeriodicCells.jl:93-100, :253-261
+ *        (called from UpdateParticleSystem!, src/internals/ParticleSystem.jl:158-164, :209-224)
+ *   _pairwise!(f, output, box, cl; parallel, output_threaded, show_progress)
+ *        src/internals/self.jl:28-45, src/internals/cross.jl:8-25
+ *        (called from pairwise!, src/API/pairwise.jl:48-63, and neighborlist!, src/API/neighborlist.jl:217-231)
+ *
+ * A Julia host package binds these with `ccall` (see INTEGRATION.md and
+ * celllistmap.jl_b200/julia/CellListMapB200.jl); Python tests bind them with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, else a clm_status error class; the message is
+ *     available from clm_last_error().  No exception crosses the ABI.
+ *   - `const void*` scalars/arrays are of the handle's dtype T (float for CLM_F32, double for
+ *     CLM_F64).  Matrices are column-major N x N with COLUMNS = lattice vectors, exactly the
+ *     memory of Julia's SMatrix{N,N,T}.  Positions are AoS n x N of T, exactly the memory of
+ *     Julia's Vector{SVector{N,T}} (== an (N,n) Matrix{T}).
+ *   - particle indices crossing the ABI are 1-based int64 (NeighborPair.i/j, src/API/NeighborPair.jl:19-33).
+ *   - pointers are caller-owned HOST memory unless the call's `on_device` / CLM_OUT_DEVICE says
+ *     they are device pointers on the handle's device.
+ *   - a handle is single-threaded, like one `pairwise!` at a time per ParticleSystem.
+ *   - there is NO CPU fallback: without a CUDA device clm_create fails with CLM_ERR_CUDA.
+ */
+#ifndef CLM_B200_H
+#define CLM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define CLM_API __attribute__((visibility("default")))
+#else
+#define CLM_API
+#endif
+
+typedef struct clm_handle clm_handle;
+
+enum clm_dtype { CLM_F32 = 0, CLM_F64 = 1 };
+/* unit-cell types: src/internals/Box.jl:5-9 */
+enum clm_cell_type { CLM_ORTHORHOMBIC = 0, CLM_TRICLINIC = 1, CLM_NONPERIODIC = 2 };
+
+enum clm_status {
+    CLM_OK = 0,
+    CLM_ERR_INVALID_COORDINATES = 1, /* ArgumentError "Invalid coordinates found"  CellOperations.jl:9-17 */
+    CLM_ERR_UNIT_CELL = 2,           /* ArgumentError "Unit cell matrix does not satisfy..."  Box.jl:243 */
+    CLM_ERR_ARGUMENT = 3,            /* ArgumentError (lcell < 1 Box.jl:192, bad enum, null pointer, ...) */
+    CLM_ERR_STATE = 4,               /* call order: box / positions missing */
+    CLM_ERR_DIMENSION = 5,           /* DimensionMismatch  CellLists.jl:740-751 */
+    CLM_ERR_CAPACITY = 6,            /* caller buffer too small (clm_neighborlist_copy) */
+    CLM_ERR_CUDA = 7,                /* ErrorException: CUDA runtime failure, or no device */
+    CLM_ERR_COMM = 8,                /* ErrorException: NCCL failure */
+    CLM_ERR_UNSUPPORTED = 9
+};
+
+/* flags of the map entry points */
+enum clm_flags {
+    CLM_RESET = 1,      /* reset=true of pairwise! (API/pairwise.jl:52-54): outputs start from zero;
+                           without it results are accumulated on the values found in the output buffers */
+    CLM_OUT_DEVICE = 2, /* ARRAY arguments of the call (outputs, and per-particle inputs such as weights and
+                           velocities) are device pointers; scalars and bin edges stay host pointers.  The call only
+                           enqueues work on the handle's stream (no host synchronisation) */
+    CLM_PROFILE = 4     /* record CUDA-event timings of this call into clm_stats */
+};
+
+/* Box record (src/internals/Box.jl:84-96); values widened to double (exact for float). */
+typedef struct clm_box_info {
+    int32_t dim, dtype, cell_type, lcell;
+    int64_t nc[3];                 /* number of computing cells per dimension (Box.jl:209-220) */
+    double cutoff, cutoff_sqr;
+    double input_unit_cell[9];     /* column-major dim x dim */
+    double aligned_unit_cell[9];
+    double rotation[9];
+    double inv_rotation[9];
+    double computing_box_min[3], computing_box_max[3];
+    double cell_size[3];
+    double origin[3];
+} clm_box_info;
+
+typedef struct clm_stats {
+    int64_t n_real[2];        /* particles of set x / y */
+    int64_t n_total[2];       /* real + image particles in the computing box (CellList.n_particles) */
+    int64_t n_cells;          /* prod(nc) */
+    int64_t n_cells_real[2];  /* cells containing at least one real particle */
+    int64_t n_tiles;          /* work items of the last build (row tiles of the reference set) */
+    int64_t n_pairs;          /* in-cutoff pairs of the last map that counts them (sum_d_d2, neighborlist) */
+    int64_t n_cutoff_band;    /* pairs with |d2 - cutoff^2| <= 1 ulp(cutoff^2) seen by the last clm_map_sum_d_d2 */
+    double build_ms;          /* device time of the last clm_build (CUDA events) */
+    double map_ms;            /* device time of the last map / neighborlist call run with CLM_PROFILE */
+    int32_t n_sm;             /* SM count of the device */
+    int32_t launches;         /* kernels launched by this handle since creation */
+} clm_stats;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+/* dim = 2|3; dtype = clm_dtype; device = CUDA ordinal; ngpus = 1 (multi-GPU slabs: clm_comm_*). */
+CLM_API int clm_create(clm_handle** h, int dim, int dtype, int device, int ngpus);
+CLM_API int clm_destroy(clm_handle* h);
+CLM_API const char* clm_last_error(clm_handle* h); /* h may be NULL: error of the last failed clm_create */
+/* run on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = the handle's own stream */
+CLM_API int clm_set_stream(clm_handle* h, void* cuda_stream);
+CLM_API int clm_synchronize(clm_handle* h);
+
+/* ---- Box(...)  src/internals/Box.jl:191-203, :330-335, :374-377 ; update_box :395-423 ------- */
+/* unitcell: N sides (is_matrix = 0) or N x N column-major matrix (is_matrix = 1); ignored for
+ * CLM_NONPERIODIC, where the box is derived from limits(x[,y]) at clm_build time. */
+CLM_API int clm_set_box(clm_handle* h, int cell_type, const void* unitcell, int is_matrix, const void* cutoff, int lcell);
+CLM_API int clm_get_box(clm_handle* h, clm_box_info* out);
+
+/* ---- positions: ParticleSystemPositions copy semantics (API/ParticleSystemPositions.jl:19-22) */
+/* set: 0 = x (reference set), 1 = y (target set; giving it makes the system a two-set system);
+ * (set = 1, aos_xyz = NULL, n = 0) removes the second set; a non-NULL pointer with n = 0 is an EMPTY
+ * second set (no pairs). */
+CLM_API int clm_set_positions(clm_handle* h, int set, const void* aos_xyz, int64_t n, int on_device);
+
+/* ---- UpdateCellList!  src/internals/CellLists.jl:727-927 ---------------------------------- */
+/* validates coordinates (NaN -> CLM_ERR_INVALID_COORDINATES with the 1-based index in the message),
+ * wraps, bins real + image particles, counting-sorts them by cell.  No-op if nothing changed. */
+CLM_API int clm_build(clm_handle* h);
+
+/* ---- _pairwise! with the compiled-in functor catalogue ------------------ */
+/* LJ: u += c12/d2^6 - c6/d2^3 (test/applications/gromacs/compare_with_gromacs.jl:9-13);
+ * params = {c6, c12}.  forces (n_x x N, may be NULL): F_i = -dU/dx_i; self-set systems update both
+ * particles of a pair (f[i] += df; f[j] -= df, docs/src/ParticleSystem/examples.md:41-47), two-set
+ * systems return the forces on the x set. */
+CLM_API int clm_map_lj(clm_handle* h, const void* c6_c12, int flags, void* energy_out, void* forces_out);
+/* Coulomb-like: u += k*w_i*w_j/d, F_i = k*w_i*w_j*(x_i-x_j)/d^3
+ * (test/examples/gravitational_potential.jl:30-34, gravitational_force.jl:38-44 with k = -9.8). */
+CLM_API int clm_map_coulomb(clm_handle* h, const void* weights_x, const void* weights_y, const void* k, int flags,
+                    void* energy_out, void* forces_out);
+/* distance histogram: counts[floor(d/width)] += 1 (test/examples/distance_histogram.jl:22-26) */
+CLM_API int clm_map_dist_hist(clm_handle* h, const void* width, int nbins, int flags, int64_t* counts);
+/* halotools-style mean pairwise velocity (test/examples/pairwise_velocities.jl:17-24):
+ * b = searchsortedfirst(rbins, r) - 1;  counts[b] += 1;  sums[b] += dot(v_i - v_j, x_i - x_j)/r;
+ * rbins has nbins+1 ascending edges, bins are right-closed. */
+CLM_API int clm_map_pairvel(clm_handle* h, const void* vel_x, const void* vel_y, const void* rbins, int nbins, int flags,
+                    int64_t* counts, void* sums);
+/* minimum distance (i, j, d) (test/examples/nearest_neighbor.jl:9-16; docs/src/ParticleSystem/examples.md:117-132);
+ * i = j = 0 and d = +Inf when no pair is within the cutoff. */
+CLM_API int clm_map_mindist(clm_handle* h, int flags, int64_t* i_out, int64_t* j_out, void* d_out);
+/* test functor f1/f2 (test/modules/Testing.jl:23-26): sum of d, sum of d2, number of pairs */
+CLM_API int clm_map_sum_d_d2(clm_handle* h, int flags, void* sum_d, void* sum_d2, int64_t* npairs);
+
+/* ---- neighborlist!  src/API/neighborlist.jl:217-231, push_pair! internals/neighborlist.jl:67-76 */
+/* Two phases so the caller can resize!() its own Vector{Tuple{Int,Int,T}}: clm_neighborlist builds the
+ * list on the device and returns its length; clm_neighborlist_copy writes the 24-byte records
+ * {int64 i; int64 j; T d (+padding)} into `records` (host, or device with on_device = 1). */
+CLM_API int clm_neighborlist(clm_handle* h, int flags, int64_t* n_out);
+CLM_API int clm_neighborlist_copy(clm_handle* h, void* records24, int64_t capacity, int on_device);
+
+CLM_API int clm_get_stats(clm_handle* h, clm_stats* out);
+/* tuning knobs (do not change results): "tile_i" = particles per warp tile (8|16|32, 0 = auto),
+ * "blocks_per_sm" (0 = auto). */
+CLM_API int clm_set_option(clm_handle* h, const char* name, int64_t value);
+CLM_API int clm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLM_B200_H */
