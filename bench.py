@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the cutoff-pair hot path.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference ...                     (the reference arm: CPU restatement on the host cores)
+
+A "step" is one pass of the hot path over one batch of synthetic input: new positions -> UpdateCellList!
+(cell-list build) -> pairwise!(LJ energy + forces) -> outputs.  Workload at N = 1: BASELINE.json configs[1]
+(1M argon-density particles, cubic PBC, cutoff 12 A, Float32; the Float64 figure rides along in `f64`).
+metric = in-cutoff pair evaluations per second (pairs with d2 <= cutoff^2, each counted once, as in the reference).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import workloads as W  # noqa: E402
+
+METRIC = "cutoff pair-evals/s (1M LJ forces)"
+UNIT = "pair-evals/s"
+# 8 flops per stencil candidate (distance test) + 20 per in-cutoff pair (LJ energy + forces)
+FLOPS_PER_CANDIDATE, FLOPS_PER_PAIR_LJ = 8.0, 20.0
+
+
+def reference_candidates(x, L, cutoff):
+    """C_st: candidate pairs of the REFERENCE's own stencil on the REFERENCE's own grid for an orthorhombic
+    self-set system (half stencil of 13 cells + same-cell upper triangle; ghost cells hold the periodic images of
+    the real cells), from the cell histogram."""
+    m = int(np.floor(L / cutoff))
+    cs = L / m
+    c = np.floor(np.mod(x.astype(np.float64), L) / cs).astype(np.int64) % m
+    h = np.bincount((c[:, 0] * m + c[:, 1]) * m + c[:, 2], minlength=m ** 3).reshape(m, m, m).astype(np.float64)
+    same = (h * (h - 1) / 2).sum()
+    vic = 0.0
+    for dx in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dz in (-1, 0, 1):
+                if (dx, dy, dz) > (0, 0, 0):   # forward half of the 26 neighbours
+                    vic += (h * np.roll(h, (-dx, -dy, -dz), axis=(0, 1, 2))).sum()
+    return same + vic
+
+
+class ClockSampler:
+    """samples nvidia-smi SM clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, device=0):
+        self.device, self.samples, self.reasons, self._stop, self.max_mhz = device, [], set(), threading.Event(), None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _q(self, fields):
+        try:
+            out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={fields}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=5).stdout.strip()
+            return [s.strip() for s in out.split(",")]
+        except Exception:
+            return None
+
+    def _run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap", "hw_power_brake_slowdown"]
+        fields = "clocks.sm,clocks.max.sm," + ",".join("clocks_throttle_reasons." + n for n in names)
+        while not self._stop.is_set():
+            r = self._q(fields)
+            if r and len(r) >= 2:
+                try:
+                    self.samples.append(float(r[0]))
+                    self.max_mhz = float(r[1])
+                    for n, v in zip(names, r[2:]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(n)
+                except ValueError:
+                    pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        self.t.start()
+
+    def stop(self):
+        self._stop.set()
+        self.t.join(timeout=10)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "MEASURED_PEAKS.json"
+    return {"hbm_gbs": 6553.6, "sm_max_mhz": 1965.0}, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------------------
+def cpu_port_run(w, dtype, reps, threads=None):
+    """the oracle (CPU restatement of the reference's algorithm incl. projection filter and batch-private outputs)
+    on the host cores: full workload, `reps` repetitions of build + map; returns (median seconds, pairs, threads)."""
+    from oracle import oracle as om
+    nt = threads or om.lib().ora_num_threads()
+    x = np.ascontiguousarray(w["x"], dtype=dtype)
+    times, npairs = [], None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        o = om.Oracle(x, w["cutoff"], unitcell=w["unitcell"].astype(dtype), dtype=dtype)   # UpdateCellList!
+        e, f = o.lj(w["c6"], w["c12"], forces=True, nbatches=nt)                              # pairwise!
+        times.append(time.perf_counter() - t0)
+        del o
+    o = om.Oracle(x, w["cutoff"], unitcell=w["unitcell"].astype(dtype), dtype=dtype)
+    npairs = o.sum_d_d2(nbatches=nt)[2]
+    return statistics.median(times), npairs, nt
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Julia and no Julia
+    toolchain exists here or on the GPU box, so this is the oracle port with all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dtype = np.float32
+    nside = args.cpu_nside
+    w = W.c2_argon(nside, dtype)
+    from oracle import oracle as om
+    nt = om.lib().ora_num_threads()
+    x = w["x"]
+    uc = w["unitcell"]
+
+    def step():
+        o = om.Oracle(x, w["cutoff"], unitcell=uc, dtype=dtype)
+        o.lj(w["c6"], w["c12"], forces=True, nbatches=nt)
+        return o
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o = step()
+    dt = time.perf_counter() - t0
+    npairs = o.sum_d_d2(nbatches=nt)[2]
+    value = npairs * args.steps / dt
+    sample = f"{nside}^3 = {nside ** 3} argon-density particles (same generator/density/cutoff as the GPU arm), build + LJ energy+forces per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: LJ energy+forces, argon-density particles, cubic PBC, cutoff 12 A", "n_particles": nside ** 3,
+                   "note": "CPU restatement of CellListMap.jl (C++/OpenMP oracle port, not Julia: no Julia toolchain on the box)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nt, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--nside", type=int, default=100, help="particles = nside^3 (100 -> the 1M-particle C2 config)")
+    ap.add_argument("--cpu-nside", type=int, default=100, help="size of the CPU arm / cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-f64", action="store_true")
+    ap.add_argument("--workload", default="auto")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import celllistmap_b200 as clm
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if world > 1:
+        from celllistmap_b200 import slab  # noqa: F401  (multi-GPU slab decomposition)
+        import bench_multi
+        return bench_multi.run(args, rank, world, local)
+
+    dev = torch.device("cuda", local)
+    peaks, peaks_src = load_peaks()
+    stream = torch.cuda.Stream(device=dev)
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def measure(dtype, steps, warmup, sample_clocks):
+        tdt = torch.float32 if dtype == np.float32 else torch.float64
+        w = W.c2_argon(args.nside, dtype)
+        n = w["x"].shape[0]
+        h = clm.Handle(3, dtype, device=local)
+        h.set_stream(stream.cuda_stream)
+        h.set_box(clm._capi.ORTHORHOMBIC, w["unitcell"], w["cutoff"], 1)
+        # ---- device-resident arm: inputs already in HBM when the timed region starts ----
+        x_dev = torch.from_numpy(w["x"]).to(dev)
+        e_dev = torch.zeros(1, dtype=tdt, device=dev)
+        f_dev = torch.zeros((n, 3), dtype=tdt, device=dev)
+        torch.cuda.synchronize()
+
+        def step_dev(profile=False):
+            h.set_positions(0, x_dev)                       # update!(sys; xpositions): owning copy, D2D
+            h.build()                                       # UpdateCellList!
+            h.map_lj(w["c6"], w["c12"], e_dev, f_dev, reset=True, profile=profile)   # pairwise!
+
+        with torch.cuda.stream(stream):
+            # pair count and reference-stencil candidates (work model), outside the timed region
+            h.set_positions(0, x_dev)
+            h.build()
+            sd, sd2, npairs = np.zeros(1, dtype), np.zeros(1, dtype), np.zeros(1, np.int64)
+            h.map_sum_d_d2(sd, sd2, npairs)
+            P_in = int(npairs[0])
+            for _ in range(warmup):
+                step_dev()
+            stream.synchronize()
+            sampler = ClockSampler(local) if sample_clocks else None
+            if sampler:
+                sampler.start()
+            l0 = h.stats().launches
+            evs = []
+            sweep_ms, build_ms = [], []
+            torch.cuda.synchronize()
+            for _ in range(steps):
+                flush_buf.zero_()                           # L2 flush between timed iterations (untimed)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                step_dev(profile=True)
+                b.record(stream)
+                b.synchronize()
+                evs.append(a.elapsed_time(b))
+                st = h.stats()
+                sweep_ms.append(st.sweep_ms)
+                build_ms.append(st.build_ms)
+            torch.cuda.synchronize()
+            launches = (h.stats().launches - l0) / steps
+            clocks = sampler.stop() if sampler else None
+            dev_ms = sum(evs) / steps
+            # ---- end-to-end arm: HOST buffers through the C ABI, H2D + D2H inside the timed region ----
+            x_pin = torch.from_numpy(w["x"]).pin_memory()
+            f_pin = torch.zeros((n, 3), dtype=tdt).pin_memory()
+            x_host, f_host, e_host = x_pin.numpy(), f_pin.numpy(), np.zeros(1, dtype)
+
+            def step_e2e():
+                h.set_positions(0, x_host)                  # H2D from pinned host memory
+                h.build()
+                h.map_lj(w["c6"], w["c12"], e_host, f_host, reset=True)   # forces + energy D2H, synchronous on return
+
+            for _ in range(3):
+                step_e2e()
+            e2e = []
+            for _ in range(steps):
+                flush_buf.zero_()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                step_e2e()
+                torch.cuda.synchronize()
+                e2e.append(time.perf_counter() - t0)
+            e2e_ms = 1e3 * sum(e2e) / steps
+        res = dict(P_in=P_in, n=n, dev_ms=dev_ms, sweep_ms=statistics.mean(sweep_ms), build_ms=statistics.mean(build_ms),
+                   e2e_ms=e2e_ms, launches=launches, clocks=clocks, w=w, energy=float(e_host[0]),
+                   h2d=int(x_host.nbytes), d2h=int(f_host.nbytes + e_host.nbytes), stats=h.stats())
+        h.close()
+        return res
+
+    r32 = measure(np.float32, args.steps, args.warmup, True)
+    r64 = None if args.no_f64 else measure(np.float64, max(3, args.steps // 2), 3, False)
+
+    C_st = reference_candidates(r32["w"]["x"], r32["w"]["L"], r32["w"]["cutoff"])
+    F_alg = FLOPS_PER_CANDIDATE * C_st + FLOPS_PER_PAIR_LJ * r32["P_in"]
+    # FP32 SIMT peak: 148 SMs x 128 lanes x 2 flop x max SM clock (no FP32-pipe figure in MEASURED_PEAKS.json:
+    # nominal from the measured max clock; B200_PROFILING.md fallback)
+    n_sm = r32["stats"].n_sm
+    sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    fp32_nominal_tf = n_sm * 128 * 2 * sm_mhz * 1e6 / 1e12
+    fp32_peak_tf = clm._capi.measure_fma_peak(np.float32, local)      # measured live: register-resident FMA loop
+    fp64_peak_tf = clm._capi.measure_fma_peak(np.float64, local)
+    achieved_tf = F_alg / (r32["sweep_ms"] * 1e-3) / 1e12
+    # algorithmic HBM bytes of the same launch: records in (16 B / particle incl. images) + forces out (12 B / particle)
+    B_alg = 16.0 * r32["stats"].n_total[0] + 12.0 * r32["n"]
+    line = {
+        "metric": METRIC, "value": r32["P_in"] / (r32["dev_ms"] * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r32["dev_ms"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2: LJ energy+forces, 1M argon-density particles, cubic PBC, cutoff 12 A (BASELINE.json configs[1])",
+                   "n_particles": r32["n"], "in_cutoff_pairs": r32["P_in"], "reference_stencil_candidates": C_st,
+                   "step": "update positions (D2D) + UpdateCellList! + pairwise!(LJ energy+forces)",
+                   "l2": "flushed between timed steps (256 MiB memset, untimed); per-step CUDA events on the launching stream"},
+        "clocks": r32["clocks"],
+        "e2e": {"value": r32["P_in"] / (r32["e2e_ms"] * 1e-3), "unit": UNIT, "ms_per_step": r32["e2e_ms"],
+                "h2d_bytes_per_step": r32["h2d"], "d2h_bytes_per_step": r32["d2h"]},
+        "gpu_launches": r32["launches"] * args.steps,
+        "roofline": {"bound": "fp32", "kernel": "k_sweep<float, MODE_ALL, FLJ<float,true>>", "achieved": achieved_tf, "peak": fp32_peak_tf,
+                     "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak_tf, "traffic": None,
+                     "algorithmic_flops_per_launch": F_alg, "kernel_ms": r32["sweep_ms"], "build_ms": r32["build_ms"],
+                     "peak_source": "FP32 FMA peak measured live by clm_measure_fma_peak (register-resident FMA loop, all SMs); "
+                                    f"nominal {fp32_nominal_tf:.1f} TFLOP/s = 148 SM x 128 lanes x 2 x sm_max_mhz from {peaks_src}; no tensor cores on this path",
+                     "fp64_peak_measured": fp64_peak_tf,
+                     "hbm": {"algorithmic_bytes_per_launch": B_alg, "achieved_gbs": B_alg / (r32["sweep_ms"] * 1e-3) / 1e9,
+                             "peak_gbs": peaks.get("hbm_gbs")}},
+        "breakdown_ms": {"step": r32["dev_ms"], "build": r32["build_ms"], "sweep_kernel": r32["sweep_ms"]},
+    }
+    if r64:
+        line["f64"] = {"value": r64["P_in"] / (r64["dev_ms"] * 1e-3), "unit": UNIT, "ms_per_step": r64["dev_ms"],
+                       "sweep_kernel_ms": r64["sweep_ms"], "build_ms": r64["build_ms"],
+                       "e2e_value": r64["P_in"] / (r64["e2e_ms"] * 1e-3), "in_cutoff_pairs": r64["P_in"]}
+    if not args.no_cpu_baseline:
+        wc = W.c2_argon(args.cpu_nside, np.float32)
+        t, npairs, nt = cpu_port_run(wc, np.float32, 3)
+        line["cpu_baseline"] = {"value": npairs / t, "unit": UNIT, "cores": nt, "kind": "port",
+                                "sample": f"full workload ({args.cpu_nside}^3 particles), median of 3 x (build + LJ energy+forces), "
+                                          "C++/OpenMP restatement of the reference (projection filter, batch-private outputs)",
+                                "seconds_per_step": t}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -24,7 +24,7 @@ SYMBOLS = [
     "clm_create", "clm_destroy", "clm_last_error", "clm_set_stream", "clm_synchronize", "clm_set_box", "clm_get_box",
     "clm_set_positions", "clm_build", "clm_map_lj", "clm_map_coulomb", "clm_map_dist_hist", "clm_map_pairvel",
     "clm_map_mindist", "clm_map_sum_d_d2", "clm_neighborlist", "clm_neighborlist_copy", "clm_get_stats",
-    "clm_set_option", "clm_version",
+    "clm_set_option", "clm_version", "clm_measure_fma_peak",
 ]
 
 
@@ -43,7 +43,7 @@ class Stats(C.Structure):
     _fields_ = [
         ("n_real", C.c_int64 * 2), ("n_total", C.c_int64 * 2), ("n_cells", C.c_int64), ("n_cells_real", C.c_int64 * 2),
         ("n_tiles", C.c_int64), ("n_pairs", C.c_int64), ("n_cutoff_band", C.c_int64),
-        ("build_ms", C.c_double), ("map_ms", C.c_double), ("n_sm", C.c_int32), ("launches", C.c_int32),
+        ("build_ms", C.c_double), ("map_ms", C.c_double), ("sweep_ms", C.c_double), ("n_sm", C.c_int32), ("launches", C.c_int32),
     ]
 
 
@@ -91,6 +91,7 @@ def lib():
     L.clm_neighborlist_copy.argtypes = [vp, vp, i64, ci]
     L.clm_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.clm_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.clm_measure_fma_peak.argtypes = [ci, ci, C.POINTER(C.c_double)]
     for name in SYMBOLS:
         getattr(L, name)
     _LIB = L
@@ -118,6 +119,15 @@ def _addr(a):
     if not a.flags["C_CONTIGUOUS"]:
         raise ValueError("arrays must be C-contiguous")
     return a.ctypes.data_as(C.c_void_p), False
+
+
+def measure_fma_peak(dtype, device=0):
+    """measured SIMT FMA peak in TFLOP/s (FP32 or FP64) of `device`."""
+    t = C.c_double(0)
+    code = lib().clm_measure_fma_peak(int(device), F32 if np.dtype(dtype) == np.float32 else F64, C.byref(t))
+    if code != 0:
+        raise ClmError(code, "FMA microbenchmark failed")
+    return t.value
 
 
 class Handle:

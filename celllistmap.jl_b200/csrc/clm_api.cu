@@ -24,6 +24,8 @@ template <class T> int Engine<T>::init(int dim_, int device_) {
     stream = own_stream;
     CLM_CK(cudaEventCreate(&ev0));
     CLM_CK(cudaEventCreate(&ev1));
+    CLM_CK(cudaEventCreate(&ev2));
+    CLM_CK(cudaEventCreate(&ev3));
     CLM_CK(dscal.ensure(DS_COUNT));
     CLM_CK(d_res.ensure(1));
     CLM_CK(d_minres.ensure(2));
@@ -44,6 +46,8 @@ template <class T> Engine<T>::~Engine() {
     if (h_res) cudaFreeHost(h_res);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    if (ev2) cudaEventDestroy(ev2);
+    if (ev3) cudaEventDestroy(ev3);
     if (own_stream) cudaStreamDestroy(own_stream);
 }
 
@@ -264,6 +268,7 @@ template <class T> int Engine<T>::build() {
 template <class T> int Engine<T>::prepare_map(int flags) {
     CLM_CK(cudaSetDevice(device));
     if (int rc = build()) return rc;
+    profile_sweep = (flags & CLM_PROFILE) != 0;
     if (flags & CLM_PROFILE) CLM_CK(cudaEventRecord(ev0, stream));
     CLM_CK(cudaMemsetAsync(d_res.p, 0, sizeof(ResultBlock), stream));
     CLM_CK(cudaMemsetAsync(dscal.p + DS_WORK, 0, sizeof(int), stream));
@@ -276,6 +281,8 @@ template <class T> int Engine<T>::finish_map(int flags) {
         float ms = 0;
         CLM_CK(cudaEventElapsedTime(&ms, ev0, ev1));
         stats.map_ms = ms;
+        CLM_CK(cudaEventElapsedTime(&ms, ev2, ev3));
+        stats.sweep_ms = ms;
     }
     return CLM_OK;
 }
@@ -375,12 +382,58 @@ template struct Engine<double>;
 
 }  // namespace clm
 
+// ---- register-resident FMA microbenchmark: the measured FP32 / FP64 SIMT roofline denominator -------
+// (MEASURED_PEAKS.json has no FP-pipe figure; bench.py measures it with this kernel)
+namespace clm {
+template <class T> __global__ void __launch_bounds__(256) k_fma_peak(T* out, int iters, T a, T b) {
+    T v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = T(threadIdx.x + k);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = v[k] * a + b;   // contracted to one FMA each: 8 independent chains
+    }
+    T s = T(0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+    if (s == T(-1)) out[0] = s;   // never true: keeps the chains alive
+}
+template <class T> static int fma_peak(int device, double* tflops) {
+    if (cudaSetDevice(device) != cudaSuccess) return CLM_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return CLM_ERR_CUDA;
+    T* d = nullptr;
+    if (cudaMalloc((void**)&d, 64) != cudaSuccess) return CLM_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int blocks = prop.multiProcessorCount * 8, iters = (sizeof(T) == 4) ? 16384 : 2048;
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        k_fma_peak<T><<<blocks, 256>>>(d, iters, T(0.999), T(0.001));
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return CLM_ERR_CUDA; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 8.0 * (double)iters * blocks * 256.0 / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = best;
+    return CLM_OK;
+}
+}  // namespace clm
+
 // ===================================================================================================
 using clm::EngineBase;
 struct clm_handle { EngineBase* e; };
 
 extern "C" {
 int clm_version(void) { return 100; }
+int clm_measure_fma_peak(int device, int dtype, double* tflops) {
+    if (!tflops) return CLM_ERR_ARGUMENT;
+    return dtype == CLM_F32 ? clm::fma_peak<float>(device, tflops) : clm::fma_peak<double>(device, tflops);
+}
 const char* clm_last_error(clm_handle* h) { return h ? h->e->err.c_str() : clm::g_create_error.c_str(); }
 
 int clm_create(clm_handle** out, int dim, int dtype, int device, int ngpus) {

@@ -72,7 +72,8 @@ template <class T> struct DevSet {
 
 template <class T> struct Engine : EngineBase {
     cudaStream_t stream = nullptr, own_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    bool profile_sweep = false;
     HostBox<T> box;
     GeomT<T> geom;
     bool box_set = false, nonperiodic = false, two_sets = false, dirty = true;
@@ -144,8 +145,10 @@ template <class T> struct Engine : EngineBase {
         if (opt_bps > 0) bps = std::min(bps, opt_bps);
         int64_t grid = (int64_t)n_sm * bps;
         grid = std::max<int64_t>(1, std::min<int64_t>(grid, (tiles_upper + (SWEEP_THREADS / 32) - 1) / (SWEEP_THREADS / 32)));
+        if (profile_sweep) CLM_CK(cudaEventRecord(ev2, stream));
         kern<<<(unsigned)grid, SWEEP_THREADS, smem, stream>>>(make_args(), f);
         CLM_CK(cudaGetLastError());
+        if (profile_sweep) CLM_CK(cudaEventRecord(ev3, stream));
         stats.launches += 1;
         last_grid = (int)grid;
         return CLM_OK;

@@ -95,6 +95,7 @@ typedef struct clm_stats {
     int64_t n_cutoff_band;    /* pairs with |d2 - cutoff^2| <= 1 ulp(cutoff^2) seen by the last clm_map_sum_d_d2 */
     double build_ms;          /* device time of the last clm_build (CUDA events) */
     double map_ms;            /* device time of the last map / neighborlist call run with CLM_PROFILE */
+    double sweep_ms;          /* device time of the pair-sweep kernel alone inside that call (CUDA events around the launch) */
     int32_t n_sm;             /* SM count of the device */
     int32_t launches;         /* kernels launched by this handle since creation */
 } clm_stats;
@@ -160,6 +161,9 @@ CLM_API int clm_get_stats(clm_handle* h, clm_stats* out);
  * "blocks_per_sm" (0 = auto). */
 CLM_API int clm_set_option(clm_handle* h, const char* name, int64_t value);
 CLM_API int clm_version(void);
+/* measurement helper: best-of-4 TFLOP/s of a register-resident FMA loop (8 independent chains per thread, all SMs
+ * resident) in FP32 (CLM_F32) or FP64 -- the SIMT roofline denominator bench.py reports against */
+CLM_API int clm_measure_fma_peak(int device, int dtype, double* tflops);
 
 #ifdef __cplusplus
 }
