@@ -302,7 +302,7 @@ def main():
         "e2e": {"value": r32["P_in"] / (r32["e2e_ms"] * 1e-3), "unit": UNIT, "ms_per_step": r32["e2e_ms"],
                 "h2d_bytes_per_step": r32["h2d"], "d2h_bytes_per_step": r32["d2h"]},
         "gpu_launches": r32["launches"] * args.steps,
-        "roofline": {"bound": "fp32", "kernel": "k_sweep<float, MODE_ALL, FLJ<float,true>>", "achieved": achieved_tf, "peak": fp32_peak_tf,
+        "roofline": {"bound": "fp32", "kernel": "k_sweep<float, MODE_ALL, FLJ<float,true,true>>", "achieved": achieved_tf, "peak": fp32_peak_tf,
                      "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak_tf, "traffic": None,
                      "algorithmic_flops_per_launch": F_alg, "kernel_ms": r32["sweep_ms"], "build_ms": r32["build_ms"],
                      "peak_source": "FP32 FMA peak measured live by clm_measure_fma_peak (register-resident FMA loop, all SMs); "

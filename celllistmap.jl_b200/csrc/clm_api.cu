@@ -39,7 +39,7 @@ template <class T> int Engine<T>::init(int dim_, int device_) {
 template <class T> Engine<T>::~Engine() {
     cudaSetDevice(device);
     if (own_stream) cudaStreamSynchronize(own_stream);
-    for (auto& s : sets) { s.pos.release(); s.rec.release(); s.cell_start.release(); s.cell_count.release(); s.cell_nreal.release(); s.aux.release(); }
+    for (auto& s : sets) { s.pos.release(); s.rec.release(); s.cell_start.release(); s.cell_count.release(); s.cell_nact.release(); s.ref_real.release(); s.aux.release(); }
     dscal.release(); scan_partial.release(); row_ntiles.release(); row_range.release(); tiles.release(); d_res.release();
     d_hcount.release(); nl.release(); d_hsum.release(); d_rbins.release(); d_forces.release(); d_minmax.release(); d_minpart.release(); d_minres.release();
     if (h_dscal) cudaFreeHost(h_dscal);
@@ -173,26 +173,63 @@ template <class T> int Engine<T>::build() {
     }
     if (!box_set) return fail(CLM_ERR_STATE, "clm_set_box must be called before clm_build");
     fill_geom(box, geom);
-    double nc_total = 1;
-    for (int k = 0; k < dim; ++k) nc_total *= (double)box.nc[k];
-    if (nc_total > 2.0e9) return fail(CLM_ERR_UNSUPPORTED, "more than 2e9 computing cells: increase the cutoff or use lcell = 1");
-    for (int k = 0; k < dim; ++k) if (box.nc[k] > 32767) return fail(CLM_ERR_UNSUPPORTED, "more than 32767 cells along one dimension");
-    ncells = (int64_t)nc_total;
+    double nref_total = 1;
+    for (int k = 0; k < dim; ++k) nref_total *= (double)box.nc[k];
+    if (nref_total > 2.0e9) return fail(CLM_ERR_UNSUPPORTED, "more than 2e9 computing cells: increase the cutoff or use lcell = 1");
+    if (box.lcell > LF_MAX) return fail(CLM_ERR_UNSUPPORTED, "lcell > 7 is not supported by the device stencil table");
+    nref = (int64_t)nref_total;
+    // device grid: split every reference cell into sub^N sub-cells, aiming at ~4 particles per device cell
+    {
+        double inner = 1;
+        for (int k = 0; k < dim; ++k) inner *= (double)std::max<int64_t>(1, box.nc[k] - 2 * box.lcell - 1);
+        const double per_cell = (double)std::max(sets[0].n, two_sets ? sets[1].n : (int64_t)0) / inner;
+        int sub = opt_sub > 0 ? opt_sub : (int)std::floor(std::pow(std::max(per_cell / 4.0, 1.0), 1.0 / dim) + 0.35);
+        sub = std::max(1, std::min(sub, LF_MAX / box.lcell));
+        while (sub > 1) {
+            double nd = nref_total * std::pow((double)sub, dim);
+            bool ok = nd <= 4.0e8;
+            for (int k = 0; k < dim; ++k) ok = ok && (box.nc[k] * sub <= 32767);
+            if (ok) break;
+            --sub;
+        }
+        for (int k = 0; k < dim; ++k) if (box.nc[k] * sub > 32767) return fail(CLM_ERR_UNSUPPORTED, "more than 32767 cells along one dimension");
+        geom.sub = sub;
+    }
+    const int sub = geom.sub, lf = box.lcell * sub;
     // device row = cells along the LAST reference dimension (see cell_of)
-    nfast = (int)box.nc[dim - 1]; nmid = (int)((dim == 3) ? box.nc[1] : box.nc[0]); nslow = (int)((dim == 3) ? box.nc[0] : 1);
+    nfast = (int)box.nc[dim - 1] * sub; nmid = (int)((dim == 3) ? box.nc[1] : box.nc[0]) * sub; nslow = (int)((dim == 3) ? box.nc[0] * sub : 1);
+    ncells = (int64_t)nfast * nmid * nslow;
     nrows = ncells / nfast;
+    // stencil rows: a row offset (dslow, dmid) is at least d_perp away; partners can only sit within
+    // sqrt(cutoff^2 - d_perp^2) along the row (1e-4 relative slack covers coordinate rounding at cell borders)
+    {
+        const double csf = (double)box.cs[dim - 1] / sub, csm = (double)((dim == 3) ? box.cs[1] : box.cs[0]) / sub, css = (double)box.cs[0] / sub;
+        const double rc2 = (double)box.cutoff * (double)box.cutoff * (1.0 + 2.0e-4);
+        std::memset(row_hw, -1, sizeof(row_hw));
+        for (int ds = -lf; ds <= lf; ++ds)
+            for (int dm = -lf; dm <= lf; ++dm) {
+                if (dim == 2 && ds != 0) continue;
+                const double gm = std::max(std::abs(dm) - 1, 0) * csm, gs = (dim == 3) ? std::max(std::abs(ds) - 1, 0) * css : 0.0;
+                const double rest = rc2 - gm * gm - gs * gs;
+                if (rest <= 0) continue;
+                const int w = std::min(lf, (int)std::ceil(std::sqrt(rest) / csf));
+                row_hw[(ds + lf) * (2 * lf + 1) + dm + lf] = (signed char)w;
+            }
+    }
     for (int s = 0; s < nsets; ++s) {
         DevSet<T>& S = sets[s];
         CLM_CK(S.cell_start.ensure((size_t)ncells + 1));
         CLM_CK(S.cell_count.ensure((size_t)ncells));
-        CLM_CK(S.cell_nreal.ensure((size_t)ncells));
+        CLM_CK(S.cell_nact.ensure((size_t)ncells));
+        CLM_CK(S.ref_real.ensure((size_t)nref));
         CLM_CK(cudaMemsetAsync(S.cell_count.p, 0, (size_t)ncells * sizeof(int), stream));
-        CLM_CK(cudaMemsetAsync(S.cell_nreal.p, 0, (size_t)ncells * sizeof(int), stream));
+        CLM_CK(cudaMemsetAsync(S.cell_nact.p, 0, (size_t)ncells * sizeof(int), stream));
+        CLM_CK(cudaMemsetAsync(S.ref_real.p, 0, (size_t)nref * sizeof(int), stream));
         int* ds = dscal.p + s * DS_SET_STRIDE;
         if (S.n > 0) {
             const int nb = (int)((S.n + 255) / 256);
-            if (dim == 3) k_bin<T, 3, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count.p, S.cell_nreal.p, nullptr, nullptr, ds);
-            else k_bin<T, 2, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count.p, S.cell_nreal.p, nullptr, nullptr, ds);
+            if (dim == 3) k_bin<T, 3, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count.p, S.cell_nact.p, S.ref_real.p, nullptr, nullptr, ds);
+            else k_bin<T, 2, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count.p, S.cell_nact.p, S.ref_real.p, nullptr, nullptr, ds);
             CLM_CK(cudaGetLastError());
             stats.launches += 1;
         }
@@ -215,30 +252,25 @@ template <class T> int Engine<T>::build() {
         if (S.n > 0) {
             const int nb = (int)((S.n + 255) / 256);
             int* ds = dscal.p + s * DS_SET_STRIDE;
-            if (dim == 3) k_bin<T, 3, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count.p, S.cell_nreal.p, S.cell_start.p, S.rec.p, ds);
-            else k_bin<T, 2, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count.p, S.cell_nreal.p, S.cell_start.p, S.rec.p, ds);
+            if (dim == 3) k_bin<T, 3, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count.p, S.cell_nact.p, S.ref_real.p, S.cell_start.p, S.rec.p, ds);
+            else k_bin<T, 2, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count.p, S.cell_nact.p, S.ref_real.p, S.cell_start.p, S.rec.p, ds);
             CLM_CK(cudaGetLastError());
             stats.launches += 1;
         }
     }
-    // tile size: particles per warp tile; small tiles (more j-slices) when cells hold few particles
-    {
-        double inner = 1;
-        for (int k = 0; k < dim; ++k) inner *= (double)std::max<int64_t>(1, box.nc[k] - 2 * box.lcell - 1);
-        const double per_cell = (double)sets[0].n / inner;
-        tile_i = opt_tile_i ? opt_tile_i : (per_cell >= 20.0 ? 32 : (per_cell >= 6.0 ? 16 : 8));
-        log2ti = (tile_i == 32) ? 5 : (tile_i == 16 ? 4 : 3);
-    }
+    // tile size: particles per warp tile (the remaining lanes split the partners into j-slices)
+    tile_i = opt_tile_i ? opt_tile_i : 8;
+    log2ti = (tile_i == 32) ? 5 : (tile_i == 16 ? 4 : 3);
     CLM_CK(row_ntiles.ensure((size_t)nrows + 1));
     CLM_CK(row_range.ensure((size_t)nrows));
     tiles_upper = sets[0].n_tot / tile_i + nrows + 1;
     CLM_CK(tiles.ensure((size_t)tiles_upper));
     {
         const int nb = (int)((nrows * 32 + 255) / 256);
-        k_rows<<<nb, 256, 0, stream>>>(sets[0].cell_nreal.p, sets[0].cell_start.p, nfast, (int)nrows, tile_i, row_ntiles.p, row_range.p, dscal.p);
+        k_rows<<<nb, 256, 0, stream>>>(sets[0].cell_nact.p, sets[0].cell_start.p, nfast, (int)nrows, tile_i, row_ntiles.p, row_range.p, dscal.p);
         stats.launches += 1;
-        if (two_sets) {
-            k_rows<<<nb, 256, 0, stream>>>(sets[1].cell_nreal.p, sets[1].cell_start.p, nfast, (int)nrows, tile_i, nullptr, nullptr, dscal.p + DS_SET_STRIDE);
+        for (int s = 0; s < nsets; ++s) {
+            k_count_flags<<<(int)std::min<int64_t>(1024, (nref + 255) / 256), 256, 0, stream>>>(sets[s].ref_real.p, (int)nref, dscal.p + s * DS_SET_STRIDE + DS_NCELLS_REAL);
             stats.launches += 1;
         }
         CLM_CK(cudaGetLastError());
@@ -373,6 +405,7 @@ template <class T> int Engine<T>::set_option(const char* name, int64_t v) {
         if (v != 0 && v != 8 && v != 16 && v != 32) return fail(CLM_ERR_ARGUMENT, "tile_i must be 0, 8, 16 or 32");
         opt_tile_i = (int)v; dirty = true; return CLM_OK;
     }
+    if (s == "sub") { if (v < 0 || v > LF_MAX) return fail(CLM_ERR_ARGUMENT, "sub must be in 0..7"); opt_sub = (int)v; dirty = true; return CLM_OK; }
     if (s == "blocks_per_sm") { if (v < 0) return fail(CLM_ERR_ARGUMENT, "blocks_per_sm must be >= 0"); opt_bps = (int)v; return CLM_OK; }
     return fail(CLM_ERR_ARGUMENT, "unknown option " + s);
 }

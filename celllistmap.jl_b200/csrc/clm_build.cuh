@@ -61,36 +61,47 @@ template <class T, int DIM> __device__ __forceinline__ void place_particle(const
     }
 }
 
-// 0-based linear cell of a point; real particles get the reference's border nudge
-// (particle_cell Box.jl:499-508, real_particle_border_case CellLists.jl:956-967).  -1 = outside the grid.
+// Cell of a point on the reference grid and on the device grid.  Reference cell: floor((p - cb_min)/cs) per
+// dimension, real particles nudged off the outermost layers (particle_cell Box.jl:499-508,
+// real_particle_border_case CellLists.jl:956-967).  Device cell: reference cell * sub + sub-cell, the sub-cell
+// from the fractional part of the same quotient, so the device grid is EXACTLY nested in the reference grid.
 //
-// DEVICE linearisation: the LAST reference dimension runs fastest (lin = c[N-1] + nc[N-1]*(c[N-2] + ...)),
+// DEVICE linearisation: the LAST reference dimension runs fastest (lin = c[N-1] + n[N-1]*(c[N-2] + ...)),
 // the transpose of the reference's column-major cell_linear_index (CellOperations.jl:256-257).  With it
 // the reference's forward stencil (Box.jl:436-457: d1 > 0 | d1 == 0, d2 > 0 | d1 == d2 == 0, d3 > 0)
-// is "later cells of the own row + every row with a larger row index within l", so the sweep visits
-// each cell pair from the SAME home cell as the reference and therefore evaluates the same periodic
-// image of every pair (bit-identical d2).
-template <class T, int DIM> __device__ __forceinline__ int cell_of(const GeomT<T>& g, const T p[3], bool real) {
-    int lin = 0;
+// is "later cells of the own row + every row with a larger row index", so the sweep can visit each
+// reference-cell pair from the SAME home cell as the reference and therefore evaluates the same periodic
+// image of every pair (bit-identical d2).  Returns false when the point is outside the grid (or NaN/Inf).
+template <class T, int DIM>
+__device__ __forceinline__ bool cell_of(const GeomT<T>& g, const T p[3], bool real, int& dev_lin, int& ref_lin) {
+    dev_lin = 0; ref_lin = 0;
 #pragma unroll
     for (int k = 0; k < DIM; ++k) {
-        const T q = floor(xdiv(xsub(p[k], g.cb_min[k]), g.cs[k]));
-        if (!(q >= T(-1) && q <= T(g.nc[k]))) return -1;  // also rejects NaN / Inf
-        int c = (int)q;
+        const T u = xdiv(xsub(p[k], g.cb_min[k]), g.cs[k]);
+        const T q = floor(u);
+        if (!(q >= T(-1) && q <= T(g.nc[k]))) return false;  // also rejects NaN / Inf
+        int c = (int)q, sc = 0;
+        if (g.sub > 1) sc = min(max((int)((u - q) * T(g.sub)), 0), g.sub - 1);
         if (real) {
-            if (c == g.lcell - 1) c += 1;
-            if (c == g.nc[k] - g.lcell) c -= 1;
+            if (c == g.lcell - 1) { c += 1; sc = 0; }
+            if (c == g.nc[k] - g.lcell) { c -= 1; sc = g.sub - 1; }
         }
-        if (c < 0 || c >= g.nc[k]) return -1;
-        lin = lin * g.nc[k] + c;
+        if (c < 0 || c >= g.nc[k]) return false;
+        ref_lin = ref_lin * g.nc[k] + c;
+        dev_lin = dev_lin * (g.nc[k] * g.sub) + c * g.sub + sc;
     }
-    return lin;
+    return true;
 }
 
+// Count pass (SCATTER = false): per-cell histograms of real + image particles.  Scatter pass: records to
+// cell_start[c] + atomic cursor.  cell_nact[c] counts the records of a cell that can act as particle i of a
+// pair: real particles, and images living in a REFERENCE cell that holds a real particle (the reference sweeps
+// exactly those cells, self.jl:56-57); ref_real[] flags reference cells with a real particle.
 template <class T, int DIM, bool SCATTER>
-static __global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256)
 k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, int n, int* __restrict__ cell_count,
-      int* __restrict__ cell_nreal, const int* __restrict__ cell_start, RecT<T>* __restrict__ rec, int* __restrict__ dscal) {
+      int* __restrict__ cell_nact, int* __restrict__ ref_real, const int* __restrict__ cell_start, RecT<T>* __restrict__ rec,
+      int* __restrict__ dscal) {
     typedef TagT<T> TG;
     const int ip = blockIdx.x * blockDim.x + threadIdx.x;
     if (ip >= n) return;
@@ -101,11 +112,12 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, int n, int*
     if (bad) { if (!SCATTER) atomicMin(&dscal[DS_NAN], ip); return; }   // _validate_coordinates, CellOperations.jl:6-21
     T p[3];
     place_particle<T, DIM>(g, x, p);
-    const int lin = cell_of<T, DIM>(g, p, true);
-    if (lin < 0) { if (!SCATTER) atomicMin(&dscal[DS_OOB], ip); return; }
+    int lin, rlin;
+    if (!cell_of<T, DIM>(g, p, true, lin, rlin)) { if (!SCATTER) atomicMin(&dscal[DS_OOB], ip); return; }
     if (!SCATTER) {
         atomicAdd(&cell_count[lin], 1);
-        atomicAdd(&cell_nreal[lin], 1);
+        atomicAdd(&cell_nact[lin], 1);
+        if (ref_real[rlin] == 0) ref_real[rlin] = 1;
     } else {
         const int slot = cell_start[lin] + atomicAdd(&cell_count[lin], 1);
         strec(&rec[slot], p[0], p[1], p[2], (typename TG::type)ip | TG::HOME);
@@ -115,9 +127,28 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, int n, int*
     // inside the computing box [cb_min, cb_max)
     constexpr int NIMG = (DIM == 3) ? 27 : 9;
     constexpr int CENTER = (DIM == 3) ? 13 : 4;
+    // orthorhombic cells: the shift of image index (i1,i2,i3) is (i1*L1, i2*L2, i3*L3) exactly, so which indices
+    // can land inside the computing box is decided per dimension; interior particles skip the enumeration
+    unsigned okmask = 0x7ffffffu;
+    if (!g.rotated && g.cell_type == CLM_ORTHO_CT) {
+        unsigned dimok[3] = {2u, 2u, 2u};   // bit (idx+1): idx allowed
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) {
+            const T lo = xadd(p[k], g.shift[(k == 0) ? CENTER - 1 : (k == 1 ? CENTER - 3 : CENTER - 9)][k]);
+            const T hi = xadd(p[k], g.shift[(k == 0) ? CENTER + 1 : (k == 1 ? CENTER + 3 : CENTER + 9)][k]);
+            if (g.cb_min[k] <= lo && lo < g.cb_max[k]) dimok[k] |= 1u;
+            if (g.cb_min[k] <= hi && hi < g.cb_max[k]) dimok[k] |= 4u;
+        }
+        if (dimok[0] == 2u && dimok[1] == 2u && (DIM == 2 || dimok[2] == 2u)) return;
+        okmask = 0u;
+        for (int img = 0; img < NIMG; ++img) {
+            const int i0 = img % 3, i1 = (img / 3) % 3, i2 = (DIM == 3) ? (img / 9) % 3 : 1;
+            if (((dimok[0] >> i0) & 1u) && ((dimok[1] >> i1) & 1u) && ((dimok[2] >> i2) & 1u)) okmask |= 1u << img;
+        }
+    }
 #pragma unroll 1
     for (int img = 0; img < NIMG; ++img) {
-        if (img == CENTER) continue;
+        if (img == CENTER || !((okmask >> img) & 1u)) continue;
         T q[3] = {T(0), T(0), T(0)};
         bool in = true;
 #pragma unroll
@@ -126,14 +157,15 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, int n, int*
             in = in && (g.cb_min[k] <= q[k]) && (q[k] < g.cb_max[k]);
         }
         if (!in) continue;
-        const int lq = cell_of<T, DIM>(g, q, false);
-        if (lq < 0) continue;
+        int lq, rq;
+        if (!cell_of<T, DIM>(g, q, false, lq, rq)) continue;
         if (!SCATTER) {
             atomicAdd(&cell_count[lq], 1);
         } else {
             const int slot = cell_start[lq] + atomicAdd(&cell_count[lq], 1);
-            const typename TG::type home = (cell_nreal[lq] > 0) ? TG::HOME : (typename TG::type)0;
-            strec(&rec[slot], q[0], q[1], q[2], (typename TG::type)ip | TG::GHOST | home);
+            const bool home = ref_real[rq] != 0;
+            if (home) atomicAdd(&cell_nact[lq], 1);
+            strec(&rec[slot], q[0], q[1], q[2], (typename TG::type)ip | TG::GHOST | (home ? TG::HOME : (typename TG::type)0));
         }
     }
 }
@@ -194,17 +226,17 @@ static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(int* __restric
 }
 
 // ---- rows and tiles -----------------------------------------------------------------------------------
-// one warp per (y,z) row of cells: first/last cell holding a real particle -> the record range
+// one warp per row of device cells: first/last cell holding a record that can act as particle i -> the record range
 // [cell_start[first], cell_start[last+1]) whose entries act as particle i, and its tile count.
 static __global__ void __launch_bounds__(256)
-k_rows(const int* __restrict__ cell_nreal, const int* __restrict__ cell_start, int nx, int nrows, int tile_i,
+k_rows(const int* __restrict__ cell_nact, const int* __restrict__ cell_start, int nx, int nrows, int tile_i,
        int* __restrict__ row_ntiles, int2* __restrict__ row_range, int* __restrict__ dscal) {
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= nrows) return;
     const int base = row * nx;
     int first = IDX_NONE, last = -1, nreal_cells = 0;
     for (int c = lane; c < nx; c += 32)
-        if (cell_nreal[base + c] > 0) { first = min(first, c); last = max(last, c); ++nreal_cells; }
+        if (cell_nact[base + c] > 0) { first = min(first, c); last = max(last, c); ++nreal_cells; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
@@ -218,7 +250,6 @@ k_rows(const int* __restrict__ cell_nreal, const int* __restrict__ cell_start, i
             row_range[row] = make_int2(a, b);
             row_ntiles[row] = (b - a + tile_i - 1) / tile_i;
         }
-        if (nreal_cells) atomicAdd(&dscal[DS_NCELLS_REAL], nreal_cells);
     }
 }
 
@@ -240,6 +271,15 @@ k_tiles(const int* __restrict__ row_tile_start, const int2* __restrict__ row_ran
     tl.k0 = k0; tl.cnt = cnt; tl.row = row;
     tl.cx = cell_x(k0) | (cell_x(k0 + cnt - 1) << 16);
     tiles[t] = tl;
+}
+
+// number of reference cells holding a real particle (CellList.n_cells_with_real_particles)
+static __global__ void __launch_bounds__(256) k_count_flags(const int* __restrict__ flags, int n, int* __restrict__ out) {
+    int c = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += (flags[i] != 0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
 // per-block min/max of the coordinates (limits(), CellOperations.jl:262-324): out[b][0..2] = min, [3..5] = max

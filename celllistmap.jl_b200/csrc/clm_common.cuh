@@ -4,10 +4,11 @@
 //   rec[n_total]      cell-sorted packed particle records (x, y, z, tag): one 128-bit (F32) or two
 //                     128-bit (F64) loads per particle; image ("ghost") particles are materialised
 //                     exactly as the reference does (internals/Box.jl:556-566), with the same tag.
-//   cell_start[nc+1]  exclusive prefix of per-cell counts; linear cell index has dimension 1 fastest
-//                     (internals/CellOperations.jl:256-257), so one (y,z) row of cells is ONE
-//                     contiguous range of rec[].
-//   tiles[n_tiles]    work items: TI consecutive records of one row + the x-range of cells they span.
+//   cell_start[nf+1]  exclusive prefix of per-cell counts over the DEVICE grid.  The device grid is the
+//                     reference grid (Box.jl:209-220) with every reference cell split into `sub` sub-cells
+//                     per dimension (sub = 1: identical grids); the LAST reference dimension runs fastest,
+//                     so one row of cells along it is ONE contiguous range of rec[].
+//   tiles[n_tiles]    work items: TI consecutive records of one row + the range of cells they span.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -82,7 +83,8 @@ template <class T> struct GeomT {
     T shift[27][3]; // aligned_unit_cell * idx for idx in {-1,0,1}^N, first index fastest
     T cb_min[3], cb_max[3], cs[3];
     T cutoff, cutoff_sqr;
-    int nc[3];      // 2-D: nc[2] = 1
+    int nc[3];      // reference grid (Box.nc); 2-D: nc[2] = 1
+    int sub;        // sub-cells per reference cell and dimension of the device grid
     int lcell;
     int dim;
     int cell_type;  // clm_cell_type

@@ -2,6 +2,7 @@
 // Host-side orchestration only: buffers, launch configuration, result staging.  No CPU compute path.
 #pragma once
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -66,7 +67,7 @@ template <class T> struct DevSet {
     int64_t n = 0;
     DBuf<RecT<T>> rec;       // cell-sorted records, real + image particles
     int64_t n_tot = 0, n_cells_real = 0;
-    DBuf<int> cell_start, cell_count, cell_nreal;
+    DBuf<int> cell_start, cell_count, cell_nact, ref_real;
     DBuf<T> aux;             // per-record auxiliary data gathered for the map in flight
 };
 
@@ -95,6 +96,9 @@ template <class T> struct Engine : EngineBase {
     int64_t nl_count = 0;
     int64_t ncells = 0, nrows = 0, tiles_upper = 0;
     int nfast = 1, nmid = 1, nslow = 1;   // device cell grid: lin = fast + nfast*(mid + nmid*slow); fast = last reference dim
+    int64_t nref = 0;                     // cells of the reference grid
+    signed char row_hw[(2 * LF_MAX + 1) * (2 * LF_MAX + 1)];   // per stencil row: half-width along the row in device cells, -1 = skip
+    int opt_sub = 0;                      // 0 = choose the sub-cell split from the particle density
     int tile_i = 32, log2ti = 5, opt_tile_i = 0, opt_bps = 0;
 
     int init(int dim_, int device_);
@@ -131,10 +135,11 @@ template <class T> struct Engine : EngineBase {
     SweepArgs<T> make_args() const {
         SweepArgs<T> a;
         const DevSet<T>& tg = sets[two_sets ? 1 : 0];
-        a.rec_i = sets[0].rec.p; a.rec_j = tg.rec.p; a.cell_start_j = tg.cell_start.p;
+        a.rec_i = sets[0].rec.p; a.rec_j = tg.rec.p; a.cell_start_i = sets[0].cell_start.p; a.cell_start_j = tg.cell_start.p;
         a.tiles = tiles.p; a.dscal = dscal.p; a.res = d_res.p;
-        a.nx = nfast; a.ny = nmid; a.nz = nslow; a.lcell = geom.lcell; a.log2ti = log2ti; a.self = two_sets ? 0 : 1;
+        a.nx = nfast; a.ny = nmid; a.nz = nslow; a.lf = geom.lcell * geom.sub; a.sub = geom.sub; a.log2ti = log2ti; a.self = two_sets ? 0 : 1;
         a.rc2 = geom.cutoff_sqr;
+        std::memcpy(a.hw, row_hw, sizeof(a.hw));
         return a;
     }
     template <int MODE, class F> int launch(const F& f, size_t smem) {

@@ -211,7 +211,7 @@ template <class T> inline void fill_geom(const HostBox<T>& B, GeomT<T>& G) {
         }
     }
     for (int j = 0; j < 3; ++j) { G.cb_min[j] = B.cb_min[j]; G.cb_max[j] = B.cb_max[j]; G.cs[j] = B.cs[j]; G.nc[j] = (int)B.nc[j]; }
-    G.cutoff = B.cutoff; G.cutoff_sqr = B.cutoff_sqr; G.lcell = B.lcell; G.dim = n; G.cell_type = B.cell_type; G.rotated = rotated ? 1 : 0;
+    G.cutoff = B.cutoff; G.cutoff_sqr = B.cutoff_sqr; G.sub = 1; G.lcell = B.lcell; G.dim = n; G.cell_type = B.cell_type; G.rotated = rotated ? 1 : 0;
 }
 
 }  // namespace clm

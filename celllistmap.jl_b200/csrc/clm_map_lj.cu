@@ -1,4 +1,5 @@
 // clm_map_lj / clm_map_coulomb: energy (+ forces) maps of the catalogue.
+#include <cmath>
 #include "clm_engine.cuh"
 
 namespace clm {
@@ -8,17 +9,26 @@ template <class T> int Engine<T>::map_lj(const void* p, int flags, void* e, void
     if (int rc = prepare_map(flags)) return rc;
     const T* c = (const T*)p;
     double scale = 1.0;
+    const bool norm = FLJ<T, true, true>::can_normalise(c[0], c[1]);
     if (f) {
         // full-shell sweep: every ordered pair (i real, j any image) adds to f_i only -> one plain store per
         // particle, no atomics, no per-batch force copies; the energy is visited twice in self-set systems
-        FLJ<T, true> fn;
-        fn.c6 = c[0]; fn.c12 = c[1];
-        if (int rc = forces_begin(f, flags, fn.fo)) return rc;
-        if (int rc = launch<MODE_ALL>(fn, 0)) return rc;
+        if (norm) {
+            FLJ<T, true, true> fn;
+            fn.set(c[0], c[1]);
+            if (int rc = forces_begin(f, flags, fn.fo)) return rc;
+            if (int rc = launch<MODE_ALL>(fn, 0)) return rc;
+        } else {
+            FLJ<T, true, false> fn;
+            fn.set(c[0], c[1]);
+            if (int rc = forces_begin(f, flags, fn.fo)) return rc;
+            if (int rc = launch<MODE_ALL>(fn, 0)) return rc;
+        }
         scale = two_sets ? 1.0 : 0.5;
     } else {
-        FLJ<T, false> fn;
-        fn.c6 = c[0]; fn.c12 = c[1];
+        // energy only: the reference's exactly-once sweep with the direct form (same pair set and arithmetic as the oracle)
+        FLJ<T, false, false> fn;
+        fn.set(c[0], c[1]);
         std::memset(&fn.fo, 0, sizeof(fn.fo));
         if (int rc = launch_reduce(fn, 0)) return rc;
     }

@@ -2,20 +2,25 @@
 // vicinal_cells.jl:4-75, NonPeriodicCells.jl:281-352) for the compiled-in functor catalogue.
 //
 // Work decomposition (B200-first, not the reference's cell-by-cell task batches):
-//   * a work item ("tile") is TI consecutive records of one (y,z) row of the cell-sorted array; one warp
-//     owns a tile: lane -> (i-slot = lane % TI, j-slice = lane / TI).  Particle i lives in registers.
-//   * for every stencil row (dy,dz) the candidate partners are ONE contiguous record range
-//     [cell_start[x_first-l], cell_start[x_last+l+1]) because cells are linearised with x fastest;
-//     all lanes of a j-slice read the same record (128-bit broadcast load, L1-resident), so the loop
-//     is ~25 FP32 instructions per candidate and has no shared-memory traffic at all.
+//   * the device grid splits every reference cell into sub^N sub-cells (clm_build.cuh) so that the candidate
+//     volume around a group of particles approaches the cutoff sphere instead of 27 cutoff-sized cells.
+//   * a work item ("tile") is TI consecutive records of one row of the cell-sorted array; one warp owns a
+//     tile: lane -> (i-slot = lane % TI, j-slice = lane / TI).  Particle i lives in registers.
+//   * for every stencil row the candidate partners are ONE contiguous record range
+//     [cell_start[first - w], cell_start[last + w + 1]) because cells are linearised along the row; the
+//     half-width w per row offset comes from a host table (rows farther than the cutoff are skipped).  All
+//     lanes of a j-slice read the same record (128-bit broadcast load, L1-resident): no shared-memory traffic.
 //   * warps fetch tiles from a global atomic counter (persistent grid = SMs x resident CTAs).
-//   * exactly-once rules are the reference's: MODE_HALF (orthorhombic / non-periodic self: later
-//     records of the own row + forward rows, real_i | real_j, self.jl:143-161, vicinal_cells.jl:33),
-//     MODE_TRI (triclinic self: full stencil, i real, index_i < index_j, self.jl:164-184,
-//     vicinal_cells.jl:53-65), MODE_ALL (two-set: full stencil, i real, cross.jl:111-129; also the
-//     full-shell force sweep, where each ordered pair contributes to f_i only so that per-particle
-//     outputs need no atomics and no per-batch output copies (the reference's A16)).
-//   * the distance test is bit-identical to the oracle's: d2 = (dx*dx + dy*dy) + dz*dz, unfused, <=.
+//   * exactly-once rules are the reference's, expressed on REFERENCE cells (device cell / sub):
+//     MODE_HALF (orthorhombic / non-periodic self): partner's reference cell is lexicographically after the
+//     home reference cell -- the reference's forward stencil, Box.jl:436-457 -- or the same cell and a later
+//     record; real_i | real_j (self.jl:143-161, vicinal_cells.jl:33); home cells hold a real particle.
+//     MODE_TRI (triclinic self): full stencil, i real, index_i < index_j (self.jl:164-184, vicinal_cells.jl:53-65).
+//     MODE_ALL (two-set: full stencil, i real, cross.jl:111-129; also the full-shell force sweep, where each
+//     ordered pair contributes to f_i only so that per-particle outputs need no atomics and no per-batch
+//     output copies, the reference's A16).
+//   * the distance test of the exact functors is bit-identical to the oracle's:
+//     d2 = (dx*dx + dy*dy) + dz*dz, unfused, <=.  Force functors (tolerance parity) contract it to FMAs.
 #pragma once
 #include "clm_common.cuh"
 #include "clm_build.cuh"
@@ -25,6 +30,7 @@ namespace clm {
 enum { MODE_HALF = 0, MODE_TRI = 1, MODE_ALL = 2 };
 constexpr int SWEEP_THREADS = 128;
 constexpr int NB_PRIV_MAX = 16;  // histograms with <= this many bins use per-thread private shared-memory bins
+constexpr int LF_MAX = 7;        // largest stencil reach in device cells (lcell * sub)
 
 // result block: accumulators every map kernel adds into (zeroed before the launch)
 enum { RB_ENERGY = 0, RB_SUM_D = 1, RB_SUM_D2 = 2, RB_F64_COUNT = 8 };
@@ -37,13 +43,15 @@ struct ResultBlock {
 template <class T> struct SweepArgs {
     const RecT<T>* rec_i;
     const RecT<T>* rec_j;
+    const int* cell_start_i;
     const int* cell_start_j;
     const Tile* tiles;
     int* dscal;          // DS_NTILES (read), DS_WORK (atomic tile counter)
     ResultBlock* res;
-    int nx, ny, nz;      // cells along the device's fast / middle / slow axis = reference dims (3,2,1) in 3-D, (2,1,-) in 2-D
-    int lcell, log2ti, self;
+    int nx, ny, nz;      // device cells along the fast / middle / slow axis = reference dims (3,2,1) in 3-D, (2,1,-) in 2-D
+    int lf, sub, log2ti, self;   // lf = lcell * sub: stencil reach in device cells
     T rc2;
+    signed char hw[(2 * LF_MAX + 1) * (2 * LF_MAX + 1)];   // [dslow + lf][dmid + lf]: half-width along the row, -1 = skip
 };
 
 template <class T> struct Ctx {   // what a functor sees for the tile in flight
@@ -75,7 +83,7 @@ template <class T> struct FSum {
     T rc2_lo, rc2_hi;   // prevfloat/nextfloat of cutoff^2
     struct Acc { double sd, sd2; unsigned long long n, band; };
     struct IAcc {};
-    static constexpr bool NEEDS_BAND = true;
+    static constexpr bool NEEDS_BAND = true, EXACT_D2 = true;
     __device__ void init(Acc& a) const { a.sd = 0; a.sd2 = 0; a.n = 0; a.band = 0; }
     __device__ void begin(IAcc&, const Ctx<T>&) const {}
     __device__ void pair(Acc& a, IAcc&, const Ctx<T>&, bool hit, bool ok, const RecT<T>&, int, T, T, T, T d2) const {
@@ -125,29 +133,51 @@ template <class T> struct ForceOut {
     }
 };
 
-// Lennard-Jones c12/d2^6 - c6/d2^3 (test/applications/gromacs/compare_with_gromacs.jl:9-13), optional forces
-template <class T, bool FORCES> struct FLJ {
+// Lennard-Jones c12/d2^6 - c6/d2^3 (test/applications/gromacs/compare_with_gromacs.jl:9-13), optional forces.
+// With q = (c12/c6) / d2^3 the pair energy is (c6^2/c12) * (q^2 - q) and the scalar force over d is
+// (6 c6^2/c12) * (2 q^2 - q) / d2: the constants leave the inner loop (applied once per tile / per kernel) and
+// the pair costs rcp + 10 FP32 instructions.  Pure c6 or pure c12 potentials use the direct form.
+template <class T, bool FORCES, bool NORM> struct FLJ {
     T c6, c12;
+    T s2, escale, fscale;   // NORM: s2 = cbrt(c12/c6), escale = c6^2/c12, fscale = 6 c6^2/c12; !NORM: the direct form
     ForceOut<T> fo;
     struct Acc { T e; };
     struct IAcc { T fx, fy, fz; };
-    static constexpr bool NEEDS_BAND = false;
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = !FORCES;   // the full-shell force sweep has tolerance parity
     __device__ void init(Acc& a) const { a.e = T(0); }
     __device__ void begin(IAcc& p, const Ctx<T>&) const { p.fx = p.fy = p.fz = T(0); }
     __device__ __forceinline__ void pair(Acc& a, IAcc& p, const Ctx<T>&, bool hit, bool, const RecT<T>&, int, T dx, T dy, T dz, T d2) const {
         const T inv = hit ? fast_rcp<T>(d2) : T(0);
-        const T r6 = inv * inv * inv;
-        a.e = xfma(r6, xfma(c12, r6, -c6), a.e);
-        if (FORCES) {
-            const T fs = inv * r6 * xfma(T(12) * c12, r6, T(-6) * c6);
-            p.fx = xfma(fs, dx, p.fx); p.fy = xfma(fs, dy, p.fy); p.fz = xfma(fs, dz, p.fz);
+        if (NORM) {
+            const T w = inv * s2;
+            const T q = w * w * w;
+            const T u = xfma(q, q, -q);        // q^2 - q
+            a.e += u;
+            if (FORCES) {
+                const T fs = inv * xfma(q, q, u);   // (2 q^2 - q) / d2
+                p.fx = xfma(fs, dx, p.fx); p.fy = xfma(fs, dy, p.fy); p.fz = xfma(fs, dz, p.fz);
+            }
+        } else {
+            const T r6 = inv * inv * inv;
+            a.e = xfma(r6, xfma(c12, r6, -c6), a.e);
+            if (FORCES) {
+                const T fs = inv * r6 * xfma(T(12) * c12, r6, T(-6) * c6);
+                p.fx = xfma(fs, dx, p.fx); p.fy = xfma(fs, dy, p.fy); p.fz = xfma(fs, dz, p.fz);
+            }
         }
     }
-    __device__ void end(IAcc& p, const Ctx<T>& c) const { if (FORCES) fo.store(c, p.fx, p.fy, p.fz); }
+    __device__ void end(IAcc& p, const Ctx<T>& c) const {
+        if (FORCES) { const T k = NORM ? fscale : T(1); fo.store(c, k * p.fx, k * p.fy, k * p.fz); }
+    }
     __device__ void finish(Acc& a, ResultBlock* res) const {
         __shared__ double sm[4];
         double e = block_sum((double)a.e, sm);
-        if (threadIdx.x == 0) atomicAdd(&res->f[RB_ENERGY], e);
+        if (threadIdx.x == 0) atomicAdd(&res->f[RB_ENERGY], e * (NORM ? (double)escale : 1.0));
+    }
+    static bool can_normalise(T c6_, T c12_) { return c6_ > T(0) && c12_ > T(0); }   // host
+    void set(T c6_, T c12_) {   // host
+        c6 = c6_; c12 = c12_; s2 = T(0); escale = T(1); fscale = T(1);
+        if (NORM) { s2 = std::cbrt(c12 / c6); escale = c6 * c6 / c12; fscale = T(6) * escale; }
     }
 };
 
@@ -159,7 +189,7 @@ template <class T, bool FORCES> struct FCoul {
     ForceOut<T> fo;
     struct Acc { T e; };
     struct IAcc { T fx, fy, fz, wi; };
-    static constexpr bool NEEDS_BAND = false;
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = !FORCES;
     __device__ void init(Acc& a) const { a.e = T(0); }
     __device__ void begin(IAcc& p, const Ctx<T>& c) const { p.fx = p.fy = p.fz = T(0); p.wi = c.active ? k * w_i[c.ki] : T(0); }
     __device__ __forceinline__ void pair(Acc& a, IAcc& p, const Ctx<T>&, bool hit, bool, const RecT<T>&, int j, T dx, T dy, T dz, T d2) const {
@@ -231,7 +261,7 @@ template <class T> struct FHist {
     HistBins<T, false> hb;
     struct Acc {};
     struct IAcc {};
-    static constexpr bool NEEDS_BAND = false;
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true;
     __device__ void init(Acc&) const { hb.init(); }
     __device__ void begin(IAcc&, const Ctx<T>&) const {}
     __device__ __forceinline__ void pair(Acc&, IAcc&, const Ctx<T>&, bool hit, bool, const RecT<T>&, int, T, T, T, T d2) const {
@@ -255,7 +285,7 @@ template <class T> struct FVel {
     HistBins<T, true> hb;
     struct Acc {};
     struct IAcc { T vx, vy, vz; };
-    static constexpr bool NEEDS_BAND = false;
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true;
     __device__ void init(Acc&) const { hb.init(); }
     __device__ void begin(IAcc& p, const Ctx<T>& c) const {
         p.vx = p.vy = p.vz = T(0);
@@ -283,7 +313,7 @@ template <class T> struct FMin {
     MinPartial* partial;   // [gridDim.x]
     struct Acc { T d2; long long i, j; };
     struct IAcc {};
-    static constexpr bool NEEDS_BAND = false;
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true;
     __device__ void init(Acc& a) const { a.d2 = CUDART_INF_T<T>(); a.i = 0; a.j = 0; }
     __device__ void begin(IAcc&, const Ctx<T>&) const {}
     __device__ static __forceinline__ bool better(T d2, long long i, long long j, T e2, long long ei, long long ej) {
@@ -323,7 +353,7 @@ template <class T> struct FList {
     unsigned long long capacity;
     struct Acc {};
     struct IAcc {};
-    static constexpr bool NEEDS_BAND = false;
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true;
     __device__ void init(Acc&) const {}
     __device__ void begin(IAcc&, const Ctx<T>&) const {}
     __device__ static __forceinline__ unsigned long long dbits(float d) { return (unsigned long long)__float_as_uint(d); }
@@ -354,13 +384,19 @@ template <class T> struct IsList<FList<T>> { static constexpr bool value = true;
 // ===================================================================================================
 // the sweep kernel
 // ===================================================================================================
+struct TrueTag { static constexpr bool value = true; };
+struct FalseTag { static constexpr bool value = false; };
+template <class T> __device__ __forceinline__ T huge_coord();
+template <> __device__ __forceinline__ float huge_coord<float>() { return 1.0e30f; }
+template <> __device__ __forceinline__ double huge_coord<double>() { return 1.0e200; }
+
 template <class T, int MODE, class F>
 __global__ void __launch_bounds__(SWEEP_THREADS)
 k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
     typedef TagT<T> TG;
     const int lane = threadIdx.x & 31;
     const int ti = 1 << a.log2ti, nslice = 32 >> a.log2ti;
-    const int l = a.lcell;
+    const int lf = a.lf, sub = a.sub, hww = 2 * lf + 1;
     typename F::Acc acc;
     f.init(acc);
     const int ntiles = a.dscal[DS_NTILES];
@@ -380,37 +416,75 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
         const typename TG::type idx_i = c.ri.tag & TG::MASK;
         typename F::IAcc ia;
         f.begin(ia, c);
+        // lanes that hold no particle i are parked far away: every distance test fails, no predicate in the loop
+        const T xi = c.active ? c.ri.x : huge_coord<T>(), yi = c.ri.y, zi = c.ri.z;
         const int iy = tl.row % a.ny, iz = tl.row / a.ny;
-        const int xa = max((tl.cx & 0xffff) - l, 0), xb = min((tl.cx >> 16) + l, a.nx - 1);
-        const int dz0 = (MODE == MODE_HALF || a.nz == 1) ? 0 : -l, dz1 = (a.nz == 1) ? 0 : l;
+        const int cxa = tl.cx & 0xffff, cxb = tl.cx >> 16;
+        // MODE_HALF: the reference cell of particle i along the row (the other two follow from the tile's row)
+        int rfx_i = 0;
+        if (MODE == MODE_HALF) {
+            const int* cs = a.cell_start_i + (size_t)tl.row * a.nx;
+            int cx = cxa;
+            while (cx < cxb && cs[cx + 1] <= c.ki) ++cx;
+            rfx_i = cx / sub;
+        }
+        const int ry_i = iy / sub, rz_i = iz / sub;
+        const int dz0 = (a.nz == 1) ? 0 : -lf, dz1 = (a.nz == 1) ? 0 : lf;
         for (int dz = dz0; dz <= dz1; ++dz) {
             const int z2 = iz + dz;
             if (z2 < 0 || z2 >= a.nz) continue;
-            const int dy0 = (MODE == MODE_HALF && dz == 0) ? 0 : -l;
-            for (int dy = dy0; dy <= l; ++dy) {
+            const int rz_j = z2 / sub;
+            if (MODE == MODE_HALF && rz_j < rz_i) continue;
+            for (int dy = -lf; dy <= lf; ++dy) {
                 const int y2 = iy + dy;
                 if (y2 < 0 || y2 >= a.ny) continue;
-                const bool own = (dy == 0 && dz == 0);
-                const int base = (z2 * a.ny + y2) * a.nx;
-                int j0 = a.cell_start_j[base + xa];
-                const int j1 = a.cell_start_j[base + xb + 1];
-                if (MODE == MODE_HALF && own) j0 = max(j0, tl.k0 + 1);   // only later records of the own row
-#pragma unroll 2
-                for (int jb = j0; jb < j1; jb += nslice) {
-                    const int j = jb + c.slice;
-                    const bool inb = j < j1;
-                    const int jc = inb ? j : (j1 - 1);
-                    const RecT<T> rj = ldrec(a.rec_j + jc);
-                    bool ok = c.active && inb;
-                    if (MODE == MODE_HALF) ok = ok && (!own || jc > c.ki) && (((c.ri.tag & rj.tag) & TG::GHOST) == 0);
-                    else if (MODE == MODE_TRI) ok = ok && (idx_i < (rj.tag & TG::MASK));
-                    else ok = ok && !(a.self && own && jc == c.ki);
-                    const T dx = xsub(c.ri.x, rj.x), dy_ = xsub(c.ri.y, rj.y), dz_ = xsub(c.ri.z, rj.z);
-                    const T d2 = xadd(xadd(xmul(dx, dx), xmul(dy_, dy_)), xmul(dz_, dz_));
-                    const bool hit = ok && (d2 <= a.rc2);
-                    if constexpr (IsList<F>::value) f.pair(acc, ia, c, hit, ok, rj, jc, dx, dy_, dz_, d2, a.res);
-                    else f.pair(acc, ia, c, hit, ok, rj, jc, dx, dy_, dz_, d2);
+                const int w = a.hw[(dz + lf) * hww + dy + lf];
+                if (w < 0) continue;
+                // relation of the partner row's reference cells to the home reference cell: < 0 behind (skipped),
+                // 0 same reference row (decided per record), > 0 forward (whole row)
+                int rel = 1;
+                if (MODE == MODE_HALF) {
+                    const int ry_j = y2 / sub;
+                    rel = (rz_j != rz_i) ? 1 : (ry_j - ry_i);
+                    if (rel < 0) continue;
                 }
+                const bool own = (dy == 0 && dz == 0);
+                const int xa = max(cxa - w, 0), xb = min(cxb + w, a.nx - 1);
+                const int* csj = a.cell_start_j + (size_t)(z2 * a.ny + y2) * a.nx;
+                const int j0 = csj[xa], j1 = csj[xb + 1];
+                // MODE_HALF, same reference row: partner must live in a later reference cell, or in the same one
+                // and be a later record: j >= thr
+                int thr = 0;
+                if (MODE == MODE_HALF && rel == 0) {
+                    const int A = csj[min((rfx_i + 1) * sub, a.nx)], B = csj[rfx_i * sub];
+                    thr = min(A, max(B, c.ki + 1));
+                }
+                // one row segment: full steps (every slice in range) without bounds logic, then one masked step.
+                // SELF_ROW: the full-shell self sweep meets its own record only in the tile's own row.
+                auto run_row = [&](auto self_row_tag) {
+                    constexpr bool SELF_ROW = decltype(self_row_tag)::value;
+                    auto body = [&](const RecT<T>* __restrict__ pj, const int jc, const bool inb) {
+                        const RecT<T> rj = ldrec(pj);
+                        bool ok = inb;
+                        if (MODE == MODE_HALF) ok = ok && (jc >= thr) && (((c.ri.tag & rj.tag) & TG::GHOST) == 0);
+                        else if (MODE == MODE_TRI) ok = ok && (idx_i < (rj.tag & TG::MASK));
+                        else if (SELF_ROW) ok = ok && (rj.tag != c.ri.tag);
+                        const T dx = xsub(xi, rj.x), dy_ = xsub(yi, rj.y), dz_ = xsub(zi, rj.z);
+                        T d2;
+                        if (F::EXACT_D2) d2 = xadd(xadd(xmul(dx, dx), xmul(dy_, dy_)), xmul(dz_, dz_));
+                        else d2 = xfma(dz_, dz_, xfma(dy_, dy_, dx * dx));
+                        const bool hit = ok && (d2 <= a.rc2);
+                        if constexpr (IsList<F>::value) f.pair(acc, ia, c, hit, ok, rj, jc, dx, dy_, dz_, d2, a.res);
+                        else f.pair(acc, ia, c, hit, ok, rj, jc, dx, dy_, dz_, d2);
+                    };
+                    const RecT<T>* pj = a.rec_j + (j0 + c.slice);
+                    int jc = j0 + c.slice;
+                    const int nfull = (j1 - j0) >> (5 - a.log2ti);
+#pragma unroll 4
+                    for (int s_ = 0; s_ < nfull; ++s_) { body(pj, jc, true); pj += nslice; jc += nslice; }
+                    if (jc - c.slice < j1) { const bool inb = jc < j1; body(inb ? pj : a.rec_j + (j1 - 1), inb ? jc : j1 - 1, inb); }
+                };
+                if (MODE == MODE_ALL && own && a.self) run_row(TrueTag()); else run_row(FalseTag());
             }
         }
         f.end(ia, c);
