@@ -31,6 +31,8 @@ enum { MODE_HALF = 0, MODE_TRI = 1, MODE_ALL = 2 };
 constexpr int SWEEP_THREADS = 128;
 constexpr int NB_PRIV_MAX = 16;  // histograms with <= this many bins use per-thread private shared-memory bins
 constexpr int LF_MAX = 7;        // largest stencil reach in device cells (lcell * sub)
+constexpr int STAGE_BYTES = 12288;                                      // per-warp staging buffer of partner records
+constexpr int STAGE_TOTAL = (SWEEP_THREADS / 32) * STAGE_BYTES + 64;    // + one mbarrier per warp; functor shared memory follows
 
 // result block: accumulators every map kernel adds into (zeroed before the launch)
 enum { RB_ENERGY = 0, RB_SUM_D = 1, RB_SUM_D2 = 2, RB_F64_COUNT = 8 };
@@ -83,7 +85,7 @@ template <class T> struct FSum {
     T rc2_lo, rc2_hi;   // prevfloat/nextfloat of cutoff^2
     struct Acc { double sd, sd2; unsigned long long n, band; };
     struct IAcc {};
-    static constexpr bool NEEDS_BAND = true, EXACT_D2 = true;
+    static constexpr bool NEEDS_BAND = true, EXACT_D2 = true, NEEDS_JC = false;
     __device__ void init(Acc& a) const { a.sd = 0; a.sd2 = 0; a.n = 0; a.band = 0; }
     __device__ void begin(IAcc&, const Ctx<T>&) const {}
     __device__ void pair(Acc& a, IAcc&, const Ctx<T>&, bool hit, bool ok, const RecT<T>&, int, T, T, T, T d2) const {
@@ -143,7 +145,7 @@ template <class T, bool FORCES, bool NORM> struct FLJ {
     ForceOut<T> fo;
     struct Acc { T e; };
     struct IAcc { T fx, fy, fz; };
-    static constexpr bool NEEDS_BAND = false, EXACT_D2 = !FORCES;   // the full-shell force sweep has tolerance parity
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = !FORCES, NEEDS_JC = false;   // the full-shell force sweep has tolerance parity
     __device__ void init(Acc& a) const { a.e = T(0); }
     __device__ void begin(IAcc& p, const Ctx<T>&) const { p.fx = p.fy = p.fz = T(0); }
     __device__ __forceinline__ void pair(Acc& a, IAcc& p, const Ctx<T>&, bool hit, bool, const RecT<T>&, int, T dx, T dy, T dz, T d2) const {
@@ -189,7 +191,7 @@ template <class T, bool FORCES> struct FCoul {
     ForceOut<T> fo;
     struct Acc { T e; };
     struct IAcc { T fx, fy, fz, wi; };
-    static constexpr bool NEEDS_BAND = false, EXACT_D2 = !FORCES;
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = !FORCES, NEEDS_JC = true;   // w_j[record]
     __device__ void init(Acc& a) const { a.e = T(0); }
     __device__ void begin(IAcc& p, const Ctx<T>& c) const { p.fx = p.fy = p.fz = T(0); p.wi = c.active ? k * w_i[c.ki] : T(0); }
     __device__ __forceinline__ void pair(Acc& a, IAcc& p, const Ctx<T>&, bool hit, bool, const RecT<T>&, int j, T dx, T dy, T dz, T d2) const {
@@ -216,11 +218,11 @@ template <class T, bool SUMS> struct HistBins {
     int nbins, priv;
     unsigned long long* g_counts;   // [nbins] global accumulators
     double* g_sums;                 // [nbins]
-    __device__ __forceinline__ unsigned int* cnt() const { extern __shared__ __align__(16) unsigned char dsm[]; return reinterpret_cast<unsigned int*>(dsm); }
+    __device__ __forceinline__ unsigned int* cnt() const { extern __shared__ __align__(128) unsigned char dsm_raw[]; return reinterpret_cast<unsigned int*>(dsm_raw + STAGE_TOTAL); }
     __device__ __forceinline__ T* sum() const {
-        extern __shared__ __align__(16) unsigned char dsm[];
+        extern __shared__ __align__(128) unsigned char dsm_raw[];
         const size_t nslots = (size_t)nbins * (priv ? SWEEP_THREADS : 1);
-        return reinterpret_cast<T*>(dsm + ((nslots * 4 + 15) / 16) * 16);
+        return reinterpret_cast<T*>(dsm_raw + STAGE_TOTAL + ((nslots * 4 + 15) / 16) * 16);
     }
     __device__ void init() const {
         const int nslots = nbins * (priv ? SWEEP_THREADS : 1);
@@ -261,7 +263,7 @@ template <class T> struct FHist {
     HistBins<T, false> hb;
     struct Acc {};
     struct IAcc {};
-    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true;
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true, NEEDS_JC = false;
     __device__ void init(Acc&) const { hb.init(); }
     __device__ void begin(IAcc&, const Ctx<T>&) const {}
     __device__ __forceinline__ void pair(Acc&, IAcc&, const Ctx<T>&, bool hit, bool, const RecT<T>&, int, T, T, T, T d2) const {
@@ -285,7 +287,7 @@ template <class T> struct FVel {
     HistBins<T, true> hb;
     struct Acc {};
     struct IAcc { T vx, vy, vz; };
-    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true;
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true, NEEDS_JC = true;
     __device__ void init(Acc&) const { hb.init(); }
     __device__ void begin(IAcc& p, const Ctx<T>& c) const {
         p.vx = p.vy = p.vz = T(0);
@@ -313,7 +315,7 @@ template <class T> struct FMin {
     MinPartial* partial;   // [gridDim.x]
     struct Acc { T d2; long long i, j; };
     struct IAcc {};
-    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true;
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true, NEEDS_JC = false;
     __device__ void init(Acc& a) const { a.d2 = CUDART_INF_T<T>(); a.i = 0; a.j = 0; }
     __device__ void begin(IAcc&, const Ctx<T>&) const {}
     __device__ static __forceinline__ bool better(T d2, long long i, long long j, T e2, long long ei, long long ej) {
@@ -353,7 +355,7 @@ template <class T> struct FList {
     unsigned long long capacity;
     struct Acc {};
     struct IAcc {};
-    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true;
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true, NEEDS_JC = false;
     __device__ void init(Acc&) const {}
     __device__ void begin(IAcc&, const Ctx<T>&) const {}
     __device__ static __forceinline__ unsigned long long dbits(float d) { return (unsigned long long)__float_as_uint(d); }
@@ -390,13 +392,64 @@ template <class T> __device__ __forceinline__ T huge_coord();
 template <> __device__ __forceinline__ float huge_coord<float>() { return 1.0e30f; }
 template <> __device__ __forceinline__ double huge_coord<double>() { return 1.0e200; }
 
+// ---- per-warp staging of partner records in shared memory (TMA 1-D bulk copies + mbarrier) ---------------------
+constexpr int STAGE_PAD = 32;                            // dummy records after the staged ones: the flat loop needs no bounds logic
+template <class T> struct StageCap { static constexpr int value = STAGE_BYTES / (int)sizeof(RecT<T>) - STAGE_PAD; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(mbar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// global -> shared, `bytes` a multiple of 16, both addresses 16-byte aligned; completion counted on `mbar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ RecT<float> ldrec_s(const RecT<float>* p) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    RecT<float> r;
+    r.x = v.x; r.y = v.y; r.z = v.z; r.tag = __float_as_uint(v.w);
+    return r;
+}
+__device__ __forceinline__ RecT<double> ldrec_s(const RecT<double>* p) {
+    const double2* q = reinterpret_cast<const double2*>(p);
+    const double2 a = q[0], b = q[1];
+    RecT<double> r;
+    r.x = a.x; r.y = a.y; r.z = b.x; r.tag = (uint64_t)__double_as_longlong(b.y);
+    return r;
+}
+
+// Row classes of one tile: skipped; DIRECT = swept straight from global memory with per-lane record thresholds
+// (MODE_HALF rows inside the home reference row, the own row of the full-shell self sweep, and every row of functors
+// that index per-record side arrays); STAGED = bulk-copied into the warp's shared-memory buffer and swept by one flat loop.
+enum { ROW_SKIP = 0, ROW_DIRECT = 1, ROW_STAGED = 2 };
+
 template <class T, int MODE, class F>
 __global__ void __launch_bounds__(SWEEP_THREADS)
 k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
     typedef TagT<T> TG;
-    const int lane = threadIdx.x & 31;
+    extern __shared__ __align__(128) unsigned char dsm_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ti = 1 << a.log2ti, nslice = 32 >> a.log2ti;
     const int lf = a.lf, sub = a.sub, hww = 2 * lf + 1;
+    const int nrows_st = (a.nz == 1) ? hww : hww * hww;
+    constexpr int CAP = StageCap<T>::value;
+    RecT<T>* const buf = reinterpret_cast<RecT<T>*>(dsm_raw + warp * STAGE_BYTES);
+    const uint32_t buf_addr = smem_u32(buf);
+    const uint32_t mbar = smem_u32(dsm_raw + (SWEEP_THREADS / 32) * STAGE_BYTES + warp * 8);
+    uint32_t parity = 0;
+    if (lane == 0) { mbar_init(mbar, 1); fence_proxy_async(); }
+    __syncwarp();
     typename F::Acc acc;
     f.init(acc);
     const int ntiles = a.dscal[DS_NTILES];
@@ -416,7 +469,7 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
         const typename TG::type idx_i = c.ri.tag & TG::MASK;
         typename F::IAcc ia;
         f.begin(ia, c);
-        // lanes that hold no particle i are parked far away: every distance test fails, no predicate in the loop
+        // lanes that hold no particle i are parked far away: every distance test fails, no predicate in the loops
         const T xi = c.active ? c.ri.x : huge_coord<T>(), yi = c.ri.y, zi = c.ri.z;
         const int iy = tl.row % a.ny, iz = tl.row / a.ny;
         const int cxa = tl.cx & 0xffff, cxb = tl.cx >> 16;
@@ -429,38 +482,62 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
             rfx_i = cx / sub;
         }
         const int ry_i = iy / sub, rz_i = iz / sub;
-        const int dz0 = (a.nz == 1) ? 0 : -lf, dz1 = (a.nz == 1) ? 0 : lf;
-        for (int dz = dz0; dz <= dz1; ++dz) {
-            const int z2 = iz + dz;
-            if (z2 < 0 || z2 >= a.nz) continue;
-            const int rz_j = z2 / sub;
-            if (MODE == MODE_HALF && rz_j < rz_i) continue;
-            for (int dy = -lf; dy <= lf; ++dy) {
-                const int y2 = iy + dy;
-                if (y2 < 0 || y2 >= a.ny) continue;
+
+        // the pair body shared by both sweeps
+        auto pair_body = [&](const RecT<T>& rj, const int jc, bool ok) {
+            const T dx = xsub(xi, rj.x), dy_ = xsub(yi, rj.y), dz_ = xsub(zi, rj.z);
+            T d2;
+            if (F::EXACT_D2) d2 = xadd(xadd(xmul(dx, dx), xmul(dy_, dy_)), xmul(dz_, dz_));
+            else d2 = xfma(dz_, dz_, xfma(dy_, dy_, dx * dx));
+            const bool hit = ok && (d2 <= a.rc2);
+            if constexpr (IsList<F>::value) f.pair(acc, ia, c, hit, ok, rj, jc, dx, dy_, dz_, d2, a.res);
+            else f.pair(acc, ia, c, hit, ok, rj, jc, dx, dy_, dz_, d2);
+        };
+
+        for (int rb = 0; rb < nrows_st; rb += 32) {
+            // ---- lane r classifies stencil row r and fetches its record range --------------------------------
+            const int r = rb + lane;
+            int cls = ROW_SKIP, j0 = 0, j1 = 0, rowbase = 0, own = 0;   // own: bit 0 = the tile's own row, bit 1 = same reference row (MODE_HALF)
+            if (r < nrows_st) {
+                const int dz = (a.nz == 1) ? 0 : r / hww - lf, dy = (a.nz == 1) ? r - lf : r % hww - lf;
+                const int z2 = iz + dz, y2 = iy + dy;
                 const int w = a.hw[(dz + lf) * hww + dy + lf];
-                if (w < 0) continue;
-                // relation of the partner row's reference cells to the home reference cell: < 0 behind (skipped),
-                // 0 same reference row (decided per record), > 0 forward (whole row)
-                int rel = 1;
-                if (MODE == MODE_HALF) {
-                    const int ry_j = y2 / sub;
-                    rel = (rz_j != rz_i) ? 1 : (ry_j - ry_i);
-                    if (rel < 0) continue;
+                bool use = (z2 >= 0 && z2 < a.nz && y2 >= 0 && y2 < a.ny && w >= 0);
+                int rel = 1;   // partner row's reference cells vs the home reference cell: < 0 behind, 0 same reference row, > 0 forward
+                if (MODE == MODE_HALF && use) {
+                    const int rz_j = z2 / sub, ry_j = y2 / sub;
+                    rel = (rz_j != rz_i) ? (rz_j - rz_i) : (ry_j - ry_i);
+                    use = rel >= 0;
                 }
-                const bool own = (dy == 0 && dz == 0);
-                const int xa = max(cxa - w, 0), xb = min(cxb + w, a.nx - 1);
-                const int* csj = a.cell_start_j + (size_t)(z2 * a.ny + y2) * a.nx;
-                const int j0 = csj[xa], j1 = csj[xb + 1];
+                if (use) {
+                    own = ((dy == 0 && dz == 0) ? 1 : 0) | ((MODE == MODE_HALF && rel == 0) ? 2 : 0);
+                    rowbase = (z2 * a.ny + y2) * a.nx;
+                    const int xa = max(cxa - w, 0), xb = min(cxb + w, a.nx - 1);
+                    j0 = a.cell_start_j[rowbase + xa];
+                    j1 = a.cell_start_j[rowbase + xb + 1];
+                    if (j1 > j0) {
+                        cls = ROW_STAGED;
+                        if (F::NEEDS_JC) cls = ROW_DIRECT;
+                        else if (MODE == MODE_HALF && rel == 0) cls = ROW_DIRECT;
+                        else if (MODE == MODE_ALL && (own & 1) && a.self) cls = ROW_DIRECT;
+                    }
+                }
+            }
+            // ---- direct rows -------------------------------------------------------------------------------------
+            unsigned mdir = __ballot_sync(0xffffffffu, cls == ROW_DIRECT);
+            while (mdir) {
+                const int src = __ffs(mdir) - 1;
+                mdir &= mdir - 1;
+                const int bj0 = __shfl_sync(0xffffffffu, j0, src), bj1 = __shfl_sync(0xffffffffu, j1, src);
+                const int brow = __shfl_sync(0xffffffffu, rowbase, src), bown = __shfl_sync(0xffffffffu, own, src);
                 // MODE_HALF, same reference row: partner must live in a later reference cell, or in the same one
                 // and be a later record: j >= thr
                 int thr = 0;
-                if (MODE == MODE_HALF && rel == 0) {
+                if (MODE == MODE_HALF && (bown & 2)) {
+                    const int* csj = a.cell_start_j + brow;
                     const int A = csj[min((rfx_i + 1) * sub, a.nx)], B = csj[rfx_i * sub];
                     thr = min(A, max(B, c.ki + 1));
                 }
-                // one row segment: full steps (every slice in range) without bounds logic, then one masked step.
-                // SELF_ROW: the full-shell self sweep meets its own record only in the tile's own row.
                 auto run_row = [&](auto self_row_tag) {
                     constexpr bool SELF_ROW = decltype(self_row_tag)::value;
                     auto body = [&](const RecT<T>* __restrict__ pj, const int jc, const bool inb) {
@@ -469,22 +546,48 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                         if (MODE == MODE_HALF) ok = ok && (jc >= thr) && (((c.ri.tag & rj.tag) & TG::GHOST) == 0);
                         else if (MODE == MODE_TRI) ok = ok && (idx_i < (rj.tag & TG::MASK));
                         else if (SELF_ROW) ok = ok && (rj.tag != c.ri.tag);
-                        const T dx = xsub(xi, rj.x), dy_ = xsub(yi, rj.y), dz_ = xsub(zi, rj.z);
-                        T d2;
-                        if (F::EXACT_D2) d2 = xadd(xadd(xmul(dx, dx), xmul(dy_, dy_)), xmul(dz_, dz_));
-                        else d2 = xfma(dz_, dz_, xfma(dy_, dy_, dx * dx));
-                        const bool hit = ok && (d2 <= a.rc2);
-                        if constexpr (IsList<F>::value) f.pair(acc, ia, c, hit, ok, rj, jc, dx, dy_, dz_, d2, a.res);
-                        else f.pair(acc, ia, c, hit, ok, rj, jc, dx, dy_, dz_, d2);
+                        pair_body(rj, jc, ok);
                     };
-                    const RecT<T>* pj = a.rec_j + (j0 + c.slice);
-                    int jc = j0 + c.slice;
-                    const int nfull = (j1 - j0) >> (5 - a.log2ti);
-#pragma unroll 4
+                    const RecT<T>* pj = a.rec_j + (bj0 + c.slice);
+                    int jc = bj0 + c.slice;
+                    const int nfull = (bj1 - bj0) >> (5 - a.log2ti);
+#pragma unroll 2
                     for (int s_ = 0; s_ < nfull; ++s_) { body(pj, jc, true); pj += nslice; jc += nslice; }
-                    if (jc - c.slice < j1) { const bool inb = jc < j1; body(inb ? pj : a.rec_j + (j1 - 1), inb ? jc : j1 - 1, inb); }
+                    if (jc - c.slice < bj1) { const bool inb = jc < bj1; body(inb ? pj : a.rec_j + (bj1 - 1), inb ? jc : bj1 - 1, inb); }
                 };
-                if (MODE == MODE_ALL && own && a.self) run_row(TrueTag()); else run_row(FalseTag());
+                if (MODE == MODE_ALL && (bown & 1) && a.self) run_row(TrueTag()); else run_row(FalseTag());
+            }
+            // ---- staged rows: prefix of the segment lengths, then chunks of at most CAP records --------------------
+            const int len = (cls == ROW_STAGED) ? (j1 - j0) : 0;
+            int incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            const int off = incl - len, total = __shfl_sync(0xffffffffu, incl, 31);
+            for (int c0 = 0; c0 < total; c0 += CAP) {
+                const int cn = min(total - c0, CAP);
+                const int lo = max(off, c0), hi = min(off + len, c0 + cn);
+                if (lane == 0) { fence_proxy_async(); mbar_expect_tx(mbar, (uint32_t)cn * (uint32_t)sizeof(RecT<T>)); }
+                __syncwarp();
+                if (hi > lo) bulk_g2s(buf_addr + (uint32_t)(lo - c0) * (uint32_t)sizeof(RecT<T>), a.rec_j + (j0 + (lo - off)), (uint32_t)(hi - lo) * (uint32_t)sizeof(RecT<T>), mbar);
+                // dummy far-away records round the chunk up to a whole number of 4-step groups
+                const int sh4 = 7 - a.log2ti, step4 = 1 << sh4, cpad = ((cn + step4 - 1) >> sh4) << sh4;   // step4 = 4 * nslice
+                if (cn + lane < cpad) strec(buf + cn + lane, -huge_coord<T>(), T(0), T(0), (typename TG::type)0);
+                mbar_wait(mbar, parity);
+                parity ^= 1u;
+                __syncwarp();
+                const RecT<T>* p = buf + c.slice;
+                auto sbody = [&](const RecT<T>* q) {
+                    const RecT<T> rj = ldrec_s(q);
+                    bool ok = true;
+                    if (MODE == MODE_HALF) ok = (((c.ri.tag & rj.tag) & TG::GHOST) == 0);
+                    else if (MODE == MODE_TRI) ok = (idx_i < (rj.tag & TG::MASK));
+                    pair_body(rj, 0, ok);
+                };
+                for (int g = 0; g < cpad; g += step4) {
+                    sbody(p); sbody(p + nslice); sbody(p + 2 * nslice); sbody(p + 3 * nslice);
+                    p += step4;
+                }
+                __syncwarp();
             }
         }
         f.end(ia, c);
