@@ -471,6 +471,22 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
         f.begin(ia, c);
         // lanes that hold no particle i are parked far away: every distance test fails, no predicate in the loops
         const T xi = c.active ? c.ri.x : huge_coord<T>(), yi = c.ri.y, zi = c.ri.z;
+        // bounding box of the tile's particles i (empty box when no lane is active: everything is culled)
+        T blo[3], bhi[3];
+        {
+            const T inf = CUDART_INF_T<T>();
+            blo[0] = c.active ? c.ri.x : inf; blo[1] = c.active ? c.ri.y : inf; blo[2] = c.active ? c.ri.z : inf;
+            bhi[0] = c.active ? c.ri.x : -inf; bhi[1] = c.active ? c.ri.y : -inf; bhi[2] = c.active ? c.ri.z : -inf;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                if (o >= ti) break;   // slices hold copies of the same particles
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    blo[k] = fmin(blo[k], __shfl_xor_sync(0xffffffffu, blo[k], o));
+                    bhi[k] = fmax(bhi[k], __shfl_xor_sync(0xffffffffu, bhi[k], o));
+                }
+            }
+        }
         const int iy = tl.row % a.ny, iz = tl.row / a.ny;
         const int cxa = tl.cx & 0xffff, cxb = tl.cx >> 16;
         // MODE_HALF: the reference cell of particle i along the row (the other two follow from the tile's row)
@@ -569,11 +585,31 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                 if (lane == 0) { fence_proxy_async(); mbar_expect_tx(mbar, (uint32_t)cn * (uint32_t)sizeof(RecT<T>)); }
                 __syncwarp();
                 if (hi > lo) bulk_g2s(buf_addr + (uint32_t)(lo - c0) * (uint32_t)sizeof(RecT<T>), a.rec_j + (j0 + (lo - off)), (uint32_t)(hi - lo) * (uint32_t)sizeof(RecT<T>), mbar);
-                // dummy far-away records round the chunk up to a whole number of 4-step groups
-                const int sh4 = 7 - a.log2ti, step4 = 1 << sh4, cpad = ((cn + step4 - 1) >> sh4) << sh4;   // step4 = 4 * nslice
-                if (cn + lane < cpad) strec(buf + cn + lane, -huge_coord<T>(), T(0), T(0), (typename TG::type)0);
                 mbar_wait(mbar, parity);
                 parity ^= 1u;
+                __syncwarp();
+                // cull: keep the staged records within the cutoff of the tile's bounding box, compacted in place.
+                // The box distance is evaluated with the same operation order as the pair distance; rounding is
+                // monotone, so box distance <= pair distance for every particle i of the tile: no pair is lost.
+                int ns = 0;
+                for (int k0 = 0; k0 < cn; k0 += 32) {
+                    const int k = k0 + lane;
+                    const bool in = k < cn;
+                    const RecT<T> rq = ldrec_s(buf + (in ? k : 0));
+                    const T ex = fmax(fmax(xsub(blo[0], rq.x), xsub(rq.x, bhi[0])), T(0));
+                    const T ey = fmax(fmax(xsub(blo[1], rq.y), xsub(rq.y, bhi[1])), T(0));
+                    const T ez = fmax(fmax(xsub(blo[2], rq.z), xsub(rq.z, bhi[2])), T(0));
+                    T dd;
+                    if (F::EXACT_D2) dd = xadd(xadd(xmul(ex, ex), xmul(ey, ey)), xmul(ez, ez));
+                    else dd = xfma(ez, ez, xfma(ey, ey, ex * ex));
+                    const bool keep = in && (dd <= a.rc2);
+                    const unsigned m = __ballot_sync(0xffffffffu, keep);   // every lane has read its record: in-place writes are safe
+                    if (keep) strec(buf + ns + __popc(m & ((1u << lane) - 1u)), rq.x, rq.y, rq.z, rq.tag);
+                    ns += __popc(m);
+                }
+                // dummy far-away records round the survivors up to a whole number of 4-step groups
+                const int sh4 = 7 - a.log2ti, step4 = 1 << sh4, cpad = ((ns + step4 - 1) >> sh4) << sh4;   // step4 = 4 * nslice
+                if (ns + lane < cpad) strec(buf + ns + lane, -huge_coord<T>(), T(0), T(0), (typename TG::type)0);
                 __syncwarp();
                 const RecT<T>* p = buf + c.slice;
                 auto sbody = [&](const RecT<T>* q) {
