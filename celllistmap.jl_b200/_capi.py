@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libclm_b200.so")
+SO_PATH = os.environ.get("CLM_SO", os.path.join(_HERE, "libclm_b200.so"))
 
 F32, F64 = 0, 1
 ORTHORHOMBIC, TRICLINIC, NONPERIODIC = 0, 1, 2

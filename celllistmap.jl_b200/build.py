@@ -11,10 +11,11 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
-SO = os.path.join(HERE, "libclm_b200.so")
+SO = os.environ.get("CLM_SO", os.path.join(HERE, "libclm_b200.so"))
 UNITS = ["clm_api", "clm_map_lj", "clm_map_hist", "clm_map_misc"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+EXTRA = os.environ.get("CLM_NVCC_EXTRA", "").split()
+FLAGS = EXTRA + ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
          "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
 

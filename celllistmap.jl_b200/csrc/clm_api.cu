@@ -39,7 +39,7 @@ template <class T> int Engine<T>::init(int dim_, int device_) {
 template <class T> Engine<T>::~Engine() {
     cudaSetDevice(device);
     if (own_stream) cudaStreamSynchronize(own_stream);
-    for (auto& s : sets) { s.pos.release(); s.rec.release(); s.cell_start.release(); s.cell_count.release(); s.cell_nact.release(); s.ref_real.release(); s.aux.release(); }
+    for (auto& s : sets) { s.pos.release(); s.rec.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
     dscal.release(); scan_partial.release(); row_ntiles.release(); row_range.release(); tiles.release(); d_res.release();
     d_hcount.release(); nl.release(); d_hsum.release(); d_rbins.release(); d_forces.release(); d_minmax.release(); d_minpart.release(); d_minres.release();
     if (h_dscal) cudaFreeHost(h_dscal);
@@ -216,73 +216,89 @@ template <class T> int Engine<T>::build() {
                 row_hw[(ds + lf) * (2 * lf + 1) + dm + lf] = (signed char)w;
             }
     }
-    for (int s = 0; s < nsets; ++s) {
-        DevSet<T>& S = sets[s];
-        CLM_CK(S.cell_start.ensure((size_t)ncells + 1));
-        CLM_CK(S.cell_count.ensure((size_t)ncells));
-        CLM_CK(S.cell_nact.ensure((size_t)ncells));
-        CLM_CK(S.ref_real.ensure((size_t)nref));
-        CLM_CK(cudaMemsetAsync(S.cell_count.p, 0, (size_t)ncells * sizeof(int), stream));
-        CLM_CK(cudaMemsetAsync(S.cell_nact.p, 0, (size_t)ncells * sizeof(int), stream));
-        CLM_CK(cudaMemsetAsync(S.ref_real.p, 0, (size_t)nref * sizeof(int), stream));
-        int* ds = dscal.p + s * DS_SET_STRIDE;
-        if (S.n > 0) {
-            const int nb = (int)((S.n + 255) / 256);
-            if (dim == 3) k_bin<T, 3, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count.p, S.cell_nact.p, S.ref_real.p, nullptr, nullptr, ds);
-            else k_bin<T, 2, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count.p, S.cell_nact.p, S.ref_real.p, nullptr, nullptr, ds);
-            CLM_CK(cudaGetLastError());
-            stats.launches += 1;
-        }
-        if (int rc = scan(S.cell_count.p, S.cell_start.p, (int)ncells, ds + DS_NTOT, S.cell_start.p + ncells)) return rc;
-    }
-    CLM_CK(cudaMemcpyAsync(h_dscal, dscal.p, DS_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
-    CLM_CK(cudaStreamSynchronize(stream));
-    for (int s = 0; s < nsets; ++s) {
-        const int* hs = h_dscal + s * DS_SET_STRIDE;
-        if (hs[DS_NAN] != IDX_NONE)
-            return fail(CLM_ERR_INVALID_COORDINATES, "Invalid coordinates found (NaN) for particle of index " + std::to_string(hs[DS_NAN] + 1) + (s ? " of the second set" : ""));
-        if (hs[DS_OOB] != IDX_NONE)
-            return fail(CLM_ERR_INVALID_COORDINATES, "Invalid coordinates found: particle of index " + std::to_string(hs[DS_OOB] + 1) + " falls outside the computing grid (non-finite coordinate?)");
-        sets[s].n_tot = hs[DS_NTOT];
-    }
-    for (int s = 0; s < nsets; ++s) {
-        DevSet<T>& S = sets[s];
-        CLM_CK(S.rec.ensure((size_t)std::max<int64_t>(S.n_tot, 1)));
-        CLM_CK(cudaMemsetAsync(S.cell_count.p, 0, (size_t)ncells * sizeof(int), stream));
-        if (S.n > 0) {
-            const int nb = (int)((S.n + 255) / 256);
-            int* ds = dscal.p + s * DS_SET_STRIDE;
-            if (dim == 3) k_bin<T, 3, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count.p, S.cell_nact.p, S.ref_real.p, S.cell_start.p, S.rec.p, ds);
-            else k_bin<T, 2, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count.p, S.cell_nact.p, S.ref_real.p, S.cell_start.p, S.rec.p, ds);
-            CLM_CK(cudaGetLastError());
-            stats.launches += 1;
-        }
-    }
     // tile size: particles per warp tile (the remaining lanes split the partners into j-slices)
     tile_i = opt_tile_i ? opt_tile_i : 8;
     log2ti = (tile_i == 32) ? 5 : (tile_i == 16 ? 4 : 3);
-    CLM_CK(row_ntiles.ensure((size_t)nrows + 1));
-    CLM_CK(row_range.ensure((size_t)nrows));
-    tiles_upper = sets[0].n_tot / tile_i + nrows + 1;
-    CLM_CK(tiles.ensure((size_t)tiles_upper));
-    {
-        const int nb = (int)((nrows * 32 + 255) / 256);
-        k_rows<<<nb, 256, 0, stream>>>(sets[0].cell_nact.p, sets[0].cell_start.p, nfast, (int)nrows, tile_i, row_ntiles.p, row_range.p, dscal.p);
-        stats.launches += 1;
+    // record capacity without a host round trip: real + image particles ~ n * volume(computing box) / volume(cell)
+    // (uniform density) with 25 % slack; a denser boundary layer is detected at the end-of-build sync and the build
+    // is repeated once with the exact size
+    double img_factor = 1.0;
+    if (box.cell_type != CLM_NONPERIODIC) {
+        double vbox = 1.0, vcell;
+        for (int k = 0; k < dim; ++k) vbox *= (double)box.cb_max[k] - (double)box.cb_min[k];
+        const T(*m)[3] = box.al;
+        vcell = (dim == 3) ? std::fabs((double)m[0][0] * ((double)m[1][1] * m[2][2] - (double)m[1][2] * m[2][1]) - (double)m[0][1] * ((double)m[1][0] * m[2][2] - (double)m[1][2] * m[2][0]) +
+                                       (double)m[0][2] * ((double)m[1][0] * m[2][1] - (double)m[1][1] * m[2][0]))
+                           : std::fabs((double)m[0][0] * m[1][1] - (double)m[0][1] * m[1][0]);
+        img_factor = std::min(std::max(vbox / std::max(vcell, 1e-300), 1.0), (dim == 3) ? 8.0 : 4.0);
+    }
+    for (int attempt = 0;; ++attempt) {
+        for (int k = 0; k < DS_COUNT; ++k) h_dscal[k] = 0;
+        h_dscal[DS_NAN] = h_dscal[DS_OOB] = h_dscal[DS_SET_STRIDE + DS_NAN] = h_dscal[DS_SET_STRIDE + DS_OOB] = IDX_NONE;
+        CLM_CK(cudaMemcpyAsync(dscal.p, h_dscal, DS_COUNT * sizeof(int), cudaMemcpyHostToDevice, stream));
         for (int s = 0; s < nsets; ++s) {
-            k_count_flags<<<(int)std::min<int64_t>(1024, (nref + 255) / 256), 256, 0, stream>>>(sets[s].ref_real.p, (int)nref, dscal.p + s * DS_SET_STRIDE + DS_NCELLS_REAL);
+            DevSet<T>& S = sets[s];
+            const size_t want = std::max<size_t>((size_t)((double)S.n * img_factor * 1.25) + 4096, (size_t)std::max<int64_t>(S.n_tot, 1));
+            CLM_CK(S.rec.ensure(want));
+            CLM_CK(S.cell_start.ensure((size_t)ncells + 2));
+            CLM_CK(S.counters.ensure((size_t)(2 * ncells + nref)));
+            S.cell_count = S.counters.p; S.cell_nact = S.counters.p + ncells; S.ref_real = S.counters.p + 2 * ncells;
+            CLM_CK(cudaMemsetAsync(S.counters.p, 0, (size_t)(2 * ncells + nref) * sizeof(int), stream));
+            CLM_CK(cudaMemsetAsync(S.cell_start.p, 0, sizeof(int), stream));
+            int* ds = dscal.p + s * DS_SET_STRIDE;
+            const int nb = (int)((S.n + 255) / 256);
+            if (S.n > 0) {
+                if (dim == 3) k_bin<T, 3, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, 0, ds);
+                else k_bin<T, 2, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, 0, ds);
+                CLM_CK(cudaGetLastError());
+                stats.launches += 1;
+            }
+            // exclusive prefix written one slot up: the scatter pass uses cell_start[c + 1] as the cursor of cell c, which
+            // leaves cell_start[0 .. ncells] = the exclusive starts once every record is placed (no second counter array)
+            if (int rc = scan(S.cell_count, S.cell_start.p + 1, (int)ncells, ds + DS_NTOT, S.cell_start.p + 1 + ncells)) return rc;
+            if (S.n > 0) {
+                if (dim == 3) k_bin<T, 3, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), ds);
+                else k_bin<T, 2, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), ds);
+                CLM_CK(cudaGetLastError());
+                stats.launches += 1;
+            }
+        }
+        CLM_CK(row_ntiles.ensure((size_t)nrows + 1));
+        CLM_CK(row_range.ensure((size_t)nrows));
+        tiles_upper = (int64_t)(sets[0].rec.cap / tile_i) + nrows + 1;
+        CLM_CK(tiles.ensure((size_t)tiles_upper));
+        {
+            const int nb = (int)((nrows * 32 + 255) / 256);
+            k_rows<<<nb, 256, 0, stream>>>(sets[0].cell_nact, sets[0].cell_start.p, nfast, (int)nrows, tile_i, row_ntiles.p, row_range.p, dscal.p);
+            stats.launches += 1;
+            for (int s = 0; s < nsets; ++s) {
+                k_count_flags<<<(int)std::min<int64_t>(1024, (nref + 255) / 256), 256, 0, stream>>>(sets[s].ref_real, (int)nref, dscal.p + s * DS_SET_STRIDE + DS_NCELLS_REAL);
+                stats.launches += 1;
+            }
+            CLM_CK(cudaGetLastError());
+            if (int rc = scan(row_ntiles.p, row_ntiles.p, (int)nrows, dscal.p + DS_NTILES, nullptr)) return rc;
+            const int nbt = (int)((tiles_upper + 255) / 256);
+            k_tiles<<<nbt, 256, 0, stream>>>(row_ntiles.p, row_range.p, sets[0].cell_start.p, nfast, (int)nrows, tile_i, dscal.p, tiles.p);
+            CLM_CK(cudaGetLastError());
             stats.launches += 1;
         }
-        CLM_CK(cudaGetLastError());
-        if (int rc = scan(row_ntiles.p, row_ntiles.p, (int)nrows, dscal.p + DS_NTILES, nullptr)) return rc;
-        const int nbt = (int)((tiles_upper + 255) / 256);
-        k_tiles<<<nbt, 256, 0, stream>>>(row_ntiles.p, row_range.p, sets[0].cell_start.p, nfast, (int)nrows, tile_i, dscal.p, tiles.p);
-        CLM_CK(cudaGetLastError());
-        stats.launches += 1;
+        CLM_CK(cudaEventRecord(ev1, stream));
+        // the one host round trip of the build: validation flags, record counts, tile count
+        CLM_CK(cudaMemcpyAsync(h_dscal, dscal.p, DS_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CLM_CK(cudaStreamSynchronize(stream));
+        bool overflow = false;
+        for (int s = 0; s < nsets; ++s) {
+            const int* hs = h_dscal + s * DS_SET_STRIDE;
+            if (hs[DS_NAN] != IDX_NONE)
+                return fail(CLM_ERR_INVALID_COORDINATES, "Invalid coordinates found (NaN) for particle of index " + std::to_string(hs[DS_NAN] + 1) + (s ? " of the second set" : ""));
+            if (hs[DS_OOB] != IDX_NONE)
+                return fail(CLM_ERR_INVALID_COORDINATES, "Invalid coordinates found: particle of index " + std::to_string(hs[DS_OOB] + 1) + " falls outside the computing grid (non-finite coordinate?)");
+            sets[s].n_tot = hs[DS_NTOT];
+            if ((size_t)sets[s].n_tot > sets[s].rec.cap) overflow = true;
+        }
+        if (!overflow) break;
+        if (attempt >= 2) return fail(CLM_ERR_CUDA, "cell-list build did not converge on a record capacity");
     }
-    CLM_CK(cudaEventRecord(ev1, stream));
-    CLM_CK(cudaMemcpyAsync(h_dscal, dscal.p, DS_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
-    CLM_CK(cudaStreamSynchronize(stream));
     float ms = 0;
     CLM_CK(cudaEventElapsedTime(&ms, ev0, ev1));
     stats.build_ms = ms;

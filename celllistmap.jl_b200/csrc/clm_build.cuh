@@ -93,15 +93,14 @@ __device__ __forceinline__ bool cell_of(const GeomT<T>& g, const T p[3], bool re
     return true;
 }
 
-// Count pass (SCATTER = false): per-cell histograms of real + image particles.  Scatter pass: records to
-// cell_start[c] + atomic cursor.  cell_nact[c] counts the records of a cell that can act as particle i of a
+// Count pass (SCATTER = false): per-cell histogram of real + image particles.  Scatter pass: records to the
+// atomic per-cell cursor.  cell_nact[c] flags cells holding a record that can act as particle i of a
 // pair: real particles, and images living in a REFERENCE cell that holds a real particle (the reference sweeps
 // exactly those cells, self.jl:56-57); ref_real[] flags reference cells with a real particle.
 template <class T, int DIM, bool SCATTER>
 __global__ void __launch_bounds__(256)
-k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, int n, int* __restrict__ cell_count,
-      int* __restrict__ cell_nact, int* __restrict__ ref_real, const int* __restrict__ cell_start, RecT<T>* __restrict__ rec,
-      int* __restrict__ dscal) {
+k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, int n, int* __restrict__ cell_cursor,
+      int* __restrict__ cell_nact, int* __restrict__ ref_real, RecT<T>* __restrict__ rec, int rec_cap, int* __restrict__ dscal) {
     typedef TagT<T> TG;
     const int ip = blockIdx.x * blockDim.x + threadIdx.x;
     if (ip >= n) return;
@@ -114,12 +113,13 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, int n, int*
     place_particle<T, DIM>(g, x, p);
     int lin, rlin;
     if (!cell_of<T, DIM>(g, p, true, lin, rlin)) { if (!SCATTER) atomicMin(&dscal[DS_OOB], ip); return; }
+    // cell_cursor: the per-cell histogram in the count pass; the per-cell write cursor (pre-loaded with the exclusive
+    // starts) in the scatter pass
+    const int slot = atomicAdd(&cell_cursor[lin], 1);
     if (!SCATTER) {
-        atomicAdd(&cell_count[lin], 1);
-        atomicAdd(&cell_nact[lin], 1);
+        if (cell_nact[lin] == 0) cell_nact[lin] = 1;
         if (ref_real[rlin] == 0) ref_real[rlin] = 1;
-    } else {
-        const int slot = cell_start[lin] + atomicAdd(&cell_count[lin], 1);
+    } else if (slot < rec_cap) {
         strec(&rec[slot], p[0], p[1], p[2], (typename TG::type)ip | TG::HOME);
     }
     if (g.cell_type == CLM_NONPERIODIC_CT) return;
@@ -159,13 +159,11 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, int n, int*
         if (!in) continue;
         int lq, rq;
         if (!cell_of<T, DIM>(g, q, false, lq, rq)) continue;
-        if (!SCATTER) {
-            atomicAdd(&cell_count[lq], 1);
-        } else {
-            const int slot = cell_start[lq] + atomicAdd(&cell_count[lq], 1);
+        const int qslot = atomicAdd(&cell_cursor[lq], 1);
+        if (SCATTER && qslot < rec_cap) {
             const bool home = ref_real[rq] != 0;
-            if (home) atomicAdd(&cell_nact[lq], 1);
-            strec(&rec[slot], q[0], q[1], q[2], (typename TG::type)ip | TG::GHOST | (home ? TG::HOME : (typename TG::type)0));
+            if (home && cell_nact[lq] == 0) cell_nact[lq] = 1;
+            strec(&rec[qslot], q[0], q[1], q[2], (typename TG::type)ip | TG::GHOST | (home ? TG::HOME : (typename TG::type)0));
         }
     }
 }

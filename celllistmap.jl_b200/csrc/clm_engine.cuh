@@ -67,7 +67,9 @@ template <class T> struct DevSet {
     int64_t n = 0;
     DBuf<RecT<T>> rec;       // cell-sorted records, real + image particles
     int64_t n_tot = 0, n_cells_real = 0;
-    DBuf<int> cell_start, cell_count, cell_nact, ref_real;
+    DBuf<int> cell_start;    // ncells + 2 entries: [0 .. ncells] = exclusive starts after the scatter pass
+    DBuf<int> counters;      // one memset: [cell_count | cell_nact | ref_real]
+    int *cell_count = nullptr, *cell_nact = nullptr, *ref_real = nullptr;
     DBuf<T> aux;             // per-record auxiliary data gathered for the map in flight
 };
 
@@ -144,7 +146,7 @@ template <class T> struct Engine : EngineBase {
     }
     template <int MODE, class F> int launch(const F& f, size_t functor_smem) {
         auto kern = k_sweep<T, MODE, F>;
-        const size_t smem = (size_t)STAGE_TOTAL + functor_smem;   // per-warp staging buffers + mbarriers, then the functor's bins
+        const size_t smem = (size_t)StageTotal<T>::value + functor_smem;   // per-warp staging buffers + mbarriers, then the functor's bins
         static size_t smem_set = 0;                                // per instantiation
         if (smem > smem_set) { CLM_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
         int bps = 0;

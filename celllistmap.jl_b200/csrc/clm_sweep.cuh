@@ -31,8 +31,16 @@ enum { MODE_HALF = 0, MODE_TRI = 1, MODE_ALL = 2 };
 constexpr int SWEEP_THREADS = 128;
 constexpr int NB_PRIV_MAX = 16;  // histograms with <= this many bins use per-thread private shared-memory bins
 constexpr int LF_MAX = 7;        // largest stencil reach in device cells (lcell * sub)
-constexpr int STAGE_BYTES = 12288;                                      // per-warp staging buffer of partner records
-constexpr int STAGE_TOTAL = (SWEEP_THREADS / 32) * STAGE_BYTES + 64;    // + one mbarrier per warp; functor shared memory follows
+// per-warp staging buffer of partner records: small buffers keep 8 CTAs (32 warps) resident per SM, which hides the
+// latency of the tile fetch / cell_start loads / bulk copies better than fewer, larger chunks (tools/tune_stage.sh)
+#ifndef CLM_STAGE_BYTES_F32
+#define CLM_STAGE_BYTES_F32 6144
+#endif
+#ifndef CLM_STAGE_BYTES_F64
+#define CLM_STAGE_BYTES_F64 8192
+#endif
+template <class T> struct StageBytes { static constexpr int value = (sizeof(T) == 4) ? CLM_STAGE_BYTES_F32 : CLM_STAGE_BYTES_F64; };
+template <class T> struct StageTotal { static constexpr int value = (SWEEP_THREADS / 32) * StageBytes<T>::value + 64; };   // + one mbarrier per warp; functor shared memory follows
 
 // result block: accumulators every map kernel adds into (zeroed before the launch)
 enum { RB_ENERGY = 0, RB_SUM_D = 1, RB_SUM_D2 = 2, RB_F64_COUNT = 8 };
@@ -218,11 +226,11 @@ template <class T, bool SUMS> struct HistBins {
     int nbins, priv;
     unsigned long long* g_counts;   // [nbins] global accumulators
     double* g_sums;                 // [nbins]
-    __device__ __forceinline__ unsigned int* cnt() const { extern __shared__ __align__(128) unsigned char dsm_raw[]; return reinterpret_cast<unsigned int*>(dsm_raw + STAGE_TOTAL); }
+    __device__ __forceinline__ unsigned int* cnt() const { extern __shared__ __align__(128) unsigned char dsm_raw[]; return reinterpret_cast<unsigned int*>(dsm_raw + StageTotal<T>::value); }
     __device__ __forceinline__ T* sum() const {
         extern __shared__ __align__(128) unsigned char dsm_raw[];
         const size_t nslots = (size_t)nbins * (priv ? SWEEP_THREADS : 1);
-        return reinterpret_cast<T*>(dsm_raw + STAGE_TOTAL + ((nslots * 4 + 15) / 16) * 16);
+        return reinterpret_cast<T*>(dsm_raw + StageTotal<T>::value + ((nslots * 4 + 15) / 16) * 16);
     }
     __device__ void init() const {
         const int nslots = nbins * (priv ? SWEEP_THREADS : 1);
@@ -394,7 +402,7 @@ template <> __device__ __forceinline__ double huge_coord<double>() { return 1.0e
 
 // ---- per-warp staging of partner records in shared memory (TMA 1-D bulk copies + mbarrier) ---------------------
 constexpr int STAGE_PAD = 32;                            // dummy records after the staged ones: the flat loop needs no bounds logic
-template <class T> struct StageCap { static constexpr int value = STAGE_BYTES / (int)sizeof(RecT<T>) - STAGE_PAD; };
+template <class T> struct StageCap { static constexpr int value = StageBytes<T>::value / (int)sizeof(RecT<T>) - STAGE_PAD; };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory"); }
@@ -444,9 +452,9 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
     const int lf = a.lf, sub = a.sub, hww = 2 * lf + 1;
     const int nrows_st = (a.nz == 1) ? hww : hww * hww;
     constexpr int CAP = StageCap<T>::value;
-    RecT<T>* const buf = reinterpret_cast<RecT<T>*>(dsm_raw + warp * STAGE_BYTES);
+    RecT<T>* const buf = reinterpret_cast<RecT<T>*>(dsm_raw + warp * StageBytes<T>::value);
     const uint32_t buf_addr = smem_u32(buf);
-    const uint32_t mbar = smem_u32(dsm_raw + (SWEEP_THREADS / 32) * STAGE_BYTES + warp * 8);
+    const uint32_t mbar = smem_u32(dsm_raw + (SWEEP_THREADS / 32) * StageBytes<T>::value + warp * 8);
     uint32_t parity = 0;
     if (lane == 0) { mbar_init(mbar, 1); fence_proxy_async(); }
     __syncwarp();
