@@ -169,6 +169,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-f64", action="store_true")
     ap.add_argument("--workload", default="auto")
+    ap.add_argument("--multi-nside", type=int, default=400, help="N > 1: lattice sites along y and z")
+    ap.add_argument("--multi-nx-per-rank", type=int, default=50, help="N > 1: lattice planes along x per rank (50 x 400 x 400 = 8M particles per GPU)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -188,8 +190,11 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if world > 1:
-        from celllistmap_b200 import slab  # noqa: F401  (multi-GPU slab decomposition)
+    if world > 1 or args.workload == "c5":
+        if world == 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            os.environ.setdefault("MASTER_PORT", "29533")
+            dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", local))
         import bench_multi
         return bench_multi.run(args, rank, world, local)
 

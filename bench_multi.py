@@ -1,0 +1,141 @@
+"""bench.py's N > 1 arm: the slab-decomposed LJ force map (BASELINE.json configs[4]) over NCCL, one rank per GPU.
+
+Workload (weak scaling): every rank generates ITS slab of the argon-density jittered lattice on its own GPU's host
+(nside_x_per_rank x nside x nside sites; 8 ranks x 50 x 400 x 400 = the 64M-particle config).  A step = halo exchange
+(NCCL send/recv of the face cell layers) + UpdateCellList! + pairwise!(LJ energy+forces) + all_reduce of the energy;
+forces stay sharded with their owners.  Timed per rank with CUDA events on the launching stream, max over ranks."""
+import json
+import statistics
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import workloads as W
+
+
+def slab_lattice(rank, world, nside, nx_per_rank, dtype):
+    """this rank's planes of the nside_x x nside x nside jittered lattice (nside_x = world * nx_per_rank)."""
+    a = W.ARGON_RHO ** (-1.0 / 3.0)
+    nx_tot = world * nx_per_rank
+    ix = np.arange(rank * nx_per_rank, (rank + 1) * nx_per_rank, dtype=np.int64)
+    g = np.arange(nside, dtype=np.int64)
+    I, J, K = np.meshgrid(ix, g, g, indexing="ij")
+    site = ((I * nside + J) * nside + K).reshape(-1)
+    n = site.shape[0]
+    sites = np.stack([I.reshape(-1), J.reshape(-1), K.reshape(-1)], 1).astype(np.float64) * a
+    # counter-based splitmix64: component c of site s is stream element 3 s + c (same values whatever the rank layout)
+    with np.errstate(over="ignore"):
+        k = (site[:, None] * 3 + np.arange(3)[None, :] + 1).astype(np.uint64)
+        z = np.uint64(W.SEED) + np.uint64(0x9E3779B97F4A7C15) * k
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    u = (z >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+    x = sites + (u - 0.5) * (0.5 * a) + 0.25 * a
+    x = x[W.shuffle_perm(W.SEED + 1 + rank, n)]
+    unitcell = np.array([a * nx_tot, a * nside, a * nside], dtype)
+    return np.ascontiguousarray(x.astype(dtype)), unitcell
+
+
+def run(args, rank, world, local):
+    import celllistmap_b200 as clm  # noqa: F401
+    from celllistmap_b200 import slab
+    import bench
+    dev = torch.device("cuda", local)
+    dtype = np.float32
+    nside = args.multi_nside
+    nx_per_rank = args.multi_nx_per_rank
+    x_host, unitcell = slab_lattice(rank, world, nside, nx_per_rank, dtype)
+    cutoff = 12.0
+    stream = torch.cuda.Stream(device=dev)
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    s = slab.SlabSystem(unitcell, cutoff, dtype=dtype, device=dev)
+    s.set_stream(stream)
+    with torch.cuda.stream(stream):
+        x_dev = torch.from_numpy(x_host).to(dev)
+        # the generator hands every rank its own planes, which is (up to jitter across a face) its slab; migrate strays
+        c = s.cell_layers(x_dev).to(torch.int64)
+        owner = s.plan.owner_of(c)
+        stray = int((owner != rank).sum())
+        n_own = x_dev.shape[0]
+        f_dev = torch.zeros((n_own, 3), dtype=torch.float32, device=dev)
+
+        def step(profile=False):
+            s.update(x_dev)                                  # halo exchange + positions to the engine
+            return s.map_lj(W.ARGON_C6, W.ARGON_C12, f_dev, profile=profile)   # build + sweep + energy all_reduce
+
+        if stray:
+            raise SystemExit(f"rank {rank}: {stray} generated particles fall outside the rank's slab (jitter across a face)")
+        for _ in range(args.warmup):
+            step()
+        s.update(x_dev)
+        sd = s.sum_d_d2()
+        P_in = sd[2]                                         # global in-cutoff pairs (all_reduced)
+        sampler = bench.ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        l0 = s.h.stats().launches
+        torch.cuda.synchronize()
+        dist.barrier()
+        times, sweep = [], []
+        for _ in range(args.steps):
+            flush_buf.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            e = step(profile=True)
+            b.record(stream)
+            b.synchronize()
+            times.append(a.elapsed_time(b))
+            sweep.append(s.h.stats().sweep_ms)
+        torch.cuda.synchronize()
+        dist.barrier()
+        launches = s.h.stats().launches - l0
+        clocks = sampler.stop() if sampler else None
+        t = torch.tensor([sum(times) / args.steps, statistics.mean(sweep), float(s.n_foreign), float(n_own)], dtype=torch.float64, device=dev)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        # end-to-end arm: host buffers in (pinned), forces + energy back to the host, inside the timed region
+        x_pin = torch.from_numpy(x_host).pin_memory()
+        f_pin = torch.zeros((n_own, 3), dtype=torch.float32).pin_memory()
+        e2e = []
+        for it in range(3 + args.steps):
+            flush_buf.zero_()
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            x_dev.copy_(x_pin, non_blocking=True)
+            e = step()
+            f_pin.copy_(f_dev, non_blocking=True)
+            e_host = e.cpu()
+            b.record(stream)
+            b.synchronize()
+            if it >= 3:
+                e2e.append(a.elapsed_time(b))
+        te = torch.tensor([sum(e2e) / len(e2e)], dtype=torch.float64, device=dev)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(tmax[0])
+        n_total = int(tsum[3])
+        line = {
+            "metric": bench.METRIC, "value": P_in / (ms * 1e-3), "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C5: LJ energy+forces, argon-density particles, cubic-lattice PBC box slab-decomposed along x, cutoff 12 A "
+                                   "(BASELINE.json configs[4]; 8 ranks = the 64M-particle case)",
+                       "n_particles": n_total, "particles_per_gpu": n_total // world, "in_cutoff_pairs": P_in,
+                       "halo_particles_per_gpu_max": int(tmax[2]),
+                       "step": "halo exchange (NCCL send/recv) + UpdateCellList! + pairwise!(LJ energy+forces) + energy all_reduce",
+                       "l2": "flushed between timed steps (256 MiB memset, untimed); per-step CUDA events, max over ranks"},
+            "clocks": clocks,
+            "e2e": {"value": P_in / (float(te[0]) * 1e-3), "unit": bench.UNIT, "ms_per_step": float(te[0]),
+                    "h2d_bytes_per_step": int(x_host.nbytes) * world, "d2h_bytes_per_step": (int(f_pin.numel()) * 4 + 4) * world},
+            "gpu_launches": launches * world,
+            "breakdown_ms": {"step_max": ms, "sweep_kernel_max": float(tmax[1])},
+            "energy": float(e_host),
+        }
+        print(json.dumps(line))
+    s.close()

@@ -24,7 +24,7 @@ SYMBOLS = [
     "clm_create", "clm_destroy", "clm_last_error", "clm_set_stream", "clm_synchronize", "clm_set_box", "clm_get_box",
     "clm_set_positions", "clm_build", "clm_map_lj", "clm_map_coulomb", "clm_map_dist_hist", "clm_map_pairvel",
     "clm_map_mindist", "clm_map_sum_d_d2", "clm_neighborlist", "clm_neighborlist_copy", "clm_get_stats",
-    "clm_set_option", "clm_version", "clm_measure_fma_peak",
+    "clm_set_option", "clm_version", "clm_measure_fma_peak", "clm_set_foreign", "clm_cell_coords",
 ]
 
 
@@ -92,6 +92,8 @@ def lib():
     L.clm_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.clm_set_option.argtypes = [vp, C.c_char_p, i64]
     L.clm_measure_fma_peak.argtypes = [ci, ci, C.POINTER(C.c_double)]
+    L.clm_set_foreign.argtypes = [vp, ci, vp, i64, ci]
+    L.clm_cell_coords.argtypes = [vp, vp, i64, ci, ci, vp]
     for name in SYMBOLS:
         getattr(L, name)
     _LIB = L
@@ -195,6 +197,29 @@ class Handle:
         if n == 0:
             p = C.c_void_p(1) if which == 1 else None  # non-NULL + n = 0: empty second set
         self._chk(self.L.clm_set_positions(self.h, int(which), p, n, 1 if dev else 0))
+
+    def set_foreign(self, which, x):
+        """particles owned by other ranks that are within the stencil reach of this rank's slab (None / empty: none)."""
+        if x is None or int(x.shape[0]) == 0:
+            self._chk(self.L.clm_set_foreign(self.h, int(which), None, 0, 0))
+            return
+        if not _is_torch(x):
+            x = np.ascontiguousarray(x, dtype=self.dtype)
+        p, dev = _addr(x)
+        self._chk(self.L.clm_set_foreign(self.h, int(which), p, int(x.shape[0]), 1 if dev else 0))
+
+    def cell_coords(self, x, axis, out=None):
+        """0-based reference-cell index along `axis` of every row of x (numpy in -> numpy out, torch CUDA in -> torch out)."""
+        n = int(x.shape[0])
+        if _is_torch(x):
+            import torch
+            out = torch.empty(n, dtype=torch.int32, device=x.device) if out is None else out
+            self._chk(self.L.clm_cell_coords(self.h, _addr(x)[0], n, 1, int(axis), _addr(out)[0]))
+            return out
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        out = np.empty(n, np.int32) if out is None else out
+        self._chk(self.L.clm_cell_coords(self.h, _addr(x)[0], n, 0, int(axis), _addr(out)[0]))
+        return out
 
     def build(self):
         self._chk(self.L.clm_build(self.h))

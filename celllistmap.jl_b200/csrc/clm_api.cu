@@ -39,7 +39,7 @@ template <class T> int Engine<T>::init(int dim_, int device_) {
 template <class T> Engine<T>::~Engine() {
     cudaSetDevice(device);
     if (own_stream) cudaStreamSynchronize(own_stream);
-    for (auto& s : sets) { s.pos.release(); s.rec.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
+    for (auto& s : sets) { s.pos.release(); s.fpos.release(); s.rec.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
     dscal.release(); scan_partial.release(); row_ntiles.release(); row_range.release(); tiles.release(); d_res.release();
     d_hcount.release(); nl.release(); d_hsum.release(); d_rbins.release(); d_forces.release(); d_minmax.release(); d_minpart.release(); d_minres.release();
     if (h_dscal) cudaFreeHost(h_dscal);
@@ -109,6 +109,52 @@ template <class T> int Engine<T>::set_positions(int set, const void* xyz, int64_
     return CLM_OK;
 }
 
+// foreign particles (slab decomposition): real particles owned by other ranks that lie within the stencil reach of
+// this rank's slab.  They are binned (with their periodic images) after the owned ones and never act as particle i.
+template <class T> int Engine<T>::set_foreign(int set, const void* xyz, int64_t n, int on_device) {
+    if (set != 0 && set != 1) return fail(CLM_ERR_ARGUMENT, "set must be 0 (x) or 1 (y)");
+    if (n < 0 || (n > 0 && !xyz)) return fail(CLM_ERR_ARGUMENT, "bad foreign particle array");
+    CLM_CK(cudaSetDevice(device));
+    DevSet<T>& s = sets[set];
+    CLM_CK(s.fpos.ensure((size_t)std::max<int64_t>(n, 1) * dim));
+    if (n) CLM_CK(cudaMemcpyAsync(s.fpos.p, xyz, (size_t)n * dim * sizeof(T), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+    s.n_foreign = n;
+    dirty = true;
+    return CLM_OK;
+}
+
+// reference-cell index along one dimension for arbitrary coordinates, with the arithmetic of the build
+template <class T> int Engine<T>::cell_coords(const void* xyz, int64_t n, int on_device, int axis, int32_t* out) {
+    if (!box_set) return fail(CLM_ERR_STATE, "clm_set_box must be called first (non-periodic boxes exist after clm_build)");
+    if (axis < 0 || axis >= dim) return fail(CLM_ERR_ARGUMENT, "axis out of range");
+    if (n <= 0) return CLM_OK;
+    if (!xyz || !out) return fail(CLM_ERR_ARGUMENT, "NULL pointer");
+    CLM_CK(cudaSetDevice(device));
+    GeomT<T> g;
+    fill_geom(box, g);
+    const T* dx = (const T*)xyz;
+    int* dout = (int*)out;
+    DBuf<T> tx;
+    DBuf<int> to;
+    if (!on_device) {
+        CLM_CK(tx.ensure((size_t)n * dim));
+        CLM_CK(to.ensure((size_t)n));
+        CLM_CK(cudaMemcpyAsync(tx.p, xyz, (size_t)n * dim * sizeof(T), cudaMemcpyHostToDevice, stream));
+        dx = tx.p; dout = to.p;
+    }
+    const int nb = (int)((n + 255) / 256);
+    if (dim == 3) k_cell_coord<T, 3><<<nb, 256, 0, stream>>>(g, dx, (int)n, axis, dout);
+    else k_cell_coord<T, 2><<<nb, 256, 0, stream>>>(g, dx, (int)n, axis, dout);
+    CLM_CK(cudaGetLastError());
+    stats.launches += 1;
+    if (!on_device) {
+        CLM_CK(cudaMemcpyAsync(out, to.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CLM_CK(cudaStreamSynchronize(stream));
+        tx.release(); to.release();
+    }
+    return CLM_OK;
+}
+
 template <class T> int Engine<T>::scan(const int* in, int* out, int n, int* total_slot, int* out_end) {
     const int nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
     CLM_CK(scan_partial.ensure((size_t)std::max(nb, 1)));
@@ -126,7 +172,7 @@ template <class T> int Engine<T>::build() {
     CLM_CK(cudaSetDevice(device));
     const int nsets = two_sets ? 2 : 1;
     for (int s = 0; s < nsets; ++s)
-        if (sets[s].n > 0x7fffffffLL / 28) return fail(CLM_ERR_UNSUPPORTED, "too many particles for 32-bit record indices");
+        if (sets[s].n + sets[s].n_foreign > 0x7fffffffLL / 28 || sets[s].n + sets[s].n_foreign > (int64_t)TagT<float>::MASK) return fail(CLM_ERR_UNSUPPORTED, "too many particles for 32-bit record indices");
     CLM_CK(cudaEventRecord(ev0, stream));
     // device scalars
     for (int k = 0; k < DS_COUNT; ++k) h_dscal[k] = 0;
@@ -238,7 +284,7 @@ template <class T> int Engine<T>::build() {
         CLM_CK(cudaMemcpyAsync(dscal.p, h_dscal, DS_COUNT * sizeof(int), cudaMemcpyHostToDevice, stream));
         for (int s = 0; s < nsets; ++s) {
             DevSet<T>& S = sets[s];
-            const size_t want = std::max<size_t>((size_t)((double)S.n * img_factor * 1.25) + 4096, (size_t)std::max<int64_t>(S.n_tot, 1));
+            const size_t want = std::max<size_t>((size_t)((double)(S.n + S.n_foreign) * img_factor * 1.25) + 4096, (size_t)std::max<int64_t>(S.n_tot, 1));
             CLM_CK(S.rec.ensure(want));
             CLM_CK(S.cell_start.ensure((size_t)ncells + 2));
             CLM_CK(S.counters.ensure((size_t)(2 * ncells + nref)));
@@ -246,19 +292,20 @@ template <class T> int Engine<T>::build() {
             CLM_CK(cudaMemsetAsync(S.counters.p, 0, (size_t)(2 * ncells + nref) * sizeof(int), stream));
             CLM_CK(cudaMemsetAsync(S.cell_start.p, 0, sizeof(int), stream));
             int* ds = dscal.p + s * DS_SET_STRIDE;
-            const int nb = (int)((S.n + 255) / 256);
-            if (S.n > 0) {
-                if (dim == 3) k_bin<T, 3, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, 0, ds);
-                else k_bin<T, 2, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, 0, ds);
+            const int64_t nall = S.n + S.n_foreign;
+            const int nb = (int)((nall + 255) / 256);
+            if (nall > 0) {
+                if (dim == 3) k_bin<T, 3, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, 0, ds);
+                else k_bin<T, 2, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, 0, ds);
                 CLM_CK(cudaGetLastError());
                 stats.launches += 1;
             }
             // exclusive prefix written one slot up: the scatter pass uses cell_start[c + 1] as the cursor of cell c, which
             // leaves cell_start[0 .. ncells] = the exclusive starts once every record is placed (no second counter array)
             if (int rc = scan(S.cell_count, S.cell_start.p + 1, (int)ncells, ds + DS_NTOT, S.cell_start.p + 1 + ncells)) return rc;
-            if (S.n > 0) {
-                if (dim == 3) k_bin<T, 3, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), ds);
-                else k_bin<T, 2, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), ds);
+            if (nall > 0) {
+                if (dim == 3) k_bin<T, 3, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), ds);
+                else k_bin<T, 2, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), ds);
                 CLM_CK(cudaGetLastError());
                 stats.launches += 1;
             }
@@ -507,6 +554,8 @@ int clm_set_box(clm_handle* h, int ct, const void* uc, int is_matrix, const void
 int clm_get_box(clm_handle* h, clm_box_info* o) { H_OR_FAIL; return h->e->get_box(o); }
 int clm_set_positions(clm_handle* h, int set, const void* xyz, int64_t n, int on_device) { H_OR_FAIL; return h->e->set_positions(set, xyz, n, on_device); }
 int clm_build(clm_handle* h) { H_OR_FAIL; return h->e->build(); }
+int clm_set_foreign(clm_handle* h, int set, const void* xyz, int64_t n, int on_device) { H_OR_FAIL; return h->e->set_foreign(set, xyz, n, on_device); }
+int clm_cell_coords(clm_handle* h, const void* xyz, int64_t n, int on_device, int axis, int32_t* out) { H_OR_FAIL; return h->e->cell_coords(xyz, n, on_device, axis, out); }
 int clm_map_lj(clm_handle* h, const void* p, int flags, void* e, void* f) { H_OR_FAIL; return h->e->map_lj(p, flags, e, f); }
 int clm_map_coulomb(clm_handle* h, const void* wx, const void* wy, const void* k, int flags, void* e, void* f) { H_OR_FAIL; return h->e->map_coulomb(wx, wy, k, flags, e, f); }
 int clm_map_dist_hist(clm_handle* h, const void* width, int nbins, int flags, int64_t* counts) { H_OR_FAIL; return h->e->map_dist_hist(width, nbins, flags, counts); }

@@ -99,15 +99,16 @@ __device__ __forceinline__ bool cell_of(const GeomT<T>& g, const T p[3], bool re
 // exactly those cells, self.jl:56-57); ref_real[] flags reference cells with a real particle.
 template <class T, int DIM, bool SCATTER>
 __global__ void __launch_bounds__(256)
-k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, int n, int* __restrict__ cell_cursor,
+k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __restrict__ fpos, int n, int n_own, int* __restrict__ cell_cursor,
       int* __restrict__ cell_nact, int* __restrict__ ref_real, RecT<T>* __restrict__ rec, int rec_cap, int* __restrict__ dscal) {
     typedef TagT<T> TG;
     const int ip = blockIdx.x * blockDim.x + threadIdx.x;
     if (ip >= n) return;
     T x[DIM];
     bool bad = false;
+    const T* src = (ip < n_own) ? pos + (size_t)ip * DIM : fpos + (size_t)(ip - n_own) * DIM;   // owned particles, then foreign ones
 #pragma unroll
-    for (int k = 0; k < DIM; ++k) { x[k] = pos[(size_t)ip * DIM + k]; bad |= (x[k] != x[k]); }
+    for (int k = 0; k < DIM; ++k) { x[k] = src[k]; bad |= (x[k] != x[k]); }
     if (bad) { if (!SCATTER) atomicMin(&dscal[DS_NAN], ip); return; }   // _validate_coordinates, CellOperations.jl:6-21
     T p[3];
     place_particle<T, DIM>(g, x, p);
@@ -115,12 +116,13 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, int n, int*
     if (!cell_of<T, DIM>(g, p, true, lin, rlin)) { if (!SCATTER) atomicMin(&dscal[DS_OOB], ip); return; }
     // cell_cursor: the per-cell histogram in the count pass; the per-cell write cursor (pre-loaded with the exclusive
     // starts) in the scatter pass
+    const typename TG::type foreign = (ip >= n_own) ? TG::FOREIGN : (typename TG::type)0;
     const int slot = atomicAdd(&cell_cursor[lin], 1);
     if (!SCATTER) {
-        if (cell_nact[lin] == 0) cell_nact[lin] = 1;
-        if (ref_real[rlin] == 0) ref_real[rlin] = 1;
+        if (!foreign) cell_nact[lin] = 1;   // flags: plain stores, every writer stores the same value
+        ref_real[rlin] = 1;
     } else if (slot < rec_cap) {
-        strec(&rec[slot], p[0], p[1], p[2], (typename TG::type)ip | TG::HOME);
+        strec(&rec[slot], p[0], p[1], p[2], (typename TG::type)ip | TG::HOME | foreign);
     }
     if (g.cell_type == CLM_NONPERIODIC_CT) return;
     // replicate_particle! (Box.jl:556-566): images x + aligned_cell*idx, idx in {-1,0,1}^N \ {0}, kept iff
@@ -162,8 +164,8 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, int n, int*
         const int qslot = atomicAdd(&cell_cursor[lq], 1);
         if (SCATTER && qslot < rec_cap) {
             const bool home = ref_real[rq] != 0;
-            if (home && cell_nact[lq] == 0) cell_nact[lq] = 1;
-            strec(&rec[qslot], q[0], q[1], q[2], (typename TG::type)ip | TG::GHOST | (home ? TG::HOME : (typename TG::type)0));
+            if (home && !foreign) cell_nact[lq] = 1;
+            strec(&rec[qslot], q[0], q[1], q[2], (typename TG::type)ip | TG::GHOST | foreign | (home ? TG::HOME : (typename TG::type)0));
         }
     }
 }
@@ -269,6 +271,25 @@ k_tiles(const int* __restrict__ row_tile_start, const int2* __restrict__ row_ran
     tl.k0 = k0; tl.cnt = cnt; tl.row = row;
     tl.cx = cell_x(k0) | (cell_x(k0 + cnt - 1) << 16);
     tiles[t] = tl;
+}
+
+// reference-cell index of every particle along reference dimension `axis` (0-based, after wrapping and the
+// border nudge) -- what a slab decomposition uses to decide ownership and halo membership with exactly the
+// arithmetic of the cell-list build.  -1: invalid coordinate.
+template <class T, int DIM>
+__global__ void __launch_bounds__(256)
+k_cell_coord(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, int n, int axis, int* __restrict__ out) {
+    const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ip >= n) return;
+    T x[DIM], p[3];
+#pragma unroll
+    for (int k = 0; k < DIM; ++k) x[k] = pos[(size_t)ip * DIM + k];
+    place_particle<T, DIM>(g, x, p);
+    const T q = floor(xdiv(xsub(p[axis], g.cb_min[axis]), g.cs[axis]));
+    int c = (q >= T(-1) && q <= T(g.nc[axis])) ? (int)q : -1;
+    if (c == g.lcell - 1) c += 1;
+    if (c == g.nc[axis] - g.lcell) c -= 1;
+    out[ip] = c;
 }
 
 // number of reference cells holding a real particle (CellList.n_cells_with_real_particles)

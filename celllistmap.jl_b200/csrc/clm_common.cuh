@@ -28,9 +28,11 @@ __device__ __forceinline__ float  xsqrt(float a)  { return __fsqrt_rn(a); }
 __device__ __forceinline__ double xsqrt(double a) { return __dsqrt_rn(a); }
 
 // ---- packed particle records ----------------------------------------------------------------------
-// tag: bit (W-1) = image particle (real == false), bit (W-2) = lives in a cell that contains at
-// least one real particle ("home" cell: the cells the reference sweeps, self.jl:56-57), low bits =
-// 0-based original index.
+// tag: bit (W-1) = image particle (real == false), bit (W-2) = lives in a REFERENCE cell that contains at
+// least one real particle ("home" cell: the cells the reference sweeps, self.jl:56-57), bit (W-3) = foreign:
+// a particle (or an image of one) owned by another rank of a slab-decomposed system -- it is a partner j
+// like any other record but never acts as particle i; low bits = 0-based index (owned particles first,
+// then the foreign ones).
 template <class T> struct RecT;
 template <> struct __align__(16) RecT<float> {
     float x, y, z;
@@ -43,11 +45,11 @@ template <> struct __align__(32) RecT<double> {
 template <class T> struct TagT;
 template <> struct TagT<float> {
     typedef uint32_t type;
-    static constexpr uint32_t GHOST = 0x80000000u, HOME = 0x40000000u, MASK = 0x3fffffffu;
+    static constexpr uint32_t GHOST = 0x80000000u, HOME = 0x40000000u, FOREIGN = 0x20000000u, MASK = 0x1fffffffu;
 };
 template <> struct TagT<double> {
     typedef uint64_t type;
-    static constexpr uint64_t GHOST = 0x8000000000000000ull, HOME = 0x4000000000000000ull, MASK = 0x3fffffffffffffffull;
+    static constexpr uint64_t GHOST = 0x8000000000000000ull, HOME = 0x4000000000000000ull, FOREIGN = 0x2000000000000000ull, MASK = 0x1fffffffffffffffull;
 };
 
 __device__ __forceinline__ RecT<float> ldrec(const RecT<float>* p) {

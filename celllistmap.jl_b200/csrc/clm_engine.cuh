@@ -26,6 +26,8 @@ struct EngineBase {
     virtual int set_box(int cell_type, const void* uc, int is_matrix, const void* cutoff, int lcell) = 0;
     virtual int get_box(clm_box_info* out) = 0;
     virtual int set_positions(int set, const void* xyz, int64_t n, int on_device) = 0;
+    virtual int set_foreign(int set, const void* xyz, int64_t n, int on_device) = 0;
+    virtual int cell_coords(const void* xyz, int64_t n, int on_device, int axis, int32_t* out) = 0;
     virtual int build() = 0;
     virtual int map_lj(const void* p, int flags, void* e, void* f) = 0;
     virtual int map_coulomb(const void* wx, const void* wy, const void* k, int flags, void* e, void* f) = 0;
@@ -65,6 +67,8 @@ template <class U> struct DBuf {
 template <class T> struct DevSet {
     DBuf<T> pos;             // caller's coordinates, AoS n x dim (owning copy, like ParticleSystemPositions)
     int64_t n = 0;
+    DBuf<T> fpos;            // foreign particles of a slab-decomposed system (owned by other ranks), AoS
+    int64_t n_foreign = 0;
     DBuf<RecT<T>> rec;       // cell-sorted records, real + image particles
     int64_t n_tot = 0, n_cells_real = 0;
     DBuf<int> cell_start;    // ncells + 2 entries: [0 .. ncells] = exclusive starts after the scatter pass
@@ -110,6 +114,8 @@ template <class T> struct Engine : EngineBase {
     int set_box(int cell_type, const void* uc, int is_matrix, const void* cutoff, int lcell) override;
     int get_box(clm_box_info* out) override;
     int set_positions(int set, const void* xyz, int64_t n, int on_device) override;
+    int set_foreign(int set, const void* xyz, int64_t n, int on_device) override;
+    int cell_coords(const void* xyz, int64_t n, int on_device, int axis, int32_t* out) override;
     int build() override;
     int map_lj(const void* p, int flags, void* e, void* f) override;
     int map_coulomb(const void* wx, const void* wy, const void* k, int flags, void* e, void* f) override;
@@ -165,6 +171,8 @@ template <class T> struct Engine : EngineBase {
     }
     // reduction-type functors run in the reference's own exactly-once mode for the system type
     template <class F> int launch_reduce(const F& f, size_t smem) {
+        if (sweep_mode() == MODE_TRI && (sets[0].n_foreign > 0))
+            return fail(CLM_ERR_UNSUPPORTED, "slab-decomposed triclinic self-set systems are not supported (the index_i < index_j rule needs global indices)");
         switch (sweep_mode()) {
             case MODE_HALF: return launch<MODE_HALF>(f, smem);
             case MODE_TRI: return launch<MODE_TRI>(f, smem);

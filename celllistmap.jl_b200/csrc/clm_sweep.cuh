@@ -473,7 +473,7 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
         c.ki = tl.k0 + (valid ? c.islot : 0);
         c.ri = ldrec(a.rec_i + c.ki);
         const bool real_i = (c.ri.tag & TG::GHOST) == 0;
-        c.active = valid && ((MODE == MODE_HALF) ? ((c.ri.tag & TG::HOME) != 0) : real_i);
+        c.active = valid && ((c.ri.tag & TG::FOREIGN) == 0) && ((MODE == MODE_HALF) ? ((c.ri.tag & TG::HOME) != 0) : real_i);
         const typename TG::type idx_i = c.ri.tag & TG::MASK;
         typename F::IAcc ia;
         f.begin(ia, c);
@@ -554,20 +554,26 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                 mdir &= mdir - 1;
                 const int bj0 = __shfl_sync(0xffffffffu, j0, src), bj1 = __shfl_sync(0xffffffffu, j1, src);
                 const int brow = __shfl_sync(0xffffffffu, rowbase, src), bown = __shfl_sync(0xffffffffu, own, src);
-                // MODE_HALF, same reference row: partner must live in a later reference cell, or in the same one
-                // and be a later record: j >= thr
-                int thr = 0;
+                // MODE_HALF, same reference row: partners in a later reference cell (j >= thrA) follow the forward rule;
+                // partners in the SAME reference cell (thrB <= j < thrA) are taken once: real-real pairs from the earlier
+                // record, real-image pairs from the real particle (the distance is symmetric, so this deviation from the
+                // reference's slot order changes nothing -- and it keeps the rule independent of the record order, which
+                // differs between the ranks of a slab-decomposed system)
+                int thrA = 0, thrB = 0;
                 if (MODE == MODE_HALF && (bown & 2)) {
                     const int* csj = a.cell_start_j + brow;
-                    const int A = csj[min((rfx_i + 1) * sub, a.nx)], B = csj[rfx_i * sub];
-                    thr = min(A, max(B, c.ki + 1));
+                    thrA = csj[min((rfx_i + 1) * sub, a.nx)];
+                    thrB = csj[rfx_i * sub];
                 }
                 auto run_row = [&](auto self_row_tag) {
                     constexpr bool SELF_ROW = decltype(self_row_tag)::value;
                     auto body = [&](const RecT<T>* __restrict__ pj, const int jc, const bool inb) {
                         const RecT<T> rj = ldrec(pj);
                         bool ok = inb;
-                        if (MODE == MODE_HALF) ok = ok && (jc >= thr) && (((c.ri.tag & rj.tag) & TG::GHOST) == 0);
+                        if (MODE == MODE_HALF) {
+                            const bool gi = (c.ri.tag & TG::GHOST) != 0, gj = (rj.tag & TG::GHOST) != 0;
+                            ok = ok && ((jc >= thrA) ? !(gi && gj) : (jc >= thrB && !gi && (gj || jc > c.ki)));
+                        }
                         else if (MODE == MODE_TRI) ok = ok && (idx_i < (rj.tag & TG::MASK));
                         else if (SELF_ROW) ok = ok && (rj.tag != c.ri.tag);
                         pair_body(rj, jc, ok);

@@ -1,0 +1,198 @@
+"""Multi-GPU slab decomposition of the cutoff-pair path (the reference is single-process).
+
+One process per GPU, `torch.distributed` for the plumbing (NCCL over NVLink on the B200 box, gloo in the CPU tests).
+The box is cut into slabs of whole REFERENCE cells along reference dimension 1.  A rank owns the particles whose
+(wrapped, nudged) cell index along that dimension falls in its slab; before every cell-list build it receives from
+its two neighbours (periodically) the particles of their `lcell` outermost cell layers -- the halo -- and hands them
+to the engine as FOREIGN particles (clm_set_foreign): partners j like any other record, never particle i.  Every pair
+evaluation of the single-GPU sweep therefore happens on exactly one rank, on bit-identical coordinates:
+
+  * per-particle outputs (forces) stay sharded with their owners -- the full-shell sweep needs no reverse exchange;
+  * scalars and histograms are summed with all_reduce; minimum distances with an all_gather + min;
+  * neighbour lists stay per rank (indices mapped to the caller's global ids), concatenation is the caller's choice.
+
+The path has ONE exchange step (the halo); it is a neighbour send/recv, not a collective reduction, so it is issued
+as batched P2P ops.  Only orthorhombic cells are supported (triclinic lattice shifts move images across slabs).
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _capi
+from ._capi import Handle
+
+
+class SlabPlan:
+    """Pure host logic: which cell layers each rank owns, who needs what.  `n_inner` = number of reference cells along
+    dimension 1 that hold real particles (Box.nc[0] - 2*lcell - 1); real cells are lcell .. lcell + n_inner - 1."""
+
+    def __init__(self, n_inner, lcell, world):
+        if world > 1 and n_inner // world < lcell:
+            raise ValueError(f"slabs would be thinner than the stencil reach: {n_inner} cell layers over {world} ranks, lcell = {lcell}")
+        self.n_inner, self.lcell, self.world = int(n_inner), int(lcell), int(world)
+        self.bounds = [lcell + (n_inner * r) // world for r in range(world + 1)]   # rank r owns [bounds[r], bounds[r+1])
+
+    def owner_of(self, c):
+        """rank owning cell layer(s) c (numpy or torch integer array)."""
+        b = self.bounds
+        if isinstance(c, torch.Tensor):
+            edges = torch.as_tensor(b[1:-1], device=c.device, dtype=c.dtype)
+            return torch.bucketize(c, edges, right=True)
+        return np.searchsorted(np.asarray(b[1:-1]), c, side="right")
+
+    def face_masks(self, c, rank):
+        """(to_lower, to_upper): which owned particles (cell layers c) the lower / upper neighbour needs."""
+        lo, hi = self.bounds[rank], self.bounds[rank + 1]
+        return c < lo + self.lcell, c >= hi - self.lcell
+
+    def neighbours(self, rank):
+        return (rank - 1) % self.world, (rank + 1) % self.world
+
+
+def exchange_halo(payloads, to_lower, to_upper, plan, rank, group=None):
+    """Send the rows selected by the face masks to the two neighbours and return what they sent us.
+
+    payloads: list of tensors with the same first extent (positions, ids, weights, ...), on any device the process
+    group can move (CUDA for nccl, CPU for gloo; CUDA tensors are staged through the host when the backend is gloo).
+    Returns a list of tensors (rows received from the upper neighbour first, then from the lower one)."""
+    world = plan.world
+    if world == 1:
+        return [p[:0] for p in payloads]
+    lower, upper = plan.neighbours(rank)
+    backend = dist.get_backend(group)
+    stage = backend == "gloo"
+    if world == 2:                      # both faces go to the same peer: one message, no duplicates
+        sends = {lower: to_lower | to_upper}
+    else:
+        sends = {lower: to_lower, upper: to_upper}
+    counts = torch.zeros(world, dtype=torch.int64)
+    for peer, m in sends.items():
+        counts[peer] = int(m.sum())
+    dev = payloads[0].device
+    comm_dev = torch.device("cpu") if stage else dev
+    all_counts = [torch.zeros(world, dtype=torch.int64, device=comm_dev) for _ in range(world)]
+    dist.all_gather(all_counts, counts.to(comm_dev), group=group)
+    out = []
+    for p in payloads:
+        ops, recv = [], {}
+        keep = []
+        for peer, m in sends.items():
+            buf = p[m].contiguous()
+            buf = buf.cpu() if stage else buf
+            keep.append(buf)
+            if buf.shape[0]:
+                ops.append(dist.P2POp(dist.isend, buf, peer, group))
+        for peer in sends:
+            n_in = int(all_counts[peer][rank])
+            r = torch.empty((n_in,) + tuple(p.shape[1:]), dtype=p.dtype, device=comm_dev)
+            recv[peer] = r
+            if n_in:
+                ops.append(dist.P2POp(dist.irecv, r, peer, group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        order = [upper, lower] if world > 2 else [upper]
+        got = torch.cat([recv[q] for q in order], dim=0)
+        out.append(got.to(dev) if stage else got)
+    return out
+
+
+class SlabSystem:
+    """One rank's share of a slab-decomposed self-set particle system on its own B200.
+
+    x_owned: (n, N) torch tensor (CUDA) or numpy array with the particles this rank owns -- use `SlabSystem.partition`
+    to split a global array.  `ids` are the caller's global 1-based particle ids of the owned particles (for neighbour
+    lists)."""
+
+    def __init__(self, unitcell, cutoff, dtype=np.float32, lcell=1, dim=3, device=None, group=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.dtype = np.dtype(dtype)
+        self.tdtype = torch.float32 if self.dtype == np.float32 else torch.float64
+        self.dim = dim
+        uc = np.asarray(unitcell, dtype=self.dtype)
+        if uc.ndim != 1:
+            raise ValueError("slab decomposition supports orthorhombic cells (unitcell = sides) only")
+        self.h = Handle(dim, self.dtype, self.device.index or 0)
+        # the engine enqueues on torch's current stream, so torch ops and collectives are ordered with its kernels
+        # (0 is the legacy default stream: CUDA's cudaStreamLegacy handle is 1)
+        self.h.set_stream(torch.cuda.current_stream(self.device).cuda_stream or 1)
+        self.h.set_box(_capi.ORTHORHOMBIC, uc, cutoff, lcell)
+        b = self.h.get_box()
+        self.plan = SlabPlan(int(b.nc[0]) - 2 * lcell - 1, lcell, self.world)
+        self.n_owned = 0
+        self.n_foreign = 0
+        self.ids = None
+        self.foreign_ids = None
+
+    def set_stream(self, stream):
+        self.h.set_stream(stream.cuda_stream or 1)
+
+    def cell_layers(self, x):
+        """reference-cell index along dimension 1, computed by the engine (same arithmetic as the build)."""
+        return self.h.cell_coords(x, 0)
+
+    def partition(self, x_global, ids=None):
+        """rows of a global coordinate array (every rank passes the same array) this rank owns."""
+        x = torch.as_tensor(x_global).to(self.device, self.tdtype).contiguous()
+        c = self.cell_layers(x)
+        mine = self.plan.owner_of(c.to(torch.int64)) == self.rank
+        gid = torch.arange(1, x.shape[0] + 1, device=self.device, dtype=torch.int64) if ids is None else torch.as_tensor(ids).to(self.device)
+        return x[mine].contiguous(), gid[mine].contiguous()
+
+    def update(self, x_owned, ids=None):
+        """halo exchange + hand owned / foreign particles to the engine (nothing is built until the next map)."""
+        x = torch.as_tensor(x_owned).to(self.device, self.tdtype).contiguous()
+        c = self.cell_layers(x).to(torch.int64)
+        to_lower, to_upper = self.plan.face_masks(c, self.rank)
+        payloads = [x] if ids is None else [x, torch.as_tensor(ids).to(self.device)]
+        got = exchange_halo(payloads, to_lower, to_upper, self.plan, self.rank, self.group)
+        self.x_owned, self.x_foreign = x, got[0].contiguous()
+        self.ids = None if ids is None else payloads[1]
+        self.foreign_ids = None if ids is None else got[1]
+        self.n_owned, self.n_foreign = int(x.shape[0]), int(self.x_foreign.shape[0])
+        self.h.set_positions(0, x)
+        self.h.set_foreign(0, self.x_foreign)
+        return self
+
+    # ---- catalogue entry points: local map + the reduction the output type needs ----
+    def map_lj(self, c6, c12, forces=None, profile=False):
+        """returns the GLOBAL energy (all_reduce) and fills `forces` (n_owned x N, device) for the owned particles."""
+        e = torch.zeros(1, dtype=self.tdtype, device=self.device)
+        self.h.map_lj(c6, c12, e, forces, reset=True, profile=profile)
+        if self.world > 1:
+            dist.all_reduce(e, group=self.group)
+        return e
+
+    def sum_d_d2(self):
+        sd, sd2, n = (torch.zeros(1, dtype=self.tdtype, device=self.device), torch.zeros(1, dtype=self.tdtype, device=self.device),
+                      torch.zeros(1, dtype=torch.int64, device=self.device))
+        self.h.map_sum_d_d2(sd, sd2, n, reset=True)
+        if self.world > 1:
+            for t in (sd, sd2, n):
+                dist.all_reduce(t, group=self.group)
+        return float(sd), float(sd2), int(n)
+
+    def dist_hist(self, width, nbins):
+        counts = torch.zeros(nbins, dtype=torch.int64, device=self.device)
+        self.h.map_dist_hist(width, counts, reset=True)
+        if self.world > 1:
+            dist.all_reduce(counts, group=self.group)
+        return counts
+
+    def neighborlist(self):
+        """this rank's part of the neighbour list as a structured numpy array with GLOBAL ids (needs `ids` in update)."""
+        n = self.h.neighborlist_count()
+        rec = np.zeros(n, dtype=_capi.nl_dtype(self.dtype))
+        if n:
+            self.h.neighborlist_copy(rec)
+        if self.ids is not None:
+            table = torch.cat([self.ids, self.foreign_ids]).cpu().numpy()
+            rec["i"] = table[rec["i"] - 1]
+            rec["j"] = table[rec["j"] - 1]
+        return rec
+
+    def close(self):
+        self.h.close()

@@ -121,6 +121,17 @@ CLM_API int clm_get_box(clm_handle* h, clm_box_info* out);
  * second set (no pairs). */
 CLM_API int clm_set_positions(clm_handle* h, int set, const void* aos_xyz, int64_t n, int on_device);
 
+/* ---- slab decomposition across GPUs (no counterpart in the reference, which is single-process) ----
+ * One handle per rank.  A rank owns the particles whose reference cell along dimension 1 falls in its slab and
+ * passes them with clm_set_positions; the particles of the neighbouring slabs within the stencil reach (lcell cells)
+ * are passed with clm_set_foreign: they are binned (with their periodic images) like any other particle and serve as
+ * partners j, but never act as particle i, so every pair evaluation of the single-GPU sweep happens on exactly one rank.
+ * Indices: owned particles 1..n, foreign ones n+1..n+n_foreign.  clm_cell_coords returns the 0-based reference-cell
+ * index along `axis` of arbitrary coordinates with exactly the arithmetic of the build (ownership / halo selection).
+ * Supported for orthorhombic and non-periodic cells (triclinic self-set systems need global-index tie-breaks). */
+CLM_API int clm_set_foreign(clm_handle* h, int set, const void* aos_xyz, int64_t n, int on_device);
+CLM_API int clm_cell_coords(clm_handle* h, const void* aos_xyz, int64_t n, int on_device, int axis, int32_t* cell_out);
+
 /* ---- UpdateCellList!  src/internals/CellLists.jl:727-927 ---------------------------------- */
 /* validates coordinates (NaN -> CLM_ERR_INVALID_COORDINATES with the 1-based index in the message),
  * wraps, bins real + image particles, counting-sorts them by cell.  No-op if nothing changed. */

@@ -1,0 +1,94 @@
+"""Host logic of the multi-GPU slab decomposition on CPU: world_size-2 and -3 process groups over gloo.
+
+No GPU and no product compute here: the cell-layer index (which the product gets from clm_cell_coords) is injected
+as a small numpy function; what is tested is ownership, face selection and the halo exchange plumbing of
+celllistmap.jl_b200/slab.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _layers(x, L, n_inner, lcell):
+    cs = L / n_inner
+    return (np.floor(np.mod(x[:, 0], L) / cs).astype(np.int64) % n_inner) + lcell
+
+
+def _worker(rank, world, port, n_inner, lcell, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import celllistmap_b200  # noqa: F401  (import shim)
+        from celllistmap_b200 import slab
+        L = 10.0
+        rng = np.random.default_rng(5)
+        x = rng.random((3000, 3)) * L
+        ids = np.arange(1, 3001)
+        c = _layers(x, L, n_inner, lcell)
+        plan = slab.SlabPlan(n_inner, lcell, world)
+        mine = plan.owner_of(c) == rank
+        xo, io, co = torch.from_numpy(x[mine]), torch.from_numpy(ids[mine]), torch.from_numpy(c[mine])
+        lo_m, hi_m = plan.face_masks(co, rank)
+        got_x, got_i = slab.exchange_halo([xo, io], lo_m, hi_m, plan, rank)
+        q.put((rank, ids[mine].tolist(), got_i.tolist(), bool(torch.equal(got_x, torch.from_numpy(x[got_i.numpy() - 1]))), plan.bounds))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_inner,lcell", [(2, 10, 1), (3, 12, 2), (2, 4, 2)])
+def test_halo_exchange_gloo(world, n_inner, lcell):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_inner, lcell, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    L = 10.0
+    x = np.random.default_rng(5).random((3000, 3)) * L
+    c = _layers(x, L, n_inner, lcell)
+    owned_all = []
+    for rank, owned, foreign, same_bits, bounds in res:
+        assert same_bits, "halo coordinates must arrive bit-identical"
+        owned_all += owned
+        lo, hi = bounds[rank], bounds[rank + 1]
+        assert all(lo <= c[i - 1] < hi for i in owned)
+        # every particle within lcell cell layers (periodically) of the slab, and not owned, must have been received
+        rel = (c - lcell)
+        need = set()
+        for i in range(3000):
+            if lo <= c[i] < hi:
+                continue
+            d_up = (rel[i] - (hi - lcell)) % n_inner          # layers above the slab top (periodic)
+            d_dn = ((lo - lcell) - 1 - rel[i]) % n_inner       # layers below the slab bottom (periodic)
+            if d_up < lcell or d_dn < lcell:
+                need.add(i + 1)
+        assert need == set(foreign), (rank, len(need), len(foreign))
+        assert len(foreign) == len(set(foreign)), "duplicate halo particles"
+    assert sorted(owned_all) == list(range(1, 3001)), "every particle is owned by exactly one rank"
+
+
+def test_plan_rejects_thin_slabs():
+    import celllistmap_b200  # noqa: F401
+    from celllistmap_b200 import slab
+    with pytest.raises(ValueError):
+        slab.SlabPlan(5, 2, 4)
+    p = slab.SlabPlan(30, 1, 8)
+    assert p.bounds[0] == 1 and p.bounds[-1] == 31
+    assert (np.diff(p.bounds) >= 3).all()
