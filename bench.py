@@ -15,7 +15,6 @@ import os
 import statistics
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -51,44 +50,44 @@ def reference_candidates(x, L, cutoff):
 
 
 class ClockSampler:
-    """samples nvidia-smi SM clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """samples nvidia-smi SM clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line):
+    one streaming `nvidia-smi -lms 20` child, started before and killed after the region."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, device=0):
-        self.device, self.samples, self.reasons, self._stop, self.max_mhz = device, [], set(), threading.Event(), None
-        self.t = threading.Thread(target=self._run, daemon=True)
-
-    def _q(self, fields):
-        try:
-            out = subprocess.run(["nvidia-smi", f"--id={self.device}", f"--query-gpu={fields}", "--format=csv,noheader,nounits"],
-                                 capture_output=True, text=True, timeout=5).stdout.strip()
-            return [s.strip() for s in out.split(",")]
-        except Exception:
-            return None
-
-    def _run(self):
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap", "hw_power_brake_slowdown"]
-        fields = "clocks.sm,clocks.max.sm," + ",".join("clocks_throttle_reasons." + n for n in names)
-        while not self._stop.is_set():
-            r = self._q(fields)
-            if r and len(r) >= 2:
-                try:
-                    self.samples.append(float(r[0]))
-                    self.max_mhz = float(r[1])
-                    for n, v in zip(names, r[2:]):
-                        if v.lower().startswith("active"):
-                            self.reasons.add(n)
-                except ValueError:
-                    pass
-            self._stop.wait(0.05)
+        self.device, self.proc = device, None
 
     def start(self):
-        self.t.start()
+        fields = "clocks.sm,clocks.max.sm," + ",".join("clocks_event_reasons." + n for n in self.NAMES)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={fields}", "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+        time.sleep(0.25)   # let the first samples arrive before the timed region starts
 
     def stop(self):
-        self._stop.set()
-        self.t.join(timeout=10)
-        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+        samples, reasons, mx = [], set(), None
+        if self.proc is not None:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=10)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            for line in out.splitlines():
+                r = [t.strip() for t in line.split(",")]
+                try:
+                    samples.append(float(r[0]))
+                    mx = float(r[1])
+                except (ValueError, IndexError):
+                    continue
+                for n, v in zip(self.NAMES, r[2:]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": statistics.median(samples) if samples else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(samples)}
 
 
 def load_peaks():
@@ -161,8 +160,8 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nside", type=int, default=100, help="particles = nside^3 (100 -> the 1M-particle C2 config)")
     ap.add_argument("--cpu-nside", type=int, default=100, help="size of the CPU arm / cpu_baseline sample")
@@ -281,7 +280,7 @@ def main():
         return res
 
     r32 = measure(np.float32, args.steps, args.warmup, True)
-    r64 = None if args.no_f64 else measure(np.float64, max(3, args.steps // 2), 3, False)
+    r64 = None if args.no_f64 else measure(np.float64, max(3, args.steps // 4), 3, False)
 
     C_st = reference_candidates(r32["w"]["x"], r32["w"]["L"], r32["w"]["cutoff"])
     F_alg = FLOPS_PER_CANDIDATE * C_st + FLOPS_PER_PAIR_LJ * r32["P_in"]

@@ -139,3 +139,5 @@ def run(args, rank, world, local):
         }
         print(json.dumps(line))
     s.close()
+    dist.barrier()
+    dist.destroy_process_group()

@@ -1,0 +1,240 @@
+# CellListMapB200.jl -- Julia host package over libclm_b200.so (include/clm_b200.h).
+#
+# Keeps the CellListMap.jl 0.10 API surface for the cutoff-pair path -- ParticleSystem, pairwise!, update!,
+# resize_output!, neighborlist, InPlaceNeighborList, neighborlist!, NeighborPair, get_computing_box -- with the pair
+# function restricted to the compiled-in catalogue (LJ / Coulomb energy and forces, distance histogram, mean pairwise
+# velocity, minimum distance, neighbour list).  All compute happens in hand-written sm_100a CUDA kernels behind the
+# C ABI; there is no CUDA.jl codegen and no CPU fallback.
+#
+# STATUS: source-complete, NOT executed in the build environment (no Julia toolchain there or on the GPU box);
+# the same ABI is exercised end to end by the Python twin celllistmap.jl_b200/api.py.
+module CellListMapB200
+
+using StaticArrays
+
+export ParticleSystem, pairwise!, update!, resize_output!, neighborlist, neighborlist!, InPlaceNeighborList,
+       NeighborPair, get_computing_box, LJEnergy, LJForces, LJEnergyAndForces, CoulombEnergy, CoulombEnergyAndForces,
+       DistanceHistogram, PairwiseVelocities, MinimumDistanceMap, MinimumDistance, EnergyAndForces
+
+const libclm = get(ENV, "CLM_B200_LIB", joinpath(@__DIR__, "..", "libclm_b200.so"))
+
+const CLM_F32, CLM_F64 = Cint(0), Cint(1)
+const CLM_ORTHORHOMBIC, CLM_TRICLINIC, CLM_NONPERIODIC = Cint(0), Cint(1), Cint(2)
+const CLM_RESET = Cint(1)
+
+struct ClmBoxInfo           # clm_box_info
+    dim::Int32; dtype::Int32; cell_type::Int32; lcell::Int32
+    nc::NTuple{3,Int64}
+    cutoff::Float64; cutoff_sqr::Float64
+    input_unit_cell::NTuple{9,Float64}; aligned_unit_cell::NTuple{9,Float64}
+    rotation::NTuple{9,Float64}; inv_rotation::NTuple{9,Float64}
+    computing_box_min::NTuple{3,Float64}; computing_box_max::NTuple{3,Float64}
+    cell_size::NTuple{3,Float64}; origin::NTuple{3,Float64}
+end
+
+# clm_status -> the exception the reference throws for the same condition (INTEGRATION.md, error table)
+function _check(h::Ptr{Cvoid}, code::Cint)
+    code == 0 && return nothing
+    msg = unsafe_string(ccall((:clm_last_error, libclm), Cstring, (Ptr{Cvoid},), h))
+    code in (1, 2, 3) && throw(ArgumentError(msg))
+    code == 5 && throw(DimensionMismatch(msg))
+    error(msg)
+end
+
+"""NeighborPair (src/API/NeighborPair.jl:19-33): what a pair function sees; consumed on the device by the catalogue."""
+struct NeighborPair{N,T}
+    i::Int; j::Int; x::SVector{N,T}; y::SVector{N,T}; d2::T
+end
+Base.getproperty(p::NeighborPair, s::Symbol) = s === :d ? sqrt(getfield(p, :d2)) : getfield(p, s)
+
+# ---- catalogue -------------------------------------------------------------------------------------------
+abstract type CatalogueFunction end
+struct LJEnergy{T} <: CatalogueFunction; c6::T; c12::T; end
+struct LJForces{T} <: CatalogueFunction; c6::T; c12::T; end
+struct LJEnergyAndForces{T} <: CatalogueFunction; c6::T; c12::T; end
+struct CoulombEnergy{T,V} <: CatalogueFunction; k::T; weights::V; weights_y::Union{V,Nothing}; end
+struct CoulombEnergyAndForces{T,V} <: CatalogueFunction; k::T; weights::V; weights_y::Union{V,Nothing}; end
+struct DistanceHistogram{T} <: CatalogueFunction; width::T; end
+struct PairwiseVelocities{T,V} <: CatalogueFunction; rbins::Vector{T}; velocities::V; velocities_y::Union{V,Nothing}; end
+struct MinimumDistanceMap <: CatalogueFunction end
+struct MinimumDistance{T}; i::Int; j::Int; d::T; end
+mutable struct EnergyAndForces{T,V}; energy::T; forces::V; end
+
+# ---- ParticleSystem (src/API/ParticleSystem.jl:142-202, AbstractParticleSystem.jl:32-60) -------------------------
+mutable struct ParticleSystem{N,T,O}
+    handle::Ptr{Cvoid}
+    xpositions::Vector{SVector{N,T}}        # owning copy (ParticleSystemPositions, src/API/ParticleSystemPositions.jl:19-22)
+    ypositions::Union{Vector{SVector{N,T}},Nothing}
+    unitcell::Union{SVector{N,T},SMatrix{N,N,T},Nothing}
+    cutoff::T
+    lcell::Int
+    output::O
+    output_name::Symbol
+    parallel::Bool
+    xupdated::Bool; yupdated::Bool; boxdirty::Bool
+end
+
+function ParticleSystem(; positions=nothing, xpositions=nothing, ypositions=nothing, unitcell=nothing, cutoff,
+                        output, output_name::Symbol=:default_output_name, parallel::Bool=true,
+                        nbatches::Tuple{Int,Int}=(0, 0), lcell=1, device::Integer=0)
+    (isnothing(positions) == isnothing(xpositions)) &&
+        throw(ArgumentError("Either `positions` OR `xpositions` must be defined."))
+    x0 = isnothing(positions) ? xpositions : positions
+    N = isnothing(unitcell) ? length(first(x0)) : size(unitcell, 1)
+    T = eltype(first(x0)) == Float32 ? Float32 : Float64
+    x = [SVector{N,T}(v) for v in x0]
+    y = isnothing(ypositions) ? nothing : [SVector{N,T}(v) for v in ypositions]
+    uc = isnothing(unitcell) ? nothing : (unitcell isa AbstractVector ? SVector{N,T}(unitcell) : SMatrix{N,N,T}(unitcell))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    code = ccall((:clm_create, libclm), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint), h, N, T == Float32 ? CLM_F32 : CLM_F64, device, 1)
+    code == 0 || error(unsafe_string(ccall((:clm_last_error, libclm), Cstring, (Ptr{Cvoid},), C_NULL)))
+    sys = ParticleSystem{N,T,typeof(output)}(h[], x, y, uc, T(cutoff), lcell, output, output_name, parallel, true, !isnothing(y), true)
+    finalizer(s -> ccall((:clm_destroy, libclm), Cint, (Ptr{Cvoid},), s.handle), sys)
+    _sync!(sys)                              # the reference builds the cell list at construction
+    return sys
+end
+
+# UpdateParticleSystem! (src/internals/ParticleSystem.jl:158-164, :209-224): rebuild only what changed
+function _sync!(sys::ParticleSystem{N,T}) where {N,T}
+    h = sys.handle
+    if sys.boxdirty
+        rc = Ref(sys.cutoff)
+        if isnothing(sys.unitcell)
+            _check(h, ccall((:clm_set_box, libclm), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Ref{T}, Cint), h, CLM_NONPERIODIC, C_NULL, 0, rc, sys.lcell))
+        elseif sys.unitcell isa SVector
+            _check(h, ccall((:clm_set_box, libclm), Cint, (Ptr{Cvoid}, Cint, Ref{SVector{N,T}}, Cint, Ref{T}, Cint), h, CLM_ORTHORHOMBIC, Ref(sys.unitcell), 0, rc, sys.lcell))
+        else   # SMatrix memory is column-major with columns = lattice vectors: exactly what the ABI takes
+            _check(h, ccall((:clm_set_box, libclm), Cint, (Ptr{Cvoid}, Cint, Ref{SMatrix{N,N,T,N*N}}, Cint, Ref{T}, Cint), h, CLM_TRICLINIC, Ref(sys.unitcell), 1, rc, sys.lcell))
+        end
+        sys.boxdirty = false; sys.xupdated = true
+    end
+    if sys.xupdated     # Vector{SVector{N,T}} is the AoS n x N memory the ABI takes: no conversion, one H2D copy
+        _check(h, ccall((:clm_set_positions, libclm), Cint, (Ptr{Cvoid}, Cint, Ptr{SVector{N,T}}, Int64, Cint), h, 0, sys.xpositions, length(sys.xpositions), 0))
+    end
+    if !isnothing(sys.ypositions) && sys.yupdated
+        _check(h, ccall((:clm_set_positions, libclm), Cint, (Ptr{Cvoid}, Cint, Ptr{SVector{N,T}}, Int64, Cint), h, 1, sys.ypositions, length(sys.ypositions), 0))
+    end
+    if sys.xupdated || sys.yupdated
+        _check(h, ccall((:clm_build, libclm), Cint, (Ptr{Cvoid},), h))      # UpdateCellList!
+        sys.xupdated = false; sys.yupdated = false
+    end
+    return sys
+end
+
+"""update!(sys; xpositions, ypositions, cutoff, unitcell, parallel) (src/API/updating.jl:165-187)"""
+function update!(sys::ParticleSystem{N,T}; positions=nothing, xpositions=nothing, ypositions=nothing, cutoff=nothing,
+                 unitcell=nothing, parallel=nothing) where {N,T}
+    (!isnothing(positions) && !isnothing(xpositions)) && throw(ArgumentError("Either `positions` OR `xpositions` must be provided, not both."))
+    x = isnothing(positions) ? xpositions : positions
+    (!isnothing(ypositions) && isnothing(sys.ypositions)) && throw(ArgumentError("ypositions can only be set for a two-set particle system"))
+    if !isnothing(x); resize!(sys.xpositions, length(x)); sys.xpositions .= SVector{N,T}.(x); sys.xupdated = true; end
+    if !isnothing(ypositions); resize!(sys.ypositions, length(ypositions)); sys.ypositions .= SVector{N,T}.(ypositions); sys.yupdated = true; end
+    if !isnothing(cutoff); sys.cutoff = T(cutoff); sys.boxdirty = true; end
+    if !isnothing(unitcell)
+        isnothing(sys.unitcell) && throw(ArgumentError("Manual updating of the unit cell of non-periodic systems is not allowed."))
+        sys.unitcell = sys.unitcell isa SVector && unitcell isa AbstractVector ? SVector{N,T}(unitcell) :
+                       SMatrix{N,N,T}(unitcell isa AbstractVector ? SMatrix{N,N,T}(Diagonal(unitcell)) : unitcell)
+        sys.boxdirty = true
+    end
+    isnothing(parallel) || (sys.parallel = parallel)
+    return sys
+end
+
+resize_output!(sys::ParticleSystem, n::Int) = (resize!(sys.output isa EnergyAndForces ? sys.output.forces : sys.output, n); sys)
+
+function get_computing_box(sys::ParticleSystem{N,T}) where {N,T}
+    _sync!(sys)
+    b = Ref{ClmBoxInfo}()
+    _check(sys.handle, ccall((:clm_get_box, libclm), Cint, (Ptr{Cvoid}, Ref{ClmBoxInfo}), sys.handle, b))
+    return (SVector{N,T}(b[].computing_box_min[1:N]), SVector{N,T}(b[].computing_box_max[1:N]))
+end
+
+# ---- pairwise! (src/API/pairwise.jl:48-63) ---------------------------------------------------------------------
+_flags(reset) = reset ? CLM_RESET : Cint(0)
+
+function pairwise!(f::LJEnergy, sys::ParticleSystem{N,T}; show_progress=false, reset=true) where {N,T}
+    _sync!(sys)
+    e = Ref(reset ? zero(T) : T(sys.output)); p = T[f.c6, f.c12]
+    _check(sys.handle, ccall((:clm_map_lj, libclm), Cint, (Ptr{Cvoid}, Ptr{T}, Cint, Ref{T}, Ptr{Cvoid}), sys.handle, p, _flags(reset), e, C_NULL))
+    return sys.output = e[]
+end
+function pairwise!(f::LJForces, sys::ParticleSystem{N,T}; show_progress=false, reset=true) where {N,T}
+    _sync!(sys)
+    length(sys.output) == length(sys.xpositions) || throw(DimensionMismatch("force output must have one entry per particle (resize_output!)"))
+    e = Ref(zero(T)); p = T[f.c6, f.c12]    # Vector{SVector{N,T}} forces: written in place by the library
+    _check(sys.handle, ccall((:clm_map_lj, libclm), Cint, (Ptr{Cvoid}, Ptr{T}, Cint, Ref{T}, Ptr{SVector{N,T}}), sys.handle, p, _flags(reset), e, sys.output))
+    return sys.output
+end
+function pairwise!(f::LJEnergyAndForces, sys::ParticleSystem{N,T}; show_progress=false, reset=true) where {N,T}
+    _sync!(sys)
+    e = Ref(reset ? zero(T) : T(sys.output.energy)); p = T[f.c6, f.c12]
+    _check(sys.handle, ccall((:clm_map_lj, libclm), Cint, (Ptr{Cvoid}, Ptr{T}, Cint, Ref{T}, Ptr{SVector{N,T}}), sys.handle, p, _flags(reset), e, sys.output.forces))
+    sys.output.energy = e[]
+    return sys.output
+end
+function pairwise!(f::CoulombEnergy, sys::ParticleSystem{N,T}; show_progress=false, reset=true) where {N,T}
+    _sync!(sys)
+    e = Ref(reset ? zero(T) : T(sys.output)); k = Ref(T(f.k))
+    wy = isnothing(f.weights_y) ? C_NULL : pointer(f.weights_y)
+    _check(sys.handle, ccall((:clm_map_coulomb, libclm), Cint, (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Ref{T}, Cint, Ref{T}, Ptr{Cvoid}), sys.handle, f.weights, wy, k, _flags(reset), e, C_NULL))
+    return sys.output = e[]
+end
+function pairwise!(f::CoulombEnergyAndForces, sys::ParticleSystem{N,T}; show_progress=false, reset=true) where {N,T}
+    _sync!(sys)
+    e = Ref(reset ? zero(T) : T(sys.output.energy)); k = Ref(T(f.k))
+    wy = isnothing(f.weights_y) ? C_NULL : pointer(f.weights_y)
+    _check(sys.handle, ccall((:clm_map_coulomb, libclm), Cint, (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Ref{T}, Cint, Ref{T}, Ptr{SVector{N,T}}), sys.handle, f.weights, wy, k, _flags(reset), e, sys.output.forces))
+    sys.output.energy = e[]
+    return sys.output
+end
+function pairwise!(f::DistanceHistogram, sys::ParticleSystem{N,T}; show_progress=false, reset=true) where {N,T}
+    _sync!(sys)                              # output::Vector{Int}
+    _check(sys.handle, ccall((:clm_map_dist_hist, libclm), Cint, (Ptr{Cvoid}, Ref{T}, Cint, Cint, Ptr{Int64}), sys.handle, Ref(T(f.width)), length(sys.output), _flags(reset), sys.output))
+    return sys.output
+end
+function pairwise!(f::PairwiseVelocities, sys::ParticleSystem{N,T}; show_progress=false, reset=true) where {N,T}
+    _sync!(sys)                              # output = (counts::Vector{Int}, sums::Vector{T}); velocities::Vector{SVector{N,T}}
+    counts, sums = sys.output
+    vy = isnothing(f.velocities_y) ? C_NULL : pointer(f.velocities_y)
+    _check(sys.handle, ccall((:clm_map_pairvel, libclm), Cint, (Ptr{Cvoid}, Ptr{SVector{N,T}}, Ptr{SVector{N,T}}, Ptr{T}, Cint, Cint, Ptr{Int64}, Ptr{T}),
+                             sys.handle, f.velocities, vy, f.rbins, length(f.rbins) - 1, _flags(reset), counts, sums))
+    return sys.output
+end
+function pairwise!(::MinimumDistanceMap, sys::ParticleSystem{N,T}; show_progress=false, reset=true) where {N,T}
+    _sync!(sys)
+    i = Ref(Int64(reset ? 0 : sys.output.i)); j = Ref(Int64(reset ? 0 : sys.output.j)); d = Ref(reset ? typemax(T) : T(sys.output.d))
+    _check(sys.handle, ccall((:clm_map_mindist, libclm), Cint, (Ptr{Cvoid}, Cint, Ref{Int64}, Ref{Int64}, Ref{T}), sys.handle, _flags(reset), i, j, d))
+    return sys.output = MinimumDistance{T}(i[], j[], d[])
+end
+pairwise!(f::Function, sys::ParticleSystem; kw...) =
+    throw(ArgumentError("arbitrary pair closures are outside the compiled-in catalogue of CellListMapB200 (LJ/Coulomb, histogram, pair velocity, minimum distance, neighbour list)"))
+
+# ---- neighbour lists (src/API/neighborlist.jl:12-15, :84-111, :159-169, :217-231, :314-340) ------------------------
+mutable struct InPlaceNeighborList{N,T}
+    sys::ParticleSystem{N,T,Nothing}
+    list::Vector{Tuple{Int,Int,T}}
+    n::Int
+end
+function InPlaceNeighborList(; x, y=nothing, cutoff, unitcell=nothing, parallel=true, show_progress=false, nbatches=(0, 0), lcell=1)
+    sys = ParticleSystem(; xpositions=x, ypositions=y, unitcell, cutoff, output=nothing, output_name=:nb, parallel, nbatches, lcell)
+    N, T = length(first(sys.xpositions)), eltype(first(sys.xpositions))
+    return InPlaceNeighborList{N,T}(sys, Tuple{Int,Int,T}[], 0)
+end
+update!(nb::InPlaceNeighborList, x, y=nothing; cutoff=nothing, unitcell=nothing, parallel=nothing) =
+    (update!(nb.sys; xpositions=x, ypositions=y, cutoff, unitcell, parallel); nb)
+function neighborlist!(nb::InPlaceNeighborList{N,T}) where {N,T}
+    _sync!(nb.sys)
+    n = Ref{Int64}(0)
+    _check(nb.sys.handle, ccall((:clm_neighborlist, libclm), Cint, (Ptr{Cvoid}, Cint, Ref{Int64}), nb.sys.handle, 0, n))
+    resize!(nb.list, n[])                    # Tuple{Int,Int,T} is the 24-byte record the library writes in place
+    n[] > 0 && _check(nb.sys.handle, ccall((:clm_neighborlist_copy, libclm), Cint, (Ptr{Cvoid}, Ptr{Tuple{Int,Int,T}}, Int64, Cint), nb.sys.handle, nb.list, n[], 0))
+    nb.n = n[]
+    return nb.list
+end
+function neighborlist(; xpositions=nothing, positions=nothing, ypositions=nothing, cutoff, unitcell=nothing, parallel=true,
+                      show_progress=false, nbatches=(0, 0), lcell=1)
+    x = isnothing(positions) ? xpositions : positions
+    return copy(neighborlist!(InPlaceNeighborList(; x, y=ypositions, cutoff, unitcell, parallel, show_progress, nbatches, lcell)))
+end
+
+end # module
