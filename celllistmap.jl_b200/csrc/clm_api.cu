@@ -263,8 +263,7 @@ template <class T> int Engine<T>::build() {
             }
     }
     // tile size: particles per warp tile (the remaining lanes split the partners into j-slices)
-    tile_i = opt_tile_i ? opt_tile_i : 8;
-    log2ti = (tile_i == 32) ? 5 : (tile_i == 16 ? 4 : 3);
+    tile_i = TILE_I;
     // record capacity without a host round trip: real + image particles ~ n * volume(computing box) / volume(cell)
     // (uniform density) with 25 % slack; a denser boundary layer is detected at the end-of-build sync and the build
     // is repeated once with the exact size
@@ -325,7 +324,7 @@ template <class T> int Engine<T>::build() {
             CLM_CK(cudaGetLastError());
             if (int rc = scan(row_ntiles.p, row_ntiles.p, (int)nrows, dscal.p + DS_NTILES, nullptr)) return rc;
             const int nbt = (int)((tiles_upper + 255) / 256);
-            k_tiles<<<nbt, 256, 0, stream>>>(row_ntiles.p, row_range.p, sets[0].cell_start.p, nfast, (int)nrows, tile_i, dscal.p, tiles.p);
+            k_tiles<<<nbt, 256, 0, stream>>>(row_ntiles.p, row_range.p, sets[0].cell_start.p, nfast, nmid, (int)nrows, tile_i, dscal.p, tiles.p);
             CLM_CK(cudaGetLastError());
             stats.launches += 1;
         }
@@ -464,10 +463,6 @@ template <class T> int Engine<T>::get_stats(clm_stats* out) {
 template <class T> int Engine<T>::set_option(const char* name, int64_t v) {
     if (!name) return fail(CLM_ERR_ARGUMENT, "option name is NULL");
     const std::string s(name);
-    if (s == "tile_i") {
-        if (v != 0 && v != 8 && v != 16 && v != 32) return fail(CLM_ERR_ARGUMENT, "tile_i must be 0, 8, 16 or 32");
-        opt_tile_i = (int)v; dirty = true; return CLM_OK;
-    }
     if (s == "sub") { if (v < 0 || v > LF_MAX) return fail(CLM_ERR_ARGUMENT, "sub must be in 0..7"); opt_sub = (int)v; dirty = true; return CLM_OK; }
     if (s == "blocks_per_sm") { if (v < 0) return fail(CLM_ERR_ARGUMENT, "blocks_per_sm must be >= 0"); opt_bps = (int)v; return CLM_OK; }
     return fail(CLM_ERR_ARGUMENT, "unknown option " + s);

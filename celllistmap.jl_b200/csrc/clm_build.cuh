@@ -255,7 +255,7 @@ k_rows(const int* __restrict__ cell_nact, const int* __restrict__ cell_start, in
 
 static __global__ void __launch_bounds__(256)
 k_tiles(const int* __restrict__ row_tile_start, const int2* __restrict__ row_range, const int* __restrict__ cell_start,
-        int nx, int nrows, int tile_i, const int* __restrict__ dscal, Tile* __restrict__ tiles) {
+        int nx, int ny, int nrows, int tile_i, const int* __restrict__ dscal, Tile* __restrict__ tiles) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= dscal[DS_NTILES]) return;
     // row = last r with row_tile_start[r] <= t
@@ -268,7 +268,7 @@ k_tiles(const int* __restrict__ row_tile_start, const int2* __restrict__ row_ran
     const int* cs = cell_start + (size_t)row * nx;   // cs[c] <= k < cs[c+1]  <=>  record k lives in cell c
     auto cell_x = [&](int k) { int a = 0, b = nx - 1; while (a < b) { const int mid = (a + b + 1) >> 1; if (cs[mid] <= k) a = mid; else b = mid - 1; } return a; };
     Tile tl;
-    tl.k0 = k0; tl.cnt = cnt; tl.row = row;
+    tl.k0 = k0; tl.cnt = cnt; tl.yz = (row % ny) | ((row / ny) << 16);
     tl.cx = cell_x(k0) | (cell_x(k0 + cnt - 1) << 16);
     tiles[t] = tl;
 }

@@ -96,7 +96,7 @@ template <class T> struct GeomT {
 struct Tile {       // 16 bytes
     int k0;         // first record of the tile
     int cnt;        // number of records (<= TI)
-    int row;        // iy + ny * iz
+    int yz;         // row coordinates: y | (z << 16)   (row = y + ny * z)
     int cx;         // cxa | (cxb << 16): x-range of the cells the records live in
 };
 

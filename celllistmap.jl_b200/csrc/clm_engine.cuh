@@ -105,7 +105,7 @@ template <class T> struct Engine : EngineBase {
     int64_t nref = 0;                     // cells of the reference grid
     signed char row_hw[(2 * LF_MAX + 1) * (2 * LF_MAX + 1)];   // per stencil row: half-width along the row in device cells, -1 = skip
     int opt_sub = 0;                      // 0 = choose the sub-cell split from the particle density
-    int tile_i = 32, log2ti = 5, opt_tile_i = 0, opt_bps = 0;
+    int tile_i = TILE_I, opt_bps = 0;
 
     int init(int dim_, int device_);
     ~Engine() override;
@@ -145,9 +145,13 @@ template <class T> struct Engine : EngineBase {
         const DevSet<T>& tg = sets[two_sets ? 1 : 0];
         a.rec_i = sets[0].rec.p; a.rec_j = tg.rec.p; a.cell_start_i = sets[0].cell_start.p; a.cell_start_j = tg.cell_start.p;
         a.tiles = tiles.p; a.dscal = dscal.p; a.res = d_res.p;
-        a.nx = nfast; a.ny = nmid; a.nz = nslow; a.lf = geom.lcell * geom.sub; a.sub = geom.sub; a.log2ti = log2ti; a.self = two_sets ? 0 : 1;
+        a.nx = nfast; a.ny = nmid; a.nz = nslow; a.lf = geom.lcell * geom.sub; a.sub = geom.sub; a.sub_magic = (unsigned)((0x100000000ull + (unsigned)geom.sub - 1) / (unsigned)geom.sub); a.self = two_sets ? 0 : 1;
         a.rc2 = geom.cutoff_sqr;
         std::memcpy(a.hw, row_hw, sizeof(a.hw));
+        {   // stencil row r -> (dslow, dmid)
+            const int lf = a.lf, hww = 2 * lf + 1;
+            for (int r = 0; r < hww * hww; ++r) { a.rdz[r] = (signed char)((nslow == 1) ? 0 : r / hww - lf); a.rdy[r] = (signed char)((nslow == 1) ? ((r < hww) ? r - lf : 0) : r % hww - lf); }
+        }
         return a;
     }
     template <int MODE, class F> int launch(const F& f, size_t functor_smem) {

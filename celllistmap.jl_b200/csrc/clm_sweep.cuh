@@ -31,6 +31,7 @@ enum { MODE_HALF = 0, MODE_TRI = 1, MODE_ALL = 2 };
 constexpr int SWEEP_THREADS = 128;
 constexpr int NB_PRIV_MAX = 16;  // histograms with <= this many bins use per-thread private shared-memory bins
 constexpr int LF_MAX = 7;        // largest stencil reach in device cells (lcell * sub)
+constexpr int TILE_I = 8, LOG2_TILE_I = 3, NSLICE = 32 / TILE_I;   // particles i per warp tile; the other lanes split the partners into j-slices
 // per-warp staging buffer of partner records: small buffers keep 8 CTAs (32 warps) resident per SM, which hides the
 // latency of the tile fetch / cell_start loads / bulk copies better than fewer, larger chunks (tools/tune_stage.sh)
 #ifndef CLM_STAGE_BYTES_F32
@@ -59,14 +60,16 @@ template <class T> struct SweepArgs {
     int* dscal;          // DS_NTILES (read), DS_WORK (atomic tile counter)
     ResultBlock* res;
     int nx, ny, nz;      // device cells along the fast / middle / slow axis = reference dims (3,2,1) in 3-D, (2,1,-) in 2-D
-    int lf, sub, log2ti, self;   // lf = lcell * sub: stencil reach in device cells
+    int lf, sub, self;   // lf = lcell * sub: stencil reach in device cells
+    unsigned sub_magic;  // ceil(2^32 / sub): x / sub == __umulhi(x, sub_magic) for the cell indices in use
     T rc2;
     signed char hw[(2 * LF_MAX + 1) * (2 * LF_MAX + 1)];   // [dslow + lf][dmid + lf]: half-width along the row, -1 = skip
+    signed char rdz[(2 * LF_MAX + 1) * (2 * LF_MAX + 1)], rdy[(2 * LF_MAX + 1) * (2 * LF_MAX + 1)];   // stencil row -> (dslow, dmid)
 };
 
 template <class T> struct Ctx {   // what a functor sees for the tile in flight
     int ki;          // record index of particle i
-    int lane, islot, slice, log2ti;
+    int lane, islot, slice;
     bool active;     // this lane holds a particle that may act as i
     RecT<T> ri;
 };
@@ -127,7 +130,8 @@ template <class T> struct ForceOut {
     int dim, accumulate, rotated;
     T inv_rot[9];
     __device__ __forceinline__ void store(const Ctx<T>& c, T fx, T fy, T fz) const {
-        for (int o = 1 << c.log2ti; o < 32; o <<= 1) {
+#pragma unroll
+        for (int o = TILE_I; o < 32; o <<= 1) {
             fx += __shfl_xor_sync(0xffffffffu, fx, o); fy += __shfl_xor_sync(0xffffffffu, fy, o); fz += __shfl_xor_sync(0xffffffffu, fz, o);
         }
         if (!c.active || c.slice != 0) return;
@@ -448,8 +452,10 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
     typedef TagT<T> TG;
     extern __shared__ __align__(128) unsigned char dsm_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ti = 1 << a.log2ti, nslice = 32 >> a.log2ti;
+    constexpr int ti = TILE_I, nslice = NSLICE;
     const int lf = a.lf, sub = a.sub, hww = 2 * lf + 1;
+    const unsigned smagic = a.sub_magic;
+    auto div_sub = [&](int v) { return (sub == 1) ? v : (int)__umulhi((unsigned)v, smagic); };   // 2^32 / 1 does not fit the magic
     const int nrows_st = (a.nz == 1) ? hww : hww * hww;
     constexpr int CAP = StageCap<T>::value;
     RecT<T>* const buf = reinterpret_cast<RecT<T>*>(dsm_raw + warp * StageBytes<T>::value);
@@ -461,14 +467,16 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
     typename F::Acc acc;
     f.init(acc);
     const int ntiles = a.dscal[DS_NTILES];
+    // the next tile index is fetched one tile ahead: the atomic's round trip overlaps the current tile's work
+    int t_next = 0;
+    if (lane == 0) t_next = atomicAdd(&a.dscal[DS_WORK], 1);
     for (;;) {
-        int t = 0;
-        if (lane == 0) t = atomicAdd(&a.dscal[DS_WORK], 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
+        const int t = __shfl_sync(0xffffffffu, t_next, 0);
         if (t >= ntiles) break;
+        if (lane == 0) t_next = atomicAdd(&a.dscal[DS_WORK], 1);
         const Tile tl = a.tiles[t];
         Ctx<T> c;
-        c.lane = lane; c.log2ti = a.log2ti; c.islot = lane & (ti - 1); c.slice = lane >> a.log2ti;
+        c.lane = lane; c.islot = lane & (ti - 1); c.slice = lane >> LOG2_TILE_I;
         const bool valid = c.islot < tl.cnt;
         c.ki = tl.k0 + (valid ? c.islot : 0);
         c.ri = ldrec(a.rec_i + c.ki);
@@ -486,8 +494,7 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
             blo[0] = c.active ? c.ri.x : inf; blo[1] = c.active ? c.ri.y : inf; blo[2] = c.active ? c.ri.z : inf;
             bhi[0] = c.active ? c.ri.x : -inf; bhi[1] = c.active ? c.ri.y : -inf; bhi[2] = c.active ? c.ri.z : -inf;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                if (o >= ti) break;   // slices hold copies of the same particles
+            for (int o = 1; o < ti; o <<= 1) {   // slices hold copies of the same particles
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     blo[k] = fmin(blo[k], __shfl_xor_sync(0xffffffffu, blo[k], o));
@@ -495,17 +502,17 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                 }
             }
         }
-        const int iy = tl.row % a.ny, iz = tl.row / a.ny;
+        const int iy = tl.yz & 0xffff, iz = tl.yz >> 16, tile_row = iz * a.ny + iy;
         const int cxa = tl.cx & 0xffff, cxb = tl.cx >> 16;
         // MODE_HALF: the reference cell of particle i along the row (the other two follow from the tile's row)
         int rfx_i = 0;
         if (MODE == MODE_HALF) {
-            const int* cs = a.cell_start_i + (size_t)tl.row * a.nx;
+            const int* cs = a.cell_start_i + (size_t)tile_row * a.nx;
             int cx = cxa;
             while (cx < cxb && cs[cx + 1] <= c.ki) ++cx;
-            rfx_i = cx / sub;
+            rfx_i = div_sub(cx);
         }
-        const int ry_i = iy / sub, rz_i = iz / sub;
+        const int ry_i = div_sub(iy), rz_i = div_sub(iz);
 
         // the pair body shared by both sweeps
         auto pair_body = [&](const RecT<T>& rj, const int jc, bool ok) {
@@ -523,13 +530,13 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
             const int r = rb + lane;
             int cls = ROW_SKIP, j0 = 0, j1 = 0, rowbase = 0, own = 0;   // own: bit 0 = the tile's own row, bit 1 = same reference row (MODE_HALF)
             if (r < nrows_st) {
-                const int dz = (a.nz == 1) ? 0 : r / hww - lf, dy = (a.nz == 1) ? r - lf : r % hww - lf;
+                const int dz = a.rdz[r], dy = a.rdy[r];
                 const int z2 = iz + dz, y2 = iy + dy;
                 const int w = a.hw[(dz + lf) * hww + dy + lf];
                 bool use = (z2 >= 0 && z2 < a.nz && y2 >= 0 && y2 < a.ny && w >= 0);
                 int rel = 1;   // partner row's reference cells vs the home reference cell: < 0 behind, 0 same reference row, > 0 forward
                 if (MODE == MODE_HALF && use) {
-                    const int rz_j = z2 / sub, ry_j = y2 / sub;
+                    const int rz_j = div_sub(z2), ry_j = div_sub(y2);
                     rel = (rz_j != rz_i) ? (rz_j - rz_i) : (ry_j - ry_i);
                     use = rel >= 0;
                 }
@@ -580,7 +587,7 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                     };
                     const RecT<T>* pj = a.rec_j + (bj0 + c.slice);
                     int jc = bj0 + c.slice;
-                    const int nfull = (bj1 - bj0) >> (5 - a.log2ti);
+                    const int nfull = (bj1 - bj0) / nslice;
 #pragma unroll 2
                     for (int s_ = 0; s_ < nfull; ++s_) { body(pj, jc, true); pj += nslice; jc += nslice; }
                     if (jc - c.slice < bj1) { const bool inb = jc < bj1; body(inb ? pj : a.rec_j + (bj1 - 1), inb ? jc : bj1 - 1, inb); }
@@ -622,7 +629,8 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                     ns += __popc(m);
                 }
                 // dummy far-away records round the survivors up to a whole number of 4-step groups
-                const int sh4 = 7 - a.log2ti, step4 = 1 << sh4, cpad = ((ns + step4 - 1) >> sh4) << sh4;   // step4 = 4 * nslice
+                constexpr int step4 = 4 * nslice;
+                const int cpad = ((ns + step4 - 1) / step4) * step4;
                 if (ns + lane < cpad) strec(buf + ns + lane, -huge_coord<T>(), T(0), T(0), (typename TG::type)0);
                 __syncwarp();
                 const RecT<T>* p = buf + c.slice;

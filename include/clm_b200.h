@@ -168,7 +168,7 @@ CLM_API int clm_neighborlist(clm_handle* h, int flags, int64_t* n_out);
 CLM_API int clm_neighborlist_copy(clm_handle* h, void* records24, int64_t capacity, int on_device);
 
 CLM_API int clm_get_stats(clm_handle* h, clm_stats* out);
-/* tuning knobs (do not change results): "tile_i" = particles per warp tile (8|16|32, 0 = auto),
+/* tuning knobs (do not change results):
  * "sub" = sub-cells per reference cell and dimension of the device grid (1..7, 0 = from the density),
  * "blocks_per_sm" (0 = auto). */
 CLM_API int clm_set_option(clm_handle* h, const char* name, int64_t value);

@@ -22,11 +22,10 @@ for dtype in dtypes:
     e_dev = torch.zeros(1, dtype=tdt, device="cuda")
     f_dev = torch.zeros((n, 3), dtype=tdt, device="cuda")
     for sub in (1, 2, 3, 4):
-        for ti in (8, 16, 32):
+        for ti in (8,):
             h = clm.Handle(3, dtype)
             h.set_box(clm._capi.ORTHORHOMBIC, w["unitcell"], w["cutoff"], 1)
             h.set_option("sub", sub)
-            h.set_option("tile_i", ti)
             h.set_positions(0, x_dev)
             h.build()
             ts, bs = [], []
