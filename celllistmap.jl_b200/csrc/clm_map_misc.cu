@@ -66,7 +66,7 @@ template <class T> int Engine<T>::neighborlist(int flags, int64_t* n_out) {
         CLM_CK(nl.ensure(capacity * 3));
         FList<T> fn;
         fn.out = nl.p; fn.capacity = capacity;
-        if (int rc = launch_reduce(fn, 0)) return rc;
+        if (int rc = launch_reduce(fn, (size_t)(SWEEP_THREADS / 32) * LIST_STAGE_BYTES)) return rc;
         if (int rc = fetch_results()) return rc;
         nl_count = (int64_t)h_res->c[RC_NLIST];
         if ((size_t)nl_count <= capacity) break;

@@ -362,35 +362,53 @@ template <class T> struct FMin {
 
 // neighbour-list emission: push_pair! (internals/neighborlist.jl:67-76) as a warp-ballot compaction;
 // records are Julia's Tuple{Int,Int,T}: {int64 i; int64 j; T d (+pad)} = 24 bytes
+// Emission is staged per warp in shared memory: hits are appended to a warp-private buffer, and a full buffer is
+// flushed with ONE global atomicAdd (instead of one per warp step on a single counter) and fully coalesced 8-byte
+// stores (instead of 24-byte-strided scattered ones).
+constexpr int LIST_STAGE_RECORDS = 160;                               // per warp: 160 records x 24 B = 3840 B
+constexpr int LIST_STAGE_BYTES = LIST_STAGE_RECORDS * 24;
 template <class T> struct FList {
     unsigned long long* out;        // capacity * 3 words
     unsigned long long capacity;
-    struct Acc {};
+    struct Acc { int cnt; };        // warp-uniform: records waiting in the warp's staging buffer
     struct IAcc {};
     static constexpr bool NEEDS_BAND = false, EXACT_D2 = true, NEEDS_JC = false;
-    __device__ void init(Acc&) const {}
+    __device__ __forceinline__ unsigned long long* stage() const {
+        extern __shared__ __align__(128) unsigned char dsm_raw[];
+        return reinterpret_cast<unsigned long long*>(dsm_raw + StageTotal<T>::value + (threadIdx.x >> 5) * LIST_STAGE_BYTES);
+    }
+    __device__ void init(Acc& a) const { a.cnt = 0; }
     __device__ void begin(IAcc&, const Ctx<T>&) const {}
     __device__ static __forceinline__ unsigned long long dbits(float d) { return (unsigned long long)__float_as_uint(d); }
     __device__ static __forceinline__ unsigned long long dbits(double d) { return (unsigned long long)__double_as_longlong(d); }
-    __device__ __forceinline__ void pair(Acc&, IAcc&, const Ctx<T>& c, bool hit, bool, const RecT<T>& rj, int, T, T, T, T d2, ResultBlock* res) const {
+    __device__ __forceinline__ void flush(Acc& a, ResultBlock* res) const {
+        const int lane = threadIdx.x & 31;
+        __syncwarp();
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(&res->c[RC_NLIST], (unsigned long long)a.cnt);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const unsigned long long* st = stage();
+        const unsigned long long room = (base < capacity) ? (capacity - base) : 0ull;
+        const int nrec = (int)((unsigned long long)a.cnt < room ? (unsigned long long)a.cnt : room);   // overflow: counted, not written
+        unsigned long long* dst = out + base * 3ull;
+        for (int w = lane; w < nrec * 3; w += 32) dst[w] = st[w];
+        a.cnt = 0;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void pair(Acc& a, IAcc&, const Ctx<T>& c, bool hit, bool, const RecT<T>& rj, int, T, T, T, T d2, ResultBlock* res) const {
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (m == 0u) return;
-        const int leader = __ffs(m) - 1;
-        unsigned long long base = 0;
-        if (c.lane == leader) base = atomicAdd(&res->c[RC_NLIST], (unsigned long long)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
         if (hit) {
-            const unsigned long long pos = base + (unsigned long long)__popc(m & ((1u << c.lane) - 1u));
-            if (pos < capacity) {
-                unsigned long long* r = out + pos * 3ull;
-                r[0] = (unsigned long long)(c.ri.tag & TagT<T>::MASK) + 1ull;
-                r[1] = (unsigned long long)(rj.tag & TagT<T>::MASK) + 1ull;
-                r[2] = dbits(xsqrt(d2));
-            }
+            unsigned long long* r = stage() + (a.cnt + __popc(m & ((1u << c.lane) - 1u))) * 3;
+            r[0] = (unsigned long long)(c.ri.tag & TagT<T>::MASK) + 1ull;
+            r[1] = (unsigned long long)(rj.tag & TagT<T>::MASK) + 1ull;
+            r[2] = dbits(xsqrt(d2));
         }
+        a.cnt += __popc(m);
+        if (a.cnt > LIST_STAGE_RECORDS - 32) flush(a, res);
     }
     __device__ void end(IAcc&, const Ctx<T>&) const {}
-    __device__ void finish(Acc&, ResultBlock*) const {}
+    __device__ void finish(Acc& a, ResultBlock* res) const { if (a.cnt > 0) flush(a, res); }
 };
 template <class F> struct IsList { static constexpr bool value = false; };
 template <class T> struct IsList<FList<T>> { static constexpr bool value = true; };
