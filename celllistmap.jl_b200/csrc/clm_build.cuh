@@ -142,15 +142,18 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
             if (g.cb_min[k] <= hi && hi < g.cb_max[k]) dimok[k] |= 4u;
         }
         if (dimok[0] == 2u && dimok[1] == 2u && (DIM == 2 || dimok[2] == 2u)) return;
-        okmask = 0u;
-        for (int img = 0; img < NIMG; ++img) {
-            const int i0 = img % 3, i1 = (img / 3) % 3, i2 = (DIM == 3) ? (img / 9) % 3 : 1;
-            if (((dimok[0] >> i0) & 1u) && ((dimok[1] >> i1) & 1u) && ((dimok[2] >> i2) & 1u)) okmask |= 1u << img;
-        }
+        // okmask bit (i0 + 3 i1 + 9 i2) = dimok0[i0] & dimok1[i1] & dimok2[i2], built by replication instead of a 27-step loop
+        const unsigned m0 = dimok[0] & 7u;                                   // bits i0
+        const unsigned m01 = ((dimok[1] & 1u) ? m0 : 0u) | ((dimok[1] & 2u) ? (m0 << 3) : 0u) | ((dimok[1] & 4u) ? (m0 << 6) : 0u);
+        okmask = (DIM == 2) ? m01 : (((dimok[2] & 1u) ? m01 : 0u) | ((dimok[2] & 2u) ? (m01 << 9) : 0u) | ((dimok[2] & 4u) ? (m01 << 18) : 0u));
     }
+    // only the candidate images are visited (a warp runs as many iterations as its busiest lane has candidates,
+    // typically 1-7 next to a face, instead of all 26)
+    okmask &= ~(1u << CENTER);
+    if (DIM == 2) okmask &= 0x1ffu;
 #pragma unroll 1
-    for (int img = 0; img < NIMG; ++img) {
-        if (img == CENTER || !((okmask >> img) & 1u)) continue;
+    for (unsigned rest = okmask; rest != 0u; rest &= rest - 1u) {
+        const int img = __ffs(rest) - 1;
         T q[3] = {T(0), T(0), T(0)};
         bool in = true;
 #pragma unroll
