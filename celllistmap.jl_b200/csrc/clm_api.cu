@@ -26,6 +26,9 @@ template <class T> int Engine<T>::init(int dim_, int device_) {
     CLM_CK(cudaEventCreate(&ev1));
     CLM_CK(cudaEventCreate(&ev2));
     CLM_CK(cudaEventCreate(&ev3));
+    CLM_CK(cudaEventCreateWithFlags(&ev_built, cudaEventDisableTiming));
+    CLM_CK(cudaEventCreate(&ev_b0));
+    CLM_CK(cudaEventCreate(&ev_b1));
     CLM_CK(dscal.ensure(DS_COUNT));
     CLM_CK(d_res.ensure(1));
     CLM_CK(d_minres.ensure(2));
@@ -48,6 +51,9 @@ template <class T> Engine<T>::~Engine() {
     if (ev1) cudaEventDestroy(ev1);
     if (ev2) cudaEventDestroy(ev2);
     if (ev3) cudaEventDestroy(ev3);
+    if (ev_built) cudaEventDestroy(ev_built);
+    if (ev_b0) cudaEventDestroy(ev_b0);
+    if (ev_b1) cudaEventDestroy(ev_b1);
     if (own_stream) cudaStreamDestroy(own_stream);
 }
 
@@ -167,13 +173,25 @@ template <class T> int Engine<T>::scan(const int* in, int* out, int n, int* tota
 }
 
 // UpdateCellList! (CellLists.jl:727-927; non-periodic NonPeriodicCells.jl:93-230)
+// clm_build: enqueue + validate, repeated when the record-capacity estimate was too small
 template <class T> int Engine<T>::build() {
+    for (;;) {
+        if (int rc = build_enqueue()) return rc;
+        const int v = build_validate();
+        if (v == CLM_RETRY_INTERNAL) continue;
+        return v;
+    }
+}
+
+// everything the build puts on the stream, ending with the D2H copy of the device scalars (validation flags, record
+// counts) and an event; nothing waits on the host
+template <class T> int Engine<T>::build_enqueue() {
     if (!dirty) return CLM_OK;
     CLM_CK(cudaSetDevice(device));
     const int nsets = two_sets ? 2 : 1;
     for (int s = 0; s < nsets; ++s)
         if (sets[s].n + sets[s].n_foreign > 0x7fffffffLL / 28 || sets[s].n + sets[s].n_foreign > (int64_t)TagT<float>::MASK) return fail(CLM_ERR_UNSUPPORTED, "too many particles for 32-bit record indices");
-    CLM_CK(cudaEventRecord(ev0, stream));
+    CLM_CK(cudaEventRecord(ev_b0, stream));
     // device scalars
     for (int k = 0; k < DS_COUNT; ++k) h_dscal[k] = 0;
     h_dscal[DS_NAN] = h_dscal[DS_OOB] = h_dscal[DS_SET_STRIDE + DS_NAN] = h_dscal[DS_SET_STRIDE + DS_OOB] = IDX_NONE;
@@ -277,7 +295,7 @@ template <class T> int Engine<T>::build() {
                            : std::fabs((double)m[0][0] * m[1][1] - (double)m[0][1] * m[1][0]);
         img_factor = std::min(std::max(vbox / std::max(vcell, 1e-300), 1.0), (dim == 3) ? 8.0 : 4.0);
     }
-    for (int attempt = 0;; ++attempt) {
+    {
         for (int k = 0; k < DS_COUNT; ++k) h_dscal[k] = 0;
         h_dscal[DS_NAN] = h_dscal[DS_OOB] = h_dscal[DS_SET_STRIDE + DS_NAN] = h_dscal[DS_SET_STRIDE + DS_OOB] = IDX_NONE;
         CLM_CK(cudaMemcpyAsync(dscal.p, h_dscal, DS_COUNT * sizeof(int), cudaMemcpyHostToDevice, stream));
@@ -328,25 +346,46 @@ template <class T> int Engine<T>::build() {
             CLM_CK(cudaGetLastError());
             stats.launches += 1;
         }
-        CLM_CK(cudaEventRecord(ev1, stream));
-        // the one host round trip of the build: validation flags, record counts, tile count
+        CLM_CK(cudaEventRecord(ev_b1, stream));
+        // the one host round trip of the build (validation flags, record counts, tile count) is only ENQUEUED here; the
+        // caller queues its map kernels behind it and then waits for this event, so the GPU never idles on the host
         CLM_CK(cudaMemcpyAsync(h_dscal, dscal.p, DS_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
-        CLM_CK(cudaStreamSynchronize(stream));
-        bool overflow = false;
-        for (int s = 0; s < nsets; ++s) {
-            const int* hs = h_dscal + s * DS_SET_STRIDE;
-            if (hs[DS_NAN] != IDX_NONE)
-                return fail(CLM_ERR_INVALID_COORDINATES, "Invalid coordinates found (NaN) for particle of index " + std::to_string(hs[DS_NAN] + 1) + (s ? " of the second set" : ""));
-            if (hs[DS_OOB] != IDX_NONE)
-                return fail(CLM_ERR_INVALID_COORDINATES, "Invalid coordinates found: particle of index " + std::to_string(hs[DS_OOB] + 1) + " falls outside the computing grid (non-finite coordinate?)");
-            sets[s].n_tot = hs[DS_NTOT];
-            if ((size_t)sets[s].n_tot > sets[s].rec.cap) overflow = true;
-        }
-        if (!overflow) break;
-        if (attempt >= 2) return fail(CLM_ERR_CUDA, "cell-list build did not converge on a record capacity");
+        CLM_CK(cudaEventRecord(ev_built, stream));
     }
+    validate_pending = true;
+    dirty = false;
+    return CLM_OK;
+}
+
+// waits for the build's device scalars and checks them.  CLM_RETRY_INTERNAL: the record capacity was too small (the
+// scatter pass dropped records); capacity is grown, the build is marked dirty and the caller must redo build + map.
+template <class T> int Engine<T>::build_validate() {
+    if (!validate_pending) return CLM_OK;
+    validate_pending = false;
+    CLM_CK(cudaEventSynchronize(ev_built));
+    const int nsets = two_sets ? 2 : 1;
+    bool overflow = false;
+    for (int s = 0; s < nsets; ++s) {
+        const int* hs = h_dscal + s * DS_SET_STRIDE;
+        if (hs[DS_NAN] != IDX_NONE) {
+            dirty = true;
+            return fail(CLM_ERR_INVALID_COORDINATES, "Invalid coordinates found (NaN) for particle of index " + std::to_string(hs[DS_NAN] + 1) + (s ? " of the second set" : ""));
+        }
+        if (hs[DS_OOB] != IDX_NONE) {
+            dirty = true;
+            return fail(CLM_ERR_INVALID_COORDINATES, "Invalid coordinates found: particle of index " + std::to_string(hs[DS_OOB] + 1) + " falls outside the computing grid (non-finite coordinate?)");
+        }
+        sets[s].n_tot = hs[DS_NTOT];
+        if ((size_t)sets[s].n_tot > sets[s].rec.cap) overflow = true;
+    }
+    if (overflow) {
+        dirty = true;
+        if (++build_retries > 3) return fail(CLM_ERR_CUDA, "cell-list build did not converge on a record capacity");
+        return CLM_RETRY_INTERNAL;
+    }
+    build_retries = 0;
     float ms = 0;
-    CLM_CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    CLM_CK(cudaEventElapsedTime(&ms, ev_b0, ev_b1));
     stats.build_ms = ms;
     stats.n_cells = ncells;
     stats.n_tiles = h_dscal[DS_NTILES];
@@ -355,13 +394,14 @@ template <class T> int Engine<T>::build() {
         stats.n_total[s] = (s < nsets) ? sets[s].n_tot : 0;
         stats.n_cells_real[s] = (s < nsets) ? h_dscal[s * DS_SET_STRIDE + DS_NCELLS_REAL] : 0;
     }
-    dirty = false;
     return CLM_OK;
 }
 
 template <class T> int Engine<T>::prepare_map(int flags) {
     CLM_CK(cudaSetDevice(device));
-    if (int rc = build()) return rc;
+    // accumulating into caller-owned DEVICE buffers cannot be redone: validate the build before anything is added
+    if ((flags & CLM_OUT_DEVICE) && !(flags & CLM_RESET)) { if (int rc = build()) return rc; }
+    else if (int rc = build_enqueue()) return rc;
     profile_sweep = (flags & CLM_PROFILE) != 0;
     if (flags & CLM_PROFILE) CLM_CK(cudaEventRecord(ev0, stream));
     CLM_CK(cudaMemsetAsync(d_res.p, 0, sizeof(ResultBlock), stream));
@@ -457,6 +497,7 @@ template <class T> int Engine<T>::forces_end(void* forces_out, int flags) {
 
 template <class T> int Engine<T>::get_stats(clm_stats* out) {
     if (!out) return fail(CLM_ERR_ARGUMENT, "output pointer is NULL");
+    { const int v = build_validate(); if (v != CLM_OK && v != CLM_RETRY_INTERNAL) return v; }
     *out = stats;
     return CLM_OK;
 }

@@ -13,6 +13,7 @@
 
 namespace clm {
 
+constexpr int CLM_RETRY_INTERNAL = -1;   // never crosses the ABI: build + map must be repeated with the grown capacity
 constexpr int DS_SET_STRIDE = 6;   // dscal block of set y starts at dscal + 6
 
 struct EngineBase {
@@ -79,7 +80,9 @@ template <class T> struct DevSet {
 
 template <class T> struct Engine : EngineBase {
     cudaStream_t stream = nullptr, own_stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_built = nullptr, ev_b0 = nullptr, ev_b1 = nullptr;
+    bool validate_pending = false;
+    int build_retries = 0;
     bool profile_sweep = false;
     HostBox<T> box;
     GeomT<T> geom;
@@ -110,13 +113,19 @@ template <class T> struct Engine : EngineBase {
     int init(int dim_, int device_);
     ~Engine() override;
     int set_stream(void* s) override { stream = s ? (cudaStream_t)s : own_stream; return CLM_OK; }
-    int synchronize() override { CLM_CK(cudaStreamSynchronize(stream)); return CLM_OK; }
+    int synchronize() override {
+        CLM_CK(cudaStreamSynchronize(stream));
+        const int v = build_validate();
+        return (v == CLM_RETRY_INTERNAL) ? fail(CLM_ERR_CAPACITY, "the record capacity of the last enqueued cell-list build was too small: repeat the call") : v;
+    }
     int set_box(int cell_type, const void* uc, int is_matrix, const void* cutoff, int lcell) override;
     int get_box(clm_box_info* out) override;
     int set_positions(int set, const void* xyz, int64_t n, int on_device) override;
     int set_foreign(int set, const void* xyz, int64_t n, int on_device) override;
     int cell_coords(const void* xyz, int64_t n, int on_device, int axis, int32_t* out) override;
     int build() override;
+    int build_enqueue();
+    int build_validate();
     int map_lj(const void* p, int flags, void* e, void* f) override;
     int map_coulomb(const void* wx, const void* wy, const void* k, int flags, void* e, void* f) override;
     int map_dist_hist(const void* width, int nbins, int flags, int64_t* counts) override;

@@ -11,6 +11,7 @@ static inline size_t hist_smem(int nbins, bool priv, size_t sum_bytes) {
 template <class T> int Engine<T>::map_dist_hist(const void* width, int nbins, int flags, int64_t* counts) {
     if (!width || !counts) return fail(CLM_ERR_ARGUMENT, "width / counts pointer is NULL");
     if (nbins < 1 || nbins > 2048) return fail(CLM_ERR_ARGUMENT, "nbins must be in 1..2048");
+    for (;;) {
     if (int rc = prepare_map(flags)) return rc;
     CLM_CK(d_hcount.ensure((size_t)nbins));
     CLM_CK(cudaMemsetAsync(d_hcount.p, 0, (size_t)nbins * sizeof(unsigned long long), stream));
@@ -18,6 +19,11 @@ template <class T> int Engine<T>::map_dist_hist(const void* width, int nbins, in
     fn.width = *(const T*)width;
     fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = nullptr;
     if (int rc = launch_reduce(fn, hist_smem(nbins, fn.hb.priv != 0, 0))) return rc;
+    const int v = build_validate();
+    if (v == CLM_RETRY_INTERNAL) continue;
+    if (v) return v;
+    break;
+    }
     std::vector<unsigned long long> hc;
     if (!(flags & CLM_OUT_DEVICE)) {
         hc.resize((size_t)nbins);
@@ -32,6 +38,7 @@ template <class T> int Engine<T>::map_pairvel(const void* vx, const void* vy, co
     if (!vx || !rbins || !counts || !sums) return fail(CLM_ERR_ARGUMENT, "velocity / rbins / output pointer is NULL");
     if (two_sets && !vy) return fail(CLM_ERR_ARGUMENT, "velocities of the second set are required for a two-set system");
     if (nbins < 1 || nbins > 1024) return fail(CLM_ERR_ARGUMENT, "nbins must be in 1..1024");
+    if (int rc = build()) return rc;   // per-record side arrays are sized by the record count: validated build first
     if (int rc = prepare_map(flags)) return rc;
     const bool dev = (flags & CLM_OUT_DEVICE) != 0;
     if (int rc = gather_aux(0, (const T*)vx, dim, geom.rotated != 0, dev)) return rc;

@@ -6,10 +6,11 @@ namespace clm {
 
 template <class T> int Engine<T>::map_lj(const void* p, int flags, void* e, void* f) {
     if (!p) return fail(CLM_ERR_ARGUMENT, "LJ parameter pointer is NULL");
-    if (int rc = prepare_map(flags)) return rc;
     const T* c = (const T*)p;
     double scale = 1.0;
     const bool norm = FLJ<T, true, true>::can_normalise(c[0], c[1]);
+    for (;;) {   // repeated only when the build's record-capacity estimate was too small (build_validate)
+    if (int rc = prepare_map(flags)) return rc;
     if (f) {
         // full-shell sweep: every ordered pair (i real, j any image) adds to f_i only -> one plain store per
         // particle, no atomics, no per-batch force copies; the energy is visited twice in self-set systems
@@ -32,6 +33,11 @@ template <class T> int Engine<T>::map_lj(const void* p, int flags, void* e, void
         std::memset(&fn.fo, 0, sizeof(fn.fo));
         if (int rc = launch_reduce(fn, 0)) return rc;
     }
+    const int v = build_validate();
+    if (v == CLM_RETRY_INTERNAL) continue;
+    if (v) return v;
+    break;
+    }
     if (!(flags & CLM_OUT_DEVICE)) { if (int rc = fetch_results()) return rc; }
     if (int rc = store_real(e, &d_res.p->f[RB_ENERGY], &h_res->f[RB_ENERGY], 1, scale, flags)) return rc;
     if (f) { if (int rc = forces_end(f, flags)) return rc; }
@@ -41,6 +47,7 @@ template <class T> int Engine<T>::map_lj(const void* p, int flags, void* e, void
 template <class T> int Engine<T>::map_coulomb(const void* wx, const void* wy, const void* k, int flags, void* e, void* f) {
     if (!wx || !k) return fail(CLM_ERR_ARGUMENT, "weights / k pointer is NULL");
     if (two_sets && !wy) return fail(CLM_ERR_ARGUMENT, "weights of the second set are required for a two-set system");
+    if (int rc = build()) return rc;   // per-record side arrays are sized by the record count: validated build first
     if (int rc = prepare_map(flags)) return rc;
     const bool dev = (flags & CLM_OUT_DEVICE) != 0;
     if (int rc = gather_aux(0, (const T*)wx, 1, false, dev)) return rc;

@@ -5,11 +5,17 @@
 namespace clm {
 
 template <class T> int Engine<T>::map_sum(int flags, void* sd, void* sd2, int64_t* np) {
-    if (int rc = prepare_map(flags)) return rc;
-    FSum<T> fn;
-    fn.rc2_lo = std::nextafter(geom.cutoff_sqr, T(0));
-    fn.rc2_hi = std::nextafter(geom.cutoff_sqr, std::numeric_limits<T>::infinity());
-    if (int rc = launch_reduce(fn, 0)) return rc;
+    for (;;) {
+        if (int rc = prepare_map(flags)) return rc;
+        FSum<T> fn;
+        fn.rc2_lo = std::nextafter(geom.cutoff_sqr, T(0));
+        fn.rc2_hi = std::nextafter(geom.cutoff_sqr, std::numeric_limits<T>::infinity());
+        if (int rc = launch_reduce(fn, 0)) return rc;
+        const int v = build_validate();
+        if (v == CLM_RETRY_INTERNAL) continue;
+        if (v) return v;
+        break;
+    }
     if (!(flags & CLM_OUT_DEVICE)) {
         if (int rc = fetch_results()) return rc;
         stats.n_pairs = (int64_t)h_res->c[RC_NPAIRS];
@@ -23,11 +29,17 @@ template <class T> int Engine<T>::map_sum(int flags, void* sd, void* sd2, int64_
 
 template <class T> int Engine<T>::map_mindist(int flags, int64_t* i, int64_t* j, void* d) {
     if (!i || !j || !d) return fail(CLM_ERR_ARGUMENT, "output pointer is NULL");
-    if (int rc = prepare_map(flags)) return rc;
-    CLM_CK(d_minpart.ensure((size_t)n_sm * 16));
-    FMin<T> fn;
-    fn.partial = d_minpart.p;
-    if (int rc = launch_reduce(fn, 0)) return rc;
+    for (;;) {
+        if (int rc = prepare_map(flags)) return rc;
+        CLM_CK(d_minpart.ensure((size_t)n_sm * 16));
+        FMin<T> fn;
+        fn.partial = d_minpart.p;
+        if (int rc = launch_reduce(fn, 0)) return rc;
+        const int v = build_validate();
+        if (v == CLM_RETRY_INTERNAL) continue;
+        if (v) return v;
+        break;
+    }
     k_min_final<<<1, 256, 0, stream>>>(d_minpart.p, last_grid, d_minres.p);
     CLM_CK(cudaGetLastError());
     stats.launches += 1;
@@ -67,6 +79,11 @@ template <class T> int Engine<T>::neighborlist(int flags, int64_t* n_out) {
         FList<T> fn;
         fn.out = nl.p; fn.capacity = capacity;
         if (int rc = launch_reduce(fn, (size_t)(SWEEP_THREADS / 32) * LIST_STAGE_BYTES)) return rc;
+        {
+            const int v = build_validate();
+            if (v == CLM_RETRY_INTERNAL) { if (int rc = prepare_map(flags & ~CLM_PROFILE)) return rc; --attempt; continue; }
+            if (v) return v;
+        }
         if (int rc = fetch_results()) return rc;
         nl_count = (int64_t)h_res->c[RC_NLIST];
         if ((size_t)nl_count <= capacity) break;
