@@ -5,6 +5,7 @@ Workload (weak scaling): every rank generates ITS slab of the argon-density jitt
 (NCCL send/recv of the face cell layers) + UpdateCellList! + pairwise!(LJ energy+forces) + all_reduce of the energy;
 forces stay sharded with their owners.  Timed per rank with CUDA events on the launching stream, max over ranks."""
 import json
+import os
 import statistics
 
 import numpy as np
@@ -78,21 +79,30 @@ def run(args, rank, world, local):
         l0 = s.h.stats().launches
         torch.cuda.synchronize()
         dist.barrier()
-        times, sweep = [], []
+        evs = []
         for _ in range(args.steps):
             flush_buf.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
-            e = step(profile=True)
+            e = step()
             b.record(stream)
-            b.synchronize()
-            times.append(a.elapsed_time(b))
-            sweep.append(s.h.stats().sweep_ms)
+            evs.append((a, b))
         torch.cuda.synchronize()
         dist.barrier()
+        times = [a.elapsed_time(b) for a, b in evs]
         launches = s.h.stats().launches - l0
         clocks = sampler.stop() if sampler else None
-        t = torch.tensor([sum(times) / args.steps, statistics.mean(sweep), float(s.n_foreign), float(n_own)], dtype=torch.float64, device=dev)
+        sweep, build = [], []
+        for _ in range(5):                                   # kernel-level durations from a separate profiled loop
+            step(profile=True)
+            st = s.h.stats()
+            sweep.append(st.sweep_ms)
+            build.append(st.build_ms)
+        if os.environ.get("CLM_BENCH_VERBOSE"):
+            st = s.h.stats()
+            print(f"[rank {rank}] step {sum(times) / args.steps:.3f} ms  sweep {statistics.mean(sweep):.3f}  build {statistics.mean(build):.3f}  "
+                  f"owned {n_own} foreign {s.n_foreign} records {st.n_total[0]} tiles {st.n_tiles} cells {st.n_cells}", flush=True)
+        t = torch.tensor([sum(times) / args.steps, statistics.mean(sweep), float(s.n_foreign), float(n_own), statistics.mean(build)], dtype=torch.float64, device=dev)
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
@@ -134,7 +144,7 @@ def run(args, rank, world, local):
             "e2e": {"value": P_in / (float(te[0]) * 1e-3), "unit": bench.UNIT, "ms_per_step": float(te[0]),
                     "h2d_bytes_per_step": int(x_host.nbytes) * world, "d2h_bytes_per_step": (int(f_pin.numel()) * 4 + 4) * world},
             "gpu_launches": launches * world,
-            "breakdown_ms": {"step_max": ms, "sweep_kernel_max": float(tmax[1])},
+            "breakdown_ms": {"step_max": ms, "sweep_kernel_max": float(tmax[1]), "build_max": float(tmax[4])},
             "energy": float(e_host),
         }
         print(json.dumps(line))

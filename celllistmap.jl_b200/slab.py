@@ -122,6 +122,9 @@ class SlabSystem:
         self.h.set_box(_capi.ORTHORHOMBIC, uc, cutoff, lcell)
         b = self.h.get_box()
         self.plan = SlabPlan(int(b.nc[0]) - 2 * lcell - 1, lcell, self.world)
+        self._inner_cells = float(np.prod([max(1, int(b.nc[k]) - 2 * lcell - 1) for k in range(dim)]))
+        self._lcell = lcell
+        self._n_global = None
         self.n_owned = 0
         self.n_foreign = 0
         self.ids = None
@@ -153,6 +156,16 @@ class SlabSystem:
         self.ids = None if ids is None else payloads[1]
         self.foreign_ids = None if ids is None else got[1]
         self.n_owned, self.n_foreign = int(x.shape[0]), int(self.x_foreign.shape[0])
+        if self._n_global is None:
+            # the engine sizes its device grid from the particle density; a rank only sees its slab, so tell it the
+            # global density (same rule as Engine::build: ~4 particles per device cell)
+            n = torch.tensor([self.n_owned], dtype=torch.int64, device=self.device)
+            if self.world > 1:
+                dist.all_reduce(n, group=self.group)
+            self._n_global = int(n)
+            per_cell = self._n_global / self._inner_cells
+            sub = int(np.floor(max(per_cell / 4.0, 1.0) ** (1.0 / self.dim) + 0.35))
+            self.h.set_option("sub", max(1, min(sub, 7 // self._lcell)))
         self.h.set_positions(0, x)
         self.h.set_foreign(0, self.x_foreign)
         return self
