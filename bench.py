@@ -281,6 +281,33 @@ def main():
         h.close()
         return res
 
+    def neighborlist_ms():
+        """BASELINE metric 2: neighbour-list build time of configs[0] (10k particles, unit cube, cutoff 0.1, Float64):
+        end to end through the reference-facing API (host positions in, host records out) and device-resident."""
+        w = W.c1_neighborlist()
+        nb = clm.InPlaceNeighborList(x=w["x"], cutoff=w["cutoff"], unitcell=w["unitcell"], device=local)
+        hh = nb.sys._h
+        for _ in range(3):
+            clm.update(nb, xpositions=w["x"])
+            lst = nb.neighborlist()
+        te = []
+        for _ in range(20):
+            t0 = time.perf_counter()
+            clm.update(nb, xpositions=w["x"])
+            lst = nb.neighborlist()
+            te.append(time.perf_counter() - t0)
+        xd = torch.from_numpy(w["x"]).to(dev)
+        td = []
+        for _ in range(20):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            hh.set_positions(0, xd)
+            hh.neighborlist_count()
+            td.append(time.perf_counter() - t0)
+        return {"config": "configs[0]: 10k random 3-D particles, orthorhombic unit cube, cutoff 0.1, Float64", "pairs": int(len(lst)),
+                "e2e_ms": 1e3 * statistics.median(te), "device_resident_ms": 1e3 * statistics.median(td),
+                "reference_published_ms": 7.978, "reference_source": "src/API/neighborlist.jl:204-207 (serial Julia, unstated CPU)"}
+
     r32 = measure(np.float32, args.steps, args.warmup, True)
     r64 = None if args.no_f64 else measure(np.float64, max(3, args.steps // 4), 3, False)
 
@@ -309,7 +336,8 @@ def main():
                 "h2d_bytes_per_step": r32["h2d"], "d2h_bytes_per_step": r32["d2h"]},
         "gpu_launches": r32["launches"] * args.steps,
         "roofline": {"bound": "fp32", "kernel": "k_sweep<float, MODE_ALL, FLJ<float,true,true>>", "achieved": achieved_tf, "peak": fp32_peak_tf,
-                     "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak_tf, "traffic": None,
+                     "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak_tf,
+                     "traffic": 24.7e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload (profiles/r1g_sweep_lj_f32.txt)",
                      "algorithmic_flops_per_launch": F_alg, "kernel_ms": r32["sweep_ms"], "build_ms": r32["build_ms"],
                      "peak_source": "FP32 FMA peak measured live by clm_measure_fma_peak (register-resident FMA loop, all SMs); "
                                     f"nominal {fp32_nominal_tf:.1f} TFLOP/s = 148 SM x 128 lanes x 2 x sm_max_mhz from {peaks_src}; no tensor cores on this path",
@@ -322,6 +350,7 @@ def main():
         line["f64"] = {"value": r64["P_in"] / (r64["dev_ms"] * 1e-3), "unit": UNIT, "ms_per_step": r64["dev_ms"],
                        "sweep_kernel_ms": r64["sweep_ms"], "build_ms": r64["build_ms"],
                        "e2e_value": r64["P_in"] / (r64["e2e_ms"] * 1e-3), "in_cutoff_pairs": r64["P_in"]}
+    line["neighborlist_build"] = neighborlist_ms()
     if not args.no_cpu_baseline:
         wc = W.c2_argon(args.cpu_nside, np.float32)
         t, npairs, nt = cpu_port_run(wc, np.float32, 3)
