@@ -429,7 +429,7 @@ template <class T> int Engine<T>::fetch_results() {
 // per-particle auxiliary input (weights / velocities) -> record order of `set`
 template <class T> int Engine<T>::gather_aux(int set, const T* aux, int ncomp, bool rotate, bool on_device) {
     DevSet<T>& S = sets[set];
-    const size_t out_n = (size_t)std::max<int64_t>(S.n_tot, 1) * (ncomp == 1 ? 1 : 4);
+    const size_t out_n = (size_t)std::max<int64_t>(S.n_tot, 1) * 4;   // one record-sized slot (4 x T) per record
     const size_t in_n = (size_t)S.n * ncomp;
     CLM_CK(S.aux.ensure(out_n + in_n + 4));
     T* staged = S.aux.p + out_n;

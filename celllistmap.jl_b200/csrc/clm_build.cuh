@@ -334,8 +334,8 @@ __global__ void __launch_bounds__(256) k_minmax(const T* __restrict__ pos, int n
     }
 }
 
-// gather per-particle auxiliary data (weights, velocities) into record order so that the sweep reads
-// it with the same broadcast/coalesced pattern as the records; velocities are rotated into the
+// gather per-particle auxiliary data (weights, velocities) into record order, one record-sized slot (4 x T) per
+// record, so that the sweep stages it with the same bulk copies as the records; velocities are rotated into the
 // aligned frame (dot(v, R^-1 d) == dot(R v, d)).
 template <class T>
 static __global__ void __launch_bounds__(256)
@@ -345,7 +345,7 @@ k_gather_aux(const RecT<T>* __restrict__ rec, int n_tot, const T* __restrict__ a
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_tot) return;
     const size_t idx = (size_t)(rec[k].tag & TG::MASK);
-    if (ncomp == 1) { out[k] = aux[idx]; return; }
+    if (ncomp == 1) { out[(size_t)k * 4 + 0] = aux[idx]; out[(size_t)k * 4 + 1] = T(0); out[(size_t)k * 4 + 2] = T(0); out[(size_t)k * 4 + 3] = T(0); return; }
     T v[3] = {T(0), T(0), T(0)};
     for (int c = 0; c < ncomp; ++c) v[c] = aux[idx * ncomp + c];
     if (rotate) {

@@ -17,7 +17,7 @@ template <class T> int Engine<T>::map_dist_hist(const void* width, int nbins, in
     CLM_CK(cudaMemsetAsync(d_hcount.p, 0, (size_t)nbins * sizeof(unsigned long long), stream));
     FHist<T> fn;
     fn.width = *(const T*)width;
-    fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = nullptr;
+    fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.off = 0; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = nullptr;
     if (int rc = launch_reduce(fn, hist_smem(nbins, fn.hb.priv != 0, 0))) return rc;
     const int v = build_validate();
     if (v == CLM_RETRY_INTERNAL) continue;
@@ -51,8 +51,9 @@ template <class T> int Engine<T>::map_pairvel(const void* vx, const void* vy, co
     CLM_CK(cudaMemcpyAsync(d_rbins.p, rbins, ((size_t)nbins + 1) * sizeof(T), cudaMemcpyHostToDevice, stream));
     FVel<T> fn;
     fn.v_i = sets[0].aux.p; fn.v_j = sets[two_sets ? 1 : 0].aux.p; fn.rbins = d_rbins.p;
-    fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = d_hsum.p;
-    if (int rc = launch_reduce(fn, hist_smem(nbins, fn.hb.priv != 0, sizeof(T)))) return rc;
+    const int aux_bytes = (SWEEP_THREADS / 32) * StageBytes<T>::value;   // side-array staging buffers precede the bins
+    fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.off = aux_bytes; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = d_hsum.p;
+    if (int rc = launch_reduce(fn, (size_t)aux_bytes + hist_smem(nbins, fn.hb.priv != 0, sizeof(T)))) return rc;
     std::vector<unsigned long long> hc;
     std::vector<double> hs;
     if (!dev) {

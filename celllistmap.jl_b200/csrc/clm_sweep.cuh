@@ -96,7 +96,7 @@ template <class T> struct FSum {
     T rc2_lo, rc2_hi;   // prevfloat/nextfloat of cutoff^2
     struct Acc { double sd, sd2; unsigned long long n, band; };
     struct IAcc {};
-    static constexpr bool NEEDS_BAND = true, EXACT_D2 = true, NEEDS_JC = false;
+    static constexpr bool NEEDS_BAND = true, EXACT_D2 = true, AUX = false;
     __device__ void init(Acc& a) const { a.sd = 0; a.sd2 = 0; a.n = 0; a.band = 0; }
     __device__ void begin(IAcc&, const Ctx<T>&) const {}
     __device__ void pair(Acc& a, IAcc&, const Ctx<T>&, bool hit, bool ok, const RecT<T>&, int, T, T, T, T d2) const {
@@ -157,7 +157,7 @@ template <class T, bool FORCES, bool NORM> struct FLJ {
     ForceOut<T> fo;
     struct Acc { T e; };
     struct IAcc { T fx, fy, fz; };
-    static constexpr bool NEEDS_BAND = false, EXACT_D2 = !FORCES, NEEDS_JC = false;   // the full-shell force sweep has tolerance parity
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = !FORCES, AUX = false;   // the full-shell force sweep has tolerance parity
     __device__ void init(Acc& a) const { a.e = T(0); }
     __device__ void begin(IAcc& p, const Ctx<T>&) const { p.fx = p.fy = p.fz = T(0); }
     __device__ __forceinline__ void pair(Acc& a, IAcc& p, const Ctx<T>&, bool hit, bool, const RecT<T>&, int, T dx, T dy, T dz, T d2) const {
@@ -198,18 +198,18 @@ template <class T, bool FORCES, bool NORM> struct FLJ {
 // Coulomb-like k*w_i*w_j/d (test/examples/gravitational_potential.jl:30-34, gravitational_force.jl:38-44)
 template <class T, bool FORCES> struct FCoul {
     T k;
-    const T* w_i;   // weights gathered into record order of set i / set j
+    const T* w_i;   // weights gathered into record order of set i / set j: one record-sized slot (w, 0, 0, 0) per record
     const T* w_j;
     ForceOut<T> fo;
     struct Acc { T e; };
     struct IAcc { T fx, fy, fz, wi; };
-    static constexpr bool NEEDS_BAND = false, EXACT_D2 = !FORCES, NEEDS_JC = true;   // w_j[record]
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = !FORCES, AUX = true;   // side array staged with the records
+    __device__ __forceinline__ const RecT<T>* aux_j() const { return reinterpret_cast<const RecT<T>*>(w_j); }
     __device__ void init(Acc& a) const { a.e = T(0); }
-    __device__ void begin(IAcc& p, const Ctx<T>& c) const { p.fx = p.fy = p.fz = T(0); p.wi = c.active ? k * w_i[c.ki] : T(0); }
-    __device__ __forceinline__ void pair(Acc& a, IAcc& p, const Ctx<T>&, bool hit, bool, const RecT<T>&, int j, T dx, T dy, T dz, T d2) const {
-        const T wj = __ldg(w_j + j);
+    __device__ void begin(IAcc& p, const Ctx<T>& c) const { p.fx = p.fy = p.fz = T(0); p.wi = c.active ? k * w_i[(size_t)c.ki * 4] : T(0); }
+    __device__ __forceinline__ void pair(Acc& a, IAcc& p, const Ctx<T>&, bool hit, bool, const RecT<T>&, const RecT<T>& aj, T dx, T dy, T dz, T d2) const {
         const T invd = hit ? rsqrt(d2) : T(0);
-        const T q = p.wi * wj * invd;     // k w_i w_j / d
+        const T q = p.wi * aj.x * invd;     // k w_i w_j / d
         a.e += q;
         if (FORCES) {
             const T g = q * invd * invd;  // k w_i w_j / d^3
@@ -228,13 +228,14 @@ template <class T, bool FORCES> struct FCoul {
 // (bank = thread, conflict free, no atomics) when nbins <= NB_PRIV_MAX, block-shared atomics otherwise
 template <class T, bool SUMS> struct HistBins {
     int nbins, priv;
+    int off;                        // bytes between the end of the record staging buffers and the bins (side-array staging buffers)
     unsigned long long* g_counts;   // [nbins] global accumulators
     double* g_sums;                 // [nbins]
-    __device__ __forceinline__ unsigned int* cnt() const { extern __shared__ __align__(128) unsigned char dsm_raw[]; return reinterpret_cast<unsigned int*>(dsm_raw + StageTotal<T>::value); }
+    __device__ __forceinline__ unsigned int* cnt() const { extern __shared__ __align__(128) unsigned char dsm_raw[]; return reinterpret_cast<unsigned int*>(dsm_raw + StageTotal<T>::value + off); }
     __device__ __forceinline__ T* sum() const {
         extern __shared__ __align__(128) unsigned char dsm_raw[];
         const size_t nslots = (size_t)nbins * (priv ? SWEEP_THREADS : 1);
-        return reinterpret_cast<T*>(dsm_raw + StageTotal<T>::value + ((nslots * 4 + 15) / 16) * 16);
+        return reinterpret_cast<T*>(dsm_raw + StageTotal<T>::value + off + ((nslots * 4 + 15) / 16) * 16);
     }
     __device__ void init() const {
         const int nslots = nbins * (priv ? SWEEP_THREADS : 1);
@@ -275,7 +276,7 @@ template <class T> struct FHist {
     HistBins<T, false> hb;
     struct Acc {};
     struct IAcc {};
-    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true, NEEDS_JC = false;
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true, AUX = false;
     __device__ void init(Acc&) const { hb.init(); }
     __device__ void begin(IAcc&, const Ctx<T>&) const {}
     __device__ __forceinline__ void pair(Acc&, IAcc&, const Ctx<T>&, bool hit, bool, const RecT<T>&, int, T, T, T, T d2) const {
@@ -299,20 +300,21 @@ template <class T> struct FVel {
     HistBins<T, true> hb;
     struct Acc {};
     struct IAcc { T vx, vy, vz; };
-    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true, NEEDS_JC = true;
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true, AUX = true;   // side array staged with the records
+    __device__ __forceinline__ const RecT<T>* aux_j() const { return reinterpret_cast<const RecT<T>*>(v_j); }
     __device__ void init(Acc&) const { hb.init(); }
     __device__ void begin(IAcc& p, const Ctx<T>& c) const {
         p.vx = p.vy = p.vz = T(0);
         if (c.active) { p.vx = v_i[(size_t)c.ki * 4]; p.vy = v_i[(size_t)c.ki * 4 + 1]; p.vz = v_i[(size_t)c.ki * 4 + 2]; }
     }
-    __device__ __forceinline__ void pair(Acc&, IAcc& p, const Ctx<T>&, bool hit, bool, const RecT<T>&, int j, T dx, T dy, T dz, T d2) const {
+    __device__ __forceinline__ void pair(Acc&, IAcc& p, const Ctx<T>&, bool hit, bool, const RecT<T>&, const RecT<T>& aj, T dx, T dy, T dz, T d2) const {
         if (hit) {
             const T r = xsqrt(d2);
             int first = 0;   // searchsortedfirst(rbins, r): number of edges < r
             for (int e = 0; e <= hb.nbins; ++e) first += (__ldg(rbins + e) < r) ? 1 : 0;
             const int b = first - 1;
             if (b >= 0 && b < hb.nbins) {
-                const T ux = p.vx - __ldg(v_j + (size_t)j * 4), uy = p.vy - __ldg(v_j + (size_t)j * 4 + 1), uz = p.vz - __ldg(v_j + (size_t)j * 4 + 2);
+                const T ux = p.vx - aj.x, uy = p.vy - aj.y, uz = p.vz - aj.z;
                 hb.add(b, ((ux * dx + uy * dy) + uz * dz) / r);
             }
         }
@@ -327,7 +329,7 @@ template <class T> struct FMin {
     MinPartial* partial;   // [gridDim.x]
     struct Acc { T d2; long long i, j; };
     struct IAcc {};
-    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true, NEEDS_JC = false;
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true, AUX = false;
     __device__ void init(Acc& a) const { a.d2 = CUDART_INF_T<T>(); a.i = 0; a.j = 0; }
     __device__ void begin(IAcc&, const Ctx<T>&) const {}
     __device__ static __forceinline__ bool better(T d2, long long i, long long j, T e2, long long ei, long long ej) {
@@ -372,7 +374,7 @@ template <class T> struct FList {
     unsigned long long capacity;
     struct Acc { int cnt; };        // warp-uniform: records waiting in the warp's staging buffer
     struct IAcc {};
-    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true, NEEDS_JC = false;
+    static constexpr bool NEEDS_BAND = false, EXACT_D2 = true, AUX = false;
     __device__ __forceinline__ unsigned long long* stage() const {
         extern __shared__ __align__(128) unsigned char dsm_raw[];
         return reinterpret_cast<unsigned long long*>(dsm_raw + StageTotal<T>::value + (threadIdx.x >> 5) * LIST_STAGE_BYTES);
@@ -477,6 +479,9 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
     const int nrows_st = (a.nz == 1) ? hww : hww * hww;
     constexpr int CAP = StageCap<T>::value;
     RecT<T>* const buf = reinterpret_cast<RecT<T>*>(dsm_raw + warp * StageBytes<T>::value);
+    // functors with a per-record side array (weights, velocities) stage it in a second per-warp buffer, slot for slot
+    RecT<T>* const abuf = reinterpret_cast<RecT<T>*>(dsm_raw + StageTotal<T>::value + warp * StageBytes<T>::value);
+    const uint32_t abuf_addr = smem_u32(abuf);
     const uint32_t buf_addr = smem_u32(buf);
     const uint32_t mbar = smem_u32(dsm_raw + (SWEEP_THREADS / 32) * StageBytes<T>::value + warp * 8);
     uint32_t parity = 0;
@@ -533,13 +538,14 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
         const int ry_i = div_sub(iy), rz_i = div_sub(iz);
 
         // the pair body shared by both sweeps
-        auto pair_body = [&](const RecT<T>& rj, const int jc, bool ok) {
+        auto pair_body = [&](const RecT<T>& rj, const RecT<T>& aj, const int jc, bool ok) {
             const T dx = xsub(xi, rj.x), dy_ = xsub(yi, rj.y), dz_ = xsub(zi, rj.z);
             T d2;
             if (F::EXACT_D2) d2 = xadd(xadd(xmul(dx, dx), xmul(dy_, dy_)), xmul(dz_, dz_));
             else d2 = xfma(dz_, dz_, xfma(dy_, dy_, dx * dx));
             const bool hit = ok && (d2 <= a.rc2);
             if constexpr (IsList<F>::value) f.pair(acc, ia, c, hit, ok, rj, jc, dx, dy_, dz_, d2, a.res);
+            else if constexpr (F::AUX) f.pair(acc, ia, c, hit, ok, rj, aj, dx, dy_, dz_, d2);   // aj: the partner's side-array slot
             else f.pair(acc, ia, c, hit, ok, rj, jc, dx, dy_, dz_, d2);
         };
 
@@ -566,8 +572,7 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                     j1 = a.cell_start_j[rowbase + xb + 1];
                     if (j1 > j0) {
                         cls = ROW_STAGED;
-                        if (F::NEEDS_JC) cls = ROW_DIRECT;
-                        else if (MODE == MODE_HALF && rel == 0) cls = ROW_DIRECT;
+                        if (MODE == MODE_HALF && rel == 0) cls = ROW_DIRECT;
                         else if (MODE == MODE_ALL && (own & 1) && a.self) cls = ROW_DIRECT;
                     }
                 }
@@ -601,7 +606,9 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                         }
                         else if (MODE == MODE_TRI) ok = ok && (idx_i < (rj.tag & TG::MASK));
                         else if (SELF_ROW) ok = ok && (rj.tag != c.ri.tag);
-                        pair_body(rj, jc, ok);
+                        RecT<T> aj = rj;
+                        if constexpr (F::AUX) aj = ldrec(f.aux_j() + jc);
+                        pair_body(rj, aj, jc, ok);
                     };
                     const RecT<T>* pj = a.rec_j + (bj0 + c.slice);
                     int jc = bj0 + c.slice;
@@ -621,9 +628,12 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
             for (int c0 = 0; c0 < total; c0 += CAP) {
                 const int cn = min(total - c0, CAP);
                 const int lo = max(off, c0), hi = min(off + len, c0 + cn);
-                if (lane == 0) { fence_proxy_async(); mbar_expect_tx(mbar, (uint32_t)cn * (uint32_t)sizeof(RecT<T>)); }
+                if (lane == 0) { fence_proxy_async(); mbar_expect_tx(mbar, (uint32_t)cn * (uint32_t)sizeof(RecT<T>) * (F::AUX ? 2u : 1u)); }
                 __syncwarp();
-                if (hi > lo) bulk_g2s(buf_addr + (uint32_t)(lo - c0) * (uint32_t)sizeof(RecT<T>), a.rec_j + (j0 + (lo - off)), (uint32_t)(hi - lo) * (uint32_t)sizeof(RecT<T>), mbar);
+                if (hi > lo) {
+                    bulk_g2s(buf_addr + (uint32_t)(lo - c0) * (uint32_t)sizeof(RecT<T>), a.rec_j + (j0 + (lo - off)), (uint32_t)(hi - lo) * (uint32_t)sizeof(RecT<T>), mbar);
+                    if constexpr (F::AUX) bulk_g2s(abuf_addr + (uint32_t)(lo - c0) * (uint32_t)sizeof(RecT<T>), f.aux_j() + (j0 + (lo - off)), (uint32_t)(hi - lo) * (uint32_t)sizeof(RecT<T>), mbar);
+                }
                 mbar_wait(mbar, parity);
                 parity ^= 1u;
                 __syncwarp();
@@ -635,6 +645,8 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                     const int k = k0 + lane;
                     const bool in = k < cn;
                     const RecT<T> rq = ldrec_s(buf + (in ? k : 0));
+                    RecT<T> aq = rq;
+                    if constexpr (F::AUX) aq = ldrec_s(abuf + (in ? k : 0));
                     const T ex = fmax(fmax(xsub(blo[0], rq.x), xsub(rq.x, bhi[0])), T(0));
                     const T ey = fmax(fmax(xsub(blo[1], rq.y), xsub(rq.y, bhi[1])), T(0));
                     const T ez = fmax(fmax(xsub(blo[2], rq.z), xsub(rq.z, bhi[2])), T(0));
@@ -643,7 +655,11 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                     else dd = xfma(ez, ez, xfma(ey, ey, ex * ex));
                     const bool keep = in && (dd <= a.rc2);
                     const unsigned m = __ballot_sync(0xffffffffu, keep);   // every lane has read its record: in-place writes are safe
-                    if (keep) strec(buf + ns + __popc(m & ((1u << lane) - 1u)), rq.x, rq.y, rq.z, rq.tag);
+                    if (keep) {
+                        const int pos = ns + __popc(m & ((1u << lane) - 1u));
+                        strec(buf + pos, rq.x, rq.y, rq.z, rq.tag);
+                        if constexpr (F::AUX) strec(abuf + pos, aq.x, aq.y, aq.z, aq.tag);
+                    }
                     ns += __popc(m);
                 }
                 // dummy far-away records round the survivors up to a whole number of 4-step groups
@@ -654,10 +670,12 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                 const RecT<T>* p = buf + c.slice;
                 auto sbody = [&](const RecT<T>* q) {
                     const RecT<T> rj = ldrec_s(q);
+                    RecT<T> aj = rj;
+                    if constexpr (F::AUX) aj = ldrec_s(abuf + (q - buf));
                     bool ok = true;
                     if (MODE == MODE_HALF) ok = (((c.ri.tag & rj.tag) & TG::GHOST) == 0);
                     else if (MODE == MODE_TRI) ok = (idx_i < (rj.tag & TG::MASK));
-                    pair_body(rj, 0, ok);
+                    pair_body(rj, aj, 0, ok);
                 };
                 for (int g = 0; g < cpad; g += step4) {
                     sbody(p); sbody(p + nslice); sbody(p + 2 * nslice); sbody(p + 3 * nslice);
