@@ -24,7 +24,7 @@ SYMBOLS = [
     "clm_create", "clm_destroy", "clm_last_error", "clm_set_stream", "clm_synchronize", "clm_set_box", "clm_get_box",
     "clm_set_positions", "clm_build", "clm_map_lj", "clm_map_coulomb", "clm_map_dist_hist", "clm_map_pairvel",
     "clm_map_mindist", "clm_map_sum_d_d2", "clm_neighborlist", "clm_neighborlist_copy", "clm_get_stats",
-    "clm_set_option", "clm_version", "clm_measure_fma_peak", "clm_set_foreign", "clm_cell_coords",
+    "clm_set_option", "clm_version", "clm_measure_fma_peak", "clm_set_foreign", "clm_cell_coords", "clm_select_layers",
 ]
 
 
@@ -94,6 +94,7 @@ def lib():
     L.clm_measure_fma_peak.argtypes = [ci, ci, C.POINTER(C.c_double)]
     L.clm_set_foreign.argtypes = [vp, ci, vp, i64, ci]
     L.clm_cell_coords.argtypes = [vp, vp, i64, ci, ci, vp]
+    L.clm_select_layers.argtypes = [vp, vp, i64, ci, C.POINTER(C.c_int32), ci, vp, vp, i64, vp]
     for name in SYMBOLS:
         getattr(L, name)
     _LIB = L
@@ -220,6 +221,12 @@ class Handle:
         out = np.empty(n, np.int32) if out is None else out
         self._chk(self.L.clm_cell_coords(self.h, _addr(x)[0], n, 0, int(axis), _addr(out)[0]))
         return out
+
+    def select_layers(self, x, axis, ranges, merge, out_a, out_b, counts):
+        """one-pass face selection (torch CUDA tensors; enqueue only): see clm_select_layers."""
+        r = (C.c_int32 * 4)(*[int(v) for v in ranges])
+        self._chk(self.L.clm_select_layers(self.h, _addr(x)[0], int(x.shape[0]), int(axis), r, 1 if merge else 0,
+                                           _addr(out_a)[0], _addr(out_b)[0], int(out_a.shape[0]), _addr(counts)[0]))
 
     def build(self):
         self._chk(self.L.clm_build(self.h))

@@ -161,6 +161,25 @@ template <class T> int Engine<T>::cell_coords(const void* xyz, int64_t n, int on
     return CLM_OK;
 }
 
+// one-pass face selection for the halo exchange (all pointers on the device, enqueue only)
+template <class T> int Engine<T>::select_layers(const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b,
+                                                int64_t capacity, int32_t* counts) {
+    if (!box_set) return fail(CLM_ERR_STATE, "clm_set_box must be called first");
+    if (axis < 0 || axis >= dim || !ranges || !counts || (n > 0 && (!xyz || !out_a || !out_b))) return fail(CLM_ERR_ARGUMENT, "bad argument");
+    if (n <= 0) return CLM_OK;
+    CLM_CK(cudaSetDevice(device));
+    GeomT<T> g;
+    fill_geom(box, g);
+    const int nb = (int)((n + 255) / 256);
+    const int4 r = make_int4(ranges[0], ranges[1], ranges[2], ranges[3]);
+    const int cap = (int)std::min<int64_t>(capacity, 0x7fffffff);
+    if (dim == 3) k_select_layers<T, 3><<<nb, 256, 0, stream>>>(g, (const T*)xyz, (int)n, axis, r, merge, (T*)out_a, (T*)out_b, cap, (int*)counts);
+    else k_select_layers<T, 2><<<nb, 256, 0, stream>>>(g, (const T*)xyz, (int)n, axis, r, merge, (T*)out_a, (T*)out_b, cap, (int*)counts);
+    CLM_CK(cudaGetLastError());
+    stats.launches += 1;
+    return CLM_OK;
+}
+
 template <class T> int Engine<T>::scan(const int* in, int* out, int n, int* total_slot, int* out_end) {
     const int nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
     CLM_CK(scan_partial.ensure((size_t)std::max(nb, 1)));
@@ -592,6 +611,7 @@ int clm_set_positions(clm_handle* h, int set, const void* xyz, int64_t n, int on
 int clm_build(clm_handle* h) { H_OR_FAIL; return h->e->build(); }
 int clm_set_foreign(clm_handle* h, int set, const void* xyz, int64_t n, int on_device) { H_OR_FAIL; return h->e->set_foreign(set, xyz, n, on_device); }
 int clm_cell_coords(clm_handle* h, const void* xyz, int64_t n, int on_device, int axis, int32_t* out) { H_OR_FAIL; return h->e->cell_coords(xyz, n, on_device, axis, out); }
+int clm_select_layers(clm_handle* h, const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b, int64_t capacity, int32_t* counts) { H_OR_FAIL; return h->e->select_layers(xyz, n, axis, ranges, merge, out_a, out_b, capacity, counts); }
 int clm_map_lj(clm_handle* h, const void* p, int flags, void* e, void* f) { H_OR_FAIL; return h->e->map_lj(p, flags, e, f); }
 int clm_map_coulomb(clm_handle* h, const void* wx, const void* wy, const void* k, int flags, void* e, void* f) { H_OR_FAIL; return h->e->map_coulomb(wx, wy, k, flags, e, f); }
 int clm_map_dist_hist(clm_handle* h, const void* width, int nbins, int flags, int64_t* counts) { H_OR_FAIL; return h->e->map_dist_hist(width, nbins, flags, counts); }

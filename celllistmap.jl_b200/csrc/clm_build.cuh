@@ -295,6 +295,46 @@ k_cell_coord(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, int 
     out[ip] = c;
 }
 
+// face selection of a slab decomposition in ONE pass: particles whose reference-cell layer along `axis` lies in
+// [r.x, r.y) are appended to list A, those in [r.z, r.w) to list B (merge != 0: either range -> list A, once).  Warp-aggregated
+// atomics; rows beyond `capacity` are counted but not written (the caller checks the counts).
+template <class T, int DIM>
+__global__ void __launch_bounds__(256)
+k_select_layers(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, int n, int axis, int4 r, int merge,
+                T* __restrict__ out_a, T* __restrict__ out_b, int capacity, int* __restrict__ counts) {
+    const int ip = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    bool in_a = false, in_b = false;
+    T x[DIM];
+    if (ip < n) {
+        T p[3];
+#pragma unroll
+        for (int k = 0; k < DIM; ++k) x[k] = pos[(size_t)ip * DIM + k];
+        place_particle<T, DIM>(g, x, p);
+        const T q = floor(xdiv(xsub(p[axis], g.cb_min[axis]), g.cs[axis]));
+        int c = (q >= T(-1) && q <= T(g.nc[axis])) ? (int)q : -1;
+        if (c == g.lcell - 1) c += 1;
+        if (c == g.nc[axis] - g.lcell) c -= 1;
+        in_a = (c >= r.x && c < r.y);
+        in_b = (c >= r.z && c < r.w);
+        if (merge) { in_a = in_a || in_b; in_b = false; }
+    }
+    auto append = [&](bool take, T* out, int* counter) {
+        const unsigned m = __ballot_sync(0xffffffffu, take);
+        if (m == 0u) return;
+        const int leader = __ffs(m) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(counter, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        const int slot = base + __popc(m & ((1u << lane) - 1u));
+        if (take && slot < capacity) {
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) out[(size_t)slot * DIM + k] = x[k];
+        }
+    };
+    append(in_a, out_a, counts);
+    append(in_b, out_b, counts + 1);
+}
+
 // number of reference cells holding a real particle (CellList.n_cells_with_real_particles)
 static __global__ void __launch_bounds__(256) k_count_flags(const int* __restrict__ flags, int n, int* __restrict__ out) {
     int c = 0;

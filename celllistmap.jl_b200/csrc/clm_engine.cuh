@@ -29,6 +29,7 @@ struct EngineBase {
     virtual int set_positions(int set, const void* xyz, int64_t n, int on_device) = 0;
     virtual int set_foreign(int set, const void* xyz, int64_t n, int on_device) = 0;
     virtual int cell_coords(const void* xyz, int64_t n, int on_device, int axis, int32_t* out) = 0;
+    virtual int select_layers(const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b, int64_t capacity, int32_t* counts) = 0;
     virtual int build() = 0;
     virtual int map_lj(const void* p, int flags, void* e, void* f) = 0;
     virtual int map_coulomb(const void* wx, const void* wy, const void* k, int flags, void* e, void* f) = 0;
@@ -123,6 +124,7 @@ template <class T> struct Engine : EngineBase {
     int set_positions(int set, const void* xyz, int64_t n, int on_device) override;
     int set_foreign(int set, const void* xyz, int64_t n, int on_device) override;
     int cell_coords(const void* xyz, int64_t n, int on_device, int axis, int32_t* out) override;
+    int select_layers(const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b, int64_t capacity, int32_t* counts) override;
     int build() override;
     int build_enqueue();
     int build_validate();

@@ -43,7 +43,7 @@ class SlabPlan:
     def face_masks(self, c, rank):
         """(to_lower, to_upper): which owned particles (cell layers c) the lower / upper neighbour needs."""
         lo, hi = self.bounds[rank], self.bounds[rank + 1]
-        return c < lo + self.lcell, c >= hi - self.lcell
+        return (c >= lo) & (c < lo + self.lcell), (c >= hi - self.lcell) & (c < hi)
 
     def neighbours(self, rank):
         return (rank - 1) % self.world, (rank + 1) % self.world
@@ -125,6 +125,7 @@ class SlabSystem:
         self._inner_cells = float(np.prod([max(1, int(b.nc[k]) - 2 * lcell - 1) for k in range(dim)]))
         self._lcell = lcell
         self._n_global = None
+        self._cap = None              # capacity of the fixed-size halo messages (set by the first, exact exchange)
         self.n_owned = 0
         self.n_foreign = 0
         self.ids = None
@@ -148,14 +149,7 @@ class SlabSystem:
     def update(self, x_owned, ids=None):
         """halo exchange + hand owned / foreign particles to the engine (nothing is built until the next map)."""
         x = torch.as_tensor(x_owned).to(self.device, self.tdtype).contiguous()
-        c = self.cell_layers(x).to(torch.int64)
-        to_lower, to_upper = self.plan.face_masks(c, self.rank)
-        payloads = [x] if ids is None else [x, torch.as_tensor(ids).to(self.device)]
-        got = exchange_halo(payloads, to_lower, to_upper, self.plan, self.rank, self.group)
-        self.x_owned, self.x_foreign = x, got[0].contiguous()
-        self.ids = None if ids is None else payloads[1]
-        self.foreign_ids = None if ids is None else got[1]
-        self.n_owned, self.n_foreign = int(x.shape[0]), int(self.x_foreign.shape[0])
+        self.n_owned = int(x.shape[0])
         if self._n_global is None:
             # the engine sizes its device grid from the particle density; a rank only sees its slab, so tell it the
             # global density (same rule as Engine::build: ~4 particles per device cell)
@@ -166,9 +160,73 @@ class SlabSystem:
             per_cell = self._n_global / self._inner_cells
             sub = int(np.floor(max(per_cell / 4.0, 1.0) ** (1.0 / self.dim) + 0.35))
             self.h.set_option("sub", max(1, min(sub, 7 // self._lcell)))
+        got = None
+        if ids is None and self.world > 1 and self._cap is not None and dist.get_backend(self.group) != "gloo":
+            got = self._exchange_fast(x)
+        if got is None:
+            c = self.cell_layers(x).to(torch.int64)
+            to_lower, to_upper = self.plan.face_masks(c, self.rank)
+            payloads = [x] if ids is None else [x, torch.as_tensor(ids).to(self.device)]
+            res = exchange_halo(payloads, to_lower, to_upper, self.plan, self.rank, self.group)
+            got = res[0].contiguous()
+            self.ids = None if ids is None else payloads[1]
+            self.foreign_ids = None if ids is None else res[1]
+            if self.world > 1:
+                # size the fixed-capacity messages of the fast path from what this exchange moved (50 % slack)
+                m = torch.tensor([max(int(to_lower.sum()), int(to_upper.sum()), int((to_lower | to_upper).sum()) if self.world == 2 else 0)],
+                                 dtype=torch.int64, device=self.device if dist.get_backend(self.group) != "gloo" else "cpu")
+                dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
+                self._alloc_fast(int(int(m) * 1.5) + 1024)
+        else:
+            self.ids = self.foreign_ids = None
+        self.x_owned, self.x_foreign = x, got
+        self.n_foreign = int(got.shape[0])
         self.h.set_positions(0, x)
         self.h.set_foreign(0, self.x_foreign)
         return self
+
+    def _alloc_fast(self, cap):
+        if self._cap is not None and cap <= self._cap:
+            return
+        d, t = self.device, self.tdtype
+        self._cap = cap
+        self._send = [torch.empty((cap, self.dim), dtype=t, device=d) for _ in range(2)]
+        self._recv = [torch.empty((cap, self.dim), dtype=t, device=d) for _ in range(2)]
+        self._cnt = torch.zeros(2, dtype=torch.int32, device=d)
+        self._rcnt = torch.zeros(2, dtype=torch.int32, device=d)
+
+    def _exchange_fast(self, x):
+        """halo exchange with ONE host synchronisation: the engine selects both faces in one pass into fixed-capacity
+        buffers, the buffers and their fill counts travel in one batch of NCCL send/recv, and only the received counts
+        are read back.  Returns None (caller falls back to the exact path) when a face outgrew the capacity."""
+        lo, hi = self.plan.bounds[self.rank], self.plan.bounds[self.rank + 1]
+        lower, upper = self.plan.neighbours(self.rank)
+        merge = self.world == 2
+        self._cnt.zero_()
+        self.h.select_layers(x, 0, (lo, lo + self._lcell, hi - self._lcell, hi), merge, self._send[0], self._send[1], self._cnt)
+        g = self.group
+        if merge:     # both faces go to the one peer as a single list
+            ops = [dist.P2POp(dist.isend, self._send[0], upper, g), dist.P2POp(dist.isend, self._cnt[0:1], upper, g),
+                   dist.P2POp(dist.irecv, self._recv[0], upper, g), dist.P2POp(dist.irecv, self._rcnt[0:1], upper, g)]
+        else:         # my lower face -> lower neighbour, my upper face -> upper neighbour; theirs come back
+            ops = [dist.P2POp(dist.isend, self._send[0], lower, g), dist.P2POp(dist.isend, self._cnt[0:1], lower, g),
+                   dist.P2POp(dist.isend, self._send[1], upper, g), dist.P2POp(dist.isend, self._cnt[1:2], upper, g),
+                   dist.P2POp(dist.irecv, self._recv[0], upper, g), dist.P2POp(dist.irecv, self._rcnt[0:1], upper, g),
+                   dist.P2POp(dist.irecv, self._recv[1], lower, g), dist.P2POp(dist.irecv, self._rcnt[1:2], lower, g)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        counts = torch.cat([self._cnt, self._rcnt]).cpu().tolist()      # the one synchronisation
+        if max(counts) > self._cap:
+            # a face outgrew the fixed-size messages (the density near a slab face rose by > 50 % since the first
+            # exchange): the rows beyond the capacity were not sent.  Every rank would have to agree on a fallback, which
+            # costs a collective per step; instead this is an error the caller resolves with reset_halo_capacity().
+            raise RuntimeError(f"halo capacity exceeded on rank {self.rank}: {max(counts)} rows > {self._cap}; call reset_halo_capacity() on every rank")
+        n_up, n_lo = counts[2], (0 if merge else counts[3])
+        return torch.cat([self._recv[0][:n_up], self._recv[1][:n_lo]], dim=0) if n_lo else self._recv[0][:n_up]
+
+    def reset_halo_capacity(self):
+        """the next update() takes the exact (collective) exchange again and re-sizes the fixed-capacity messages."""
+        self._cap = None
 
     # ---- catalogue entry points: local map + the reduction the output type needs ----
     def map_lj(self, c6, c12, forces=None, profile=False):

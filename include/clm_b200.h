@@ -131,6 +131,12 @@ CLM_API int clm_set_positions(clm_handle* h, int set, const void* aos_xyz, int64
  * Supported for orthorhombic and non-periodic cells (triclinic self-set systems need global-index tie-breaks). */
 CLM_API int clm_set_foreign(clm_handle* h, int set, const void* aos_xyz, int64_t n, int on_device);
 CLM_API int clm_cell_coords(clm_handle* h, const void* aos_xyz, int64_t n, int on_device, int axis, int32_t* cell_out);
+/* one-pass face selection for the halo exchange; every pointer except `ranges` is a DEVICE pointer and the call only
+ * enqueues.  Particles whose cell layer along `axis` is in [ranges[0], ranges[1]) are appended (AoS rows of T) to out_a,
+ * those in [ranges[2], ranges[3]) to out_b; merge != 0: either range -> out_a, each particle once.  counts_dev[0..1] must be
+ * zeroed by the caller and receive the list lengths; rows beyond `capacity` are counted but not written. */
+CLM_API int clm_select_layers(clm_handle* h, const void* aos_xyz, int64_t n, int axis, const int32_t ranges[4], int merge,
+                              void* out_a, void* out_b, int64_t capacity, int32_t* counts_dev);
 
 /* ---- UpdateCellList!  src/internals/CellLists.jl:727-927 ---------------------------------- */
 /* validates coordinates (NaN -> CLM_ERR_INVALID_COORDINATES with the 1-based index in the message),
