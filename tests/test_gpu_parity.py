@@ -409,3 +409,58 @@ def test_c2_full_size_properties(clm, dtype):
     sd_b, sd2_b, npairs_b = clm.pairwise(clm.SumDistances(), clm.ParticleSystem(xpositions=x2, unitcell=w["unitcell"], cutoff=w["cutoff"], output=None))
     if dtype == np.float64:
         assert abs(npairs_b - npairs) <= 2 and abs(sd2_b - sd2) <= 1e-9 * sd2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# capacity estimates that are too small: the engine must notice and repeat build / emission with the exact size
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_record_capacity_retry_clustered_corner(clm, oracle_mod, dtype):
+    """every particle sits in a corner of the cell and has 7 periodic images: 8x the records of the uniform estimate"""
+    rng = np.random.default_rng(77)
+    x = (0.45 * rng.random((6000, 3))).astype(dtype)
+    uc = np.array([10.0, 10.0, 10.0], dtype)
+    sys = clm.ParticleSystem(xpositions=x, unitcell=uc, cutoff=1.0, output=None)
+    assert sys.stats().n_total[0] == 8 * 6000
+    sd, sd2, n = clm.pairwise(clm.SumDistances(), sys)
+    o = oracle_mod.Oracle(x, 1.0, unitcell=uc, dtype=dtype)
+    assert n == o.sum_d_d2()[2]
+    # the retry also happens when the build is only enqueued behind a map (fresh system, first call is a map)
+    nl = clm.neighborlist(xpositions=x, cutoff=1.0, unitcell=uc)
+    assert_lists_identical(nl, o.neighborlist())
+    h = clm.Handle(3, dtype)
+    h.set_box(clm._capi.ORTHORHOMBIC, uc, 1.0, 1)
+    h.set_positions(0, x)
+    e, f = np.zeros(1, dtype), np.zeros((6000, 3), dtype)
+    h.map_lj(1e-4, 1e-8, e, f)          # first call on a dirty handle: enqueue, overflow, repeat
+    we, wf = oracle_mod.Oracle(x.astype(np.float64), 1.0, unitcell=uc.astype(np.float64)).lj(1e-4, 1e-8, forces=True)
+    assert np.abs(f - wf).max() <= (1e-9 if dtype == np.float64 else 2e-3) * np.abs(wf).max()
+    h.close()
+
+
+def test_neighborlist_capacity_retry_clustered(clm, oracle_mod):
+    """a dense blob in a large periodic cell has far more pairs than the uniform-density size hint"""
+    rng = np.random.default_rng(78)
+    x = 50.0 + 2.0 * rng.random((3000, 3))
+    nl = clm.neighborlist(xpositions=x, cutoff=1.5, unitcell=[100.0, 100.0, 100.0])
+    want = oracle_mod.Oracle(x, 1.5, unitcell=[100.0, 100.0, 100.0]).neighborlist()
+    assert len(want[0]) > 1_000_000
+    assert_lists_identical(nl, want)
+
+
+def test_device_outputs_accumulate(clm, oracle_mod):
+    """CLM_OUT_DEVICE without CLM_RESET adds onto the caller's device buffers"""
+    import torch
+    w = W.c2_argon(12, np.float64, cutoff=8.0)
+    n = w["x"].shape[0]
+    h = clm.Handle(3, np.float64)
+    h.set_box(clm._capi.ORTHORHOMBIC, w["unitcell"], w["cutoff"], 1)
+    h.set_positions(0, torch.from_numpy(w["x"]).cuda())
+    e = torch.full((1,), 5.0, dtype=torch.float64, device="cuda")
+    f = torch.ones((n, 3), dtype=torch.float64, device="cuda")
+    h.map_lj(w["c6"], w["c12"], e, f, reset=False)
+    h.map_lj(w["c6"], w["c12"], e, f, reset=False)
+    h.synchronize()
+    we, wf = oracle_mod.Oracle(w["x"], w["cutoff"], unitcell=w["unitcell"]).lj(w["c6"], w["c12"], forces=True)
+    assert abs(float(e) - (5.0 + 2 * we)) <= 1e-10 * abs(we)
+    assert np.abs(f.cpu().numpy() - (1.0 + 2 * wf)).max() <= 1e-10 * np.abs(wf).max()
+    h.close()
