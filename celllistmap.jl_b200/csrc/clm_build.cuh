@@ -97,78 +97,103 @@ __device__ __forceinline__ bool cell_of(const GeomT<T>& g, const T p[3], bool re
 // atomic per-cell cursor.  cell_nact[c] flags cells holding a record that can act as particle i of a
 // pair: real particles, and images living in a REFERENCE cell that holds a real particle (the reference sweeps
 // exactly those cells, self.jl:56-57); ref_real[] flags reference cells with a real particle.
+__device__ __forceinline__ float shfl_t(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ double shfl_t(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
 template <class T, int DIM, bool SCATTER>
 __global__ void __launch_bounds__(256)
 k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __restrict__ fpos, int n, int n_own, int* __restrict__ cell_cursor,
       int* __restrict__ cell_nact, int* __restrict__ ref_real, RecT<T>* __restrict__ rec, int rec_cap, int* __restrict__ dscal) {
     typedef TagT<T> TG;
-    const int ip = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ip >= n) return;
-    T x[DIM];
-    bool bad = false;
-    const T* src = (ip < n_own) ? pos + (size_t)ip * DIM : fpos + (size_t)(ip - n_own) * DIM;   // owned particles, then foreign ones
-#pragma unroll
-    for (int k = 0; k < DIM; ++k) { x[k] = src[k]; bad |= (x[k] != x[k]); }
-    if (bad) { if (!SCATTER) atomicMin(&dscal[DS_NAN], ip); return; }   // _validate_coordinates, CellOperations.jl:6-21
-    T p[3];
-    place_particle<T, DIM>(g, x, p);
-    int lin, rlin;
-    if (!cell_of<T, DIM>(g, p, true, lin, rlin)) { if (!SCATTER) atomicMin(&dscal[DS_OOB], ip); return; }
-    // cell_cursor: the per-cell histogram in the count pass; the per-cell write cursor (pre-loaded with the exclusive
-    // starts) in the scatter pass
-    const typename TG::type foreign = (ip >= n_own) ? TG::FOREIGN : (typename TG::type)0;
-    const int slot = atomicAdd(&cell_cursor[lin], 1);
-    if (!SCATTER) {
-        if (!foreign) cell_nact[lin] = 1;   // flags: plain stores, every writer stores the same value
-        ref_real[rlin] = 1;
-    } else if (slot < rec_cap) {
-        strec(&rec[slot], p[0], p[1], p[2], (typename TG::type)ip | TG::HOME | foreign);
-    }
-    if (g.cell_type == CLM_NONPERIODIC_CT) return;
-    // replicate_particle! (Box.jl:556-566): images x + aligned_cell*idx, idx in {-1,0,1}^N \ {0}, kept iff
-    // inside the computing box [cb_min, cb_max)
+    const int ip = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     constexpr int NIMG = (DIM == 3) ? 27 : 9;
     constexpr int CENTER = (DIM == 3) ? 13 : 4;
-    // orthorhombic cells: the shift of image index (i1,i2,i3) is (i1*L1, i2*L2, i3*L3) exactly, so which indices
-    // can land inside the computing box is decided per dimension; interior particles skip the enumeration
-    unsigned okmask = 0x7ffffffu;
-    if (!g.rotated && g.cell_type == CLM_ORTHO_CT) {
-        unsigned dimok[3] = {2u, 2u, 2u};   // bit (idx+1): idx allowed
+    T p[3] = {T(0), T(0), T(0)};
+    unsigned okmask = 0u;      // candidate images of this lane's particle (none for invalid / interior / non-periodic)
+    if (ip < n) {
+        T x[DIM];
+        bool bad = false;
+        const T* src = (ip < n_own) ? pos + (size_t)ip * DIM : fpos + (size_t)(ip - n_own) * DIM;   // owned particles, then foreign ones
 #pragma unroll
-        for (int k = 0; k < DIM; ++k) {
-            const T lo = xadd(p[k], g.shift[(k == 0) ? CENTER - 1 : (k == 1 ? CENTER - 3 : CENTER - 9)][k]);
-            const T hi = xadd(p[k], g.shift[(k == 0) ? CENTER + 1 : (k == 1 ? CENTER + 3 : CENTER + 9)][k]);
-            if (g.cb_min[k] <= lo && lo < g.cb_max[k]) dimok[k] |= 1u;
-            if (g.cb_min[k] <= hi && hi < g.cb_max[k]) dimok[k] |= 4u;
+        for (int k = 0; k < DIM; ++k) { x[k] = src[k]; bad |= (x[k] != x[k]); }
+        int lin = 0, rlin = 0;
+        if (bad) {
+            if (!SCATTER) atomicMin(&dscal[DS_NAN], ip);     // _validate_coordinates, CellOperations.jl:6-21
+        } else {
+            place_particle<T, DIM>(g, x, p);
+            if (!cell_of<T, DIM>(g, p, true, lin, rlin)) { if (!SCATTER) atomicMin(&dscal[DS_OOB], ip); bad = true; }
         }
-        if (dimok[0] == 2u && dimok[1] == 2u && (DIM == 2 || dimok[2] == 2u)) return;
-        // okmask bit (i0 + 3 i1 + 9 i2) = dimok0[i0] & dimok1[i1] & dimok2[i2], built by replication instead of a 27-step loop
-        const unsigned m0 = dimok[0] & 7u;                                   // bits i0
-        const unsigned m01 = ((dimok[1] & 1u) ? m0 : 0u) | ((dimok[1] & 2u) ? (m0 << 3) : 0u) | ((dimok[1] & 4u) ? (m0 << 6) : 0u);
-        okmask = (DIM == 2) ? m01 : (((dimok[2] & 1u) ? m01 : 0u) | ((dimok[2] & 2u) ? (m01 << 9) : 0u) | ((dimok[2] & 4u) ? (m01 << 18) : 0u));
+        if (!bad) {
+            // cell_cursor: the per-cell histogram in the count pass; the per-cell write cursor (pre-loaded with the
+            // exclusive starts) in the scatter pass
+            const typename TG::type foreign = (ip >= n_own) ? TG::FOREIGN : (typename TG::type)0;
+            const int slot = atomicAdd(&cell_cursor[lin], 1);
+            if (!SCATTER) {
+                if (!foreign) cell_nact[lin] = 1;   // flags: plain stores, every writer stores the same value
+                ref_real[rlin] = 1;
+            } else if (slot < rec_cap) {
+                strec(&rec[slot], p[0], p[1], p[2], (typename TG::type)ip | TG::HOME | foreign);
+            }
+            // replicate_particle! (Box.jl:556-566): images x + aligned_cell*idx, idx in {-1,0,1}^N \ {0}, kept iff inside the
+            // computing box [cb_min, cb_max).  Orthorhombic cells: the shift of image index (i1,i2,i3) is (i1*L1, i2*L2, i3*L3)
+            // exactly, so which indices can land inside the computing box is decided per dimension.
+            if (g.cell_type != CLM_NONPERIODIC_CT) {
+                okmask = (DIM == 3) ? 0x7ffffffu : 0x1ffu;
+                if (!g.rotated && g.cell_type == CLM_ORTHO_CT) {
+                    unsigned dimok[3] = {2u, 2u, 2u};   // bit (idx+1): idx allowed
+#pragma unroll
+                    for (int k = 0; k < DIM; ++k) {
+                        const T lo = xadd(p[k], g.shift[(k == 0) ? CENTER - 1 : (k == 1 ? CENTER - 3 : CENTER - 9)][k]);
+                        const T hi = xadd(p[k], g.shift[(k == 0) ? CENTER + 1 : (k == 1 ? CENTER + 3 : CENTER + 9)][k]);
+                        if (g.cb_min[k] <= lo && lo < g.cb_max[k]) dimok[k] |= 1u;
+                        if (g.cb_min[k] <= hi && hi < g.cb_max[k]) dimok[k] |= 4u;
+                    }
+                    // okmask bit (i0 + 3 i1 + 9 i2) = dimok0[i0] & dimok1[i1] & dimok2[i2], built by replication
+                    const unsigned m0 = dimok[0] & 7u;
+                    const unsigned m01 = ((dimok[1] & 1u) ? m0 : 0u) | ((dimok[1] & 2u) ? (m0 << 3) : 0u) | ((dimok[1] & 4u) ? (m0 << 6) : 0u);
+                    okmask = (DIM == 2) ? m01 : (((dimok[2] & 1u) ? m01 : 0u) | ((dimok[2] & 2u) ? (m01 << 9) : 0u) | ((dimok[2] & 4u) ? (m01 << 18) : 0u));
+                }
+                okmask &= ~(1u << CENTER);
+            }
+        }
     }
-    // only the candidate images are visited (a warp runs as many iterations as its busiest lane has candidates,
-    // typically 1-7 next to a face, instead of all 26)
-    okmask &= ~(1u << CENTER);
-    if (DIM == 2) okmask &= 0x1ffu;
-#pragma unroll 1
-    for (unsigned rest = okmask; rest != 0u; rest &= rest - 1u) {
-        const int img = __ffs(rest) - 1;
+    // The (particle, image) candidates of the WARP are dealt evenly to its lanes: a warp next to a cell face holds a
+    // handful of candidates in a few lanes, and would otherwise run as many divergent iterations as its busiest lane.
+    const int cnt = __popc(okmask);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int excl = incl - cnt;
+    for (int w0 = 0; w0 < total; w0 += 32) {
+        const int w = w0 + lane;
+        int s = 0;   // source lane: the first lane whose inclusive count exceeds w
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) { const int v = __shfl_sync(0xffffffffu, incl, s + step - 1); if (v <= w) s += step; }
+        s = min(s, 31);
+        const int k_th = w - __shfl_sync(0xffffffffu, excl, s);
+        const unsigned m = __shfl_sync(0xffffffffu, okmask, s);
+        const int ips = __shfl_sync(0xffffffffu, ip, s);
+        const T px = shfl_t(p[0], s), py = shfl_t(p[1], s), pz = shfl_t(p[2], s);
+        if (w >= total) continue;
+        const int img = (int)__fns(m, 0u, k_th + 1);
+        const T ps[3] = {px, py, pz};
         T q[3] = {T(0), T(0), T(0)};
         bool in = true;
 #pragma unroll
         for (int k = 0; k < DIM; ++k) {
-            q[k] = xadd(p[k], g.shift[img][k]);
+            q[k] = xadd(ps[k], g.shift[img][k]);
             in = in && (g.cb_min[k] <= q[k]) && (q[k] < g.cb_max[k]);
         }
         if (!in) continue;
         int lq, rq;
         if (!cell_of<T, DIM>(g, q, false, lq, rq)) continue;
+        const typename TG::type foreign = (ips >= n_own) ? TG::FOREIGN : (typename TG::type)0;
         const int qslot = atomicAdd(&cell_cursor[lq], 1);
         if (SCATTER && qslot < rec_cap) {
             const bool home = ref_real[rq] != 0;
             if (home && !foreign) cell_nact[lq] = 1;
-            strec(&rec[qslot], q[0], q[1], q[2], (typename TG::type)ip | TG::GHOST | foreign | (home ? TG::HOME : (typename TG::type)0));
+            strec(&rec[qslot], q[0], q[1], q[2], (typename TG::type)ips | TG::GHOST | foreign | (home ? TG::HOME : (typename TG::type)0));
         }
     }
 }
