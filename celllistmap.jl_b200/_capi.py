@@ -25,6 +25,7 @@ SYMBOLS = [
     "clm_set_positions", "clm_build", "clm_map_lj", "clm_map_coulomb", "clm_map_dist_hist", "clm_map_pairvel",
     "clm_map_mindist", "clm_map_sum_d_d2", "clm_neighborlist", "clm_neighborlist_copy", "clm_get_stats",
     "clm_set_option", "clm_version", "clm_measure_fma_peak", "clm_set_foreign", "clm_cell_coords", "clm_select_layers",
+    "clm_custom_compile", "clm_custom_log", "clm_map_custom", "clm_custom_check",
 ]
 
 
@@ -45,6 +46,10 @@ class Stats(C.Structure):
         ("n_tiles", C.c_int64), ("n_pairs", C.c_int64), ("n_cutoff_band", C.c_int64),
         ("build_ms", C.c_double), ("map_ms", C.c_double), ("sweep_ms", C.c_double), ("n_sm", C.c_int32), ("launches", C.c_int32),
     ]
+
+
+class CustomInfo(C.Structure):
+    _fields_ = [("nscalar", C.c_int32), ("npart", C.c_int32), ("naux", C.c_int32), ("hist", C.c_int32)]
 
 
 class ClmError(RuntimeError):
@@ -95,6 +100,11 @@ def lib():
     L.clm_set_foreign.argtypes = [vp, ci, vp, i64, ci]
     L.clm_cell_coords.argtypes = [vp, vp, i64, ci, ci, vp]
     L.clm_select_layers.argtypes = [vp, vp, i64, ci, C.POINTER(C.c_int32), ci, vp, vp, i64, vp]
+    L.clm_custom_compile.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(CustomInfo)]
+    L.clm_custom_log.restype = C.c_char_p
+    L.clm_custom_log.argtypes = [vp]
+    L.clm_map_custom.argtypes = [vp, C.c_int32, vp, ci, vp, vp, ci, ci, vp, vp, vp, vp]
+    L.clm_custom_check.argtypes = [C.c_char_p, C.c_char_p, ci, C.c_char_p, i64]
     for name in SYMBOLS:
         getattr(L, name)
     _LIB = L
@@ -131,6 +141,17 @@ def measure_fma_peak(dtype, device=0):
     if code != 0:
         raise ClmError(code, "FMA microbenchmark failed")
     return t.value
+
+
+def custom_check(source, name, dtype=np.float64):
+    """compile-only check of a user pair function (every sweep mode; needs libnvrtc, no device).  Returns the NVRTC
+    log; raises ClmError if the source does not compile."""
+    buf = C.create_string_buffer(1 << 16)
+    code = lib().clm_custom_check(source.encode(), name.encode(), F32 if np.dtype(dtype) == np.float32 else F64, buf, len(buf))
+    log = buf.value.decode(errors="replace")
+    if code != 0:
+        raise ClmError(code, log)
+    return log
 
 
 class Handle:
@@ -281,6 +302,25 @@ class Handle:
     def map_sum_d_d2(self, sum_d, sum_d2, npairs, reset=True, profile=False):
         fl = self._flags(reset, (sum_d, sum_d2, npairs), profile)
         self._chk(self.L.clm_map_sum_d_d2(self.h, fl, _addr(sum_d)[0], _addr(sum_d2)[0], _addr(npairs)[0]))
+
+    def custom_compile(self, source, name):
+        """compile a user pair function (CUDA C++ source of a struct `name`, see include/clm_b200.h); returns
+        (functor_id, CustomInfo)."""
+        fid, info = C.c_int32(-1), CustomInfo()
+        self._chk(self.L.clm_custom_compile(self.h, source.encode(), name.encode(), C.byref(fid), C.byref(info)))
+        return fid.value, info
+
+    def custom_log(self):
+        return self.L.clm_custom_log(self.h).decode(errors="replace")
+
+    def map_custom(self, fid, params=(), aux_x=None, aux_y=None, scalars=None, per_particle=None, hist_counts=None, hist_sums=None,
+                   reset=True, profile=False):
+        par = np.ascontiguousarray(params, dtype=self.dtype).ravel()
+        fl = self._flags(reset, (scalars, per_particle, hist_counts, hist_sums, aux_x, aux_y), profile)
+        nbins = int(hist_counts.shape[0]) if hist_counts is not None else 0
+        self._chk(self.L.clm_map_custom(self.h, int(fid), par.ctypes.data_as(C.c_void_p) if par.size else None, int(par.size),
+                                        _addr(aux_x)[0], _addr(aux_y)[0], nbins, fl, _addr(scalars)[0], _addr(per_particle)[0],
+                                        _addr(hist_counts)[0], _addr(hist_sums)[0]))
 
     def neighborlist_count(self, profile=False):
         n = C.c_int64(0)

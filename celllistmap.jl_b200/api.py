@@ -29,7 +29,7 @@ __all__ = [
     "InPlaceNeighborList", "neighborlist_", "get_computing_box", "Box", "NeighborPair", "DimensionMismatch",
     "LJEnergy", "LJForces", "LJEnergyAndForces", "CoulombEnergy", "CoulombForces", "CoulombEnergyAndForces",
     "DistanceHistogram", "PairwiseVelocities", "MinimumDistanceMap", "SumDistances", "MinimumDistance",
-    "EnergyAndForces", "wrap_relative_to",
+    "EnergyAndForces", "wrap_relative_to", "CustomPairFunction", "CustomOutput",
 ]
 
 
@@ -237,6 +237,76 @@ class MinimumDistanceMap(_Functor):
             i[0], j[0], d[0] = sys.output.i, sys.output.j, sys.output.d
         sys._h.map_mindist(i, j, d, reset=reset)
         return MinimumDistance(i[0], j[0], d[0])
+
+
+class CustomOutput:
+    """compound output of a CustomPairFunction: `scalars` T[NSCALAR], `per_particle` (n, NPART) T, `hist_counts`
+    int64[nbins], `hist_sums` T[nbins]; fields the functor does not declare stay None."""
+    __slots__ = ("scalars", "per_particle", "hist_counts", "hist_sums")
+
+    def __init__(self, scalars=None, per_particle=None, hist_counts=None, hist_sums=None):
+        self.scalars, self.per_particle, self.hist_counts, self.hist_sums = scalars, per_particle, hist_counts, hist_sums
+
+
+class CustomPairFunction(_Functor):
+    """A user pair function: the GPU counterpart of passing an arbitrary closure to pairwise!(f, sys)
+    (src/API/pairwise.jl:48-63).  `source` is CUDA C++ defining a stateless struct `name` (interface in
+    include/clm_b200.h, csrc/clm_custom.cuh); it is compiled at run time with NVRTC into the same sweep kernel the
+    catalogue uses.  `params` (<= 16 numbers) are handed to the functor as par[]; `aux` / `aux_y` are (n, NAUX)
+    per-particle side arrays of the two sets.  Output: a CustomOutput with the default `+` reduction
+    (src/API/parallel_custom.jl:53-54, :116-123, :213)."""
+
+    def __init__(self, source, name, params=(), aux=None, aux_y=None):
+        self.source, self.name, self.params, self.aux, self.aux_y = source, name, tuple(params), aux, aux_y
+        self._compiled = {}   # handle -> (functor id, info)
+
+    def check(self, dtype=np.float64):
+        """compile-only check (needs libnvrtc, no device); returns the NVRTC log."""
+        try:
+            return _capi.custom_check(self.source, self.name, dtype)
+        except ClmError as e:
+            _raise(e)
+
+    def _get(self, sys):
+        key = id(sys._h)
+        if key not in self._compiled:
+            self._compiled[key] = sys._h.custom_compile(self.source, self.name)
+        return self._compiled[key]
+
+    def info(self, sys):
+        i = self._get(sys)[1]
+        return {"nscalar": i.nscalar, "npart": i.npart, "naux": i.naux, "hist": i.hist}
+
+    def run(self, sys, reset):
+        fid, info = self._get(sys)
+        out, T, n = sys.output, sys.dtype, len(sys.xpositions)
+        if not isinstance(out, CustomOutput):
+            raise TypeError("CustomPairFunction needs a CustomOutput as output")
+        ok = lambda a, shape, dt: isinstance(a, np.ndarray) and a.dtype == dt and a.shape == shape and a.flags["C_CONTIGUOUS"]
+        if info.nscalar and not ok(out.scalars, (info.nscalar,), T):
+            raise DimensionMismatch(f"output.scalars must be a contiguous ({info.nscalar},) {T} array")
+        if info.npart and not ok(out.per_particle, (n, info.npart), T):
+            raise DimensionMismatch(f"output.per_particle must be a contiguous ({n}, {info.npart}) {T} array (resize it with resize_output)")
+        if info.hist:
+            if not (isinstance(out.hist_counts, np.ndarray) and out.hist_counts.ndim == 1 and ok(out.hist_counts, out.hist_counts.shape, np.int64)
+                    and ok(out.hist_sums, out.hist_counts.shape, T)):
+                raise DimensionMismatch("output.hist_counts / hist_sums must be contiguous int64[nbins] / T[nbins] arrays")
+        ax = ay = None
+        if info.naux:
+            if self.aux is None:
+                raise ValueError("the functor reads per-particle side arrays: aux is required")
+            ax = np.ascontiguousarray(self.aux, dtype=T).reshape(-1, info.naux)
+            if ax.shape[0] != n:
+                raise DimensionMismatch("aux must have one row per particle")
+            if sys.ypositions is not None:
+                if self.aux_y is None:
+                    raise ValueError("aux_y is required for a two-set system")
+                ay = np.ascontiguousarray(self.aux_y, dtype=T).reshape(-1, info.naux)
+                if ay.shape[0] != len(sys.ypositions):
+                    raise DimensionMismatch("aux_y must have one row per particle of the second set")
+        sys._h.map_custom(fid, self.params, ax, ay, out.scalars if info.nscalar else None, out.per_particle if info.npart else None,
+                          out.hist_counts if info.hist else None, out.hist_sums if info.hist else None, reset=reset)
+        return out
 
 
 def _check_force_output(sys, f):
@@ -454,8 +524,8 @@ class ParticleSystem:
 def pairwise(f, sys, *, show_progress=False, reset=True):
     """pairwise!(f, sys; show_progress, reset) (src/API/pairwise.jl:48-63)."""
     if not isinstance(f, _Functor):
-        raise TypeError("f must be one of the compiled-in catalogue functors (arbitrary closures are out of scope: "
-                        "SURVEY.md §2 row 13)")
+        raise TypeError("f must be one of the compiled-in catalogue functors or a CustomPairFunction (CUDA C++ source compiled "
+                        "at run time); Python closures cannot run on the device (SURVEY.md §2 row 13)")
     sys._sync()
     try:
         sys.output = f.run(sys, reset)
@@ -497,12 +567,14 @@ def update(sys, *, positions=None, xpositions=None, ypositions=None, cutoff=None
 def resize_output(sys, n):
     """resize_output!(sys, n) (src/API/updating.jl:18-25): array outputs follow the particle count."""
     out = sys.output
-    arr = out.forces if isinstance(out, EnergyAndForces) else out
+    arr = out.forces if isinstance(out, EnergyAndForces) else (out.per_particle if isinstance(out, CustomOutput) else out)
     new = np.zeros((n,) + arr.shape[1:], arr.dtype)
     m = min(n, arr.shape[0])
     new[:m] = arr[:m]
     if isinstance(out, EnergyAndForces):
         out.forces = new
+    elif isinstance(out, CustomOutput):
+        out.per_particle = new
     else:
         sys.output = new
     return sys

@@ -45,6 +45,7 @@ template <class T> Engine<T>::~Engine() {
     for (auto& s : sets) { s.pos.release(); s.fpos.release(); s.rec.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
     dscal.release(); scan_partial.release(); row_ntiles.release(); row_range.release(); tiles.release(); d_res.release();
     d_hcount.release(); nl.release(); d_hsum.release(); d_rbins.release(); d_forces.release(); d_minmax.release(); d_minpart.release(); d_minres.release();
+    custom_store_free(custom_store);
     if (h_dscal) cudaFreeHost(h_dscal);
     if (h_res) cudaFreeHost(h_res);
     if (ev0) cudaEventDestroy(ev0);
@@ -474,14 +475,14 @@ template <class T> int Engine<T>::store_real(void* out, const double* dev_src, c
     }
     return CLM_OK;
 }
-template <class T> int Engine<T>::store_i64(int64_t* out, const unsigned long long* dev_src, const unsigned long long* host_src, int n, int flags) {
+template <class T> int Engine<T>::store_i64(int64_t* out, const unsigned long long* dev_src, const unsigned long long* host_src, int n, int flags, int shift) {
     if (!out) return CLM_OK;
     if (flags & CLM_OUT_DEVICE) {
-        k_store_i64<<<(n + 127) / 128, 128, 0, stream>>>((long long*)out, dev_src, n, (flags & CLM_RESET) ? 0 : 1);
+        k_store_i64<<<(n + 127) / 128, 128, 0, stream>>>((long long*)out, dev_src, n, (flags & CLM_RESET) ? 0 : 1, shift);
         CLM_CK(cudaGetLastError());
         stats.launches += 1;
     } else {
-        for (int k = 0; k < n; ++k) out[k] = ((flags & CLM_RESET) ? 0 : out[k]) + (int64_t)host_src[k];
+        for (int k = 0; k < n; ++k) out[k] = ((flags & CLM_RESET) ? 0 : out[k]) + (int64_t)(host_src[k] >> shift);
     }
     return CLM_OK;
 }
@@ -496,9 +497,10 @@ template <class T> int Engine<T>::forces_begin(void* forces_out, int flags, Forc
     fo.forces = d_forces.p; fo.accumulate = 0;
     return CLM_OK;
 }
-template <class T> int Engine<T>::forces_end(void* forces_out, int flags) {
+template <class T> int Engine<T>::forces_end(void* forces_out, int flags) { return part_end(forces_out, flags, dim); }
+template <class T> int Engine<T>::part_end(void* forces_out, int flags, int ncomp) {
     if (flags & CLM_OUT_DEVICE) return CLM_OK;
-    const size_t cnt = (size_t)sets[0].n * dim;
+    const size_t cnt = (size_t)sets[0].n * ncomp;
     if (cnt == 0) return CLM_OK;
     if (flags & CLM_RESET) {
         CLM_CK(cudaMemcpyAsync(forces_out, d_forces.p, cnt * sizeof(T), cudaMemcpyDeviceToHost, stream));
@@ -622,4 +624,12 @@ int clm_neighborlist(clm_handle* h, int flags, int64_t* n) { H_OR_FAIL; return h
 int clm_neighborlist_copy(clm_handle* h, void* rec, int64_t cap, int on_device) { H_OR_FAIL; return h->e->neighborlist_copy(rec, cap, on_device); }
 int clm_get_stats(clm_handle* h, clm_stats* o) { H_OR_FAIL; return h->e->get_stats(o); }
 int clm_set_option(clm_handle* h, const char* name, int64_t v) { H_OR_FAIL; return h->e->set_option(name, v); }
+int clm_custom_compile(clm_handle* h, const char* source, const char* name, int32_t* id, clm_custom_info* info) { H_OR_FAIL; return h->e->custom_compile(source, name, id, info); }
+const char* clm_custom_log(clm_handle* h) { return h ? h->e->custom_log() : ""; }
+int clm_map_custom(clm_handle* h, int32_t id, const void* params, int nparams, const void* aux_x, const void* aux_y, int nbins, int flags,
+                   void* scalars_out, void* part_out, int64_t* hist_counts, void* hist_sums) {
+    H_OR_FAIL;
+    return h->e->map_custom(id, params, nparams, aux_x, aux_y, nbins, flags, scalars_out, part_out, hist_counts, hist_sums);
+}
+int clm_custom_check(const char* source, const char* name, int dtype, char* log, int64_t log_capacity) { return clm::custom_check(source, name, dtype, log, log_capacity); }
 }

@@ -10,8 +10,15 @@
 //                     so one row of cells along it is ONE contiguous range of rec[].
 //   tiles[n_tiles]    work items: TI consecutive records of one row + the range of cells they span.
 #pragma once
+#ifdef __CUDACC_RTC__   // run-time compilation of user pair functions (clm_rtc.cu): no host headers
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 
 namespace clm {
 

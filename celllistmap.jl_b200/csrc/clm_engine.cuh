@@ -41,7 +41,13 @@ struct EngineBase {
     virtual int neighborlist_copy(void* rec, int64_t cap, int on_device) = 0;
     virtual int get_stats(clm_stats* out) = 0;
     virtual int set_option(const char* name, int64_t v) = 0;
+    virtual int custom_compile(const char* source, const char* name, int32_t* id_out, clm_custom_info* info) = 0;
+    virtual const char* custom_log() = 0;
+    virtual int map_custom(int32_t id, const void* params, int nparams, const void* aux_x, const void* aux_y, int nbins, int flags,
+                           void* scalars_out, void* part_out, int64_t* hist_counts, void* hist_sums) = 0;
 };
+void custom_store_free(void* store);   // clm_rtc.cu
+int custom_check(const char* source, const char* name, int dtype, char* log_out, int64_t log_cap);
 
 #define CLM_CK(call)                                                                                          \
     do {                                                                                                      \
@@ -138,6 +144,12 @@ template <class T> struct Engine : EngineBase {
     int neighborlist_copy(void* rec, int64_t cap, int on_device) override;
     int get_stats(clm_stats* out) override;
     int set_option(const char* name, int64_t v) override;
+    // run-time compiled user pair functions (clm_rtc.cu)
+    void* custom_store = nullptr;
+    int custom_compile(const char* source, const char* name, int32_t* id_out, clm_custom_info* info) override;
+    const char* custom_log() override;
+    int map_custom(int32_t id, const void* params, int nparams, const void* aux_x, const void* aux_y, int nbins, int flags,
+                   void* scalars_out, void* part_out, int64_t* hist_counts, void* hist_sums) override;
 
     // ---- helpers shared by the map translation units ----
     int scan(const int* in, int* out, int n, int* total_slot, int* out_end);
@@ -147,9 +159,10 @@ template <class T> struct Engine : EngineBase {
     int fetch_results();                              // result block -> h_res (synchronises)
     int gather_aux(int set, const T* aux_host_or_dev, int ncomp, bool rotate, bool on_device);
     int store_real(void* out, const double* dev_src, const double* host_src, int n, double scale, int flags);
-    int store_i64(int64_t* out, const unsigned long long* dev_src, const unsigned long long* host_src, int n, int flags);
+    int store_i64(int64_t* out, const unsigned long long* dev_src, const unsigned long long* host_src, int n, int flags, int shift = 0);   // shift: counts of a full-shell self sweep are halved
     int forces_begin(void* forces_out, int flags, ForceOut<T>& fo);
     int forces_end(void* forces_out, int flags);
+    int part_end(void* out, int flags, int ncomp);     // per-particle output of `ncomp` components: staging buffer -> caller's host array
 
     SweepArgs<T> make_args() const {
         SweepArgs<T> a;

@@ -188,11 +188,13 @@ template <class T, bool FORCES, bool NORM> struct FLJ {
         double e = block_sum((double)a.e, sm);
         if (threadIdx.x == 0) atomicAdd(&res->f[RB_ENERGY], e * (NORM ? (double)escale : 1.0));
     }
+#ifndef __CUDACC_RTC__
     static bool can_normalise(T c6_, T c12_) { return c6_ > T(0) && c12_ > T(0); }   // host
     void set(T c6_, T c12_) {   // host
         c6 = c6_; c12 = c12_; s2 = T(0); escale = T(1); fscale = T(1);
         if (NORM) { s2 = std::cbrt(c12 / c6); escale = c6 * c6 / c12; fscale = T(6) * escale; }
     }
+#endif
 };
 
 // Coulomb-like k*w_i*w_j/d (test/examples/gravitational_potential.jl:30-34, gravitational_force.jl:38-44)
@@ -716,9 +718,9 @@ template <class T> __global__ void k_store_real(T* __restrict__ out, const doubl
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) out[k] = (T)((accumulate ? (double)out[k] : 0.0) + scale * src[k]);
 }
-static __global__ void k_store_i64(long long* __restrict__ out, const unsigned long long* __restrict__ src, int n, int accumulate) {
+static __global__ void k_store_i64(long long* __restrict__ out, const unsigned long long* __restrict__ src, int n, int accumulate, int shift) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < n) out[k] = (accumulate ? out[k] : 0ll) + (long long)src[k];
+    if (k < n) out[k] = (accumulate ? out[k] : 0ll) + (long long)(src[k] >> shift);
 }
 
 }  // namespace clm

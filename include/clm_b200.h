@@ -166,6 +166,43 @@ CLM_API int clm_map_mindist(clm_handle* h, int flags, int64_t* i_out, int64_t* j
 /* test functor f1/f2 (test/modules/Testing.jl:23-26): sum of d, sum of d2, number of pairs */
 CLM_API int clm_map_sum_d_d2(clm_handle* h, int flags, void* sum_d, void* sum_d2, int64_t* npairs);
 
+/* ---- _pairwise! with a USER pair function ---------------------------- */
+/* The reference's pairwise!(f, sys) (src/API/pairwise.jl:48-63) takes an arbitrary Julia closure f(pair, output) and
+ * reduces per-task output copies with copy_output / reset_output! / reducer! = `+` for numbers, static vectors and
+ * arrays of them (src/API/parallel_custom.jl:53-54, :116-123, :213).  Here the closure body is CUDA C++ source text,
+ * compiled at run time with NVRTC (libnvrtc is opened on first use) into the same sm_100a sweep kernel the catalogue
+ * uses.  `source` defines a stateless struct `functor_name`:
+ *
+ *     struct MyPair {
+ *         static constexpr int NSCALAR = 1;   // scalar outputs summed over the pairs                    (0..8)
+ *         static constexpr int NPART   = 3;   // per-particle output components, output[i] += ...        (0..4)
+ *         static constexpr int NAUX    = 1;   // per-particle input components (masses, charges, ...)    (0..4)
+ *         static constexpr int HIST    = 0;   // 1: histogram output, counts[bin] += 1; sums[bin] += v
+ *         template <class T, class Out>
+ *         __device__ void operator()(const clm::NeighborPair<T>& p, const T* par, Out& out) const {
+ *             // p.i, p.j (1-based), p.x[3], p.y[3] (y - x = minimum-image vector), p.d2, p.d(), p.ai[], p.aj[]
+ *             out.add_scalar(0, ...); out.add_i(k, ...); out.add_hist(bin, v);
+ *         }
+ *     };
+ *
+ * NeighborPair mirrors src/API/NeighborPair.jl:19-33.  Functors without per-particle outputs visit every pair once, in
+ * the reference's own mode; functors with per-particle outputs are called once per ORDERED pair (full shell, add_i adds
+ * to particle p.i only) and their scalar / histogram outputs are halved for self-set systems: the functor must be
+ * symmetric under the exchange of the two particles, as in the reference, where the orientation of (i, j) is unspecified.
+ * Errors: CLM_ERR_ARGUMENT with the NVRTC log in clm_last_error() / clm_custom_log() when the source does not compile,
+ * CLM_ERR_UNSUPPORTED when libnvrtc cannot be opened. */
+typedef struct clm_custom_info { int32_t nscalar, npart, naux, hist; } clm_custom_info;
+CLM_API int clm_custom_compile(clm_handle* h, const char* source, const char* functor_name, int32_t* functor_id, clm_custom_info* info_out);
+CLM_API const char* clm_custom_log(clm_handle* h); /* NVRTC log of the last compilation of this handle */
+/* params: nparams (<= 16) values of T handed to the functor as par[]; aux_x / aux_y: n x NAUX side arrays of the two sets
+ * (aux_y only for two-set systems); scalars_out: NSCALAR values of T; per_particle_out: n_x x NPART of T;
+ * hist_counts[nbins] / hist_sums[nbins] (T).  CLM_RESET / CLM_OUT_DEVICE as for the catalogue maps. */
+CLM_API int clm_map_custom(clm_handle* h, int32_t functor_id, const void* params, int nparams, const void* aux_x, const void* aux_y,
+                           int nbins, int flags, void* scalars_out, void* per_particle_out, int64_t* hist_counts, void* hist_sums);
+/* compile-only check of a user pair function for every sweep mode (needs libnvrtc, no device); the NVRTC log is
+ * copied into log (NUL-terminated, truncated to log_capacity) */
+CLM_API int clm_custom_check(const char* source, const char* functor_name, int dtype, char* log, int64_t log_capacity);
+
 /* ---- neighborlist!  src/API/neighborlist.jl:217-231, push_pair! internals/neighborlist.jl:67-76 */
 /* Two phases so the caller can resize!() its own Vector{Tuple{Int,Int,T}}: clm_neighborlist builds the
  * list on the device and returns its length; clm_neighborlist_copy writes the 24-byte records

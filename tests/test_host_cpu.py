@@ -81,3 +81,34 @@ def test_workload_generators_are_reproducible():
     full = W.c2_argon(8, np.float64)["x"]
     key = lambda x: sorted(map(tuple, np.round(x, 9).tolist()))
     assert key(np.concatenate(parts)) == key(full)
+
+
+USER_SRC = """
+struct Coordination {   // per-particle neighbour count + sum of 1/d
+    static constexpr int NSCALAR = 1, NPART = 1, NAUX = 0, HIST = 0;
+    template <class T, class Out>
+    __device__ void operator()(const clm::NeighborPair<T>& p, const T* par, Out& out) const {
+        out.add_scalar(0, par[0] / p.d());
+        out.add_i(0, T(1));
+    }
+};
+"""
+
+
+def test_user_pair_function_compiles_without_a_device(clm):
+    """clm_custom_check: NVRTC compiles a user functor against the embedded device headers for every sweep mode and
+    both precisions (compile only -- no compute, no device)."""
+    f = clm.CustomPairFunction(USER_SRC, "Coordination", params=(1.0,))
+    try:
+        f.check(np.float32)
+    except RuntimeError as e:
+        if "libnvrtc not found" in str(e):
+            pytest.skip("libnvrtc is not installed here")
+        raise
+    f.check(np.float64)
+    with pytest.raises(ValueError, match=r"user_pair_function\(\d+\): error"):
+        clm.CustomPairFunction(USER_SRC.replace("p.d()", "p.dist()"), "Coordination").check()
+    with pytest.raises(ValueError, match="NSCALAR must be in 0..8"):
+        clm.CustomPairFunction(USER_SRC.replace("NSCALAR = 1", "NSCALAR = 9"), "Coordination").check()
+    with pytest.raises(ValueError, match="identifier"):
+        clm.CustomPairFunction(USER_SRC, "not an identifier").check()
