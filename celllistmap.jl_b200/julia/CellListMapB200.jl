@@ -2,9 +2,10 @@
 #
 # Keeps the CellListMap.jl 0.10 API surface for the cutoff-pair path -- ParticleSystem, pairwise!, update!,
 # resize_output!, neighborlist, InPlaceNeighborList, neighborlist!, NeighborPair, get_computing_box -- with the pair
-# function restricted to the compiled-in catalogue (LJ / Coulomb energy and forces, distance histogram, mean pairwise
-# velocity, minimum distance, neighbour list).  All compute happens in hand-written sm_100a CUDA kernels behind the
-# C ABI; there is no CUDA.jl codegen and no CPU fallback.
+# function either one of the compiled-in catalogue (LJ / Coulomb energy and forces, distance histogram, mean pairwise
+# velocity, minimum distance, neighbour list) or a CustomPairFunction: CUDA C++ source text that the library compiles at
+# run time with NVRTC into the same sweep kernel (a Julia closure cannot run on the device).  All compute happens in
+# hand-written sm_100a CUDA kernels behind the C ABI; there is no CUDA.jl codegen and no CPU fallback.
 #
 # STATUS: source-complete, NOT executed in the build environment (no Julia toolchain there or on the GPU box);
 # the same ABI is exercised end to end by the Python twin celllistmap.jl_b200/api.py.
@@ -14,7 +15,8 @@ using StaticArrays
 
 export ParticleSystem, pairwise!, update!, resize_output!, neighborlist, neighborlist!, InPlaceNeighborList,
        NeighborPair, get_computing_box, LJEnergy, LJForces, LJEnergyAndForces, CoulombEnergy, CoulombEnergyAndForces,
-       DistanceHistogram, PairwiseVelocities, MinimumDistanceMap, MinimumDistance, EnergyAndForces
+       DistanceHistogram, PairwiseVelocities, MinimumDistanceMap, MinimumDistance, EnergyAndForces,
+       CustomPairFunction, CustomOutput
 
 const libclm = get(ENV, "CLM_B200_LIB", joinpath(@__DIR__, "..", "libclm_b200.so"))
 
@@ -140,7 +142,7 @@ function update!(sys::ParticleSystem{N,T}; positions=nothing, xpositions=nothing
     return sys
 end
 
-resize_output!(sys::ParticleSystem, n::Int) = (resize!(sys.output isa EnergyAndForces ? sys.output.forces : sys.output, n); sys)
+resize_output!(sys::ParticleSystem, n::Int) = (resize!(sys.output isa EnergyAndForces ? sys.output.forces : (sys.output isa CustomOutput ? sys.output.per_particle : sys.output), n); sys)
 
 function get_computing_box(sys::ParticleSystem{N,T}) where {N,T}
     _sync!(sys)
@@ -206,8 +208,48 @@ function pairwise!(::MinimumDistanceMap, sys::ParticleSystem{N,T}; show_progress
     _check(sys.handle, ccall((:clm_map_mindist, libclm), Cint, (Ptr{Cvoid}, Cint, Ref{Int64}, Ref{Int64}, Ref{T}), sys.handle, _flags(reset), i, j, d))
     return sys.output = MinimumDistance{T}(i[], j[], d[])
 end
+# ---- user pair functions: CUDA C++ source compiled at run time (clm_custom_compile / clm_map_custom) ----------------
+struct ClmCustomInfo; nscalar::Int32; npart::Int32; naux::Int32; hist::Int32; end
+"""A user pair function: `source` defines a stateless struct `name` (interface: include/clm_b200.h).  `params` (<= 16)
+reach the functor as par[]; `aux`/`aux_y` are per-particle side arrays (Vector{T} or Vector{SVector{NAUX,T}})."""
+mutable struct CustomPairFunction
+    source::String; name::String; params::Vector{Float64}; aux; aux_y
+    compiled::Dict{Ptr{Cvoid},Tuple{Int32,ClmCustomInfo}}
+end
+CustomPairFunction(source, name; params=Float64[], aux=nothing, aux_y=nothing) =
+    CustomPairFunction(source, name, collect(Float64, params), aux, aux_y, Dict{Ptr{Cvoid},Tuple{Int32,ClmCustomInfo}}())
+"""Output of a CustomPairFunction, reduced with `+` like the reference's default reducer (src/API/parallel_custom.jl:213)."""
+mutable struct CustomOutput{T,P}
+    scalars::Vector{T}          # NSCALAR
+    per_particle::P             # Vector{SVector{NPART,T}} (or Vector{T} for NPART == 1), one entry per particle of set x
+    hist_counts::Vector{Int}
+    hist_sums::Vector{T}
+end
+function _compiled(f::CustomPairFunction, sys::ParticleSystem)
+    get!(f.compiled, sys.handle) do
+        id = Ref{Int32}(-1); info = Ref{ClmCustomInfo}()
+        _check(sys.handle, ccall((:clm_custom_compile, libclm), Cint, (Ptr{Cvoid}, Cstring, Cstring, Ref{Int32}, Ref{ClmCustomInfo}), sys.handle, f.source, f.name, id, info))
+        (id[], info[])
+    end
+end
+function pairwise!(f::CustomPairFunction, sys::ParticleSystem{N,T}; show_progress=false, reset=true) where {N,T}
+    _sync!(sys)
+    id, info = _compiled(f, sys)
+    out = sys.output::CustomOutput
+    info.nscalar > 0 && length(out.scalars) != info.nscalar && throw(DimensionMismatch("output.scalars must have NSCALAR entries"))
+    info.npart > 0 && length(out.per_particle) != length(sys.xpositions) && throw(DimensionMismatch("output.per_particle must have one entry per particle (resize_output!)"))
+    info.naux > 0 && isnothing(f.aux) && throw(ArgumentError("the functor reads per-particle side arrays: aux is required"))
+    par = T.(f.params)
+    ptr(a) = isnothing(a) ? C_NULL : Ptr{Cvoid}(pointer(a))
+    GC.@preserve par f out _check(sys.handle, ccall((:clm_map_custom, libclm), Cint,
+        (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Int64}, Ptr{Cvoid}),
+        sys.handle, id, isempty(par) ? C_NULL : ptr(par), length(par), ptr(f.aux), ptr(f.aux_y), info.hist != 0 ? length(out.hist_counts) : 0, _flags(reset),
+        info.nscalar > 0 ? ptr(out.scalars) : C_NULL, info.npart > 0 ? ptr(out.per_particle) : C_NULL,
+        info.hist != 0 ? pointer(out.hist_counts) : Ptr{Int64}(C_NULL), info.hist != 0 ? ptr(out.hist_sums) : C_NULL))
+    return out
+end
 pairwise!(f::Function, sys::ParticleSystem; kw...) =
-    throw(ArgumentError("arbitrary pair closures are outside the compiled-in catalogue of CellListMapB200 (LJ/Coulomb, histogram, pair velocity, minimum distance, neighbour list)"))
+    throw(ArgumentError("a Julia closure cannot run on the device: use a catalogue functor (LJ/Coulomb, histogram, pair velocity, minimum distance, neighbour list) or a CustomPairFunction (CUDA C++ source compiled at run time)"))
 
 # ---- neighbour lists (src/API/neighborlist.jl:12-15, :84-111, :159-169, :217-231, :314-340) ------------------------
 mutable struct InPlaceNeighborList{N,T}
