@@ -43,7 +43,7 @@ template <class T> Engine<T>::~Engine() {
     cudaSetDevice(device);
     if (own_stream) cudaStreamSynchronize(own_stream);
     for (auto& s : sets) { s.pos.release(); s.fpos.release(); s.rec.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
-    dscal.release(); scan_partial.release(); row_ntiles.release(); row_range.release(); tiles.release(); d_res.release();
+    dscal.release(); tiles.release(); d_res.release();
     d_hcount.release(); nl.release(); d_hsum.release(); d_rbins.release(); d_forces.release(); d_minmax.release(); d_minpart.release(); d_minres.release();
     custom_store_free(custom_store);
     if (h_dscal) cudaFreeHost(h_dscal);
@@ -181,16 +181,6 @@ template <class T> int Engine<T>::select_layers(const void* xyz, int64_t n, int 
     return CLM_OK;
 }
 
-template <class T> int Engine<T>::scan(const int* in, int* out, int n, int* total_slot, int* out_end) {
-    const int nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
-    CLM_CK(scan_partial.ensure((size_t)std::max(nb, 1)));
-    k_scan_local<<<nb, SCAN_THREADS, 0, stream>>>(in, out, n, scan_partial.p);
-    k_scan_partials<<<1, SCAN_THREADS, 0, stream>>>(scan_partial.p, nb, total_slot, out_end);
-    k_scan_add<<<nb, SCAN_THREADS, 0, stream>>>(out, n, scan_partial.p);
-    CLM_CK(cudaGetLastError());
-    stats.launches += 3;
-    return CLM_OK;
-}
 
 // UpdateCellList! (CellLists.jl:727-927; non-periodic NonPeriodicCells.jl:93-230)
 // clm_build: enqueue + validate, repeated when the record-capacity estimate was too small
@@ -284,6 +274,8 @@ template <class T> int Engine<T>::build_enqueue() {
     nfast = (int)box.nc[dim - 1] * sub; nmid = (int)((dim == 3) ? box.nc[1] : box.nc[0]) * sub; nslow = (int)((dim == 3) ? box.nc[0] * sub : 1);
     ncells = (int64_t)nfast * nmid * nslow;
     nrows = ncells / nfast;
+    const int64_t ncp = nrows * (nfast + 1);   // per-cell arrays have a row pitch of nfast + 1 (clm_build.cuh)
+    if (ncp + 2 > 0x7fffffff) return fail(CLM_ERR_UNSUPPORTED, "device cell grid too large");
     // stencil rows: a row offset (dslow, dmid) is at least d_perp away; partners can only sit within
     // sqrt(cutoff^2 - d_perp^2) along the row (1e-4 relative slack covers coordinate rounding at cell borders)
     {
@@ -323,11 +315,10 @@ template <class T> int Engine<T>::build_enqueue() {
             DevSet<T>& S = sets[s];
             const size_t want = std::max<size_t>((size_t)((double)(S.n + S.n_foreign) * img_factor * 1.25) + 4096, (size_t)std::max<int64_t>(S.n_tot, 1));
             CLM_CK(S.rec.ensure(want));
-            CLM_CK(S.cell_start.ensure((size_t)ncells + 2));
-            CLM_CK(S.counters.ensure((size_t)(2 * ncells + nref)));
-            S.cell_count = S.counters.p; S.cell_nact = S.counters.p + ncells; S.ref_real = S.counters.p + 2 * ncells;
-            CLM_CK(cudaMemsetAsync(S.counters.p, 0, (size_t)(2 * ncells + nref) * sizeof(int), stream));
-            CLM_CK(cudaMemsetAsync(S.cell_start.p, 0, sizeof(int), stream));
+            CLM_CK(S.cell_start.ensure((size_t)ncp + 2));
+            CLM_CK(S.counters.ensure((size_t)(2 * ncp + nref)));
+            S.cell_count = S.counters.p; S.cell_nact = S.counters.p + ncp; S.ref_real = S.counters.p + 2 * ncp;
+            CLM_CK(cudaMemsetAsync(S.counters.p, 0, (size_t)(2 * ncp + nref) * sizeof(int), stream));
             int* ds = dscal.p + s * DS_SET_STRIDE;
             const int64_t nall = S.n + S.n_foreign;
             const int nb = (int)((nall + 255) / 256);
@@ -337,9 +328,11 @@ template <class T> int Engine<T>::build_enqueue() {
                 CLM_CK(cudaGetLastError());
                 stats.launches += 1;
             }
-            // exclusive prefix written one slot up: the scatter pass uses cell_start[c + 1] as the cursor of cell c, which
-            // leaves cell_start[0 .. ncells] = the exclusive starts once every record is placed (no second counter array)
-            if (int rc = scan(S.cell_count, S.cell_start.p + 1, (int)ncells, ds + DS_NTOT, S.cell_start.p + 1 + ncells)) return rc;
+            // per-row starts, written one slot up: the scatter pass uses cell_start[c + 1] as the cursor of cell c, which
+            // leaves the row's exclusive starts behind once every record is placed (no second counter array)
+            k_row_starts<<<(int)((nrows * 32 + 255) / 256), 256, 0, stream>>>(S.cell_count, S.cell_start.p, nfast, (int)nrows, ds + DS_NTOT);
+            CLM_CK(cudaGetLastError());
+            stats.launches += 1;
             if (nall > 0) {
                 if (dim == 3) k_bin<T, 3, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), ds);
                 else k_bin<T, 2, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), ds);
@@ -347,22 +340,14 @@ template <class T> int Engine<T>::build_enqueue() {
                 stats.launches += 1;
             }
         }
-        CLM_CK(row_ntiles.ensure((size_t)nrows + 1));
-        CLM_CK(row_range.ensure((size_t)nrows));
         tiles_upper = (int64_t)(sets[0].rec.cap / tile_i) + nrows + 1;
         CLM_CK(tiles.ensure((size_t)tiles_upper));
-        {
-            const int nb = (int)((nrows * 32 + 255) / 256);
-            k_rows<<<nb, 256, 0, stream>>>(sets[0].cell_nact, sets[0].cell_start.p, nfast, (int)nrows, tile_i, row_ntiles.p, row_range.p, dscal.p);
-            stats.launches += 1;
-            for (int s = 0; s < nsets; ++s) {
-                k_count_flags<<<(int)std::min<int64_t>(1024, (nref + 255) / 256), 256, 0, stream>>>(sets[s].ref_real, (int)nref, dscal.p + s * DS_SET_STRIDE + DS_NCELLS_REAL);
-                stats.launches += 1;
-            }
-            CLM_CK(cudaGetLastError());
-            if (int rc = scan(row_ntiles.p, row_ntiles.p, (int)nrows, dscal.p + DS_NTILES, nullptr)) return rc;
-            const int nbt = (int)((tiles_upper + 255) / 256);
-            k_tiles<<<nbt, 256, 0, stream>>>(row_ntiles.p, row_range.p, sets[0].cell_start.p, nfast, nmid, (int)nrows, tile_i, dscal.p, tiles.p);
+        for (int s = 0; s < nsets; ++s) {
+            // set 0: tiles + real-cell count; set 1 (the partner set of a two-set system): real-cell count only
+            const int rows = (s == 0) ? (int)nrows : 0;
+            const int nb = (int)std::max<int64_t>(((int64_t)rows * 32 + 255) / 256, std::min<int64_t>(256, (nref + 255) / 256));
+            k_row_tiles<<<nb, 256, 0, stream>>>(sets[s].cell_nact, sets[s].cell_start.p, nfast, nmid, rows, tile_i, tiles.p, (int)std::min<int64_t>(tiles_upper, 0x7fffffff), dscal.p + s * DS_SET_STRIDE,
+                                               sets[s].ref_real, (int)nref);
             CLM_CK(cudaGetLastError());
             stats.launches += 1;
         }

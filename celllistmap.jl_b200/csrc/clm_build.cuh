@@ -4,11 +4,16 @@
 //
 // The reference builds an array of heap-allocated per-cell vectors; here the list is ONE
 // counting sort into a cell-sorted packed record array:
-//   k_bin_count   : wrap + rotate each particle, enumerate its 3^N-1 lattice images, keep those inside
+//   k_bin<count>  : wrap + rotate each particle, enumerate its 3^N-1 lattice images, keep those inside
 //                   the computing box, histogram real+image particles per cell (global atomics)
-//   scan          : exclusive prefix over cells (3 small kernels, reduce-then-scan)
-//   k_bin_scatter : same traversal, records scattered to cell_start[c] + atomic cursor
-//   k_rows/k_tiles: row-aligned work items for the sweep
+//   k_row_starts  : one warp per ROW of device cells: prefix of the row's counts; the row's base comes from one
+//                   atomicAdd on the record counter, so rows are contiguous but placed in arbitrary order -- the
+//                   sweep only ever reads record ranges inside one row.  Replaces a 3-kernel global scan.
+//   k_bin<scatter>: same traversal, records scattered to the per-cell atomic cursor
+//   k_row_tiles   : one warp per row: the row's active record range cut into tiles, appended to the tile array with
+//                   one atomicAdd per row (tile order is irrelevant: tiles are dealt out by a work counter)
+// Every per-cell array is laid out with a row pitch of nx + 1 entries: cell_start[row * (nx + 1) + x] is the first
+// record of cell x of the row and entry nx is the end of the row.
 // All of it is HBM/latency bound integer + a few dozen flops per particle: no tensor cores.
 // Algorithmic bytes per particle: read N*sizeof(T) twice, write (1+g)*sizeof(Rec),
 // plus 8*n_cells for the histogram/prefix arrays, g = image fraction.
@@ -20,6 +25,7 @@ namespace clm {
 constexpr int IDX_NONE = 0x7fffffff;
 // device scalar block (ints)
 enum { DS_NAN = 0, DS_OOB = 1, DS_NTOT = 2, DS_NTILES = 3, DS_WORK = 4, DS_NCELLS_REAL = 5, DS_COUNT = 16 };
+constexpr int DS_SET_STRIDE_DEV = 6;   // the scalar block of the second set starts at dscal + 6
 
 // p = rotation * (M * frac(M \ x)), every operation rounded separately in T
 // (CellLists.jl:944-945; CellOperations.jl:56-66, :91-94).  Non-periodic: coordinates are used as given.
@@ -88,7 +94,7 @@ __device__ __forceinline__ bool cell_of(const GeomT<T>& g, const T p[3], bool re
         }
         if (c < 0 || c >= g.nc[k]) return false;
         ref_lin = ref_lin * g.nc[k] + c;
-        dev_lin = dev_lin * (g.nc[k] * g.sub) + c * g.sub + sc;
+        dev_lin = dev_lin * (g.nc[k] * g.sub + ((k == DIM - 1) ? 1 : 0)) + c * g.sub + sc;   // row pitch nx + 1
     }
     return true;
 }
@@ -198,107 +204,80 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
     }
 }
 
-// ---- exclusive scan of int32 (reduce-then-scan, 4096 items per block) -------------------------------
-constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 16, SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
-
-__device__ __forceinline__ int block_exclusive_scan_256(int v, int* total) {
-    __shared__ int wsum[8];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) wsum[w] = inc;
-    __syncthreads();
-    int woff = 0, tot = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { int s = wsum[k]; if (k < w) woff += s; tot += s; }
-    *total = tot;
-    __syncthreads();
-    return woff + inc - v;
-}
-
-static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_local(const int* __restrict__ in, int* __restrict__ out, int n, int* __restrict__ partial) {
-    const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
-    int v[SCAN_ITEMS], s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? in[base + k] : 0; s += v[k]; }
-    int total;
-    int off = block_exclusive_scan_256(s, &total);
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) out[base + k] = off; off += v[k]; }
-    if (threadIdx.x == 0) partial[blockIdx.x] = total;
-}
-// one block: exclusive scan of the per-block totals (any count), grand total to *total_out and out_end
-static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_partials(int* __restrict__ partial, int nb, int* __restrict__ total_out, int* __restrict__ out_end) {
-    __shared__ int carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    for (int b0 = 0; b0 < nb; b0 += SCAN_THREADS) {
-        const int i = b0 + threadIdx.x;
-        const int v = (i < nb) ? partial[i] : 0;
-        int total;
-        const int ex = block_exclusive_scan_256(v, &total);
-        const int carry = carry_s;
-        if (i < nb) partial[i] = carry + ex;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + total;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) { *total_out = carry_s; if (out_end) *out_end = carry_s; }
-}
-static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(int* __restrict__ out, int n, const int* __restrict__ partial) {
-    const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
-    const int add = partial[blockIdx.x];
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) if (base + k < n) out[base + k] += add;
-}
-
-// ---- rows and tiles -----------------------------------------------------------------------------------
-// one warp per row of device cells: first/last cell holding a record that can act as particle i -> the record range
-// [cell_start[first], cell_start[last+1]) whose entries act as particle i, and its tile count.
+// ---- row starts ------------------------------------------------------------------------------------------
+// One warp per row of device cells.  cs = cell_start + 1 is the cursor array of the scatter pass: the cursor of cell x
+// of a row is cs[row * px + x], pre-loaded with the cell's first record; once every record is placed it holds the
+// cell's END, i.e. cell_start[row * px + x + 1] = start of cell x + 1, and cell_start[row * px] (never incremented)
+// stays the start of the row: no second counter array.
 static __global__ void __launch_bounds__(256)
-k_rows(const int* __restrict__ cell_nact, const int* __restrict__ cell_start, int nx, int nrows, int tile_i,
-       int* __restrict__ row_ntiles, int2* __restrict__ row_range, int* __restrict__ dscal) {
+k_row_starts(const int* __restrict__ cell_count, int* __restrict__ cell_start, int nx, int nrows, int* __restrict__ ntot) {
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (row >= nrows) return;
-    const int base = row * nx;
-    int first = IDX_NONE, last = -1, nreal_cells = 0;
+    const int px = nx + 1;
+    const int* cnt = cell_count + (size_t)row * px;
+    int* cs = cell_start + (size_t)row * px;
+    int total = 0;
+    for (int c = lane; c < nx; c += 32) total += cnt[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    int base = 0;
+    if (lane == 0) base = (total > 0) ? atomicAdd(ntot, total) : 0;
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane == 0) cs[0] = base;
+    for (int c0 = 0; c0 < nx; c0 += 32) {
+        const int c = c0 + lane;
+        const int v = (c < nx) ? cnt[c] : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (c < nx) cs[c + 1] = base + inc - v;    // cursor of cell c = its first record
+        base += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
+// ---- tiles ------------------------------------------------------------------------------------------------
+// One warp per row: first/last cell holding a record that can act as particle i -> the record range
+// [cell_start[first], cell_start[last + 1]) cut into tiles of tile_i records, appended to the tile array.  The threads
+// also count the reference cells holding a real particle (CellList.n_cells_with_real_particles).
+static __global__ void __launch_bounds__(256)
+k_row_tiles(const int* __restrict__ cell_nact, const int* __restrict__ cell_start, int nx, int ny, int nrows, int tile_i,
+            Tile* __restrict__ tiles, int tiles_cap, int* __restrict__ dscal, const int* __restrict__ ref_flags, int nref) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = gtid >> 5, lane = threadIdx.x & 31;
+    {
+        int c = 0;
+        for (int i = gtid; i < nref; i += gridDim.x * blockDim.x) c += (ref_flags[i] != 0);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0 && c) atomicAdd(&dscal[DS_NCELLS_REAL], c);
+    }
+    if (row >= nrows) return;
+    const int px = nx + 1;
+    const int* act = cell_nact + (size_t)row * px;
+    const int* cs = cell_start + (size_t)row * px;   // cs[c] <= k < cs[c+1]  <=>  record k lives in cell c
+    int first = IDX_NONE, last = -1;
     for (int c = lane; c < nx; c += 32)
-        if (cell_nact[base + c] > 0) { first = min(first, c); last = max(last, c); ++nreal_cells; }
+        if (act[c] > 0) { first = min(first, c); last = max(last, c); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
         last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-        nreal_cells += __shfl_xor_sync(0xffffffffu, nreal_cells, o);
     }
-    if (lane == 0) {
-        int a = 0, b = 0;
-        if (last >= 0) { a = cell_start[base + first]; b = cell_start[base + last + 1]; }
-        if (row_range) {
-            row_range[row] = make_int2(a, b);
-            row_ntiles[row] = (b - a + tile_i - 1) / tile_i;
-        }
+    if (last < 0) return;
+    const int a = cs[first], b = cs[last + 1];
+    const int ntiles = (b - a + tile_i - 1) / tile_i;
+    int base = 0;
+    if (lane == 0 && ntiles > 0) base = atomicAdd(&dscal[DS_NTILES], ntiles);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    auto cell_x = [&](int k) { int lo = first, hi = last; while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (cs[mid] <= k) lo = mid; else hi = mid - 1; } return lo; };
+    for (int t = lane; t < ntiles; t += 32) {
+        const int k0 = a + t * tile_i;
+        const int cnt = min(tile_i, b - k0);
+        Tile tl;
+        tl.k0 = k0; tl.cnt = cnt; tl.yz = (row % ny) | ((row / ny) << 16);
+        tl.cx = cell_x(k0) | (cell_x(k0 + cnt - 1) << 16);
+        if (base + t < tiles_cap) tiles[base + t] = tl;   // beyond the capacity only when the record capacity overflowed: the build is repeated
     }
-}
-
-static __global__ void __launch_bounds__(256)
-k_tiles(const int* __restrict__ row_tile_start, const int2* __restrict__ row_range, const int* __restrict__ cell_start,
-        int nx, int ny, int nrows, int tile_i, const int* __restrict__ dscal, Tile* __restrict__ tiles) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= dscal[DS_NTILES]) return;
-    // row = last r with row_tile_start[r] <= t
-    int lo = 0, hi = nrows - 1;
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (row_tile_start[mid] <= t) lo = mid; else hi = mid - 1; }
-    const int row = lo;
-    const int2 rr = row_range[row];
-    const int k0 = rr.x + (t - row_tile_start[row]) * tile_i;
-    const int cnt = min(tile_i, rr.y - k0);
-    const int* cs = cell_start + (size_t)row * nx;   // cs[c] <= k < cs[c+1]  <=>  record k lives in cell c
-    auto cell_x = [&](int k) { int a = 0, b = nx - 1; while (a < b) { const int mid = (a + b + 1) >> 1; if (cs[mid] <= k) a = mid; else b = mid - 1; } return a; };
-    Tile tl;
-    tl.k0 = k0; tl.cnt = cnt; tl.yz = (row % ny) | ((row / ny) << 16);
-    tl.cx = cell_x(k0) | (cell_x(k0 + cnt - 1) << 16);
-    tiles[t] = tl;
 }
 
 // reference-cell index of every particle along reference dimension `axis` (0-based, after wrapping and the
@@ -358,15 +337,6 @@ k_select_layers(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, i
     };
     append(in_a, out_a, counts);
     append(in_b, out_b, counts + 1);
-}
-
-// number of reference cells holding a real particle (CellList.n_cells_with_real_particles)
-static __global__ void __launch_bounds__(256) k_count_flags(const int* __restrict__ flags, int n, int* __restrict__ out) {
-    int c = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += (flags[i] != 0);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
 // per-block min/max of the coordinates (limits(), CellOperations.jl:262-324): out[b][0..2] = min, [3..5] = max

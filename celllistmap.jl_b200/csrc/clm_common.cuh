@@ -4,10 +4,11 @@
 //   rec[n_total]      cell-sorted packed particle records (x, y, z, tag): one 128-bit (F32) or two
 //                     128-bit (F64) loads per particle; image ("ghost") particles are materialised
 //                     exactly as the reference does (internals/Box.jl:556-566), with the same tag.
-//   cell_start[nf+1]  exclusive prefix of per-cell counts over the DEVICE grid.  The device grid is the
-//                     reference grid (Box.jl:209-220) with every reference cell split into `sub` sub-cells
-//                     per dimension (sub = 1: identical grids); the LAST reference dimension runs fastest,
-//                     so one row of cells along it is ONE contiguous range of rec[].
+//   cell_start[]      first record of every cell of the DEVICE grid, row pitch nx + 1 (entry nx = end of the row).
+//                     The device grid is the reference grid (Box.jl:209-220) with every reference cell split into
+//                     `sub` sub-cells per dimension (sub = 1: identical grids); the LAST reference dimension runs
+//                     fastest, so one row of cells along it is ONE contiguous range of rec[] (rows themselves are
+//                     placed in arbitrary order: their bases come from an atomic counter, clm_build.cuh).
 //   tiles[n_tiles]    work items: TI consecutive records of one row + the range of cells they span.
 #pragma once
 #ifdef __CUDACC_RTC__   // run-time compilation of user pair functions (clm_rtc.cu): no host headers

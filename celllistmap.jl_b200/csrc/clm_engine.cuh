@@ -14,7 +14,7 @@
 namespace clm {
 
 constexpr int CLM_RETRY_INTERNAL = -1;   // never crosses the ABI: build + map must be repeated with the grown capacity
-constexpr int DS_SET_STRIDE = 6;   // dscal block of set y starts at dscal + 6
+constexpr int DS_SET_STRIDE = DS_SET_STRIDE_DEV;   // dscal block of set y starts at dscal + 6
 
 struct EngineBase {
     std::string err;
@@ -79,7 +79,7 @@ template <class T> struct DevSet {
     int64_t n_foreign = 0;
     DBuf<RecT<T>> rec;       // cell-sorted records, real + image particles
     int64_t n_tot = 0, n_cells_real = 0;
-    DBuf<int> cell_start;    // ncells + 2 entries: [0 .. ncells] = exclusive starts after the scatter pass
+    DBuf<int> cell_start;    // row pitch nfast + 1: [row * pitch + x] = first record of cell x, entry nfast = end of the row (after the scatter pass)
     DBuf<int> counters;      // one memset: [cell_count | cell_nact | ref_real]
     int *cell_count = nullptr, *cell_nact = nullptr, *ref_real = nullptr;
     DBuf<T> aux;             // per-record auxiliary data gathered for the map in flight
@@ -97,8 +97,7 @@ template <class T> struct Engine : EngineBase {
     T np_cutoff = 0;
     int np_lcell = 1;
     DevSet<T> sets[2];
-    DBuf<int> dscal, scan_partial, row_ntiles;
-    DBuf<int2> row_range;
+    DBuf<int> dscal;
     DBuf<Tile> tiles;
     int* h_dscal = nullptr;          // pinned
     DBuf<ResultBlock> d_res;
@@ -152,7 +151,6 @@ template <class T> struct Engine : EngineBase {
                    void* scalars_out, void* part_out, int64_t* hist_counts, void* hist_sums) override;
 
     // ---- helpers shared by the map translation units ----
-    int scan(const int* in, int* out, int n, int* total_slot, int* out_end);
     int sweep_mode() const { return two_sets ? MODE_ALL : (box.cell_type == CLM_TRICLINIC ? MODE_TRI : MODE_HALF); }
     int prepare_map(int flags);                       // build if needed, zero the result block and the work counter
     int finish_map(int flags);                        // CLM_PROFILE timing
@@ -171,6 +169,7 @@ template <class T> struct Engine : EngineBase {
         a.tiles = tiles.p; a.dscal = dscal.p; a.res = d_res.p;
         a.nx = nfast; a.ny = nmid; a.nz = nslow; a.lf = geom.lcell * geom.sub; a.sub = geom.sub; a.sub_magic = (unsigned)((0x100000000ull + (unsigned)geom.sub - 1) / (unsigned)geom.sub); a.self = two_sets ? 0 : 1;
         a.rc2 = geom.cutoff_sqr;
+        a.rec_cap_i = (int)std::min<size_t>(sets[0].rec.cap, 0x7fffffff); a.rec_cap_j = (int)std::min<size_t>(tg.rec.cap, 0x7fffffff);
         std::memcpy(a.hw, row_hw, sizeof(a.hw));
         {   // stencil row r -> (dslow, dmid)
             const int lf = a.lf, hww = 2 * lf + 1;

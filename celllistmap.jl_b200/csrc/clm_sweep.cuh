@@ -61,6 +61,8 @@ template <class T> struct SweepArgs {
     ResultBlock* res;
     int nx, ny, nz;      // device cells along the fast / middle / slow axis = reference dims (3,2,1) in 3-D, (2,1,-) in 2-D
     int lf, sub, self;   // lf = lcell * sub: stencil reach in device cells
+    int rec_cap_i, rec_cap_j;   // record capacities: a build whose record count overflowed them is repeated by the host,
+                                // and the sweep queued behind it must not touch the truncated arrays
     unsigned sub_magic;  // ceil(2^32 / sub): x / sub == __umulhi(x, sub_magic) for the cell indices in use
     T rc2;
     signed char hw[(2 * LF_MAX + 1) * (2 * LF_MAX + 1)];   // [dslow + lf][dmid + lf]: half-width along the row, -1 = skip
@@ -463,9 +465,26 @@ __device__ __forceinline__ RecT<double> ldrec_s(const RecT<double>* p) {
     return r;
 }
 
+// min / max over the particles of a tile (every j-slice holds a copy of the same TILE_I particles, so a whole-warp
+// reduction gives the same result): one CREDUX per value in FP32 (sm_100a redux.sync.min/max.f32), shuffles in FP64
+__device__ __forceinline__ float tile_min(float v) { float r; asm volatile("redux.sync.min.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ float tile_max(float v) { float r; asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v)); return r; }
+__device__ __forceinline__ double tile_min(double v) {
+#pragma unroll
+    for (int o = 1; o < TILE_I; o <<= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double tile_max(double v) {
+#pragma unroll
+    for (int o = 1; o < TILE_I; o <<= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
 // Row classes of one tile: skipped; DIRECT = swept straight from global memory with per-lane record thresholds
-// (MODE_HALF rows inside the home reference row, the own row of the full-shell self sweep, and every row of functors
-// that index per-record side arrays); STAGED = bulk-copied into the warp's shared-memory buffer and swept by one flat loop.
+// (MODE_HALF rows inside the home reference row); STAGED = bulk-copied into the warp's shared-memory buffer and swept
+// by one flat loop.  The own row of the full-shell self sweep is staged too: the tile's own records are blanked in the
+// staging buffer and the pairs inside the tile are evaluated from registers (shuffles), which needs no self test in the
+// flat loop.
 enum { ROW_SKIP = 0, ROW_DIRECT = 1, ROW_STAGED = 2 };
 
 template <class T, int MODE, class F>
@@ -489,6 +508,7 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
     uint32_t parity = 0;
     if (lane == 0) { mbar_init(mbar, 1); fence_proxy_async(); }
     __syncwarp();
+    if (a.dscal[DS_NTOT] > a.rec_cap_i || a.dscal[DS_SET_STRIDE_DEV + DS_NTOT] > a.rec_cap_j) return;   // overflowed build: results are discarded
     typename F::Acc acc;
     f.init(acc);
     const int ntiles = a.dscal[DS_NTILES];
@@ -516,23 +536,15 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
         T blo[3], bhi[3];
         {
             const T inf = CUDART_INF_T<T>();
-            blo[0] = c.active ? c.ri.x : inf; blo[1] = c.active ? c.ri.y : inf; blo[2] = c.active ? c.ri.z : inf;
-            bhi[0] = c.active ? c.ri.x : -inf; bhi[1] = c.active ? c.ri.y : -inf; bhi[2] = c.active ? c.ri.z : -inf;
-#pragma unroll
-            for (int o = 1; o < ti; o <<= 1) {   // slices hold copies of the same particles
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    blo[k] = fmin(blo[k], __shfl_xor_sync(0xffffffffu, blo[k], o));
-                    bhi[k] = fmax(bhi[k], __shfl_xor_sync(0xffffffffu, bhi[k], o));
-                }
-            }
+            blo[0] = tile_min(c.active ? c.ri.x : inf); blo[1] = tile_min(c.active ? c.ri.y : inf); blo[2] = tile_min(c.active ? c.ri.z : inf);
+            bhi[0] = tile_max(c.active ? c.ri.x : -inf); bhi[1] = tile_max(c.active ? c.ri.y : -inf); bhi[2] = tile_max(c.active ? c.ri.z : -inf);
         }
         const int iy = tl.yz & 0xffff, iz = tl.yz >> 16, tile_row = iz * a.ny + iy;
         const int cxa = tl.cx & 0xffff, cxb = tl.cx >> 16;
         // MODE_HALF: the reference cell of particle i along the row (the other two follow from the tile's row)
         int rfx_i = 0;
         if (MODE == MODE_HALF) {
-            const int* cs = a.cell_start_i + (size_t)tile_row * a.nx;
+            const int* cs = a.cell_start_i + (size_t)tile_row * (a.nx + 1);   // per-cell arrays: row pitch nx + 1 (clm_build.cuh)
             int cx = cxa;
             while (cx < cxb && cs[cx + 1] <= c.ki) ++cx;
             rfx_i = div_sub(cx);
@@ -568,14 +580,13 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                 }
                 if (use) {
                     own = ((dy == 0 && dz == 0) ? 1 : 0) | ((MODE == MODE_HALF && rel == 0) ? 2 : 0);
-                    rowbase = (z2 * a.ny + y2) * a.nx;
+                    rowbase = (z2 * a.ny + y2) * (a.nx + 1);
                     const int xa = max(cxa - w, 0), xb = min(cxb + w, a.nx - 1);
                     j0 = a.cell_start_j[rowbase + xa];
                     j1 = a.cell_start_j[rowbase + xb + 1];
                     if (j1 > j0) {
                         cls = ROW_STAGED;
                         if (MODE == MODE_HALF && rel == 0) cls = ROW_DIRECT;
-                        else if (MODE == MODE_ALL && (own & 1) && a.self) cls = ROW_DIRECT;
                     }
                 }
             }
@@ -607,7 +618,6 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                             ok = ok && ((jc >= thrA) ? !(gi && gj) : (jc >= thrB && !gi && (gj || jc > c.ki)));
                         }
                         else if (MODE == MODE_TRI) ok = ok && (idx_i < (rj.tag & TG::MASK));
-                        else if (SELF_ROW) ok = ok && (rj.tag != c.ri.tag);
                         RecT<T> aj = rj;
                         if constexpr (F::AUX) aj = ldrec(f.aux_j() + jc);
                         pair_body(rj, aj, jc, ok);
@@ -619,7 +629,7 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                     for (int s_ = 0; s_ < nfull; ++s_) { body(pj, jc, true); pj += nslice; jc += nslice; }
                     if (jc - c.slice < bj1) { const bool inb = jc < bj1; body(inb ? pj : a.rec_j + (bj1 - 1), inb ? jc : bj1 - 1, inb); }
                 };
-                if (MODE == MODE_ALL && (bown & 1) && a.self) run_row(TrueTag()); else run_row(FalseTag());
+                run_row(FalseTag());
             }
             // ---- staged rows: prefix of the segment lengths, then chunks of at most CAP records --------------------
             const int len = (cls == ROW_STAGED) ? (j1 - j0) : 0;
@@ -627,6 +637,12 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
             const int off = incl - len, total = __shfl_sync(0xffffffffu, incl, 31);
+            // full-shell self sweep: where the tile's own records sit in the staged sequence (-1: own row not in this batch)
+            int own_lo = -1;
+            if (MODE == MODE_ALL && a.self) {
+                const unsigned mown = __ballot_sync(0xffffffffu, (own & 1) && cls == ROW_STAGED);
+                if (mown) own_lo = __shfl_sync(0xffffffffu, off + (tl.k0 - j0), __ffs(mown) - 1);
+            }
             for (int c0 = 0; c0 < total; c0 += CAP) {
                 const int cn = min(total - c0, CAP);
                 const int lo = max(off, c0), hi = min(off + len, c0 + cn);
@@ -639,35 +655,44 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                 mbar_wait(mbar, parity);
                 parity ^= 1u;
                 __syncwarp();
+                // far-away dummy records: (1) round the chunk up to a whole number of warp-wide cull steps (no bounds logic
+                // in the cull loop), (2) blank the tile's own records (full-shell self sweep: those pairs come from registers)
+                if (cn + lane < ((cn + 31) & ~31)) strec(buf + cn + lane, -huge_coord<T>(), T(0), T(0), (typename TG::type)0);
+                if (MODE == MODE_ALL && a.self) {
+                    const int pos = own_lo - c0 + lane;
+                    if (own_lo >= 0 && lane < tl.cnt && pos >= 0 && pos < cn) strec(buf + pos, -huge_coord<T>(), T(0), T(0), (typename TG::type)0);
+                }
+                __syncwarp();
                 // cull: keep the staged records within the cutoff of the tile's bounding box, compacted in place.
                 // The box distance is evaluated with the same operation order as the pair distance; rounding is
                 // monotone, so box distance <= pair distance for every particle i of the tile: no pair is lost.
                 int ns = 0;
-                for (int k0 = 0; k0 < cn; k0 += 32) {
-                    const int k = k0 + lane;
-                    const bool in = k < cn;
-                    const RecT<T> rq = ldrec_s(buf + (in ? k : 0));
-                    RecT<T> aq = rq;
-                    if constexpr (F::AUX) aq = ldrec_s(abuf + (in ? k : 0));
-                    const T ex = fmax(fmax(xsub(blo[0], rq.x), xsub(rq.x, bhi[0])), T(0));
-                    const T ey = fmax(fmax(xsub(blo[1], rq.y), xsub(rq.y, bhi[1])), T(0));
-                    const T ez = fmax(fmax(xsub(blo[2], rq.z), xsub(rq.z, bhi[2])), T(0));
-                    T dd;
-                    if (F::EXACT_D2) dd = xadd(xadd(xmul(ex, ex), xmul(ey, ey)), xmul(ez, ez));
-                    else dd = xfma(ez, ez, xfma(ey, ey, ex * ex));
-                    const bool keep = in && (dd <= a.rc2);
-                    const unsigned m = __ballot_sync(0xffffffffu, keep);   // every lane has read its record: in-place writes are safe
-                    if (keep) {
-                        const int pos = ns + __popc(m & ((1u << lane) - 1u));
-                        strec(buf + pos, rq.x, rq.y, rq.z, rq.tag);
-                        if constexpr (F::AUX) strec(abuf + pos, aq.x, aq.y, aq.z, aq.tag);
+                {
+                    const unsigned lt = (1u << lane) - 1u;
+                    const RecT<T>* q = buf + lane;
+                    for (int k0 = 0; k0 < cn; k0 += 32, q += 32) {
+                        const RecT<T> rq = ldrec_s(q);
+                        RecT<T> aq = rq;
+                        if constexpr (F::AUX) aq = ldrec_s(abuf + (q - buf));
+                        const T ex = fmax(fmax(xsub(blo[0], rq.x), xsub(rq.x, bhi[0])), T(0));
+                        const T ey = fmax(fmax(xsub(blo[1], rq.y), xsub(rq.y, bhi[1])), T(0));
+                        const T ez = fmax(fmax(xsub(blo[2], rq.z), xsub(rq.z, bhi[2])), T(0));
+                        T dd;
+                        if (F::EXACT_D2) dd = xadd(xadd(xmul(ex, ex), xmul(ey, ey)), xmul(ez, ez));
+                        else dd = xfma(ez, ez, xfma(ey, ey, ex * ex));
+                        const bool keep = (dd <= a.rc2);
+                        const unsigned m = __ballot_sync(0xffffffffu, keep);   // every lane has read its record: in-place writes are safe
+                        if (keep) {
+                            const int pos = ns + __popc(m & lt);
+                            strec(buf + pos, rq.x, rq.y, rq.z, rq.tag);
+                            if constexpr (F::AUX) strec(abuf + pos, aq.x, aq.y, aq.z, aq.tag);
+                        }
+                        ns += __popc(m);
                     }
-                    ns += __popc(m);
                 }
-                // dummy far-away records round the survivors up to a whole number of 4-step groups
-                constexpr int step4 = 4 * nslice;
-                const int cpad = ((ns + step4 - 1) / step4) * step4;
-                if (ns + lane < cpad) strec(buf + ns + lane, -huge_coord<T>(), T(0), T(0), (typename TG::type)0);
+                // dummy far-away records round the survivors up to a whole warp step (one record per j-slice)
+                const int nsteps = (ns + nslice - 1) / nslice;
+                if (ns + lane < nsteps * nslice) strec(buf + ns + lane, -huge_coord<T>(), T(0), T(0), (typename TG::type)0);
                 __syncwarp();
                 const RecT<T>* p = buf + c.slice;
                 auto sbody = [&](const RecT<T>* q) {
@@ -679,11 +704,30 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                     else if (MODE == MODE_TRI) ok = (idx_i < (rj.tag & TG::MASK));
                     pair_body(rj, aj, 0, ok);
                 };
-                for (int g = 0; g < cpad; g += step4) {
+                int g = 0;
+#pragma unroll 1
+                for (; g + 8 <= nsteps; g += 8) {
                     sbody(p); sbody(p + nslice); sbody(p + 2 * nslice); sbody(p + 3 * nslice);
-                    p += step4;
+                    sbody(p + 4 * nslice); sbody(p + 5 * nslice); sbody(p + 6 * nslice); sbody(p + 7 * nslice);
+                    p += 8 * nslice;
                 }
+#pragma unroll 1
+                for (; g < nsteps; ++g) { sbody(p); p += nslice; }
                 __syncwarp();
+            }
+        }
+        // full-shell self sweep: the pairs INSIDE the tile, partner records taken from the registers of the lanes that hold them
+        if (MODE == MODE_ALL && a.self) {
+#pragma unroll
+            for (int s_ = 0; s_ < TILE_I / NSLICE; ++s_) {
+                const int js = c.slice + NSLICE * s_;
+                RecT<T> rj;
+                rj.x = __shfl_sync(0xffffffffu, c.ri.x, js); rj.y = __shfl_sync(0xffffffffu, c.ri.y, js); rj.z = __shfl_sync(0xffffffffu, c.ri.z, js);
+                rj.tag = __shfl_sync(0xffffffffu, c.ri.tag, js);
+                const bool ok = (js != c.islot) && (js < tl.cnt);
+                RecT<T> aj = rj;
+                if constexpr (F::AUX) aj = ldrec(f.aux_j() + (tl.k0 + (js < tl.cnt ? js : 0)));
+                pair_body(rj, aj, tl.k0 + js, ok);
             }
         }
         f.end(ia, c);
