@@ -120,7 +120,15 @@ template <class T> struct FSum {
 
 template <class T> __device__ __forceinline__ T fast_rcp(T x);
 template <> __device__ __forceinline__ float fast_rcp<float>(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-template <> __device__ __forceinline__ double fast_rcp<double>(double x) { return 1.0 / x; }
+// FP64: hardware seed (MUFU.RCP64H, ~20 bits) + one cubic correction r0 * (1 + e + e^2), e = 1 - x r0: relative error
+// ~2^-60, three DFMAs.  The IEEE division 1.0 / x costs two more DFMAs and a slow-path branch for nothing the 1e-10
+// tolerance of the force maps could see.
+template <> __device__ __forceinline__ double fast_rcp<double>(double x) {
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(x));
+    const double e = fma(-x, r0, 1.0);
+    return fma(r0, fma(e, e, e), r0);
+}
 template <class T> __device__ __forceinline__ T xfma(T a, T b, T c);
 template <> __device__ __forceinline__ float xfma<float>(float a, float b, float c) { return fmaf(a, b, c); }
 template <> __device__ __forceinline__ double xfma<double>(double a, double b, double c) { return fma(a, b, c); }
@@ -487,8 +495,12 @@ __device__ __forceinline__ double tile_max(double v) {
 // flat loop.
 enum { ROW_SKIP = 0, ROW_DIRECT = 1, ROW_STAGED = 2 };
 
+// resident CTAs per SM the register allocation aims at (measured, C2 LJ forces: F32 8 CTAs = 64 registers 0.473 ms,
+// 10 CTAs = 48 registers 0.515 ms, 6 CTAs 0.488 ms; F64 is limited to 6 CTAs by its 8 KB staging buffers: 80 registers,
+// no spills 1.03 ms vs 1.11 ms with 64 registers)
+template <class T> struct SweepMinBlocks { static constexpr int value = (sizeof(T) == 4) ? 8 : 6; };
 template <class T, int MODE, class F>
-__global__ void __launch_bounds__(SWEEP_THREADS)
+__global__ void __launch_bounds__(SWEEP_THREADS, SweepMinBlocks<T>::value)
 k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
     typedef TagT<T> TG;
     extern __shared__ __align__(128) unsigned char dsm_raw[];
