@@ -51,6 +51,8 @@ template <class T> int Engine<T>::map_pairvel(const void* vx, const void* vy, co
     CLM_CK(cudaMemcpyAsync(d_rbins.p, rbins, ((size_t)nbins + 1) * sizeof(T), cudaMemcpyHostToDevice, stream));
     FVel<T> fn;
     fn.v_i = sets[0].aux.p; fn.v_j = sets[two_sets ? 1 : 0].aux.p; fn.rbins = d_rbins.p;
+    fn.inline_edges = (nbins + 1 <= VEL_EDGES_INLINE) ? 1 : 0;
+    for (int e = 0; e < VEL_EDGES_INLINE; ++e) fn.edges[e] = (fn.inline_edges && e <= nbins) ? ((const T*)rbins)[e] : T(0);
     const int aux_bytes = (SWEEP_THREADS / 32) * StageBytes<T>::value;   // side-array staging buffers precede the bins
     fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.off = aux_bytes; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = d_hsum.p;
     if (int rc = launch_reduce(fn, (size_t)aux_bytes + hist_smem(nbins, fn.hb.priv != 0, sizeof(T)))) return rc;

@@ -305,10 +305,13 @@ template <class T> struct FHist {
 template <class T> struct Vec4T;
 template <> struct Vec4T<float> { typedef float4 type; };
 template <> struct Vec4T<double> { typedef double4 type; };
+constexpr int VEL_EDGES_INLINE = 33;   // bin edges kept in the kernel parameters (constant bank) up to this many
 template <class T> struct FVel {
     const T* v_i;     // velocities gathered into record order, 4 components per record, aligned frame
     const T* v_j;
     const T* rbins;   // nbins+1 ascending edges (device)
+    T edges[VEL_EDGES_INLINE];   // the same edges when nbins + 1 <= VEL_EDGES_INLINE (inline_edges != 0)
+    int inline_edges;
     HistBins<T, true> hb;
     struct Acc {};
     struct IAcc { T vx, vy, vz; };
@@ -323,11 +326,16 @@ template <class T> struct FVel {
         if (hit) {
             const T r = xsqrt(d2);
             int first = 0;   // searchsortedfirst(rbins, r): number of edges < r
-            for (int e = 0; e <= hb.nbins; ++e) first += (__ldg(rbins + e) < r) ? 1 : 0;
+            if (inline_edges) {
+#pragma unroll 1
+                for (int e = 0; e <= hb.nbins; ++e) first += (edges[e] < r) ? 1 : 0;
+            } else {
+                for (int e = 0; e <= hb.nbins; ++e) first += (__ldg(rbins + e) < r) ? 1 : 0;
+            }
             const int b = first - 1;
             if (b >= 0 && b < hb.nbins) {
                 const T ux = p.vx - aj.x, uy = p.vy - aj.y, uz = p.vz - aj.z;
-                hb.add(b, ((ux * dx + uy * dy) + uz * dz) / r);
+                hb.add(b, ((ux * dx + uy * dy) + uz * dz) * fast_rcp<T>(r));   // sums have tolerance parity; counts are exact
             }
         }
     }
@@ -498,9 +506,10 @@ enum { ROW_SKIP = 0, ROW_DIRECT = 1, ROW_STAGED = 2 };
 // resident CTAs per SM the register allocation aims at (measured, C2 LJ forces: F32 8 CTAs = 64 registers 0.473 ms,
 // 10 CTAs = 48 registers 0.515 ms, 6 CTAs 0.488 ms; F64 is limited to 6 CTAs by its 8 KB staging buffers: 80 registers,
 // no spills 1.03 ms vs 1.11 ms with 64 registers)
-template <class T> struct SweepMinBlocks { static constexpr int value = (sizeof(T) == 4) ? 8 : 6; };
+// Functors that stage a side array double the staging memory (F32 4 CTAs, F64 3 CTAs per SM): no reason to squeeze their registers.
+template <class T, bool AUX> struct SweepMinBlocks { static constexpr int value = (sizeof(T) == 4) ? (AUX ? 4 : 8) : (AUX ? 3 : 6); };
 template <class T, int MODE, class F>
-__global__ void __launch_bounds__(SWEEP_THREADS, SweepMinBlocks<T>::value)
+__global__ void __launch_bounds__(SWEEP_THREADS, SweepMinBlocks<T, F::AUX>::value)
 k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
     typedef TagT<T> TG;
     extern __shared__ __align__(128) unsigned char dsm_raw[];
@@ -614,16 +623,29 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                 // record, real-image pairs from the real particle (the distance is symmetric, so this deviation from the
                 // reference's slot order changes nothing -- and it keeps the rule independent of the record order, which
                 // differs between the ranks of a slab-decomposed system)
-                int thrA = 0, thrB = 0;
+                int thrA = 0, thrB = 0, lo_row = bj0;
                 if (MODE == MODE_HALF && (bown & 2)) {
                     const int* csj = a.cell_start_j + brow;
                     thrA = csj[min((rfx_i + 1) * sub, a.nx)];
                     thrB = csj[rfx_i * sub];
+                    // no lane takes a partner that sits before the reference cell of the tile's first record
+                    lo_row = max(bj0, csj[div_sub(cxa) * sub]);
                 }
-                auto run_row = [&](auto self_row_tag) {
-                    constexpr bool SELF_ROW = decltype(self_row_tag)::value;
-                    auto body = [&](const RecT<T>* __restrict__ pj, const int jc, const bool inb) {
-                        const RecT<T> rj = ldrec(pj);
+                // the row is bulk-copied piecewise into the warp's staging buffer (record order kept: the rules above
+                // need the record index) and swept from shared memory
+                for (int p0 = lo_row; p0 < bj1; p0 += CAP) {
+                    const int pn = min(CAP, bj1 - p0);
+                    if (lane == 0) {
+                        fence_proxy_async();
+                        mbar_expect_tx(mbar, (uint32_t)pn * (uint32_t)sizeof(RecT<T>) * (F::AUX ? 2u : 1u));
+                        bulk_g2s(buf_addr, a.rec_j + p0, (uint32_t)pn * (uint32_t)sizeof(RecT<T>), mbar);
+                        if constexpr (F::AUX) bulk_g2s(abuf_addr, f.aux_j() + p0, (uint32_t)pn * (uint32_t)sizeof(RecT<T>), mbar);
+                    }
+                    mbar_wait(mbar, parity);
+                    parity ^= 1u;
+                    __syncwarp();
+                    auto body = [&](const RecT<T>* q, const int jc, const bool inb) {
+                        const RecT<T> rj = ldrec_s(q);
                         bool ok = inb;
                         if (MODE == MODE_HALF) {
                             const bool gi = (c.ri.tag & TG::GHOST) != 0, gj = (rj.tag & TG::GHOST) != 0;
@@ -631,17 +653,23 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                         }
                         else if (MODE == MODE_TRI) ok = ok && (idx_i < (rj.tag & TG::MASK));
                         RecT<T> aj = rj;
-                        if constexpr (F::AUX) aj = ldrec(f.aux_j() + jc);
+                        if constexpr (F::AUX) aj = ldrec_s(abuf + (q - buf));
                         pair_body(rj, aj, jc, ok);
                     };
-                    const RecT<T>* pj = a.rec_j + (bj0 + c.slice);
-                    int jc = bj0 + c.slice;
-                    const int nfull = (bj1 - bj0) / nslice;
-#pragma unroll 2
-                    for (int s_ = 0; s_ < nfull; ++s_) { body(pj, jc, true); pj += nslice; jc += nslice; }
-                    if (jc - c.slice < bj1) { const bool inb = jc < bj1; body(inb ? pj : a.rec_j + (bj1 - 1), inb ? jc : bj1 - 1, inb); }
-                };
-                run_row(FalseTag());
+                    const RecT<T>* q = buf + c.slice;
+                    int jc = p0 + c.slice;
+                    const int nfull = pn / nslice;
+                    int s_ = 0;
+#pragma unroll 1
+                    for (; s_ + 4 <= nfull; s_ += 4) {
+                        body(q, jc, true); body(q + nslice, jc + nslice, true); body(q + 2 * nslice, jc + 2 * nslice, true); body(q + 3 * nslice, jc + 3 * nslice, true);
+                        q += 4 * nslice; jc += 4 * nslice;
+                    }
+#pragma unroll 1
+                    for (; s_ < nfull; ++s_) { body(q, jc, true); q += nslice; jc += nslice; }
+                    if (jc - c.slice < p0 + pn) { const bool inb = jc < p0 + pn; body(inb ? q : buf, jc, inb); }
+                    __syncwarp();
+                }
             }
             // ---- staged rows: prefix of the segment lengths, then chunks of at most CAP records --------------------
             const int len = (cls == ROW_STAGED) ? (j1 - j0) : 0;
