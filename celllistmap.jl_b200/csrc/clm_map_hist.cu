@@ -1,4 +1,6 @@
 // clm_map_dist_hist / clm_map_pairvel: histogram maps of the catalogue.
+#include <cmath>
+#include <limits>
 #include "clm_engine.cuh"
 
 namespace clm {
@@ -15,10 +17,12 @@ template <class T> int Engine<T>::map_dist_hist(const void* width, int nbins, in
     if (int rc = prepare_map(flags)) return rc;
     CLM_CK(d_hcount.ensure((size_t)nbins));
     CLM_CK(cudaMemsetAsync(d_hcount.p, 0, (size_t)nbins * sizeof(unsigned long long), stream));
-    FHist<T> fn;
-    fn.width = *(const T*)width;
-    fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.off = 0; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = nullptr;
-    if (int rc = launch_reduce(fn, hist_smem(nbins, fn.hb.priv != 0, 0))) return rc;
+    auto run = [&](auto fn) -> int {
+        fn.width = *(const T*)width;
+        fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.off = 0; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = nullptr;
+        return launch_reduce(fn, hist_smem(nbins, fn.hb.priv != 0, 0));
+    };
+    if (int rc = (nbins <= NB_PRIV_MAX) ? run(FHist<T, 1>()) : run(FHist<T, 0>())) return rc;
     const int v = build_validate();
     if (v == CLM_RETRY_INTERNAL) continue;
     if (v) return v;
@@ -32,6 +36,18 @@ template <class T> int Engine<T>::map_dist_hist(const void* width, int nbins, in
     }
     if (int rc = store_i64(counts, d_hcount.p, hc.data(), nbins, flags)) return rc;
     return finish_map(flags);
+}
+
+// smallest x >= 0 with sqrt_rn(x) > edge (std::sqrt is correctly rounded, like the device's __fsqrt_rn / __dsqrt_rn)
+template <class T> static T sqrt_threshold(T edge) {
+    if (!(edge >= T(0))) return (edge != edge) ? std::numeric_limits<T>::infinity() : T(0);   // NaN edge: never exceeded; negative: always
+    if (std::isinf(edge)) return std::numeric_limits<T>::infinity();
+    const T inf = std::numeric_limits<T>::infinity();
+    T x = edge * edge;
+    if (std::isinf(x)) x = std::numeric_limits<T>::max();
+    while (x > T(0) && std::sqrt(x) > edge) x = std::nextafter(x, T(-1));       // walk down to a value that does not exceed
+    while (x < inf && !(std::sqrt(x) > edge)) x = std::nextafter(x, inf);       // then up to the first one that does
+    return x;
 }
 
 template <class T> int Engine<T>::map_pairvel(const void* vx, const void* vy, const void* rbins, int nbins, int flags, int64_t* counts, void* sums) {
@@ -49,13 +65,20 @@ template <class T> int Engine<T>::map_pairvel(const void* vx, const void* vy, co
     CLM_CK(cudaMemsetAsync(d_hcount.p, 0, (size_t)nbins * sizeof(unsigned long long), stream));
     CLM_CK(cudaMemsetAsync(d_hsum.p, 0, (size_t)nbins * sizeof(double), stream));
     CLM_CK(cudaMemcpyAsync(d_rbins.p, rbins, ((size_t)nbins + 1) * sizeof(T), cudaMemcpyHostToDevice, stream));
-    FVel<T> fn;
-    fn.v_i = sets[0].aux.p; fn.v_j = sets[two_sets ? 1 : 0].aux.p; fn.rbins = d_rbins.p;
-    fn.inline_edges = (nbins + 1 <= VEL_EDGES_INLINE) ? 1 : 0;
-    for (int e = 0; e < VEL_EDGES_INLINE; ++e) fn.edges[e] = (fn.inline_edges && e <= nbins) ? ((const T*)rbins)[e] : T(0);
     const int aux_bytes = (SWEEP_THREADS / 32) * StageBytes<T>::value;   // side-array staging buffers precede the bins
-    fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.off = aux_bytes; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = d_hsum.p;
-    if (int rc = launch_reduce(fn, (size_t)aux_bytes + hist_smem(nbins, fn.hb.priv != 0, sizeof(T)))) return rc;
+    auto run = [&](auto fn) -> int {
+        fn.v_i = sets[0].aux.p; fn.v_j = sets[two_sets ? 1 : 0].aux.p; fn.rbins = d_rbins.p;
+        fn.inline_edges = (nbins + 1 <= VEL_EDGES_INLINE) ? 1 : 0;
+        for (int e = 0; e < VEL_EDGES_INLINE; ++e) fn.thr2[e] = (fn.inline_edges && e <= nbins) ? sqrt_threshold(((const T*)rbins)[e]) : std::numeric_limits<T>::infinity();
+        fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.off = aux_bytes; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = d_hsum.p;
+        return launch_reduce(fn, (size_t)aux_bytes + hist_smem(nbins, fn.hb.priv != 0, sizeof(T)));
+    };
+    int lrc;
+    if (nbins + 1 <= 8) lrc = run(FVel<T, 1, 1>());                       // <= 7 bins: private bins (NB_PRIV_MAX = 16)
+    else if (nbins <= NB_PRIV_MAX) lrc = run(FVel<T, 2, 1>());
+    else if (nbins + 1 <= VEL_EDGES_INLINE) lrc = run(FVel<T, 2, 0>());
+    else lrc = run(FVel<T, 0, 0>());
+    if (lrc) return lrc;
     std::vector<unsigned long long> hc;
     std::vector<double> hs;
     if (!dev) {

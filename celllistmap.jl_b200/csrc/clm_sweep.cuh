@@ -129,6 +129,15 @@ template <> __device__ __forceinline__ double fast_rcp<double>(double x) {
     const double e = fma(-x, r0, 1.0);
     return fma(r0, fma(e, e, e), r0);
 }
+// 1/sqrt(x) for the tolerance-parity sums: hardware seed + one cubic correction y (1 + e/2 + 3 e^2 / 8), e = 1 - x y^2
+template <class T> __device__ __forceinline__ T fast_rsqrt(T x);
+template <> __device__ __forceinline__ float fast_rsqrt<float>(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+template <> __device__ __forceinline__ double fast_rsqrt<double>(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
+}
 template <class T> __device__ __forceinline__ T xfma(T a, T b, T c);
 template <> __device__ __forceinline__ float xfma<float>(float a, float b, float c) { return fmaf(a, b, c); }
 template <> __device__ __forceinline__ double xfma<double>(double a, double b, double c) { return fma(a, b, c); }
@@ -238,7 +247,8 @@ template <class T, bool FORCES> struct FCoul {
 
 // histogram storage shared by the two histogram functors: per-thread private bins in shared memory
 // (bank = thread, conflict free, no atomics) when nbins <= NB_PRIV_MAX, block-shared atomics otherwise
-template <class T, bool SUMS> struct HistBins {
+// PRIV: 1 / 0 = storage kind fixed at compile time (one code path per pair body), -1 = chosen at run time (`priv`)
+template <class T, bool SUMS, int PRIV = -1> struct HistBins {
     int nbins, priv;
     int off;                        // bytes between the end of the record staging buffers and the bins (side-array staging buffers)
     unsigned long long* g_counts;   // [nbins] global accumulators
@@ -246,16 +256,17 @@ template <class T, bool SUMS> struct HistBins {
     __device__ __forceinline__ unsigned int* cnt() const { extern __shared__ __align__(128) unsigned char dsm_raw[]; return reinterpret_cast<unsigned int*>(dsm_raw + StageTotal<T>::value + off); }
     __device__ __forceinline__ T* sum() const {
         extern __shared__ __align__(128) unsigned char dsm_raw[];
-        const size_t nslots = (size_t)nbins * (priv ? SWEEP_THREADS : 1);
+        const size_t nslots = (size_t)nbins * (is_priv() ? SWEEP_THREADS : 1);
         return reinterpret_cast<T*>(dsm_raw + StageTotal<T>::value + off + ((nslots * 4 + 15) / 16) * 16);
     }
+    __device__ __forceinline__ bool is_priv() const { return (PRIV < 0) ? (priv != 0) : (PRIV != 0); }
     __device__ void init() const {
-        const int nslots = nbins * (priv ? SWEEP_THREADS : 1);
+        const int nslots = nbins * (is_priv() ? SWEEP_THREADS : 1);
         for (int k = threadIdx.x; k < nslots; k += SWEEP_THREADS) { cnt()[k] = 0u; if (SUMS) sum()[k] = T(0); }
         __syncthreads();
     }
     __device__ __forceinline__ void add(int b, T v) const {
-        if (priv) {
+        if (is_priv()) {
             const int s = b * SWEEP_THREADS + threadIdx.x;
             cnt()[s] += 1u;
             if (SUMS) sum()[s] += v;
@@ -266,7 +277,7 @@ template <class T, bool SUMS> struct HistBins {
     }
     __device__ void flush() const {
         __syncthreads();
-        if (priv) {
+        if (is_priv()) {
             const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
             for (int b = w; b < nbins; b += SWEEP_THREADS / 32) {
                 unsigned long long c = 0; double s = 0;
@@ -283,9 +294,9 @@ template <class T, bool SUMS> struct HistBins {
 };
 
 // distance histogram: counts[floor(d/width)] += 1 (test/examples/distance_histogram.jl:22-26)
-template <class T> struct FHist {
+template <class T, int PRIV> struct FHist {
     T width;
-    HistBins<T, false> hb;
+    HistBins<T, false, PRIV> hb;
     struct Acc {};
     struct IAcc {};
     static constexpr bool NEEDS_BAND = false, EXACT_D2 = true, AUX = false;
@@ -306,13 +317,16 @@ template <class T> struct Vec4T;
 template <> struct Vec4T<float> { typedef float4 type; };
 template <> struct Vec4T<double> { typedef double4 type; };
 constexpr int VEL_EDGES_INLINE = 33;   // bin edges kept in the kernel parameters (constant bank) up to this many
-template <class T> struct FVel {
+template <class T, int EDGE_MODE, int PRIV> struct FVel {   // EDGE_MODE 1: <= 8 edges inline, 2: <= VEL_EDGES_INLINE inline, 0: edges in global memory
     const T* v_i;     // velocities gathered into record order, 4 components per record, aligned frame
     const T* v_j;
     const T* rbins;   // nbins+1 ascending edges (device)
-    T edges[VEL_EDGES_INLINE];   // the same edges when nbins + 1 <= VEL_EDGES_INLINE (inline_edges != 0)
+    // inline_edges != 0 (nbins + 1 <= VEL_EDGES_INLINE): thr2[e] = the smallest d2 whose correctly rounded square root
+    // exceeds edge e, computed on the host -- sqrt_rn is monotone, so (rbins[e] < sqrt(d2)) == (d2 >= thr2[e]) EXACTLY
+    // and the bin search needs no square root
+    T thr2[VEL_EDGES_INLINE];
     int inline_edges;
-    HistBins<T, true> hb;
+    HistBins<T, true, PRIV> hb;
     struct Acc {};
     struct IAcc { T vx, vy, vz; };
     static constexpr bool NEEDS_BAND = false, EXACT_D2 = true, AUX = true;   // side array staged with the records
@@ -324,18 +338,21 @@ template <class T> struct FVel {
     }
     __device__ __forceinline__ void pair(Acc&, IAcc& p, const Ctx<T>&, bool hit, bool, const RecT<T>&, const RecT<T>& aj, T dx, T dy, T dz, T d2) const {
         if (hit) {
-            const T r = xsqrt(d2);
-            int first = 0;   // searchsortedfirst(rbins, r): number of edges < r
-            if (inline_edges) {
+            int first = 0;   // searchsortedfirst(rbins, r): number of edges < r = sqrt(d2)
+            if (EDGE_MODE == 1) {          // straight-line compares against the constant bank (unused slots hold +inf)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) first += (d2 >= thr2[e]) ? 1 : 0;
+            } else if (EDGE_MODE == 2) {
 #pragma unroll 1
-                for (int e = 0; e <= hb.nbins; ++e) first += (edges[e] < r) ? 1 : 0;
+                for (int e = 0; e <= hb.nbins; ++e) first += (d2 >= thr2[e]) ? 1 : 0;
             } else {
+                const T r = xsqrt(d2);
                 for (int e = 0; e <= hb.nbins; ++e) first += (__ldg(rbins + e) < r) ? 1 : 0;
             }
             const int b = first - 1;
             if (b >= 0 && b < hb.nbins) {
                 const T ux = p.vx - aj.x, uy = p.vy - aj.y, uz = p.vz - aj.z;
-                hb.add(b, ((ux * dx + uy * dy) + uz * dz) * fast_rcp<T>(r));   // sums have tolerance parity; counts are exact
+                hb.add(b, ((ux * dx + uy * dy) + uz * dz) * fast_rsqrt<T>(d2));   // sums have tolerance parity; counts are exact
             }
         }
     }
