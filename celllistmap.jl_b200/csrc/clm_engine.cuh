@@ -179,7 +179,7 @@ template <class T> struct Engine : EngineBase {
     }
     template <int MODE, class F> int launch(const F& f, size_t functor_smem) {
         auto kern = k_sweep<T, MODE, F>;
-        const size_t smem = (size_t)StageTotal<T>::value + functor_smem;   // per-warp staging buffers + mbarriers, then the functor's bins
+        const size_t smem = (size_t)StageTotal<T, F::AUX>::value + functor_smem;   // per-warp staging buffers + mbarriers, then the functor's bins
         static size_t smem_set = 0;                                // per instantiation
         if (smem > smem_set) { CLM_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
         int bps = 0;

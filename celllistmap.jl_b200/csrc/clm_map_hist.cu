@@ -19,7 +19,7 @@ template <class T> int Engine<T>::map_dist_hist(const void* width, int nbins, in
     CLM_CK(cudaMemsetAsync(d_hcount.p, 0, (size_t)nbins * sizeof(unsigned long long), stream));
     auto run = [&](auto fn) -> int {
         fn.width = *(const T*)width;
-        fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.off = 0; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = nullptr;
+        fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.off = StageTotal<T, false>::value; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = nullptr;
         return launch_reduce(fn, hist_smem(nbins, fn.hb.priv != 0, 0));
     };
     if (int rc = (nbins <= NB_PRIV_MAX) ? run(FHist<T, 1>()) : run(FHist<T, 0>())) return rc;
@@ -65,12 +65,12 @@ template <class T> int Engine<T>::map_pairvel(const void* vx, const void* vy, co
     CLM_CK(cudaMemsetAsync(d_hcount.p, 0, (size_t)nbins * sizeof(unsigned long long), stream));
     CLM_CK(cudaMemsetAsync(d_hsum.p, 0, (size_t)nbins * sizeof(double), stream));
     CLM_CK(cudaMemcpyAsync(d_rbins.p, rbins, ((size_t)nbins + 1) * sizeof(T), cudaMemcpyHostToDevice, stream));
-    const int aux_bytes = (SWEEP_THREADS / 32) * StageBytes<T>::value;   // side-array staging buffers precede the bins
+    const int aux_bytes = (SWEEP_THREADS / 32) * StageBytes<T, true>::value;   // side-array staging buffers precede the bins
     auto run = [&](auto fn) -> int {
         fn.v_i = sets[0].aux.p; fn.v_j = sets[two_sets ? 1 : 0].aux.p; fn.rbins = d_rbins.p;
         fn.inline_edges = (nbins + 1 <= VEL_EDGES_INLINE) ? 1 : 0;
         for (int e = 0; e < VEL_EDGES_INLINE; ++e) fn.thr2[e] = (fn.inline_edges && e <= nbins) ? sqrt_threshold(((const T*)rbins)[e]) : std::numeric_limits<T>::infinity();
-        fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.off = aux_bytes; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = d_hsum.p;
+        fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.off = StageTotal<T, true>::value + aux_bytes; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = d_hsum.p;
         return launch_reduce(fn, (size_t)aux_bytes + hist_smem(nbins, fn.hb.priv != 0, sizeof(T)));
     };
     int lrc;

@@ -59,13 +59,13 @@ template <class T> int Engine<T>::map_coulomb(const void* wx, const void* wy, co
         FCoul<T, true> fn;
         fn.k = *(const T*)k; fn.w_i = wi; fn.w_j = wj;
         if (int rc = forces_begin(f, flags, fn.fo)) return rc;
-        if (int rc = launch<MODE_ALL>(fn, (size_t)(SWEEP_THREADS / 32) * StageBytes<T>::value)) return rc;
+        if (int rc = launch<MODE_ALL>(fn, (size_t)(SWEEP_THREADS / 32) * StageBytes<T, true>::value)) return rc;
         scale = two_sets ? 1.0 : 0.5;
     } else {
         FCoul<T, false> fn;
         fn.k = *(const T*)k; fn.w_i = wi; fn.w_j = wj;
         std::memset(&fn.fo, 0, sizeof(fn.fo));
-        if (int rc = launch_reduce(fn, (size_t)(SWEEP_THREADS / 32) * StageBytes<T>::value)) return rc;
+        if (int rc = launch_reduce(fn, (size_t)(SWEEP_THREADS / 32) * StageBytes<T, true>::value)) return rc;
     }
     if (!dev) { if (int rc = fetch_results()) return rc; }
     if (int rc = store_real(e, &d_res.p->f[RB_ENERGY], &h_res->f[RB_ENERGY], 1, scale, flags)) return rc;
