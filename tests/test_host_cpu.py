@@ -112,3 +112,20 @@ def test_user_pair_function_compiles_without_a_device(clm):
         clm.CustomPairFunction(USER_SRC.replace("NSCALAR = 1", "NSCALAR = 9"), "Coordination").check()
     with pytest.raises(ValueError, match="identifier"):
         clm.CustomPairFunction(USER_SRC, "not an identifier").check()
+
+
+def test_header_is_plain_c_and_library_loads_from_c(clm):
+    """include/clm_b200.h compiles as strict C99 and a C program can dlopen the library and call it."""
+    import shutil
+    import subprocess
+    import tempfile
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    exe = os.path.join(tempfile.mkdtemp(prefix="clm_abi_"), "abi_check")
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c_abi", "abi_check.c"), "-o", exe, "-ldl"])
+    out = subprocess.run([exe, clm.SO_PATH], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "version 100" in out.stdout
+    assert f"sizeof clm_box_info {ctypes.sizeof(clm._capi.BoxInfo)} clm_stats {ctypes.sizeof(clm._capi.Stats)} clm_custom_info {ctypes.sizeof(clm._capi.CustomInfo)}" in out.stdout
+    assert "Dimension must be 2 or 3" in out.stdout
