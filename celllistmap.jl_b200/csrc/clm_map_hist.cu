@@ -10,15 +10,47 @@ static inline size_t hist_smem(int nbins, bool priv, size_t sum_bytes) {
     return ((slots * 4 + 15) / 16) * 16 + slots * sum_bytes;
 }
 
+// thresholds of the distance histogram: thr[b] = smallest d2 >= 0 with floor(sqrt_rn(d2) / width) >= b, b = 0 .. nbins,
+// found by walking neighbouring floating-point numbers around the real-number guess (std::sqrt and the division are
+// correctly rounded, like the device's __fsqrt_rn / __fdiv_rn)
+template <class T> static bool hist_thresholds(T width, int nbins, std::vector<T>& thr) {
+    if (!(width > T(0)) || std::isinf(width)) return false;
+    const T inf = std::numeric_limits<T>::infinity();
+    auto bin_of_r = [&](T r) { return std::floor(r / width); };
+    thr.assign((size_t)nbins + 1, T(0));
+    for (int b = 1; b <= nbins; ++b) {
+        // smallest r with floor(r / width) >= b
+        T r = (T)b * width;
+        if (std::isinf(r)) { thr[b] = inf; continue; }
+        int guard = 0;
+        while (r > T(0) && bin_of_r(std::nextafter(r, T(-1))) >= (T)b && ++guard < 64) r = std::nextafter(r, T(-1));
+        while (bin_of_r(r) < (T)b && ++guard < 128) r = std::nextafter(r, inf);
+        // smallest d2 with sqrt_rn(d2) >= r
+        T x = r * r;
+        if (std::isinf(x)) { thr[b] = inf; continue; }
+        while (x > T(0) && std::sqrt(std::nextafter(x, T(-1))) >= r && ++guard < 192) x = std::nextafter(x, T(-1));
+        while (std::sqrt(x) < r && ++guard < 256) x = std::nextafter(x, inf);
+        if (guard >= 255) return false;   // pathological width: use the direct form
+        thr[b] = x;
+    }
+    return true;
+}
+
 template <class T> int Engine<T>::map_dist_hist(const void* width, int nbins, int flags, int64_t* counts) {
     if (!width || !counts) return fail(CLM_ERR_ARGUMENT, "width / counts pointer is NULL");
     if (nbins < 1 || nbins > 2048) return fail(CLM_ERR_ARGUMENT, "nbins must be in 1..2048");
+    std::vector<T> thr;
+    const bool use_thr = hist_thresholds(*(const T*)width, nbins, thr);
     for (;;) {
     if (int rc = prepare_map(flags)) return rc;
     CLM_CK(d_hcount.ensure((size_t)nbins));
     CLM_CK(cudaMemsetAsync(d_hcount.p, 0, (size_t)nbins * sizeof(unsigned long long), stream));
+    if (use_thr) {
+        CLM_CK(d_rbins.ensure((size_t)nbins + 1));
+        CLM_CK(cudaMemcpyAsync(d_rbins.p, thr.data(), ((size_t)nbins + 1) * sizeof(T), cudaMemcpyHostToDevice, stream));
+    }
     auto run = [&](auto fn) -> int {
-        fn.width = *(const T*)width;
+        fn.width = *(const T*)width; fn.inv_width = T(1) / fn.width; fn.thr = use_thr ? d_rbins.p : nullptr;
         fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.off = StageTotal<T, false>::value; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = nullptr;
         return launch_reduce(fn, hist_smem(nbins, fn.hb.priv != 0, 0));
     };

@@ -304,8 +304,16 @@ template <class T, bool SUMS, int PRIV = -1> struct HistBins {
 };
 
 // distance histogram: counts[floor(d/width)] += 1 (test/examples/distance_histogram.jl:22-26)
+// The bin of a pair is floor(sqrt_rn(d2) / width) in T arithmetic -- monotone in d2, so it is decided EXACTLY by a table
+// of d2 thresholds computed on the host with the same correctly rounded operations (thr[b] = smallest d2 whose bin is
+// >= b).  The device guesses the bin with the hardware rsqrt seed and corrects the guess against the table: no IEEE
+// square root or division in the pair body.  thr == nullptr: the direct form.
+template <class T> __device__ __forceinline__ T rsqrt_seed(T x);
+template <> __device__ __forceinline__ float rsqrt_seed<float>(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+template <> __device__ __forceinline__ double rsqrt_seed<double>(double x) { double r; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x)); return r; }
 template <class T, int PRIV> struct FHist {
-    T width;
+    T width, inv_width;
+    const T* thr;     // nbins + 1 ascending thresholds on d2 (device), or nullptr
     HistBins<T, false, PRIV> hb;
     struct Acc {};
     struct IAcc {};
@@ -314,8 +322,16 @@ template <class T, int PRIV> struct FHist {
     __device__ void begin(IAcc&, const Ctx<T>&) const {}
     __device__ __forceinline__ void pair(Acc&, IAcc&, const Ctx<T>&, bool hit, bool, const RecT<T>&, int, T, T, T, T d2) const {
         if (hit) {
-            const T q = floor(xdiv(xsqrt(d2), width));
-            if (q >= T(0) && q < T(hb.nbins)) hb.add((int)q, T(0));
+            if (thr != nullptr) {
+                int b = (int)fmin(d2 * rsqrt_seed<T>(fmax(d2, T(1e-30))) * inv_width, T(hb.nbins));   // guess; d2 = 0 -> bin 0
+                b = max(b, 0);
+                while (b > 0 && d2 < __ldg(thr + b)) --b;
+                while (b < hb.nbins && d2 >= __ldg(thr + b + 1)) ++b;
+                if (b < hb.nbins) hb.add(b, T(0));
+            } else {
+                const T q = floor(xdiv(xsqrt(d2), width));
+                if (q >= T(0) && q < T(hb.nbins)) hb.add((int)q, T(0));
+            }
         }
     }
     __device__ void end(IAcc&, const Ctx<T>&) const {}

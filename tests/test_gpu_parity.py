@@ -229,6 +229,30 @@ def test_distance_histogram_exact(clm, oracle_mod, dtype, nbins):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("width,nbins", [(0.25, 8), (0.5, 4), (0.1, 20), (1.0 / 3.0, 6), (0.0625, 32)])
+def test_histograms_distances_on_bin_edges(clm, oracle_mod, dtype, width, nbins):
+    """lattice positions (spacing 0.5, exactly representable): many distances sit EXACTLY on bin edges, which is where
+    the table-driven bin search of the device (d2 thresholds of the correctly rounded sqrt / division) must agree with
+    the direct floor(sqrt(d2) / width) and searchsortedfirst(rbins, sqrt(d2)) of the reference"""
+    g = np.arange(12) * 0.5
+    x = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(dtype)
+    uc = np.array([6.0, 6.0, 6.0], dtype)
+    cutoff = 2.0
+    sys = clm.ParticleSystem(xpositions=x, unitcell=uc, cutoff=cutoff, output=np.zeros(nbins, np.int64))
+    h = clm.pairwise(clm.DistanceHistogram(dtype(width)), sys)
+    o = oracle_mod.Oracle(x, cutoff, unitcell=uc, dtype=dtype)
+    assert np.array_equal(h, o.dist_hist(dtype(width), nbins))
+    assert h.sum() > 10000
+    # pair-velocity bins: edges at multiples of the same width (right-closed bins)
+    nb = min(nbins, int(cutoff / width))
+    rbins = (np.arange(nb + 1) * dtype(width)).astype(dtype)
+    v = np.random.default_rng(3).random(x.shape).astype(dtype)
+    sys2 = clm.ParticleSystem(xpositions=x, unitcell=uc, cutoff=cutoff, output=(np.zeros(nb, np.int64), np.zeros(nb, dtype)))
+    counts, _ = clm.pairwise(clm.PairwiseVelocities(rbins, v), sys2)
+    assert np.array_equal(counts, o.pairvel(v, rbins)[0])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("kind", ["ortho", "triclinic"])
 def test_pairwise_velocities(clm, oracle_mod, dtype, dim, kind):
