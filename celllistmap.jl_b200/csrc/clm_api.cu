@@ -435,10 +435,11 @@ template <class T> int Engine<T>::fetch_results() {
 template <class T> int Engine<T>::gather_aux(int set, const T* aux, int ncomp, bool rotate, bool on_device) {
     DevSet<T>& S = sets[set];
     const size_t out_n = (size_t)std::max<int64_t>(S.n_tot, 1) * 4;   // one record-sized slot (4 x T) per record
-    const size_t in_n = (size_t)S.n * ncomp;
+    // owned particles first, then the foreign (halo) particles of a slab-decomposed system: one row each
+    const size_t in_n = (size_t)(S.n + S.n_foreign) * ncomp;
     CLM_CK(S.aux.ensure(out_n + in_n + 4));
     T* staged = S.aux.p + out_n;
-    if (S.n == 0) return CLM_OK;
+    if (S.n + S.n_foreign == 0) return CLM_OK;
     CLM_CK(cudaMemcpyAsync(staged, aux, in_n * sizeof(T), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
     const int nb = (int)((S.n_tot + 255) / 256);
     if (nb) k_gather_aux<T><<<nb, 256, 0, stream>>>(S.rec.p, (int)S.n_tot, staged, ncomp, geom, rotate ? 1 : 0, S.aux.p);

@@ -8,6 +8,7 @@ to the engine as FOREIGN particles (clm_set_foreign): partners j like any other 
 evaluation of the single-GPU sweep therefore happens on exactly one rank, on bit-identical coordinates:
 
   * per-particle outputs (forces) stay sharded with their owners -- the full-shell sweep needs no reverse exchange;
+  * per-particle INPUTS of a pair function (weights, velocities, user side arrays) travel with the halo (`aux`);
   * scalars and histograms are summed with all_reduce; minimum distances with an all_gather + min;
   * neighbour lists stay per rank (indices mapped to the caller's global ids), concatenation is the caller's choice.
 
@@ -146,10 +147,13 @@ class SlabSystem:
         gid = torch.arange(1, x.shape[0] + 1, device=self.device, dtype=torch.int64) if ids is None else torch.as_tensor(ids).to(self.device)
         return x[mine].contiguous(), gid[mine].contiguous()
 
-    def update(self, x_owned, ids=None):
-        """halo exchange + hand owned / foreign particles to the engine (nothing is built until the next map)."""
+    def update(self, x_owned, ids=None, aux=None):
+        """halo exchange + hand owned / foreign particles to the engine (nothing is built until the next map).
+        `aux`: (n_owned, k) per-particle side data (weights, velocities, ...) that the halo particles carry along."""
         x = torch.as_tensor(x_owned).to(self.device, self.tdtype).contiguous()
         self.n_owned = int(x.shape[0])
+        if aux is not None:
+            aux = torch.as_tensor(aux).to(self.device, self.tdtype).reshape(self.n_owned, -1).contiguous()
         if self._n_global is None:
             # the engine sizes its device grid from the particle density; a rank only sees its slab, so tell it the
             # global density (same rule as Engine::build: ~4 particles per device cell)
@@ -161,16 +165,18 @@ class SlabSystem:
             sub = int(np.floor(max(per_cell / 4.0, 1.0) ** (1.0 / self.dim) + 0.35))
             self.h.set_option("sub", max(1, min(sub, 7 // self._lcell)))
         got = None
-        if ids is None and self.world > 1 and self._cap is not None and dist.get_backend(self.group) != "gloo":
+        if ids is None and aux is None and self.world > 1 and self._cap is not None and dist.get_backend(self.group) != "gloo":
             got = self._exchange_fast(x)
         if got is None:
             c = self.cell_layers(x).to(torch.int64)
             to_lower, to_upper = self.plan.face_masks(c, self.rank)
-            payloads = [x] if ids is None else [x, torch.as_tensor(ids).to(self.device)]
+            payloads = [x] + ([] if ids is None else [torch.as_tensor(ids).to(self.device)]) + ([] if aux is None else [aux])
             res = exchange_halo(payloads, to_lower, to_upper, self.plan, self.rank, self.group)
             got = res[0].contiguous()
             self.ids = None if ids is None else payloads[1]
             self.foreign_ids = None if ids is None else res[1]
+            # side data of owned + foreign particles, in the engine's index order (owned first)
+            self.aux = None if aux is None else torch.cat([aux, res[-1]], dim=0).contiguous()
             if self.world > 1:
                 # size the fixed-capacity messages of the fast path from what this exchange moved (50 % slack)
                 m = torch.tensor([max(int(to_lower.sum()), int(to_upper.sum()), int((to_lower | to_upper).sum()) if self.world == 2 else 0)],
@@ -178,7 +184,7 @@ class SlabSystem:
                 dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
                 self._alloc_fast(int(int(m) * 1.5) + 1024)
         else:
-            self.ids = self.foreign_ids = None
+            self.ids = self.foreign_ids = self.aux = None
         self.x_owned, self.x_foreign = x, got
         self.n_foreign = int(got.shape[0])
         self.h.set_positions(0, x)
@@ -236,6 +242,71 @@ class SlabSystem:
         if self.world > 1:
             dist.all_reduce(e, group=self.group)
         return e
+
+    def _need_aux(self, k):
+        if getattr(self, "aux", None) is None or self.aux.shape[1] != k:
+            raise ValueError(f"this map reads {k} side value(s) per particle: pass them as update(x, aux=...) so that the halo carries them")
+        return self.aux
+
+    def map_coulomb(self, k, forces=None, profile=False):
+        """k w_i w_j / d with the weights given as update(..., aux=w): GLOBAL energy, forces of the owned particles."""
+        w = self._need_aux(1)
+        e = torch.zeros(1, dtype=self.tdtype, device=self.device)
+        self.h.map_coulomb(k, w, None, e, forces, reset=True, profile=profile)
+        if self.world > 1:
+            dist.all_reduce(e, group=self.group)
+        return e
+
+    def pairvel(self, rbins):
+        """mean pairwise velocity histogram with the velocities given as update(..., aux=v): GLOBAL (counts, sums)."""
+        v = self._need_aux(self.dim)
+        nb = len(rbins) - 1
+        counts = torch.zeros(nb, dtype=torch.int64, device=self.device)
+        sums = torch.zeros(nb, dtype=self.tdtype, device=self.device)
+        self.h.map_pairvel(v, None, np.asarray(rbins, dtype=self.dtype), counts, sums, reset=True)
+        if self.world > 1:
+            dist.all_reduce(counts, group=self.group)
+            dist.all_reduce(sums, group=self.group)
+        return counts, sums
+
+    def mindist(self):
+        """(i, j, d) of the closest pair of the GLOBAL system (global ids when update() was given `ids`, else rank-local
+        indices of the winning rank); ties are broken by the smaller (i, j) as on one GPU."""
+        i, j = np.zeros(1, np.int64), np.zeros(1, np.int64)
+        d = np.full(1, np.inf, self.dtype)
+        self.h.map_mindist(i, j, d, reset=True)
+        if self.ids is not None and i[0] > 0:
+            table = torch.cat([self.ids, self.foreign_ids]).cpu().numpy()
+            i[0], j[0] = table[i[0] - 1], table[j[0] - 1]
+        cand = [(float(d[0]), int(i[0]), int(j[0]))]
+        if self.world > 1:
+            allc = [None] * self.world
+            dist.all_gather_object(allc, cand[0], group=self.group)
+            cand = [c for c in allc if c[1] > 0] or [cand[0]]
+        best = min(cand, key=lambda c: (c[0], min(c[1], c[2]), max(c[1], c[2])))
+        return best[1], best[2], best[0]
+
+    def map_custom(self, source, name, params=(), scalars=0, per_particle=0, nbins=0):
+        """a run-time compiled user pair function (clm_map_custom); side arrays come from update(..., aux=...).
+        Returns (scalars, per_particle, hist_counts, hist_sums): scalars and histograms are GLOBAL (all_reduce), the
+        per-particle output covers the owned particles."""
+        key = (source, name)
+        if not hasattr(self, "_custom"):
+            self._custom = {}
+        if key not in self._custom:
+            self._custom[key] = self.h.custom_compile(source, name)
+        fid, info = self._custom[key]
+        aux = self._need_aux(info.naux) if info.naux else None
+        sc = torch.zeros(info.nscalar, dtype=self.tdtype, device=self.device) if info.nscalar else None
+        pp = torch.zeros((self.n_owned, info.npart), dtype=self.tdtype, device=self.device) if info.npart else None
+        hc = torch.zeros(nbins, dtype=torch.int64, device=self.device) if info.hist else None
+        hs = torch.zeros(nbins, dtype=self.tdtype, device=self.device) if info.hist else None
+        self.h.map_custom(fid, params, aux, None, sc, pp, hc, hs, reset=True)
+        if self.world > 1:
+            for t in (sc, hc, hs):
+                if t is not None:
+                    dist.all_reduce(t, group=self.group)
+        return sc, pp, hc, hs
 
     def sum_d_d2(self):
         sd, sd2, n = (torch.zeros(1, dtype=self.tdtype, device=self.device), torch.zeros(1, dtype=self.tdtype, device=self.device),

@@ -126,7 +126,8 @@ CLM_API int clm_set_positions(clm_handle* h, int set, const void* aos_xyz, int64
  * passes them with clm_set_positions; the particles of the neighbouring slabs within the stencil reach (lcell cells)
  * are passed with clm_set_foreign: they are binned (with their periodic images) like any other particle and serve as
  * partners j, but never act as particle i, so every pair evaluation of the single-GPU sweep happens on exactly one rank.
- * Indices: owned particles 1..n, foreign ones n+1..n+n_foreign.  clm_cell_coords returns the 0-based reference-cell
+ * Indices: owned particles 1..n, foreign ones n+1..n+n_foreign; per-particle INPUT side arrays of a map (weights,
+ * velocities, aux_x / aux_y) then have n + n_foreign rows in that order, per-particle OUTPUTS n rows.  clm_cell_coords returns the 0-based reference-cell
  * index along `axis` of arbitrary coordinates with exactly the arithmetic of the build (ownership / halo selection).
  * Supported for orthorhombic and non-periodic cells (triclinic self-set systems need global-index tie-breaks). */
 CLM_API int clm_set_foreign(clm_handle* h, int set, const void* aos_xyz, int64_t n, int on_device);

@@ -21,6 +21,18 @@ def _free_port():
     return p
 
 
+CUSTOM_SRC = """
+struct WeightedCount {   // scalar: sum par0 w_i w_j; per particle: sum_j w_j
+    static constexpr int NSCALAR = 1, NPART = 1, NAUX = 1, HIST = 0;
+    template <class T, class Out>
+    __device__ void operator()(const clm::NeighborPair<T>& p, const T* par, Out& out) const {
+        out.add_scalar(0, par[0] * p.ai[0] * p.aj[0]);
+        out.add_i(0, p.aj[0]);
+    }
+};
+"""
+
+
 def _worker(rank, world, port, case, q):
     import torch
     import torch.distributed as dist
@@ -31,7 +43,26 @@ def _worker(rank, world, port, case, q):
         torch.cuda.set_device(0)
         import celllistmap_b200  # noqa: F401
         from celllistmap_b200 import slab
-        dtype = np.float64 if case == "list" else np.float32
+        dtype = np.float64 if case in ("list", "aux") else np.float32
+        if case == "aux":
+            # side arrays travel with the halo: Coulomb weights, pair velocities, a user pair function
+            w = W.c1_neighborlist(5000)
+            rng = np.random.default_rng(9)
+            wts, vel = 0.5 + rng.random(5000), rng.random((5000, 3))
+            s = slab.SlabSystem(w["unitcell"], w["cutoff"], dtype=dtype)
+            xo, ids = s.partition(w["x"])
+            own = ids.cpu().numpy() - 1
+            s.update(xo, ids, aux=wts[own])
+            f = torch.zeros((s.n_owned, 3), dtype=torch.float64, device="cuda")
+            e = s.map_coulomb(-9.8, f)
+            sc, pp, _, _ = s.map_custom(CUSTOM_SRC, "WeightedCount", params=(2.0,))
+            mi, mj, md = s.mindist()
+            s.update(xo, ids, aux=vel[own])
+            counts, sums = s.pairvel(np.array([0.0, 0.02, 0.04, 0.06, 0.08, 0.1]))
+            q.put((rank, own.tolist(), f.cpu().numpy().tolist(), float(e), sc.cpu().numpy().tolist(), pp.cpu().numpy().tolist(),
+                   (mi, mj, md), counts.cpu().numpy().tolist(), sums.cpu().numpy().tolist()))
+            s.close()
+            return
         if case == "list":
             w = W.c1_neighborlist(6000)
         else:
@@ -99,3 +130,37 @@ def test_slab_lj_forces(oracle_mod, world):
         assert r[4] > 0
     assert seen.all()
     assert np.abs(f - wf).max() <= 4e-5 * np.abs(wf).max()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_side_arrays(oracle_mod, world):
+    """Coulomb energy + forces, a user pair function, the minimum distance and the pair-velocity histogram of a
+    slab-decomposed system equal the single-process results (side arrays exchanged with the halo)."""
+    res = _run(world, "aux")
+    w = W.c1_neighborlist(5000)
+    rng = np.random.default_rng(9)
+    wts, vel = 0.5 + rng.random(5000), rng.random((5000, 3))
+    o = oracle_mod.Oracle(w["x"], w["cutoff"], unitcell=w["unitcell"])
+    we, wf = o.coulomb(-9.8, wts, forces=True)
+    i, j, d = o.neighborlist()
+    i, j = i - 1, j - 1
+    want_sc = 2.0 * (wts[i] * wts[j]).sum()
+    want_pp = np.zeros(5000)
+    np.add.at(want_pp, i, wts[j])
+    np.add.at(want_pp, j, wts[i])
+    rbins = np.array([0.0, 0.02, 0.04, 0.06, 0.08, 0.1])
+    wc, ws = o.pairvel(vel, rbins)
+    k = np.argmin(d)
+    f, pp = np.zeros((5000, 3)), np.zeros(5000)
+    for r in res:
+        own = np.array(r[1])
+        f[own] = np.array(r[2])
+        pp[own] = np.array(r[5])[:, 0]
+        assert abs(r[3] - we) <= 1e-10 * abs(we)
+        assert abs(r[4][0] - want_sc) <= 1e-10 * want_sc
+        mi, mj, md = r[6]
+        assert md == d[k] and {mi, mj} == {int(i[k]) + 1, int(j[k]) + 1}
+        assert r[7] == wc.tolist()
+        assert np.abs(np.array(r[8]) - ws).max() <= 1e-10 * np.abs(ws).max()
+    assert np.abs(f - wf).max() <= 1e-9 * np.abs(wf).max()
+    assert np.abs(pp - want_pp).max() <= 1e-10 * want_pp.max()
