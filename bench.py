@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--cpu-nside", type=int, default=100, help="size of the CPU arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-f64", action="store_true")
+    ap.add_argument("--no-nl", action="store_true", help="N > 1: skip the neighbour-list build timing")
     ap.add_argument("--workload", default="auto")
     ap.add_argument("--multi-nside", type=int, default=400, help="N > 1: lattice sites along y and z")
     ap.add_argument("--multi-nx-per-rank", type=int, default=50, help="N > 1: lattice planes along x per rank (50 x 400 x 400 = 8M particles per GPU)")

@@ -127,6 +127,32 @@ def run(args, rank, world, local):
                 e2e.append(a.elapsed_time(b))
         te = torch.tensor([sum(e2e) / len(e2e)], dtype=torch.float64, device=dev)
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        # BASELINE metric 2 at N GPUs: neighbour-list build (halo exchange + cell-list build + emission, per-rank lists left
+        # on the device), max over ranks
+        nl_ms, nl_pairs = [], 0
+        if not args.no_nl:
+            for it in range(4):
+                flush_buf.zero_()
+                torch.cuda.synchronize()
+                dist.barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                s.update(x_dev)
+                nl_pairs = s.h.neighborlist_count()          # synchronous: the record count comes back to the host
+                b.record(stream)
+                b.synchronize()
+                if it >= 1:
+                    nl_ms.append(a.elapsed_time(b))
+            tn = torch.tensor([statistics.mean(nl_ms), float(nl_pairs)], dtype=torch.float64, device=dev)
+            tn_max, tn_sum = tn.clone(), tn.clone()
+            dist.all_reduce(tn_max, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tn_sum, op=dist.ReduceOp.SUM)
+        # reference-stencil candidates of the GLOBAL system (roofline work model): cell histogram summed over ranks
+        m = [int(np.floor(float(unitcell[k]) / cutoff)) for k in range(3)]
+        cs = [float(unitcell[k]) / m[k] for k in range(3)]
+        ci = [torch.clamp((torch.remainder(x_dev[:, k].double(), float(unitcell[k])) / cs[k]).floor().long(), 0, m[k] - 1) for k in range(3)]
+        hist = torch.bincount((ci[0] * m[1] + ci[1]) * m[2] + ci[2], minlength=m[0] * m[1] * m[2]).double()
+        dist.all_reduce(hist)
     if rank == 0:
         ms = float(tmax[0])
         n_total = int(tsum[3])
@@ -147,6 +173,25 @@ def run(args, rank, world, local):
             "breakdown_ms": {"step_max": ms, "sweep_kernel_max": float(tmax[1]), "build_max": float(tmax[4])},
             "energy": float(e_host),
         }
+        # roofline of the dominant kernel (k_sweep), per rank: algorithmic flops of the rank's share of the pairs over the
+        # slowest rank's kernel time, against the FP32 FMA peak measured live on this GPU
+        h = hist.cpu().numpy().reshape(m)
+        C_st = (h * (h - 1) / 2).sum()
+        for dx in (-1, 0, 1):
+            for dy in (-1, 0, 1):
+                for dz in (-1, 0, 1):
+                    if (dx, dy, dz) > (0, 0, 0):
+                        C_st += (h * np.roll(h, (-dx, -dy, -dz), axis=(0, 1, 2))).sum()
+        F_alg = (bench.FLOPS_PER_CANDIDATE * C_st + bench.FLOPS_PER_PAIR_LJ * P_in) / world
+        peak = clm._capi.measure_fma_peak(np.float32, local)
+        ach = F_alg / (float(tmax[1]) * 1e-3) / 1e12
+        line["roofline"] = {"bound": "fp32", "kernel": "k_sweep<float, MODE_ALL, FLJ<float,true,true>> (per rank, slowest rank)", "achieved": ach,
+                            "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                            "algorithmic_flops_per_launch": F_alg, "kernel_ms": float(tmax[1]),
+                            "peak_source": "FP32 FMA peak measured live by clm_measure_fma_peak on rank 0's GPU; no tensor cores on this path"}
+        if not args.no_nl:
+            line["neighborlist_build"] = {"config": "the same slab-decomposed system, cutoff 12 A: halo exchange + cell-list build + emission, per-rank lists left on the device",
+                                          "pairs": int(tn_sum[1]), "ms_max_over_ranks": float(tn_max[0])}
         print(json.dumps(line))
     s.close()
     dist.barrier()

@@ -258,7 +258,6 @@ class CustomPairFunction(_Functor):
 
     def __init__(self, source, name, params=(), aux=None, aux_y=None):
         self.source, self.name, self.params, self.aux, self.aux_y = source, name, tuple(params), aux, aux_y
-        self._compiled = {}   # handle -> (functor id, info)
 
     def check(self, dtype=np.float64):
         """compile-only check (needs libnvrtc, no device); returns the NVRTC log."""
@@ -268,10 +267,12 @@ class CustomPairFunction(_Functor):
             _raise(e)
 
     def _get(self, sys):
-        key = id(sys._h)
-        if key not in self._compiled:
-            self._compiled[key] = sys._h.custom_compile(self.source, self.name)
-        return self._compiled[key]
+        # compiled functors belong to the handle (one NVRTC compilation per handle, sweep mode and functor source)
+        cache = sys._h.__dict__.setdefault("_custom_cache", {})
+        key = (self.source, self.name)
+        if key not in cache:
+            cache[key] = sys._h.custom_compile(self.source, self.name)
+        return cache[key]
 
     def info(self, sys):
         i = self._get(sys)[1]
