@@ -8,9 +8,12 @@
 //     tile: lane -> (i-slot = lane % TI, j-slice = lane / TI).  Particle i lives in registers.
 //   * for every stencil row the candidate partners are ONE contiguous record range
 //     [cell_start[first - w], cell_start[last + w + 1]) because cells are linearised along the row; the
-//     half-width w per row offset comes from a host table (rows farther than the cutoff are skipped).  All
-//     lanes of a j-slice read the same record (128-bit broadcast load, L1-resident): no shared-memory traffic.
-//   * warps fetch tiles from a global atomic counter (persistent grid = SMs x resident CTAs).
+//     half-width w per row offset comes from a host table (rows farther than the cutoff are skipped).
+//   * the row ranges of a tile are bulk-copied (TMA 1-D copies, one per row, issued by the lane that classified the
+//     row) into the warp's shared-memory staging buffer, culled against the bounding box of the tile's particles and
+//     compacted in place; one flat loop then evaluates 32 pairs per warp step, every lane of a j-slice reading the
+//     same staged record (128-bit broadcast LDS).
+//   * warps fetch tiles from a global atomic counter, one tile ahead (persistent grid = SMs x resident CTAs).
 //   * exactly-once rules are the reference's, expressed on REFERENCE cells (device cell / sub):
 //     MODE_HALF (orthorhombic / non-periodic self): partner's reference cell is lexicographically after the
 //     home reference cell -- the reference's forward stencil, Box.jl:436-457 -- or the same cell and a later
@@ -481,8 +484,6 @@ template <class T> struct IsList<FList<T>> { static constexpr bool value = true;
 // ===================================================================================================
 // the sweep kernel
 // ===================================================================================================
-struct TrueTag { static constexpr bool value = true; };
-struct FalseTag { static constexpr bool value = false; };
 template <class T> __device__ __forceinline__ T huge_coord();
 template <> __device__ __forceinline__ float huge_coord<float>() { return 1.0e30f; }
 template <> __device__ __forceinline__ double huge_coord<double>() { return 1.0e200; }
@@ -539,9 +540,9 @@ __device__ __forceinline__ double tile_max(double v) {
     return v;
 }
 
-// Row classes of one tile: skipped; DIRECT = swept straight from global memory with per-lane record thresholds
-// (MODE_HALF rows inside the home reference row); STAGED = bulk-copied into the warp's shared-memory buffer and swept
-// by one flat loop.  The own row of the full-shell self sweep is staged too: the tile's own records are blanked in the
+// Row classes of one tile: skipped; STAGED = bulk-copied into the warp's shared-memory buffer, culled and swept by one
+// flat loop.  MODE_HALF rows inside the home reference row additionally have a DIRECT part (the reference cells the tile
+// itself touches): bulk-copied uncompacted and swept with per-lane record thresholds.  The own row of the full-shell self sweep is staged too: the tile's own records are blanked in the
 // staging buffer and the pairs inside the tile are evaluated from registers (shuffles), which needs no self test in the
 // flat loop.
 enum { ROW_SKIP = 0, ROW_DIRECT = 1, ROW_STAGED = 2 };
@@ -632,6 +633,7 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
             // ---- lane r classifies stencil row r and fetches its record range --------------------------------
             const int r = rb + lane;
             int cls = ROW_SKIP, j0 = 0, j1 = 0, rowbase = 0, own = 0;   // own: bit 0 = the tile's own row, bit 1 = same reference row (MODE_HALF)
+            int dj0 = 0, dj1 = 0;   // MODE_HALF, same reference row: the part of the row that needs the per-lane (record-order) rule
             if (r < nrows_st) {
                 const int dz = a.rdz[r], dy = a.rdy[r];
                 const int z2 = iz + dz, y2 = iy + dy;
@@ -649,31 +651,38 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                     const int xa = max(cxa - w, 0), xb = min(cxb + w, a.nx - 1);
                     j0 = a.cell_start_j[rowbase + xa];
                     j1 = a.cell_start_j[rowbase + xb + 1];
-                    if (j1 > j0) {
-                        cls = ROW_STAGED;
-                        if (MODE == MODE_HALF && rel == 0) cls = ROW_DIRECT;
+                    if (MODE == MODE_HALF && rel == 0) {
+                        // Partners before the reference cell of the tile's first record are never taken; partners after the
+                        // reference cell of its LAST record follow the plain forward rule for every lane and go through the
+                        // staged path (cull + flat loop) like the rows of later reference rows.  Only the reference cells
+                        // the tile itself touches need the per-lane rule.
+                        const int* csj = a.cell_start_j + rowbase;
+                        const int tsplit = csj[min((div_sub(cxb) + 1) * sub, a.nx)];
+                        dj0 = max(j0, csj[div_sub(cxa) * sub]);
+                        dj1 = min(j1, tsplit);
+                        j0 = max(j0, tsplit);
                     }
+                    if (j1 > j0) cls = ROW_STAGED;
                 }
             }
             // ---- direct rows -------------------------------------------------------------------------------------
-            unsigned mdir = __ballot_sync(0xffffffffu, cls == ROW_DIRECT);
+            unsigned mdir = (MODE == MODE_HALF) ? __ballot_sync(0xffffffffu, dj1 > dj0) : 0u;
             while (mdir) {
                 const int src = __ffs(mdir) - 1;
                 mdir &= mdir - 1;
-                const int bj0 = __shfl_sync(0xffffffffu, j0, src), bj1 = __shfl_sync(0xffffffffu, j1, src);
+                const int bj0 = __shfl_sync(0xffffffffu, dj0, src), bj1 = __shfl_sync(0xffffffffu, dj1, src);
                 const int brow = __shfl_sync(0xffffffffu, rowbase, src), bown = __shfl_sync(0xffffffffu, own, src);
                 // MODE_HALF, same reference row: partners in a later reference cell (j >= thrA) follow the forward rule;
                 // partners in the SAME reference cell (thrB <= j < thrA) are taken once: real-real pairs from the earlier
                 // record, real-image pairs from the real particle (the distance is symmetric, so this deviation from the
                 // reference's slot order changes nothing -- and it keeps the rule independent of the record order, which
                 // differs between the ranks of a slab-decomposed system)
-                int thrA = 0, thrB = 0, lo_row = bj0;
+                int thrA = 0, thrB = 0;
+                const int lo_row = bj0;
                 if (MODE == MODE_HALF && (bown & 2)) {
                     const int* csj = a.cell_start_j + brow;
                     thrA = csj[min((rfx_i + 1) * sub, a.nx)];
                     thrB = csj[rfx_i * sub];
-                    // no lane takes a partner that sits before the reference cell of the tile's first record
-                    lo_row = max(bj0, csj[div_sub(cxa) * sub]);
                 }
                 // the row is bulk-copied piecewise into the warp's staging buffer (record order kept: the rules above
                 // need the record index) and swept from shared memory
