@@ -666,61 +666,79 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                 }
             }
             // ---- direct rows -------------------------------------------------------------------------------------
-            unsigned mdir = (MODE == MODE_HALF) ? __ballot_sync(0xffffffffu, dj1 > dj0) : 0u;
-            while (mdir) {
-                const int src = __ffs(mdir) - 1;
-                mdir &= mdir - 1;
-                const int bj0 = __shfl_sync(0xffffffffu, dj0, src), bj1 = __shfl_sync(0xffffffffu, dj1, src);
-                const int brow = __shfl_sync(0xffffffffu, rowbase, src), bown = __shfl_sync(0xffffffffu, own, src);
-                // MODE_HALF, same reference row: partners in a later reference cell (j >= thrA) follow the forward rule;
-                // partners in the SAME reference cell (thrB <= j < thrA) are taken once: real-real pairs from the earlier
-                // record, real-image pairs from the real particle (the distance is symmetric, so this deviation from the
-                // reference's slot order changes nothing -- and it keeps the rule independent of the record order, which
-                // differs between the ranks of a slab-decomposed system)
-                int thrA = 0, thrB = 0;
-                const int lo_row = bj0;
-                if (MODE == MODE_HALF && (bown & 2)) {
-                    const int* csj = a.cell_start_j + brow;
-                    thrA = csj[min((rfx_i + 1) * sub, a.nx)];
-                    thrB = csj[rfx_i * sub];
-                }
-                // the row is bulk-copied piecewise into the warp's staging buffer (record order kept: the rules above
-                // need the record index) and swept from shared memory
-                for (int p0 = lo_row; p0 < bj1; p0 += CAP) {
-                    const int pn = min(CAP, bj1 - p0);
-                    if (lane == 0) {
-                        fence_proxy_async();
-                        mbar_expect_tx(mbar, (uint32_t)pn * (uint32_t)sizeof(RecT<T>) * (F::AUX ? 2u : 1u));
-                        bulk_g2s(buf_addr, a.rec_j + p0, (uint32_t)pn * (uint32_t)sizeof(RecT<T>), mbar);
-                        if constexpr (F::AUX) bulk_g2s(abuf_addr, f.aux_j() + p0, (uint32_t)pn * (uint32_t)sizeof(RecT<T>), mbar);
-                    }
-                    mbar_wait(mbar, parity);
-                    parity ^= 1u;
-                    __syncwarp();
-                    auto body = [&](const RecT<T>* q, const int jc, const bool inb) {
-                        const RecT<T> rj = ldrec_s(q);
-                        bool ok = inb;
-                        if (MODE == MODE_HALF) {
-                            const bool gi = (c.ri.tag & TG::GHOST) != 0, gj = (rj.tag & TG::GHOST) != 0;
-                            ok = ok && ((jc >= thrA) ? !(gi && gj) : (jc >= thrB && !gi && (gj || jc > c.ki)));
+            if (MODE == MODE_HALF) {
+                unsigned mdir = __ballot_sync(0xffffffffu, dj1 > dj0);
+                if (mdir) {
+                    // All direct segments of the tile are bulk-copied in ONE pass (one expect_tx, one wait) when they fit the
+                    // staging buffer together -- they are short: the reference cells the tile touches, a few device rows --
+                    // and row by row, piecewise, when they do not.  Record order is kept: the rules below need the record index.
+                    const int dlen = max(dj1 - dj0, 0);
+                    int dincl = dlen;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, dincl, o); if (lane >= o) dincl += v; }
+                    const int doff = dincl - dlen, dtotal = __shfl_sync(0xffffffffu, dincl, 31);
+                    const bool batched = dtotal <= CAP;
+                    if (batched) {
+                        if (lane == 0) { fence_proxy_async(); mbar_expect_tx(mbar, (uint32_t)dtotal * (uint32_t)sizeof(RecT<T>) * (F::AUX ? 2u : 1u)); }
+                        __syncwarp();
+                        if (dlen > 0) {
+                            bulk_g2s(buf_addr + (uint32_t)doff * (uint32_t)sizeof(RecT<T>), a.rec_j + dj0, (uint32_t)dlen * (uint32_t)sizeof(RecT<T>), mbar);
+                            if constexpr (F::AUX) bulk_g2s(abuf_addr + (uint32_t)doff * (uint32_t)sizeof(RecT<T>), f.aux_j() + dj0, (uint32_t)dlen * (uint32_t)sizeof(RecT<T>), mbar);
                         }
-                        else if (MODE == MODE_TRI) ok = ok && (idx_i < (rj.tag & TG::MASK));
-                        RecT<T> aj = rj;
-                        if constexpr (F::AUX) aj = ldrec_s(abuf + (q - buf));
-                        pair_body(rj, aj, jc, ok);
-                    };
-                    const RecT<T>* q = buf + c.slice;
-                    int jc = p0 + c.slice;
-                    const int nfull = pn / nslice;
-                    int s_ = 0;
-#pragma unroll 1
-                    for (; s_ + 4 <= nfull; s_ += 4) {
-                        body(q, jc, true); body(q + nslice, jc + nslice, true); body(q + 2 * nslice, jc + 2 * nslice, true); body(q + 3 * nslice, jc + 3 * nslice, true);
-                        q += 4 * nslice; jc += 4 * nslice;
+                        mbar_wait(mbar, parity);
+                        parity ^= 1u;
+                        __syncwarp();
                     }
+                    while (mdir) {
+                        const int src = __ffs(mdir) - 1;
+                        mdir &= mdir - 1;
+                        const int bj0 = __shfl_sync(0xffffffffu, dj0, src), bj1 = __shfl_sync(0xffffffffu, dj1, src);
+                        const int brow = __shfl_sync(0xffffffffu, rowbase, src), boff = __shfl_sync(0xffffffffu, doff, src);
+                        // Partners in a later reference cell (j >= thrA) follow the forward rule; partners in the SAME reference
+                        // cell (thrB <= j < thrA) are taken once: real-real pairs from the earlier record, real-image pairs from
+                        // the real particle (the distance is symmetric, so this deviation from the reference's slot order changes
+                        // nothing -- and it keeps the rule independent of the record order, which differs between the ranks of a
+                        // slab-decomposed system)
+                        const int* csj = a.cell_start_j + brow;
+                        const int thrA = csj[min((rfx_i + 1) * sub, a.nx)], thrB = csj[rfx_i * sub];
+                        for (int p0 = bj0; p0 < bj1; p0 += CAP) {
+                            const int pn = min(CAP, bj1 - p0);
+                            const RecT<T>* base = buf + boff;
+                            if (!batched) {
+                                base = buf;
+                                if (lane == 0) {
+                                    fence_proxy_async();
+                                    mbar_expect_tx(mbar, (uint32_t)pn * (uint32_t)sizeof(RecT<T>) * (F::AUX ? 2u : 1u));
+                                    bulk_g2s(buf_addr, a.rec_j + p0, (uint32_t)pn * (uint32_t)sizeof(RecT<T>), mbar);
+                                    if constexpr (F::AUX) bulk_g2s(abuf_addr, f.aux_j() + p0, (uint32_t)pn * (uint32_t)sizeof(RecT<T>), mbar);
+                                }
+                                mbar_wait(mbar, parity);
+                                parity ^= 1u;
+                                __syncwarp();
+                            }
+                            auto body = [&](const RecT<T>* q, const int jc, const bool inb) {
+                                const RecT<T> rj = ldrec_s(q);
+                                const bool gi = (c.ri.tag & TG::GHOST) != 0, gj = (rj.tag & TG::GHOST) != 0;
+                                const bool ok = inb && ((jc >= thrA) ? !(gi && gj) : (jc >= thrB && !gi && (gj || jc > c.ki)));
+                                RecT<T> aj = rj;
+                                if constexpr (F::AUX) aj = ldrec_s(abuf + (q - buf));
+                                pair_body(rj, aj, jc, ok);
+                            };
+                            const RecT<T>* q = base + c.slice;
+                            int jc = p0 + c.slice;
+                            const int nfull = pn / nslice;
+                            int s_ = 0;
 #pragma unroll 1
-                    for (; s_ < nfull; ++s_) { body(q, jc, true); q += nslice; jc += nslice; }
-                    if (jc - c.slice < p0 + pn) { const bool inb = jc < p0 + pn; body(inb ? q : buf, jc, inb); }
+                            for (; s_ + 4 <= nfull; s_ += 4) {
+                                body(q, jc, true); body(q + nslice, jc + nslice, true); body(q + 2 * nslice, jc + 2 * nslice, true); body(q + 3 * nslice, jc + 3 * nslice, true);
+                                q += 4 * nslice; jc += 4 * nslice;
+                            }
+#pragma unroll 1
+                            for (; s_ < nfull; ++s_) { body(q, jc, true); q += nslice; jc += nslice; }
+                            if (jc - c.slice < p0 + pn) { const bool inb = jc < p0 + pn; body(inb ? q : base, jc, inb); }
+                            if (!batched) __syncwarp();
+                        }
+                    }
                     __syncwarp();
                 }
             }
