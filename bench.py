@@ -338,7 +338,7 @@ def main():
         "gpu_launches": r32["launches"] * args.steps,
         "roofline": {"bound": "fp32", "kernel": "k_sweep<float, MODE_ALL, FLJ<float,true,true>>", "achieved": achieved_tf, "peak": fp32_peak_tf,
                      "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak_tf,
-                     "traffic": 23.35e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload (profiles/r1k_sweep_lj_f32.txt)",
+                     "traffic": 22.57e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload (profiles/r1_final_kernels.txt; the 12 MB of forces stay in the 126 MB L2)",
                      "algorithmic_flops_per_launch": F_alg, "kernel_ms": r32["sweep_ms"], "build_ms": r32["build_ms"],
                      "peak_source": "FP32 FMA peak measured live by clm_measure_fma_peak (register-resident FMA loop, all SMs); "
                                     f"nominal {fp32_nominal_tf:.1f} TFLOP/s = 148 SM x 128 lanes x 2 x sm_max_mhz from {peaks_src}; no tensor cores on this path",
