@@ -19,19 +19,19 @@ template <class T> static bool hist_thresholds(T width, int nbins, std::vector<T
     auto bin_of_r = [&](T r) { return std::floor(r / width); };
     thr.assign((size_t)nbins + 1, T(0));
     for (int b = 1; b <= nbins; ++b) {
-        // smallest r with floor(r / width) >= b
+        // smallest r with floor(r / width) >= b: walk from the real-number guess b * width (a few ulps at most)
         T r = (T)b * width;
         if (std::isinf(r)) { thr[b] = inf; continue; }
-        int guard = 0;
-        while (r > T(0) && bin_of_r(std::nextafter(r, T(-1))) >= (T)b && ++guard < 64) r = std::nextafter(r, T(-1));
-        while (bin_of_r(r) < (T)b && ++guard < 128) r = std::nextafter(r, inf);
+        int steps = 0;
+        while (r > T(0) && bin_of_r(std::nextafter(r, T(-1))) >= (T)b) { r = std::nextafter(r, T(-1)); if (++steps > 64) return false; }
+        while (bin_of_r(r) < (T)b) { r = std::nextafter(r, inf); if (++steps > 128) return false; }
         // smallest d2 with sqrt_rn(d2) >= r
         T x = r * r;
         if (std::isinf(x)) { thr[b] = inf; continue; }
-        while (x > T(0) && std::sqrt(std::nextafter(x, T(-1))) >= r && ++guard < 192) x = std::nextafter(x, T(-1));
-        while (std::sqrt(x) < r && ++guard < 256) x = std::nextafter(x, inf);
-        if (guard >= 255) return false;   // pathological width: use the direct form
-        thr[b] = x;
+        steps = 0;
+        while (x > T(0) && std::sqrt(std::nextafter(x, T(-1))) >= r) { x = std::nextafter(x, T(-1)); if (++steps > 64) return false; }
+        while (std::sqrt(x) < r) { x = std::nextafter(x, inf); if (++steps > 128) return false; }
+        thr[b] = x;   // a walk that does not converge (pathological width: denormal, huge) falls back to the direct form
     }
     return true;
 }
@@ -71,14 +71,18 @@ template <class T> int Engine<T>::map_dist_hist(const void* width, int nbins, in
 }
 
 // smallest x >= 0 with sqrt_rn(x) > edge (std::sqrt is correctly rounded, like the device's __fsqrt_rn / __dsqrt_rn)
-template <class T> static T sqrt_threshold(T edge) {
+template <class T> static T sqrt_threshold(T edge, bool& converged) {
     if (!(edge >= T(0))) return (edge != edge) ? std::numeric_limits<T>::infinity() : T(0);   // NaN edge: never exceeded; negative: always
     if (std::isinf(edge)) return std::numeric_limits<T>::infinity();
     const T inf = std::numeric_limits<T>::infinity();
     T x = edge * edge;
     if (std::isinf(x)) x = std::numeric_limits<T>::max();
-    while (x > T(0) && std::sqrt(x) > edge) x = std::nextafter(x, T(-1));       // walk down to a value that does not exceed
-    while (x < inf && !(std::sqrt(x) > edge)) x = std::nextafter(x, inf);       // then up to the first one that does
+    // edge * edge is within a few ulps of the threshold: walk down to a value that does not exceed, then up to the first
+    // one that does (denormal d2 ranges, where the walk would be long, cannot occur between distinct particles)
+    int k = 0;
+    for (; k < 4096 && x > T(0) && std::sqrt(x) > edge; ++k) x = std::nextafter(x, T(-1));
+    for (; k < 4096 && x < inf && !(std::sqrt(x) > edge); ++k) x = std::nextafter(x, inf);
+    if (k >= 4096) converged = false;   // the caller falls back to the direct form (sqrt on the device)
     return x;
 }
 
@@ -98,15 +102,19 @@ template <class T> int Engine<T>::map_pairvel(const void* vx, const void* vy, co
     CLM_CK(cudaMemsetAsync(d_hsum.p, 0, (size_t)nbins * sizeof(double), stream));
     CLM_CK(cudaMemcpyAsync(d_rbins.p, rbins, ((size_t)nbins + 1) * sizeof(T), cudaMemcpyHostToDevice, stream));
     const int aux_bytes = (SWEEP_THREADS / 32) * StageBytes<T, true>::value;   // side-array staging buffers precede the bins
+    bool thr_ok = true;
+    T thr2[VEL_EDGES_INLINE];
+    for (int e = 0; e < VEL_EDGES_INLINE; ++e) thr2[e] = (e <= nbins && nbins + 1 <= VEL_EDGES_INLINE) ? sqrt_threshold(((const T*)rbins)[e], thr_ok) : std::numeric_limits<T>::infinity();
     auto run = [&](auto fn) -> int {
         fn.v_i = sets[0].aux.p; fn.v_j = sets[two_sets ? 1 : 0].aux.p; fn.rbins = d_rbins.p;
         fn.inline_edges = (nbins + 1 <= VEL_EDGES_INLINE) ? 1 : 0;
-        for (int e = 0; e < VEL_EDGES_INLINE; ++e) fn.thr2[e] = (fn.inline_edges && e <= nbins) ? sqrt_threshold(((const T*)rbins)[e]) : std::numeric_limits<T>::infinity();
+        for (int e = 0; e < VEL_EDGES_INLINE; ++e) fn.thr2[e] = (fn.inline_edges && e <= nbins) ? thr2[e] : std::numeric_limits<T>::infinity();
         fn.hb.nbins = nbins; fn.hb.priv = (nbins <= NB_PRIV_MAX) ? 1 : 0; fn.hb.off = StageTotal<T, true>::value + aux_bytes; fn.hb.g_counts = d_hcount.p; fn.hb.g_sums = d_hsum.p;
         return launch_reduce(fn, (size_t)aux_bytes + hist_smem(nbins, fn.hb.priv != 0, sizeof(T)));
     };
     int lrc;
-    if (nbins + 1 <= 8) lrc = run(FVel<T, 1, 1>());                       // <= 7 bins: private bins (NB_PRIV_MAX = 16)
+    if (!thr_ok) lrc = (nbins <= NB_PRIV_MAX) ? run(FVel<T, 0, 1>()) : run(FVel<T, 0, 0>());
+    else if (nbins + 1 <= 8) lrc = run(FVel<T, 1, 1>());                       // <= 7 bins: private bins (NB_PRIV_MAX = 16)
     else if (nbins <= NB_PRIV_MAX) lrc = run(FVel<T, 2, 1>());
     else if (nbins + 1 <= VEL_EDGES_INLINE) lrc = run(FVel<T, 2, 0>());
     else lrc = run(FVel<T, 0, 0>());

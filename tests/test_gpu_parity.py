@@ -252,6 +252,22 @@ def test_histograms_distances_on_bin_edges(clm, oracle_mod, dtype, width, nbins)
     assert np.array_equal(counts, o.pairvel(v, rbins)[0])
 
 
+def test_pairwise_velocities_pathological_edges(clm, oracle_mod):
+    """bin edges whose squares underflow (the host cannot tabulate exact d2 thresholds for them: the map falls back to the
+    direct sqrt form) and more edges than fit the kernel parameters: counts stay exact"""
+    rng = np.random.default_rng(23)
+    x, uc = random_system(rng, 2500, 3, "ortho", np.float64)
+    v = rng.random(x.shape)
+    o = oracle_mod.Oracle(x, 2.0, unitcell=uc)
+    for rbins in (np.array([0.0, 1e-200, 0.4, 0.8, 1.2, 1.6, 2.0]), np.linspace(0.0, 2.0, 41), np.linspace(0.0, 2.0, 14)):
+        nb = len(rbins) - 1
+        sys = clm.ParticleSystem(xpositions=x, unitcell=uc, cutoff=2.0, output=(np.zeros(nb, np.int64), np.zeros(nb)))
+        counts, sums = clm.pairwise(clm.PairwiseVelocities(rbins, v), sys)
+        wc, ws = o.pairvel(v, rbins)
+        assert np.array_equal(counts, wc)
+        assert np.abs(sums - ws).max() <= 1e-10 * max(np.abs(ws).max(), 1.0)
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("kind", ["ortho", "triclinic"])
