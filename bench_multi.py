@@ -130,6 +130,10 @@ def run(args, rank, world, local):
         # BASELINE metric 2 at N GPUs: neighbour-list build (halo exchange + cell-list build + emission, per-rank lists left
         # on the device), max over ranks
         nl_ms, nl_pairs = [], 0
+        # ~77.4 in-cutoff pairs per particle at this density and cutoff, 24-byte records: skip when the per-rank list would
+        # not comfortably fit next to the particle arrays (the 64M-particle single-GPU run: 119 GB)
+        if not args.no_nl and n_own * 77.4 * 24 * 1.2 > 60e9:
+            args.no_nl = True
         if not args.no_nl:
             for it in range(4):
                 flush_buf.zero_()
