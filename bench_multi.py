@@ -132,7 +132,9 @@ def run(args, rank, world, local):
         nl_ms, nl_pairs = [], 0
         # ~77.4 in-cutoff pairs per particle at this density and cutoff, 24-byte records: skip when the per-rank list would
         # not comfortably fit next to the particle arrays (the 64M-particle single-GPU run: 119 GB)
-        if not args.no_nl and n_own * 77.4 * 24 * 1.2 > 60e9:
+        big = torch.tensor([1.0 if n_own * 77.4 * 24 * 1.2 > 60e9 else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(big, op=dist.ReduceOp.MAX)           # one decision for every rank (the timing below has collectives)
+        if float(big) > 0:
             args.no_nl = True
         if not args.no_nl:
             for it in range(4):
