@@ -42,8 +42,11 @@ def _worker(rank, world, port, n_inner, lcell, q):
         mine = plan.owner_of(c) == rank
         xo, io, co = torch.from_numpy(x[mine]), torch.from_numpy(ids[mine]), torch.from_numpy(c[mine])
         lo_m, hi_m = plan.face_masks(co, rank)
-        got_x, got_i = slab.exchange_halo([xo, io], lo_m, hi_m, plan, rank)
-        q.put((rank, ids[mine].tolist(), got_i.tolist(), bool(torch.equal(got_x, torch.from_numpy(x[got_i.numpy() - 1]))), plan.bounds))
+        # a per-particle side array (weights, velocities, user inputs) travels with the halo like the coordinates
+        aux = np.stack([np.sin(ids), np.cos(ids)], 1)
+        got_x, got_i, got_a = slab.exchange_halo([xo, io, torch.from_numpy(aux[mine])], lo_m, hi_m, plan, rank)
+        same = bool(torch.equal(got_x, torch.from_numpy(x[got_i.numpy() - 1]))) and bool(torch.equal(got_a, torch.from_numpy(aux[got_i.numpy() - 1])))
+        q.put((rank, ids[mine].tolist(), got_i.tolist(), same, plan.bounds))
     finally:
         dist.destroy_process_group()
 
@@ -65,7 +68,7 @@ def test_halo_exchange_gloo(world, n_inner, lcell):
     c = _layers(x, L, n_inner, lcell)
     owned_all = []
     for rank, owned, foreign, same_bits, bounds in res:
-        assert same_bits, "halo coordinates must arrive bit-identical"
+        assert same_bits, "halo coordinates and side arrays must arrive bit-identical, row for row"
         owned_all += owned
         lo, hi = bounds[rank], bounds[rank + 1]
         assert all(lo <= c[i - 1] < hi for i in owned)
