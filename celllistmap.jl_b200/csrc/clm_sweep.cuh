@@ -545,7 +545,7 @@ __device__ __forceinline__ double tile_max(double v) {
 // itself touches): bulk-copied uncompacted and swept with per-lane record thresholds.  The own row of the full-shell self sweep is staged too: the tile's own records are blanked in the
 // staging buffer and the pairs inside the tile are evaluated from registers (shuffles), which needs no self test in the
 // flat loop.
-enum { ROW_SKIP = 0, ROW_DIRECT = 1, ROW_STAGED = 2 };
+enum { ROW_SKIP = 0, ROW_STAGED = 2 };
 
 // resident CTAs per SM the register allocation aims at (measured, C2 LJ forces: F32 8 CTAs = 64 registers 0.473 ms,
 // 10 CTAs = 48 registers 0.515 ms, 6 CTAs 0.488 ms; F64 is limited to 6 CTAs by its 8 KB staging buffers: 80 registers,
@@ -632,7 +632,7 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
         for (int rb = 0; rb < nrows_st; rb += 32) {
             // ---- lane r classifies stencil row r and fetches its record range --------------------------------
             const int r = rb + lane;
-            int cls = ROW_SKIP, j0 = 0, j1 = 0, rowbase = 0, own = 0;   // own: bit 0 = the tile's own row, bit 1 = same reference row (MODE_HALF)
+            int cls = ROW_SKIP, j0 = 0, j1 = 0, rowbase = 0, own = 0;   // own: the tile's own row
             int dj0 = 0, dj1 = 0;   // MODE_HALF, same reference row: the part of the row that needs the per-lane (record-order) rule
             if (r < nrows_st) {
                 const int dz = a.rdz[r], dy = a.rdy[r];
@@ -646,7 +646,7 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                     use = rel >= 0;
                 }
                 if (use) {
-                    own = ((dy == 0 && dz == 0) ? 1 : 0) | ((MODE == MODE_HALF && rel == 0) ? 2 : 0);
+                    own = (dy == 0 && dz == 0) ? 1 : 0;
                     rowbase = (z2 * a.ny + y2) * (a.nx + 1);
                     const int xa = max(cxa - w, 0), xb = min(cxb + w, a.nx - 1);
                     j0 = a.cell_start_j[rowbase + xa];
