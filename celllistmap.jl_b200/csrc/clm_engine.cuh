@@ -180,8 +180,9 @@ template <class T> struct Engine : EngineBase {
     template <int MODE, class F> int launch(const F& f, size_t functor_smem) {
         auto kern = k_sweep<T, MODE, F>;
         const size_t smem = (size_t)StageTotal<T, F::AUX>::value + functor_smem;   // per-warp staging buffers + mbarriers, then the functor's bins
-        static size_t smem_set = 0;                                // per instantiation
-        if (smem > smem_set) { CLM_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); smem_set = smem; }
+        static size_t smem_set[64] = {0};                          // per instantiation and device (the attribute is per device)
+        size_t& set = smem_set[device & 63];
+        if (smem > set) { CLM_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = smem; }
         int bps = 0;
         CLM_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SWEEP_THREADS, smem));
         if (bps < 1) return fail(CLM_ERR_CUDA, "sweep kernel does not fit on an SM");
