@@ -12,6 +12,7 @@
 module CellListMapB200
 
 using StaticArrays
+using LinearAlgebra: Diagonal
 
 export ParticleSystem, pairwise!, update!, resize_output!, neighborlist, neighborlist!, InPlaceNeighborList,
        NeighborPair, get_computing_box, LJEnergy, LJForces, LJEnergyAndForces, CoulombEnergy, CoulombEnergyAndForces,
@@ -103,10 +104,11 @@ function _sync!(sys::ParticleSystem{N,T}) where {N,T}
         rc = Ref(sys.cutoff)
         if isnothing(sys.unitcell)
             _check(h, ccall((:clm_set_box, libclm), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Cint, Ref{T}, Cint), h, CLM_NONPERIODIC, C_NULL, 0, rc, sys.lcell))
-        elseif sys.unitcell isa SVector
-            _check(h, ccall((:clm_set_box, libclm), Cint, (Ptr{Cvoid}, Cint, Ref{SVector{N,T}}, Cint, Ref{T}, Cint), h, CLM_ORTHORHOMBIC, Ref(sys.unitcell), 0, rc, sys.lcell))
-        else   # SMatrix memory is column-major with columns = lattice vectors: exactly what the ABI takes
-            _check(h, ccall((:clm_set_box, libclm), Cint, (Ptr{Cvoid}, Cint, Ref{SMatrix{N,N,T,N*N}}, Cint, Ref{T}, Cint), h, CLM_TRICLINIC, Ref(sys.unitcell), 1, rc, sys.lcell))
+        else   # sides -> orthorhombic, matrix -> triclinic; SMatrix memory is column-major with columns = lattice vectors: what the ABI takes
+            uc = collect(T, vec(sys.unitcell))
+            is_matrix = sys.unitcell isa SVector ? 0 : 1
+            GC.@preserve uc _check(h, ccall((:clm_set_box, libclm), Cint, (Ptr{Cvoid}, Cint, Ptr{T}, Cint, Ref{T}, Cint),
+                                            h, is_matrix == 1 ? CLM_TRICLINIC : CLM_ORTHORHOMBIC, uc, is_matrix, rc, sys.lcell))
         end
         sys.boxdirty = false; sys.xupdated = true
     end
