@@ -106,3 +106,13 @@ PATHOLOGICAL_2D_CELLS = [
     np.array([[1.0, 0.2], [0.0, 1.2]]), np.array([[1.0, 0.2], [0.2, 1.2]]), np.array([[1.2, 0.2], [0.2, 1.2]]),
 ]
 # test_pathological matrices (test/modules/Testing.jl:572-585) incl. negative entries are generated in the tests.
+
+
+# cell_limits(align_cell(m)) (test/internals/CellOperations.jl:159-194): bounding box of the aligned cell's vertices.
+# (matrix with COLUMNS = lattice vectors as in the reference, expected lo, expected hi, exact?)
+CELL_LIMITS_KATS = [
+    ([[10.0, 5.0], [5.0, 10.0]], [0.0, 0.0], [20.12461179749811, 6.708203932499369], False),          # :168-171
+    ([[10.0, 5.0], [0.0, 10.0]], [0.0, -8.94427190999916], [15.652475842498529, 0.0], False),          # :176-179
+    ([[1.0, 0.0, 0.0], [0.0, 2.0, 0.0], [0.0, 0.0, 1.0]], [0.0, -1.0, 0.0], [2.0, 0.0, 1.0], True),    # :184-188
+    ([[1.0, 0.0, 0.0], [0.0, 2.0, 0.0], [0.0, 0.0, 3.0]], [0.0, 0.0, -1.0], [3.0, 2.0, 0.0], True),    # :190-194
+]

@@ -351,6 +351,12 @@ def test_grid_kats(clm):
     c = K.COMPUTING_BOX_KAT
     lo, hi = clm.get_computing_box(clm.ParticleSystem(xpositions=np.zeros((1, 3)), unitcell=c["unitcell"], cutoff=c["cutoff"], output=0.0))
     assert np.allclose(lo, c["lo"], atol=1e-15) and np.allclose(hi, c["hi"], atol=1e-15)
+    # align_cell + cell_limits of the reference (test/internals/CellOperations.jl:159-194) through the product's Box
+    for m, want_lo, want_hi, _ in K.CELL_LIMITS_KATS:
+        m = np.array(m, dtype=np.float64)
+        rc = 0.05
+        lo, hi = clm.get_computing_box(clm.ParticleSystem(xpositions=np.zeros((1, m.shape[0])), unitcell=m, cutoff=rc, output=0.0))
+        assert np.allclose(lo + rc, want_lo, rtol=1e-12, atol=1e-10) and np.allclose(hi - rc, want_hi, rtol=1e-12, atol=1e-10)
 
 
 def test_boundary_kats(clm):

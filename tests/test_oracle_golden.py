@@ -133,3 +133,26 @@ def test_nan_is_rejected(oracle_mod):
     assert "Invalid coordinates" in str(ei.value) and "index 7" in str(ei.value)
     with pytest.raises(oracle_mod.OracleError):  # unit cell check (Box.jl:243)
         oracle_mod.Oracle(x[:5], 0.6, unitcell=[1.0, 1.0, 1.0])
+
+
+@pytest.mark.parametrize("kat", K.CELL_LIMITS_KATS, ids=lambda k: str(k[0]))
+def test_align_cell_and_cell_limits_kats(oracle_mod, kat):
+    """align_cell + cell_limits of the reference (src/internals/CellOperations.jl:337-479) through the oracle's Box:
+    a triclinic box's computing box is (lo - lcell*cs, hi + lcell*cs) with cs = cutoff/lcell and origin = 0
+    (Box.jl:252), so the limits of the aligned cell are recovered from it."""
+    m, lo, hi, exact = kat
+    m = np.array(m, dtype=np.float64)
+    n = m.shape[0]
+    cutoff = 0.05
+    o = oracle_mod.Oracle(np.zeros((1, n)), cutoff, unitcell=m, triclinic=True)
+    b = o.box()
+    got_lo, got_hi = b["cb_min"] + cutoff, b["cb_max"] - cutoff
+    if exact:
+        assert np.allclose(got_lo, lo, rtol=0, atol=1e-15) and np.allclose(got_hi, hi, rtol=0, atol=1e-15)
+    else:
+        assert np.allclose(got_lo, lo, rtol=1e-12, atol=1e-10) and np.allclose(got_hi, hi, rtol=1e-12, atol=1e-10)
+    # the aligned cell keeps the lattice: first (longest) vector along +x, same volume
+    a = b["aligned_unit_cell"]
+    assert abs(abs(np.linalg.det(a)) - abs(np.linalg.det(m))) <= 1e-12 * abs(np.linalg.det(m))
+    k = int(np.argmax(np.linalg.norm(m, axis=0)))
+    assert np.allclose(a[:, k][1:], 0.0, atol=1e-12) and a[0, k] > 0
