@@ -116,3 +116,15 @@ CELL_LIMITS_KATS = [
     ([[1.0, 0.0, 0.0], [0.0, 2.0, 0.0], [0.0, 0.0, 1.0]], [0.0, -1.0, 0.0], [2.0, 0.0, 1.0], True),    # :184-188
     ([[1.0, 0.0, 0.0], [0.0, 2.0, 0.0], [0.0, 0.0, 3.0]], [0.0, 0.0, -1.0], [3.0, 2.0, 0.0], True),    # :190-194
 ]
+
+# align_cell (test/internals/CellOperations.jl:113-128): (m, aligned m, rotation R) with l = sqrt(2)/2; COLUMNS = lattice vectors
+_L = 2.0 ** 0.5 / 2.0
+ALIGN_CELL_KATS = [
+    ([[_L, 0.0], [_L, 1.0]], [[1.0, _L], [0.0, _L]], [[_L, _L], [-_L, _L]]),          # :117-120
+    ([[-_L, 0.0], [_L, 1.0]], [[1.0, _L], [0.0, -_L]], [[-_L, _L], [-_L, -_L]]),       # :122-125
+]
+# wrap_relative_to (test/internals/CellOperations.jl:7-26): (x, y, wrap(x rel. y), wrap(y rel. x)), cell sides +-10
+WRAP_RELATIVE_KATS = [
+    ([15.0, 13.0], [4.0, 2.0], [5.0, 3.0], [14.0, 12.0]),
+    ([-7.0, -6.0], [1.0, 2.0], [3.0, 4.0], [-9.0, -8.0]),
+]

@@ -129,3 +129,13 @@ def test_header_is_plain_c_and_library_loads_from_c(clm):
     assert "version 100" in out.stdout
     assert f"sizeof clm_box_info {ctypes.sizeof(clm._capi.BoxInfo)} clm_stats {ctypes.sizeof(clm._capi.Stats)} clm_custom_info {ctypes.sizeof(clm._capi.CustomInfo)}" in out.stdout
     assert "Dimension must be 2 or 3" in out.stdout
+
+
+def test_wrap_relative_to_kats(clm):
+    """public helper wrap_relative_to (src/internals/CellOperations.jl:102-127) against the reference's own vectors,
+    with matrix and side-vector cells of either sign (test/internals/CellOperations.jl:7-26)"""
+    from golden import kats as K
+    for x, y, xy, yx in K.WRAP_RELATIVE_KATS:
+        for cell in (np.diag([10.0, 10.0]), np.diag([-10.0, -10.0]), [10.0, 10.0], [-10.0, -10.0]):
+            assert np.allclose(clm.wrap_relative_to(x, y, cell), xy, atol=1e-12)
+            assert np.allclose(clm.wrap_relative_to(y, x, cell), yx, atol=1e-12)

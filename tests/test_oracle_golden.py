@@ -156,3 +156,28 @@ def test_align_cell_and_cell_limits_kats(oracle_mod, kat):
     assert abs(abs(np.linalg.det(a)) - abs(np.linalg.det(m))) <= 1e-12 * abs(np.linalg.det(m))
     k = int(np.argmax(np.linalg.norm(m, axis=0)))
     assert np.allclose(a[:, k][1:], 0.0, atol=1e-12) and a[0, k] > 0
+
+
+@pytest.mark.parametrize("kat", K.ALIGN_CELL_KATS, ids=["l0l1", "-l0l1"])
+def test_align_cell_2d_kats(oracle_mod, kat):
+    """align_cell in 2-D (src/internals/CellOperations.jl:353-375): aligned matrix and rotation"""
+    m, want_a, want_r = (np.array(v, dtype=np.float64) for v in kat)
+    b = oracle_mod.Oracle(np.zeros((1, 2)), 0.05, unitcell=m, triclinic=True).box()
+    assert np.allclose(b["aligned_unit_cell"], want_a, atol=1e-14)
+    assert np.allclose(b["rotation"], want_r, atol=1e-14)
+    assert np.allclose(b["rotation"] @ b["inv_rotation"], np.eye(2), atol=1e-14)
+
+
+def test_align_cell_3d_random_rotations(oracle_mod):
+    """a rotated diag(3, 2, 1) cell is brought back with its longest vector along +x and the plane of the other two
+    containing the x axis (test/internals/CellOperations.jl:138-150)"""
+    rng = np.random.default_rng(4)
+    m = np.diag([3.0, 2.0, 1.0])
+    for _ in range(5):
+        q, _r = np.linalg.qr(rng.standard_normal((3, 3)))
+        if np.linalg.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        b = oracle_mod.Oracle(np.zeros((1, 3)), 0.05, unitcell=q @ m, triclinic=True).box()
+        a = b["aligned_unit_cell"]
+        assert np.allclose(a[:, 0], m[:, 0], atol=1e-12)
+        assert np.allclose(np.cross([1.0, 0.0, 0.0], np.cross(a[:, 1], a[:, 2])), 0.0, atol=1e-10)
