@@ -610,6 +610,7 @@ class InPlaceNeighborList:
         self.show_progress = show_progress
         self._list = np.zeros(0, dtype=nl_dtype(self.sys.dtype))
         self.n = 0
+        self.n_cutoff_band = 0   # pairs of the last list whose d2 lies within 1 ulp of cutoff^2 (north_star: reported separately)
 
     def update(self, x=None, y=None, *, cutoff=None, unitcell=None, parallel=None):
         """update!(system, x, [y]; cutoff, unitcell, parallel) (src/API/neighborlist.jl:159-169)."""
@@ -629,6 +630,7 @@ class InPlaceNeighborList:
         except ClmError as e:
             _raise(e)
         self.n = n
+        self.n_cutoff_band = int(s._h.stats().n_cutoff_band)
         s.output = self._list[:n]
         return s.output
 

@@ -42,9 +42,9 @@ template <class T> int Engine<T>::init(int dim_, int device_) {
 template <class T> Engine<T>::~Engine() {
     cudaSetDevice(device);
     if (own_stream) cudaStreamSynchronize(own_stream);
-    for (auto& s : sets) { s.pos.release(); s.fpos.release(); s.rec.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
+    for (auto& s : sets) { s.pos.release(); s.fpos.release(); s.rec.release(); s.rec_n3.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
     dscal.release(); tiles.release(); d_res.release();
-    d_hcount.release(); nl.release(); d_hsum.release(); d_rbins.release(); d_forces.release(); d_minmax.release(); d_minpart.release(); d_minres.release();
+    d_hcount.release(); nl.release(); d_hsum.release(); d_rbins.release(); d_forces.release(); d_facc.release(); d_minmax.release(); d_minpart.release(); d_minres.release();
     custom_store_free(custom_store);
     if (h_dscal) cudaFreeHost(h_dscal);
     if (h_res) cudaFreeHost(h_res);
@@ -315,6 +315,7 @@ template <class T> int Engine<T>::build_enqueue() {
             DevSet<T>& S = sets[s];
             const size_t want = std::max<size_t>((size_t)((double)(S.n + S.n_foreign) * img_factor * 1.25) + 4096, (size_t)std::max<int64_t>(S.n_tot, 1));
             CLM_CK(S.rec.ensure(want));
+            if (want_n3 && s == 0) CLM_CK(S.rec_n3.ensure(S.rec.cap));
             CLM_CK(S.cell_start.ensure((size_t)ncp + 2));
             CLM_CK(S.counters.ensure((size_t)(2 * ncp + nref)));
             S.cell_count = S.counters.p; S.cell_nact = S.counters.p + ncp; S.ref_real = S.counters.p + 2 * ncp;
@@ -323,8 +324,8 @@ template <class T> int Engine<T>::build_enqueue() {
             const int64_t nall = S.n + S.n_foreign;
             const int nb = (int)((nall + 255) / 256);
             if (nall > 0) {
-                if (dim == 3) k_bin<T, 3, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, 0, ds);
-                else k_bin<T, 2, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, 0, ds);
+                if (dim == 3) k_bin<T, 3, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, nullptr, 0, ds);
+                else k_bin<T, 2, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, nullptr, 0, ds);
                 CLM_CK(cudaGetLastError());
                 stats.launches += 1;
             }
@@ -334,8 +335,8 @@ template <class T> int Engine<T>::build_enqueue() {
             CLM_CK(cudaGetLastError());
             stats.launches += 1;
             if (nall > 0) {
-                if (dim == 3) k_bin<T, 3, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), ds);
-                else k_bin<T, 2, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), ds);
+                if (dim == 3) k_bin<T, 3, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, (want_n3 && s == 0) ? S.rec_n3.p : nullptr, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), ds);
+                else k_bin<T, 2, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, (want_n3 && s == 0) ? S.rec_n3.p : nullptr, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), ds);
                 CLM_CK(cudaGetLastError());
                 stats.launches += 1;
             }
@@ -359,6 +360,7 @@ template <class T> int Engine<T>::build_enqueue() {
     }
     validate_pending = true;
     dirty = false;
+    have_n3 = want_n3;
     return CLM_OK;
 }
 
@@ -512,6 +514,7 @@ template <class T> int Engine<T>::set_option(const char* name, int64_t v) {
     if (!name) return fail(CLM_ERR_ARGUMENT, "option name is NULL");
     const std::string s(name);
     if (s == "sub") { if (v < 0 || v > LF_MAX) return fail(CLM_ERR_ARGUMENT, "sub must be in 0..7"); opt_sub = (int)v; dirty = true; return CLM_OK; }
+    if (s == "n3") { opt_n3 = (v < 0) ? -1 : (v ? 1 : 0); return CLM_OK; }
     if (s == "blocks_per_sm") { if (v < 0) return fail(CLM_ERR_ARGUMENT, "blocks_per_sm must be >= 0"); opt_bps = (int)v; return CLM_OK; }
     return fail(CLM_ERR_ARGUMENT, "unknown option " + s);
 }

@@ -109,13 +109,14 @@ __device__ __forceinline__ double shfl_t(double v, int src) { return __shfl_sync
 template <class T, int DIM, bool SCATTER>
 __global__ void __launch_bounds__(256)
 k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __restrict__ fpos, int n, int n_own, int* __restrict__ cell_cursor,
-      int* __restrict__ cell_nact, int* __restrict__ ref_real, RecT<T>* __restrict__ rec, int rec_cap, int* __restrict__ dscal) {
+      int* __restrict__ cell_nact, int* __restrict__ ref_real, RecT<T>* __restrict__ rec, RecT<T>* __restrict__ rec_n3, int rec_cap, int* __restrict__ dscal) {
     typedef TagT<T> TG;
     const int ip = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     constexpr int NIMG = (DIM == 3) ? 27 : 9;
     constexpr int CENTER = (DIM == 3) ? 13 : 4;
     T p[3] = {T(0), T(0), T(0)};
     unsigned okmask = 0u;      // candidate images of this lane's particle (none for invalid / interior / non-periodic)
+    int real_slot = 0;         // scatter pass: where this lane's real record went
     if (ip < n) {
         T x[DIM];
         bool bad = false;
@@ -139,7 +140,10 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
                 ref_real[rlin] = 1;
             } else if (slot < rec_cap) {
                 strec(&rec[slot], p[0], p[1], p[2], (typename TG::type)ip | TG::HOME | foreign);
+                // slot-tagged twin of the record array (clm_sweep_n3.cuh): 4th word = slot of the particle's real record
+                if (rec_n3) strec(&rec_n3[slot], p[0], p[1], p[2], (typename TG::type)(unsigned)slot);
             }
+            real_slot = slot;
             // replicate_particle! (Box.jl:556-566): images x + aligned_cell*idx, idx in {-1,0,1}^N \ {0}, kept iff inside the
             // computing box [cb_min, cb_max).  Orthorhombic cells: the shift of image index (i1,i2,i3) is (i1*L1, i2*L2, i3*L3)
             // exactly, so which indices can land inside the computing box is decided per dimension.
@@ -180,6 +184,7 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
         const int k_th = w - __shfl_sync(0xffffffffu, excl, s);
         const unsigned m = __shfl_sync(0xffffffffu, okmask, s);
         const int ips = __shfl_sync(0xffffffffu, ip, s);
+        const int rslot = __shfl_sync(0xffffffffu, real_slot, s);
         const T px = shfl_t(p[0], s), py = shfl_t(p[1], s), pz = shfl_t(p[2], s);
         if (w >= total) continue;
         const int img = (int)__fns(m, 0u, k_th + 1);
@@ -200,6 +205,7 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
             const bool home = ref_real[rq] != 0;
             if (home && !foreign) cell_nact[lq] = 1;
             strec(&rec[qslot], q[0], q[1], q[2], (typename TG::type)ips | TG::GHOST | foreign | (home ? TG::HOME : (typename TG::type)0));
+            if (rec_n3) strec(&rec_n3[qslot], q[0], q[1], q[2], (typename TG::type)((unsigned)rslot | 0x80000000u));   // image -> its original's slot | GHOST
         }
     }
 }

@@ -67,23 +67,27 @@ template <class T, class U> struct FCustom {
     static_assert(NS >= 0 && NS <= CUSTOM_MAX_SCALAR, "NSCALAR must be in 0..8");
     static_assert(NP >= 0 && NP <= CUSTOM_MAX_PART, "NPART must be in 0..4");
     static_assert(NA >= 0 && NA <= CUSTOM_MAX_AUX, "NAUX must be in 0..4");
-    struct Acc { T s[NS > 0 ? NS : 1]; };
-    struct IAcc { T v[NP > 0 ? NP : 1]; T a[4]; };
+    // scalar outputs: summed in T over one tile only, folded into a double per thread at the end of the tile (a Float32
+    // accumulator that lives for the whole persistent kernel loses the 1e-5 bar on million-particle systems)
+    struct Acc { double s[NS > 0 ? NS : 1]; };
+    struct IAcc { T v[NP > 0 ? NP : 1]; T a[4]; T s[NS > 0 ? NS : 1]; };
     static constexpr bool NEEDS_BAND = false, EXACT_D2 = true, AUX = (NA > 0);
 
     __device__ __forceinline__ const RecT<T>* aux_j() const { return reinterpret_cast<const RecT<T>*>(ax_j); }
     __device__ void init(Acc& a) const {
 #pragma unroll
-        for (int k = 0; k < (NS > 0 ? NS : 1); ++k) a.s[k] = T(0);
+        for (int k = 0; k < (NS > 0 ? NS : 1); ++k) a.s[k] = 0.0;
         if (HAS_HIST) hb.init();
     }
     __device__ void begin(IAcc& p, const Ctx<T>& c) const {
 #pragma unroll
         for (int k = 0; k < (NP > 0 ? NP : 1); ++k) p.v[k] = T(0);
 #pragma unroll
+        for (int k = 0; k < (NS > 0 ? NS : 1); ++k) p.s[k] = T(0);
+#pragma unroll
         for (int k = 0; k < 4; ++k) p.a[k] = (AUX && c.active && k < NA) ? ax_i[(size_t)c.ki * 4 + k] : T(0);
     }
-    __device__ __forceinline__ void call(Acc& a, IAcc& p, const Ctx<T>& c, const RecT<T>& rj, const T* aj, T d2) const {
+    __device__ __forceinline__ void call(Acc&, IAcc& p, const Ctx<T>& c, const RecT<T>& rj, const T* aj, T d2) const {
         NeighborPair<T> np;
         np.i = (long long)(c.ri.tag & TagT<T>::MASK) + 1;
         np.j = (long long)(rj.tag & TagT<T>::MASK) + 1;
@@ -100,7 +104,7 @@ template <class T, class U> struct FCustom {
         np.d2 = d2;
         np.ai = p.a; np.aj = aj;
         PairOutput<T, NS, NP, HAS_HIST> out;
-        out.s = a.s; out.pi = p.v; out.hb = &hb;
+        out.s = p.s; out.pi = p.v; out.hb = &hb;
         U()(np, par, out);
     }
     // functors without side arrays
@@ -114,7 +118,9 @@ template <class T, class U> struct FCustom {
             call(a, p, c, rj, av, d2);
         }
     }
-    __device__ void end(IAcc& p, const Ctx<T>& c) const {
+    __device__ void end(Acc& a, IAcc& p, const Ctx<T>& c) const {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) a.s[k] += (double)p.s[k];
         if (NP == 0) return;
         T v[NP > 0 ? NP : 1];
 #pragma unroll
@@ -132,7 +138,7 @@ template <class T, class U> struct FCustom {
         __shared__ double sm[4];
 #pragma unroll
         for (int k = 0; k < NS; ++k) {
-            const double s = block_sum((double)a.s[k], sm);
+            const double s = block_sum(a.s[k], sm);
             if (threadIdx.x == 0) atomicAdd(&res->f[k], s);
         }
         if (HAS_HIST) hb.flush();

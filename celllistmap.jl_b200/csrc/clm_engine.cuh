@@ -6,10 +6,12 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <type_traits>
 #include "clm_common.cuh"
 #include "clm_geometry.hpp"
 #include "clm_build.cuh"
 #include "clm_sweep.cuh"
+#include "clm_sweep_n3.cuh"
 
 namespace clm {
 
@@ -78,6 +80,8 @@ template <class T> struct DevSet {
     DBuf<T> fpos;            // foreign particles of a slab-decomposed system (owned by other ranks), AoS
     int64_t n_foreign = 0;
     DBuf<RecT<T>> rec;       // cell-sorted records, real + image particles
+    DBuf<RecT<T>> rec_n3;    // slot-tagged twin of rec (4th word = slot of the particle's real record | GHOST), written by the
+                             // scatter pass once a Newton's-third-law force map has been asked for (clm_sweep_n3.cuh)
     int64_t n_tot = 0, n_cells_real = 0;
     DBuf<int> cell_start;    // row pitch nfast + 1: [row * pitch + x] = first record of cell x, entry nfast = end of the row (after the scatter pass)
     DBuf<int> counters;      // one memset: [cell_count | cell_nact | ref_real]
@@ -115,6 +119,13 @@ template <class T> struct Engine : EngineBase {
     signed char row_hw[(2 * LF_MAX + 1) * (2 * LF_MAX + 1)];   // per stencil row: half-width along the row in device cells, -1 = skip
     int opt_sub = 0;                      // 0 = choose the sub-cell split from the particle density
     int tile_i = TILE_I, opt_bps = 0;
+    // self-set force maps: 1 = Newton's-third-law sweep (k_sweep_n3: every pair once, from the same periodic images as the
+    // reference, so Float32 forces match the reference's Float32 arithmetic to ~1e-6), 0 = full-shell k_sweep<MODE_ALL>
+    // (faster, but a pair that crosses the periodic boundary is evaluated from two different image pairs: 5.6e-5 in
+    // Float32 on the 1M-particle C2 system), -1 = by precision: Float32 -> 1, Float64 -> 0 (full shell: 1e-13, 10 % faster)
+    int opt_n3 = -1;
+    bool want_n3 = false, have_n3 = false;   // slot-tagged records requested / present in the current cell list
+    DBuf<T> d_facc;                       // record-ordered force accumulator rows (4 x T per record slot), all zero between maps
 
     int init(int dim_, int device_);
     ~Engine() override;
@@ -206,6 +217,39 @@ template <class T> struct Engine : EngineBase {
             case MODE_TRI: return launch<MODE_TRI>(f, smem);
             default: return launch<MODE_ALL>(f, smem);
         }
+    }
+    // Newton's-third-law force sweep of a self-set system (clm_sweep_n3.cuh): sweep into the record-ordered accumulator,
+    // then gather into the caller's particle order
+    bool n3_usable() const { return (opt_n3 < 0 ? sizeof(T) == 4 : opt_n3 != 0) && !two_sets && sets[0].n_foreign == 0; }
+    int n3_request() { want_n3 = true; if (!have_n3) dirty = true; return CLM_OK; }   // the list in place has no slot-tagged records: rebuild
+    template <int MODE, class F> int launch_n3(const F& f, T* out, int accumulate, T scale) {
+        auto kern = k_sweep_n3<T, MODE, F>;
+        const size_t smem = (size_t)N3Smem<T, F::AUX>::value;
+        static size_t smem_set[64] = {0};
+        size_t& set = smem_set[device & 63];
+        if (smem > set) { CLM_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = smem; }
+        int bps = 0;
+        CLM_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SWEEP_THREADS, smem));
+        if (bps < 1) return fail(CLM_ERR_CUDA, "sweep kernel does not fit on an SM");
+        if (opt_bps > 0) bps = std::min(bps, opt_bps);
+        int64_t grid = (int64_t)n_sm * bps;
+        grid = std::max<int64_t>(1, std::min<int64_t>(grid, (tiles_upper + (SWEEP_THREADS / 32) - 1) / (SWEEP_THREADS / 32)));
+        DevSet<T>& S = sets[0];
+        const size_t old_cap = d_facc.cap;
+        CLM_CK(d_facc.ensure(S.rec.cap * 4));
+        if (d_facc.cap != old_cap) CLM_CK(cudaMemsetAsync(d_facc.p, 0, d_facc.cap * sizeof(T), stream));
+        SweepArgs<T> a = make_args();
+        a.rec_j = S.rec_n3.p;
+        if (profile_sweep) CLM_CK(cudaEventRecord(ev2, stream));
+        kern<<<(unsigned)grid, SWEEP_THREADS, smem, stream>>>(a, f, S.rec.p, d_facc.p);
+        CLM_CK(cudaGetLastError());
+        if (profile_sweep) CLM_CK(cudaEventRecord(ev3, stream));
+        const int nb = (int)std::min<int64_t>((int64_t)n_sm * 8, (int64_t)(S.rec.cap + 255) / 256);
+        k_force_finish<T><<<std::max(nb, 1), 256, 0, stream>>>(S.rec.p, d_facc.p, dscal.p, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), out, dim, scale, accumulate, geom.rotated, geom);
+        CLM_CK(cudaGetLastError());
+        stats.launches += 2;
+        last_grid = (int)grid;
+        return CLM_OK;
     }
     int last_grid = 0;
 };

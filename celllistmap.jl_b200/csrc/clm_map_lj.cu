@@ -9,9 +9,28 @@ template <class T> int Engine<T>::map_lj(const void* p, int flags, void* e, void
     const T* c = (const T*)p;
     double scale = 1.0;
     const bool norm = FLJ<T, true, true>::can_normalise(c[0], c[1]);
+    const bool n3 = f && n3_usable();
     for (;;) {   // repeated only when the build's record-capacity estimate was too small (build_validate)
+    if (n3) n3_request();
     if (int rc = prepare_map(flags)) return rc;
-    if (f) {
+    if (n3) {
+        // self-set forces: every pair once, both particles updated (clm_sweep_n3.cuh)
+        ForceOut<T> fo;
+        if (int rc = forces_begin(f, flags, fo)) return rc;
+        const int mode = sweep_mode();
+        int rc;
+        if (norm) {
+            N3LJ<T, true, true> fn;
+            fn.set(c[0], c[1]);
+            rc = (mode == MODE_TRI) ? launch_n3<MODE_TRI>(fn, fo.forces, fo.accumulate, fn.fscale) : launch_n3<MODE_HALF>(fn, fo.forces, fo.accumulate, fn.fscale);
+        } else {
+            N3LJ<T, false, true> fn;
+            fn.set(c[0], c[1]);
+            rc = (mode == MODE_TRI) ? launch_n3<MODE_TRI>(fn, fo.forces, fo.accumulate, T(1)) : launch_n3<MODE_HALF>(fn, fo.forces, fo.accumulate, T(1));
+        }
+        if (rc) return rc;
+        scale = 1.0;
+    } else if (f) {
         // full-shell sweep: every ordered pair (i real, j any image) adds to f_i only -> one plain store per
         // particle, no atomics, no per-batch force copies; the energy is visited twice in self-set systems
         if (norm) {
@@ -47,6 +66,8 @@ template <class T> int Engine<T>::map_lj(const void* p, int flags, void* e, void
 template <class T> int Engine<T>::map_coulomb(const void* wx, const void* wy, const void* k, int flags, void* e, void* f) {
     if (!wx || !k) return fail(CLM_ERR_ARGUMENT, "weights / k pointer is NULL");
     if (two_sets && !wy) return fail(CLM_ERR_ARGUMENT, "weights of the second set are required for a two-set system");
+    const bool n3 = f && n3_usable();
+    if (n3) n3_request();
     if (int rc = build()) return rc;   // per-record side arrays are sized by the record count: validated build first
     if (int rc = prepare_map(flags)) return rc;
     const bool dev = (flags & CLM_OUT_DEVICE) != 0;
@@ -55,7 +76,15 @@ template <class T> int Engine<T>::map_coulomb(const void* wx, const void* wy, co
     const T* wi = sets[0].aux.p;
     const T* wj = sets[two_sets ? 1 : 0].aux.p;
     double scale = 1.0;
-    if (f) {
+    if (n3) {
+        // self-set forces: every pair once, both particles updated (clm_sweep_n3.cuh)
+        ForceOut<T> fo;
+        if (int rc = forces_begin(f, flags, fo)) return rc;
+        N3Coul<T, true> fn;
+        fn.k = *(const T*)k; fn.w_rec = wi; fn.fscale = T(1);
+        const int rc = (sweep_mode() == MODE_TRI) ? launch_n3<MODE_TRI>(fn, fo.forces, fo.accumulate, T(1)) : launch_n3<MODE_HALF>(fn, fo.forces, fo.accumulate, T(1));
+        if (rc) return rc;
+    } else if (f) {
         FCoul<T, true> fn;
         fn.k = *(const T*)k; fn.w_i = wi; fn.w_j = wj;
         if (int rc = forces_begin(f, flags, fn.fo)) return rc;

@@ -1,5 +1,6 @@
 // clm_map_sum_d_d2 (test functor), clm_map_mindist, clm_neighborlist(+copy).
 #include <cmath>
+#include <limits>
 #include "clm_engine.cuh"
 
 namespace clm {
@@ -78,6 +79,8 @@ template <class T> int Engine<T>::neighborlist(int flags, int64_t* n_out) {
         CLM_CK(nl.ensure(capacity * 3));
         FList<T> fn;
         fn.out = nl.p; fn.capacity = capacity;
+        fn.rc2_lo = std::nextafter(geom.cutoff_sqr, T(0));
+        fn.rc2_hi = std::nextafter(geom.cutoff_sqr, std::numeric_limits<T>::infinity());
         if (int rc = launch_reduce(fn, (size_t)(SWEEP_THREADS / 32) * LIST_STAGE_BYTES)) return rc;
         {
             const int v = build_validate();
@@ -92,6 +95,7 @@ template <class T> int Engine<T>::neighborlist(int flags, int64_t* n_out) {
         if (attempt == 2) return fail(CLM_ERR_CAPACITY, "neighbour list did not fit after resizing");
     }
     stats.n_pairs = nl_count;
+    stats.n_cutoff_band = (int64_t)h_res->c[RC_NBAND];
     *n_out = nl_count;
     return finish_map(flags);
 }

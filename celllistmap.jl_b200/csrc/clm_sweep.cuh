@@ -102,7 +102,7 @@ template <class T> __device__ __forceinline__ T block_sum(T v, T* smem /* >= 4 *
 
 // ===================================================================================================
 // functor catalogue.  Every functor: Acc (per thread, whole kernel), IAcc (per
-// particle i, one tile), init / begin / pair / end / finish.  pair() is called by all 32 lanes with a
+// particle i, one tile), init / begin / pair / end (folds the tile into Acc) / finish.  pair() is called by all 32 lanes with a
 // `hit` predicate so that warp collectives inside it are legal.
 // ===================================================================================================
 
@@ -118,7 +118,7 @@ template <class T> struct FSum {
         if (hit) { a.sd += (double)xsqrt(d2); a.sd2 += (double)d2; a.n += 1; }
         if (ok && d2 >= rc2_lo && d2 <= rc2_hi) a.band += 1;
     }
-    __device__ void end(IAcc&, const Ctx<T>&) const {}
+    __device__ void end(Acc&, IAcc&, const Ctx<T>&) const {}
     __device__ void finish(Acc& a, ResultBlock* res) const {
         __shared__ double sm[4];
         __shared__ unsigned long long smc[4];
@@ -187,37 +187,41 @@ template <class T, bool FORCES, bool NORM> struct FLJ {
     T c6, c12;
     T s2, escale, fscale;   // NORM: s2 = cbrt(c12/c6), escale = c6^2/c12, fscale = 6 c6^2/c12; !NORM: the direct form
     ForceOut<T> fo;
-    struct Acc { T e; };
-    struct IAcc { T fx, fy, fz; };
+    // the energy is summed in T only over ONE tile (a few hundred terms per thread) and folded into a double per thread
+    // at the end of the tile: a Float32 accumulator that lives for the whole persistent kernel loses the 1e-5 bar on
+    // million-particle systems (thousands of mixed-sign terms per thread)
+    struct Acc { double e; };
+    struct IAcc { T fx, fy, fz, e; };
     static constexpr bool NEEDS_BAND = false, EXACT_D2 = !FORCES, AUX = false;   // the full-shell force sweep has tolerance parity
-    __device__ void init(Acc& a) const { a.e = T(0); }
-    __device__ void begin(IAcc& p, const Ctx<T>&) const { p.fx = p.fy = p.fz = T(0); }
-    __device__ __forceinline__ void pair(Acc& a, IAcc& p, const Ctx<T>&, bool hit, bool, const RecT<T>&, int, T dx, T dy, T dz, T d2) const {
+    __device__ void init(Acc& a) const { a.e = 0.0; }
+    __device__ void begin(IAcc& p, const Ctx<T>&) const { p.fx = p.fy = p.fz = T(0); p.e = T(0); }
+    __device__ __forceinline__ void pair(Acc&, IAcc& p, const Ctx<T>&, bool hit, bool, const RecT<T>&, int, T dx, T dy, T dz, T d2) const {
         const T inv = hit ? fast_rcp<T>(d2) : T(0);
         if (NORM) {
             const T w = inv * s2;
             const T q = w * w * w;
             const T u = xfma(q, q, -q);        // q^2 - q
-            a.e += u;
+            p.e += u;
             if (FORCES) {
                 const T fs = inv * xfma(q, q, u);   // (2 q^2 - q) / d2
                 p.fx = xfma(fs, dx, p.fx); p.fy = xfma(fs, dy, p.fy); p.fz = xfma(fs, dz, p.fz);
             }
         } else {
             const T r6 = inv * inv * inv;
-            a.e = xfma(r6, xfma(c12, r6, -c6), a.e);
+            p.e = xfma(r6, xfma(c12, r6, -c6), p.e);
             if (FORCES) {
                 const T fs = inv * r6 * xfma(T(12) * c12, r6, T(-6) * c6);
                 p.fx = xfma(fs, dx, p.fx); p.fy = xfma(fs, dy, p.fy); p.fz = xfma(fs, dz, p.fz);
             }
         }
     }
-    __device__ void end(IAcc& p, const Ctx<T>& c) const {
+    __device__ void end(Acc& a, IAcc& p, const Ctx<T>& c) const {
+        a.e += (double)p.e;
         if (FORCES) { const T k = NORM ? fscale : T(1); fo.store(c, k * p.fx, k * p.fy, k * p.fz); }
     }
     __device__ void finish(Acc& a, ResultBlock* res) const {
         __shared__ double sm[4];
-        double e = block_sum((double)a.e, sm);
+        double e = block_sum(a.e, sm);
         if (threadIdx.x == 0) atomicAdd(&res->f[RB_ENERGY], e * (NORM ? (double)escale : 1.0));
     }
 #ifndef __CUDACC_RTC__
@@ -235,25 +239,27 @@ template <class T, bool FORCES> struct FCoul {
     const T* w_i;   // weights gathered into record order of set i / set j: one record-sized slot (w, 0, 0, 0) per record
     const T* w_j;
     ForceOut<T> fo;
-    struct Acc { T e; };
-    struct IAcc { T fx, fy, fz, wi; };
+    struct Acc { double e; };   // per-tile partial in T, folded into a double per tile (see FLJ)
+    struct IAcc { T fx, fy, fz, wi, e; };
     static constexpr bool NEEDS_BAND = false, EXACT_D2 = !FORCES, AUX = true;   // side array staged with the records
     __device__ __forceinline__ const RecT<T>* aux_j() const { return reinterpret_cast<const RecT<T>*>(w_j); }
-    __device__ void init(Acc& a) const { a.e = T(0); }
-    __device__ void begin(IAcc& p, const Ctx<T>& c) const { p.fx = p.fy = p.fz = T(0); p.wi = c.active ? k * w_i[(size_t)c.ki * 4] : T(0); }
-    __device__ __forceinline__ void pair(Acc& a, IAcc& p, const Ctx<T>&, bool hit, bool, const RecT<T>&, const RecT<T>& aj, T dx, T dy, T dz, T d2) const {
+    __device__ void init(Acc& a) const { a.e = 0.0; }
+    __device__ void begin(IAcc& p, const Ctx<T>& c) const { p.fx = p.fy = p.fz = T(0); p.e = T(0); p.wi = c.active ? k * w_i[(size_t)c.ki * 4] : T(0); }
+    __device__ __forceinline__ void pair(Acc&, IAcc& p, const Ctx<T>&, bool hit, bool, const RecT<T>&, const RecT<T>& aj, T dx, T dy, T dz, T d2) const {
         const T invd = hit ? fast_rsqrt<T>(d2) : T(0);
-        const T q = p.wi * aj.x * invd;     // k w_i w_j / d
-        a.e += q;
+        // the side-array slot of a padding record is never initialised (it may hold NaN / Inf left in shared memory by an
+        // earlier kernel, and NaN * 0 = NaN): a miss contributes an explicit zero
+        const T q = hit ? p.wi * aj.x * invd : T(0);     // k w_i w_j / d
+        p.e += q;
         if (FORCES) {
             const T g = q * invd * invd;  // k w_i w_j / d^3
             p.fx = xfma(g, dx, p.fx); p.fy = xfma(g, dy, p.fy); p.fz = xfma(g, dz, p.fz);
         }
     }
-    __device__ void end(IAcc& p, const Ctx<T>& c) const { if (FORCES) fo.store(c, p.fx, p.fy, p.fz); }
+    __device__ void end(Acc& a, IAcc& p, const Ctx<T>& c) const { a.e += (double)p.e; if (FORCES) fo.store(c, p.fx, p.fy, p.fz); }
     __device__ void finish(Acc& a, ResultBlock* res) const {
         __shared__ double sm[4];
-        double e = block_sum((double)a.e, sm);
+        double e = block_sum(a.e, sm);
         if (threadIdx.x == 0) atomicAdd(&res->f[RB_ENERGY], e);
     }
 };
@@ -337,7 +343,7 @@ template <class T, int PRIV> struct FHist {
             }
         }
     }
-    __device__ void end(IAcc&, const Ctx<T>&) const {}
+    __device__ void end(Acc&, IAcc&, const Ctx<T>&) const {}
     __device__ void finish(Acc&, ResultBlock*) const { hb.flush(); }
 };
 
@@ -385,7 +391,7 @@ template <class T, int EDGE_MODE, int PRIV> struct FVel {   // EDGE_MODE 1: <= 8
             }
         }
     }
-    __device__ void end(IAcc&, const Ctx<T>&) const {}
+    __device__ void end(Acc&, IAcc&, const Ctx<T>&) const {}
     __device__ void finish(Acc&, ResultBlock*) const { hb.flush(); }
 };
 
@@ -407,7 +413,7 @@ template <class T> struct FMin {
             if (better(d2, i, j, a.d2, a.i, a.j)) { a.d2 = d2; a.i = i; a.j = j; }
         }
     }
-    __device__ void end(IAcc&, const Ctx<T>&) const {}
+    __device__ void end(Acc&, IAcc&, const Ctx<T>&) const {}
     __device__ void finish(Acc& a, ResultBlock*) const {
         __shared__ MinPartial sm[SWEEP_THREADS / 32];
         T d2 = a.d2; long long i = a.i, j = a.j;
@@ -438,14 +444,15 @@ constexpr int LIST_STAGE_BYTES = LIST_STAGE_RECORDS * 24;
 template <class T> struct FList {
     unsigned long long* out;        // capacity * 3 words
     unsigned long long capacity;
-    struct Acc { int cnt; };        // warp-uniform: records waiting in the warp's staging buffer
+    T rc2_lo, rc2_hi;               // prevfloat / nextfloat of cutoff^2: the at-cutoff band is counted next to the list
+    struct Acc { int cnt; unsigned band; };   // warp-uniform: records waiting in the warp's staging buffer, at-cutoff pairs seen
     struct IAcc {};
     static constexpr bool NEEDS_BAND = false, EXACT_D2 = true, AUX = false;
     __device__ __forceinline__ unsigned long long* stage() const {
         extern __shared__ __align__(128) unsigned char dsm_raw[];
         return reinterpret_cast<unsigned long long*>(dsm_raw + StageTotal<T>::value + (threadIdx.x >> 5) * LIST_STAGE_BYTES);
     }
-    __device__ void init(Acc& a) const { a.cnt = 0; }
+    __device__ void init(Acc& a) const { a.cnt = 0; a.band = 0u; }
     __device__ void begin(IAcc&, const Ctx<T>&) const {}
     __device__ static __forceinline__ unsigned long long dbits(float d) { return (unsigned long long)__float_as_uint(d); }
     __device__ static __forceinline__ unsigned long long dbits(double d) { return (unsigned long long)__double_as_longlong(d); }
@@ -463,7 +470,10 @@ template <class T> struct FList {
         a.cnt = 0;
         __syncwarp();
     }
-    __device__ __forceinline__ void pair(Acc& a, IAcc&, const Ctx<T>& c, bool hit, bool, const RecT<T>& rj, int, T, T, T, T d2, ResultBlock* res) const {
+    __device__ __forceinline__ void pair(Acc& a, IAcc&, const Ctx<T>& c, bool hit, bool ok, const RecT<T>& rj, int, T, T, T, T d2, ResultBlock* res) const {
+        // pairs whose d2 is within 1 ulp of cutoff^2 (north_star: "reported separately"; the reference documents that such
+        // pairs may fall on either side, docs/src/neighborlists.md:12)
+        a.band += __popc(__ballot_sync(0xffffffffu, ok && d2 >= rc2_lo && d2 <= rc2_hi));
         const unsigned m = __ballot_sync(0xffffffffu, hit);
         if (m == 0u) return;
         if (hit) {
@@ -475,8 +485,11 @@ template <class T> struct FList {
         a.cnt += __popc(m);
         if (a.cnt > LIST_STAGE_RECORDS - 32) flush(a, res);
     }
-    __device__ void end(IAcc&, const Ctx<T>&) const {}
-    __device__ void finish(Acc& a, ResultBlock* res) const { if (a.cnt > 0) flush(a, res); }
+    __device__ void end(Acc&, IAcc&, const Ctx<T>&) const {}
+    __device__ void finish(Acc& a, ResultBlock* res) const {
+        if (a.cnt > 0) flush(a, res);
+        if ((threadIdx.x & 31) == 0 && a.band) atomicAdd(&res->c[RC_NBAND], (unsigned long long)a.band);
+    }
 };
 template <class F> struct IsList { static constexpr bool value = false; };
 template <class T> struct IsList<FList<T>> { static constexpr bool value = true; };
@@ -841,7 +854,7 @@ k_sweep(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f) {
                 pair_body(rj, aj, tl.k0 + js, ok);
             }
         }
-        f.end(ia, c);
+        f.end(acc, ia, c);
     }
     f.finish(acc, a.res);
 }

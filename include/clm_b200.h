@@ -92,7 +92,8 @@ typedef struct clm_stats {
     int64_t n_cells_real[2];  /* cells containing at least one real particle */
     int64_t n_tiles;          /* work items of the last build (row tiles of the reference set) */
     int64_t n_pairs;          /* in-cutoff pairs of the last map that counts them (sum_d_d2, neighborlist) */
-    int64_t n_cutoff_band;    /* pairs with |d2 - cutoff^2| <= 1 ulp(cutoff^2) seen by the last clm_map_sum_d_d2 */
+    int64_t n_cutoff_band;    /* pairs with |d2 - cutoff^2| <= 1 ulp(cutoff^2) seen by the last clm_map_sum_d_d2 / clm_neighborlist:
+                                 the at-cutoff band of north_star, "reported separately" (docs/src/neighborlists.md:12) */
     double build_ms;          /* device time of the last clm_build (CUDA events) */
     double map_ms;            /* device time of the last map / neighborlist call run with CLM_PROFILE */
     double sweep_ms;          /* device time of the pair-sweep kernel alone inside that call (CUDA events around the launch) */

@@ -97,10 +97,10 @@ def test_custom_scalars(clm, oracle_mod, dtype, kind, two):
     want = np.array([(2.0 / d).sum(), (wx.astype(np.float64)[i - 1] * wj * d * d).sum(), float(len(d))])
     tol = RTOL[np.dtype(dtype)]
     assert out.scalars[2] == want[2]
-    assert np.all(np.abs(out.scalars[:2] - want[:2]) <= 4 * tol * np.abs(want[:2])), (out.scalars, want)
+    assert np.all(np.abs(out.scalars[:2] - want[:2]) <= tol * np.abs(want[:2])), (out.scalars, want)
     # reset = false accumulates on the values found in the output (API/pairwise.jl:52-54)
     out2 = clm.pairwise(f, sys, reset=False)
-    assert np.all(np.abs(out2.scalars - 2 * want) <= 8 * tol * np.abs(want))
+    assert np.all(np.abs(out2.scalars - 2 * want) <= 2 * tol * np.abs(want))
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -132,10 +132,16 @@ def test_custom_per_particle(clm, oracle_mod, dtype, kind, two):
     tol = RTOL[np.dtype(dtype)]
     assert np.array_equal(out.per_particle[:, 0], want[:, 0].astype(dtype))
     scale = np.abs(want[:, 1:]).max()
-    # forces are sums of terms of mixed sign: absolute error relative to the largest component
-    assert np.abs(out.per_particle[:, 1:] - want[:, 1:]).max() <= 20 * tol * scale
+    # forces are sums of terms of mixed sign: absolute error relative to the largest component.  `want` is Float64
+    # arithmetic on the same inputs: for Float32 inputs the distance to it is bounded by the conditioning of the wrapped
+    # coordinates (a d^-2 force at the closest pair: 3 * 4 ulp(coordinate) / d_min, tests/parity_util.py)
+    from parity_util import conditioning_bound
+    err = np.abs(out.per_particle[:, 1:] - want[:, 1:]).max() / scale
+    bound = max(tol, conditioning_bound(dtype, 13.0, float(d.min()), 2))
+    print(f"[parity] custom gravity {kind} two={two} {np.dtype(dtype).name}: max|F - F64| / max|F| = {err:.3e} (bound {bound:.3e})")
+    assert err <= bound
     e = (ww / d).sum()
-    assert abs(out.scalars[0] - e) <= 4 * tol * abs(e)
+    assert abs(out.scalars[0] - e) <= tol * abs(e)
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -157,7 +163,7 @@ def test_custom_histogram(clm, oracle_mod, dtype, kind, nbins):
     assert np.array_equal(out.hist_counts, want_c)
     assert out.scalars[0] == len(d)
     tol = RTOL[np.dtype(dtype)]
-    assert np.all(np.abs(out.hist_sums - want_s) <= 4 * tol * np.maximum(want_s, 1.0))
+    assert np.all(np.abs(out.hist_sums - want_s) <= tol * np.maximum(want_s, 1.0))
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])

@@ -13,7 +13,7 @@ from golden import kats as K
 
 pytestmark = pytest.mark.gpu
 
-RTOL = {np.dtype(np.float64): 1e-10, np.dtype(np.float32): 1e-5}
+from parity_util import RTOL, conditioning_bound, force_report
 
 
 @pytest.fixture(scope="module")
@@ -154,14 +154,14 @@ def test_lj_energy_forces(clm, oracle_mod, dtype, kind, dim):
     tol = RTOL[np.dtype(dtype)]
     escale = np.abs(oracle_mod.Oracle(x.astype(np.float64), cutoff, unitcell=None if uc is None else uc.astype(np.float64)).lj(c6, -c12))
     assert abs(out.energy - we) <= tol * max(abs(we), escale)
+    # forces: the bar holds against the oracle in the SAME precision (bit-identical wrapped coordinates); the distance to
+    # Float64 arithmetic is reported and bounded by the conditioning of the coordinates (tests/parity_util.py)
     fscale = np.abs(wf).max()
     ftol = tol * fscale
-    if dtype == np.float32:
-        # Float32 coordinates condition a r^-13 force badly (13 * eps * L / r): the bar is the stated 1e-5 OR the error
-        # the reference's own Float32 arithmetic (the oracle run in Float32) makes on the same input
-        f32_ref = oracle_mod.Oracle(x, cutoff, unitcell=uc, dtype=np.float32).lj(c6, c12, forces=True)[1]
-        ftol = max(ftol, 2.0 * np.abs(f32_ref - wf).max())
-    assert np.abs(out.forces - wf).max() <= ftol
+    f_same = wf if dtype == np.float64 else oracle_mod.Oracle(x, cutoff, unitcell=uc, dtype=dtype).lj(c6, c12, forces=True)[1]
+    err_same, err_64, _ = force_report(f"LJ {kind} {dim}-D {np.dtype(dtype).name}", out.forces, f_same, wf)
+    assert err_same <= tol
+    assert err_64 <= max(tol, conditioning_bound(dtype, 1.3 * m, 0.75, 12))
     # energy-only map (reference's exactly-once sweep) agrees too
     sys2 = clm.ParticleSystem(xpositions=x, unitcell=uc, cutoff=cutoff, output=0.0)
     e2 = clm.pairwise(clm.LJEnergy(c6, c12), sys2)
@@ -171,7 +171,7 @@ def test_lj_energy_forces(clm, oracle_mod, dtype, kind, dim):
     assert abs(e3 - 2 * we) <= 2 * tol * max(abs(we), escale)
     f_before = out.forces.copy()
     clm.pairwise(clm.LJEnergyAndForces(c6, c12), sys, reset=False)
-    assert np.abs(sys.output.forces - 2 * f_before).max() <= 4 * ftol
+    assert np.abs(sys.output.forces - 2 * f_before).max() <= ftol
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -188,8 +188,14 @@ def test_lj_cross_forces(clm, oracle_mod, dtype):
     out = clm.pairwise(clm.LJEnergyAndForces(4.0, 4.0), sys)
     we, wf = oracle_mod.Oracle(x.astype(np.float64), 2.5, unitcell=uc.astype(np.float64), y=y.astype(np.float64)).lj(4.0, 4.0, forces=True)
     tol = RTOL[np.dtype(dtype)]
-    assert abs(out.energy - we) <= 20 * tol * abs(we)
-    assert np.abs(out.forces - wf).max() <= 4 * tol * np.abs(wf).max()
+    # mixed-sign energy: the scale of the sum is the sum of the magnitudes (attractive + repulsive parts)
+    escale = abs(oracle_mod.Oracle(x.astype(np.float64), 2.5, unitcell=uc.astype(np.float64), y=y.astype(np.float64)).lj(4.0, -4.0))
+    print(f"[parity] LJ cross {np.dtype(dtype).name}: |E - E_oracle64| / sum|terms| = {abs(out.energy - we) / escale:.3e}")
+    assert abs(out.energy - we) <= tol * max(abs(we), escale)
+    f_same = wf if dtype == np.float64 else oracle_mod.Oracle(x, 2.5, unitcell=uc, y=y, dtype=dtype).lj(4.0, 4.0, forces=True)[1]
+    err_same, err_64, _ = force_report(f"LJ cross {np.dtype(dtype).name}", out.forces, f_same, wf)
+    assert err_same <= tol
+    assert err_64 <= max(tol, conditioning_bound(dtype, 1.3 * m, 0.75, 12))
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -207,10 +213,14 @@ def test_coulomb(clm, oracle_mod, dtype, kind):
     out = clm.pairwise(clm.CoulombEnergyAndForces(-9.8, w), sys)
     we, wf = oracle_mod.Oracle(x.astype(np.float64), 2.6, unitcell=uc.astype(np.float64)).coulomb(-9.8, w.astype(np.float64), forces=True)
     tol = RTOL[np.dtype(dtype)]
-    assert abs(out.energy - we) <= 4 * tol * abs(we)
-    assert np.abs(out.forces - wf).max() <= 4 * tol * np.abs(wf).max()
+    print(f"[parity] Coulomb {kind} {np.dtype(dtype).name}: |E - E_oracle64| / |E| = {abs(out.energy - we) / abs(we):.3e}")
+    assert abs(out.energy - we) <= tol * abs(we)
+    f_same = wf if dtype == np.float64 else oracle_mod.Oracle(x, 2.6, unitcell=uc, dtype=dtype).coulomb(-9.8, w, forces=True)[1]
+    err_same, err_64, _ = force_report(f"Coulomb {kind} {np.dtype(dtype).name}", out.forces, f_same, wf)
+    assert err_same <= tol
+    assert err_64 <= max(tol, conditioning_bound(dtype, 1.3 * m, 0.7, 2))
     e = clm.pairwise(clm.CoulombEnergy(-9.8, w), clm.ParticleSystem(xpositions=x, unitcell=uc, cutoff=2.6, output=0.0))
-    assert abs(e - we) <= 4 * tol * abs(we)
+    assert abs(e - we) <= tol * abs(we)
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -282,8 +292,13 @@ def test_pairwise_velocities(clm, oracle_mod, dtype, dim, kind):
     # different order (and against Float64 to bound the Float32 error)
     wc, ws = oracle_mod.Oracle(x, 2.0, unitcell=uc, dtype=dtype).pairvel(v, rbins)
     assert np.array_equal(counts, wc)
-    scale = np.abs(ws).max()
-    assert np.abs(sums - ws).max() <= (1e-9 if dtype == np.float64 else 2e-4) * scale
+    # sums of SIGNED terms dv.r/|r| (uncorrelated velocities: the sum itself is ~ sqrt(count), not a scale): the bar is
+    # relative to the sum of the term magnitudes, ~0.3 per pair for velocities uniform in [0,1)^dim.  Reference: the oracle
+    # in the same precision -- the SAME pair set; Float64 arithmetic on Float32 inputs moves a pair that sits within
+    # rounding of the cutoff across it, which changes a bin's sum by one whole term
+    err = np.abs(sums - ws) / (0.3 * np.maximum(counts, 1))
+    print(f"[parity] pair velocities {kind} {dim}-D {np.dtype(dtype).name}: max |sum - oracle| / sum|terms| = {err.max():.3e}")
+    assert err.max() <= RTOL[np.dtype(dtype)]
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -444,7 +459,7 @@ def test_c2_full_size_properties(clm, dtype):
     assert np.abs(f.sum(0)).max() <= (1e-9 if dtype == np.float64 else 2e-3) * fmax * np.sqrt(n)
     # energy of the exactly-once sweep == half-summed full-shell energy
     e_once = clm.pairwise(clm.LJEnergy(w["c6"], w["c12"]), clm.ParticleSystem(xpositions=w["x"], unitcell=w["unitcell"], cutoff=w["cutoff"], output=0.0))
-    assert abs(e_once - out.energy) <= (1e-10 if dtype == np.float64 else 2e-5) * abs(e_once)
+    assert abs(e_once - out.energy) <= RTOL[np.dtype(dtype)] * abs(e_once)
     # pair count == analytic expectation within statistics, and equals the list length of the neighbour list
     sd, sd2, npairs = clm.pairwise(clm.SumDistances(), clm.ParticleSystem(xpositions=w["x"], unitcell=w["unitcell"], cutoff=w["cutoff"], output=None))
     expect = 0.5 * n * W.ARGON_RHO * 4.0 / 3.0 * np.pi * w["cutoff"] ** 3
@@ -479,7 +494,11 @@ def test_record_capacity_retry_clustered_corner(clm, oracle_mod, dtype):
     e, f = np.zeros(1, dtype), np.zeros((6000, 3), dtype)
     h.map_lj(1e-4, 1e-8, e, f)          # first call on a dirty handle: enqueue, overflow, repeat
     we, wf = oracle_mod.Oracle(x.astype(np.float64), 1.0, unitcell=uc.astype(np.float64)).lj(1e-4, 1e-8, forces=True)
-    assert np.abs(f - wf).max() <= (1e-9 if dtype == np.float64 else 2e-3) * np.abs(wf).max()
+    # random positions in a corner: some pairs are nearly on top of each other and the largest force is conditioned by
+    # rounding the coordinates alone; the bar holds against the oracle in the same precision
+    f_same = wf if dtype == np.float64 else oracle_mod.Oracle(x, 1.0, unitcell=uc, dtype=dtype).lj(1e-4, 1e-8, forces=True)[1]
+    err_same, _, _ = force_report(f"LJ clustered corner {np.dtype(dtype).name}", f, f_same, wf)
+    assert err_same <= RTOL[np.dtype(dtype)]
     h.close()
 
 
@@ -510,3 +529,38 @@ def test_device_outputs_accumulate(clm, oracle_mod):
     assert abs(float(e) - (5.0 + 2 * we)) <= 1e-10 * abs(we)
     assert np.abs(f.cpu().numpy() - (1.0 + 2 * wf)).max() <= 1e-10 * np.abs(wf).max()
     h.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# at-cutoff band (north_star: pairs within 1 ulp of the cutoff are "reported separately"; the reference documents that
+# such pairs may fall on either side, docs/src/neighborlists.md:12, the test being d2 <= cutoff_sqr, vicinal_cells.jl:35-36)
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_cutoff_band_reported(clm, oracle_mod, dtype):
+    # lattice with spacing 0.5 and cutoff 2.0: every site has 6 partners at d2 == 4.0 EXACTLY (+-4 steps along an axis) and
+    # no other pair within an ulp of it -> 3 band pairs per site, all of them inside the list (d2 <= cutoff^2)
+    g = np.arange(12) * 0.5
+    x = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(dtype)
+    uc = np.array([6.0, 6.0, 6.0], dtype)
+    nb = clm.InPlaceNeighborList(x=x, cutoff=2.0, unitcell=uc)
+    nl = nb.neighborlist()
+    want = oracle_mod.Oracle(x, 2.0, unitcell=uc, dtype=dtype).neighborlist()
+    assert_lists_identical(nl.copy(), want)
+    on_cutoff = int((want[2] == dtype(2.0)).sum())
+    assert on_cutoff == 3 * x.shape[0]
+    assert nb.n_cutoff_band == on_cutoff
+    # the reduction map reports the same band
+    sys = clm.ParticleSystem(xpositions=x, unitcell=uc, cutoff=2.0, output=None)
+    clm.pairwise(clm.SumDistances(), sys)
+    assert sys.stats().n_cutoff_band == on_cutoff
+    # a cutoff one ulp below loses exactly those pairs, and they are still reported as the band
+    rc = np.nextafter(dtype(2.0), dtype(0.0))
+    nb2 = clm.InPlaceNeighborList(x=x, cutoff=rc, unitcell=uc)
+    nl2 = nb2.neighborlist()
+    want2 = oracle_mod.Oracle(x, rc, unitcell=uc, dtype=dtype).neighborlist()
+    assert_lists_identical(nl2.copy(), want2)
+    assert len(nl2) == len(nl) - on_cutoff
+    # random positions: no pair within an ulp of the cutoff, the band is empty
+    xr = np.random.default_rng(4).random((4000, 3)).astype(dtype)
+    nb3 = clm.InPlaceNeighborList(x=xr, cutoff=0.11, unitcell=np.ones(3, dtype))
+    nb3.neighborlist()
+    assert nb3.n_cutoff_band == 0
