@@ -25,28 +25,66 @@ if ROOT not in sys.path:
 
 import workloads as W  # noqa: E402
 
+
+def host_threads():
+    """threads the CPU arms use: every core this process may run on.  torchrun exports OMP_NUM_THREADS=1 to its children;
+    the OpenMP runtime of the oracle reads the variable when the library is loaded, so it is set here, before the import."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    return n
+
+
+def src_hash():
+    """hash of the CUDA sources the shipped library was built from: ties profiles/r2_traffic.json to a binary"""
+    import hashlib
+    h = hashlib.sha1()
+    d = os.path.join(ROOT, "celllistmap.jl_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:12]
+
+
+def measured_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel_key` from the committed ncu capture
+    (profiles/r2_traffic.json, written by tools/traffic_from_ncu.py from one `ncu --set full` run of tools/prof_c2.py)"""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(p):
+        return None, "no profiles/r2_traffic.json"
+    t = json.load(open(p))
+    v = t.get("kernels", {}).get(kernel_key)
+    note = f"profiles/r2_traffic.json ({t.get('report')}; sources {t.get('src_hash')}" + ("" if t.get("src_hash") == src_hash() else f", CURRENT sources {src_hash()}: capture is from an older build") + ")"
+    return v, note
+
 METRIC = "cutoff pair-evals/s (1M LJ forces)"
 UNIT = "pair-evals/s"
 # SURVEY.md §8(d): 8 flops per stencil candidate (distance test) + 20 per in-cutoff pair (LJ energy + forces)
 FLOPS_PER_CANDIDATE, FLOPS_PER_PAIR_LJ = 8.0, 20.0
 
 
-def reference_candidates(x, L, cutoff):
-    """C_st: candidate pairs of the REFERENCE's own stencil on the REFERENCE's own grid for an orthorhombic
-    self-set system (half stencil of 13 cells + same-cell upper triangle; ghost cells hold the periodic images of
-    the real cells), from the cell histogram."""
-    m = int(np.floor(L / cutoff))
-    cs = L / m
-    c = np.floor(np.mod(x.astype(np.float64), L) / cs).astype(np.int64) % m
-    h = np.bincount((c[:, 0] * m + c[:, 1]) * m + c[:, 2], minlength=m ** 3).reshape(m, m, m).astype(np.float64)
-    same = (h * (h - 1) / 2).sum()
-    vic = 0.0
-    for dx in (-1, 0, 1):
-        for dy in (-1, 0, 1):
-            for dz in (-1, 0, 1):
-                if (dx, dy, dz) > (0, 0, 0):   # forward half of the 26 neighbours
-                    vic += (h * np.roll(h, (-dx, -dy, -dz), axis=(0, 1, 2))).sum()
-    return same + vic
+def reference_candidates(x, sides, cutoff):
+    """C_st: candidate pairs of the REFERENCE's own stencil on the REFERENCE's own grid for an orthorhombic self-set
+    system in 2-D or 3-D (forward half of the 8 / 26 neighbour cells + same-cell upper triangle; ghost cells hold the
+    periodic images of the real cells), from the cell histogram."""
+    sides = np.atleast_1d(np.asarray(sides, np.float64))
+    dim = x.shape[1]
+    if sides.size == 1:
+        sides = np.full(dim, float(sides[0]))
+    m = np.floor(sides / cutoff).astype(np.int64)
+    cs = sides / m
+    c = np.floor(np.mod(x.astype(np.float64), sides) / cs).astype(np.int64) % m
+    lin = c[:, 0]
+    for k in range(1, dim):
+        lin = lin * m[k] + c[:, k]
+    h = np.bincount(lin, minlength=int(np.prod(m))).reshape(tuple(m)).astype(np.float64)
+    total = (h * (h - 1) / 2).sum()
+    import itertools
+    for d in itertools.product((-1, 0, 1), repeat=dim):
+        if d > (0,) * dim:   # forward half of the neighbours
+            total += (h * np.roll(h, tuple(-v for v in d), axis=tuple(range(dim)))).sum()
+    return total
 
 
 class ClockSampler:

@@ -12,7 +12,7 @@ SO_PATH = os.environ.get("CLM_SO", os.path.join(_HERE, "libclm_b200.so"))
 
 F32, F64 = 0, 1
 ORTHORHOMBIC, TRICLINIC, NONPERIODIC = 0, 1, 2
-RESET, OUT_DEVICE, PROFILE = 1, 2, 4
+RESET, OUT_DEVICE, PROFILE, ASYNC = 1, 2, 4, 8
 
 STATUS_NAMES = {
     0: "CLM_OK", 1: "CLM_ERR_INVALID_COORDINATES", 2: "CLM_ERR_UNIT_CELL", 3: "CLM_ERR_ARGUMENT", 4: "CLM_ERR_STATE",
@@ -22,7 +22,7 @@ STATUS_NAMES = {
 # every symbol include/clm_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "clm_create", "clm_destroy", "clm_last_error", "clm_set_stream", "clm_synchronize", "clm_set_box", "clm_get_box",
-    "clm_set_positions", "clm_build", "clm_map_lj", "clm_map_coulomb", "clm_map_dist_hist", "clm_map_pairvel",
+    "clm_set_positions", "clm_set_positions_async", "clm_build", "clm_map_lj", "clm_map_coulomb", "clm_map_dist_hist", "clm_map_pairvel",
     "clm_map_mindist", "clm_map_sum_d_d2", "clm_neighborlist", "clm_neighborlist_copy", "clm_get_stats",
     "clm_set_option", "clm_version", "clm_measure_fma_peak", "clm_set_foreign", "clm_cell_coords", "clm_select_layers",
     "clm_custom_compile", "clm_custom_log", "clm_map_custom", "clm_custom_check",
@@ -85,6 +85,7 @@ def lib():
     L.clm_set_box.argtypes = [vp, ci, vp, ci, vp, ci]
     L.clm_get_box.argtypes = [vp, C.POINTER(BoxInfo)]
     L.clm_set_positions.argtypes = [vp, ci, vp, i64, ci]
+    L.clm_set_positions_async.argtypes = [vp, ci, vp, i64]
     L.clm_build.argtypes = [vp]
     L.clm_map_lj.argtypes = [vp, vp, ci, vp, vp]
     L.clm_map_coulomb.argtypes = [vp, vp, vp, vp, ci, vp, vp]
@@ -220,6 +221,17 @@ class Handle:
             p = C.c_void_p(1) if which == 1 else None  # non-NULL + n = 0: empty second set
         self._chk(self.L.clm_set_positions(self.h, int(which), p, n, 1 if dev else 0))
 
+    def set_positions_async(self, which, x):
+        """pipelined frames: x is a PINNED host array (numpy view of a pinned torch tensor) of the handle's dtype; the copy
+        is enqueued on the handle's copy-in stream and the call returns at once (see clm_set_positions_async)."""
+        if _is_torch(x):
+            if x.is_cuda:
+                raise ValueError("set_positions_async takes pinned HOST memory")
+            x = x.numpy()
+        if x.dtype != self.dtype or not x.flags["C_CONTIGUOUS"]:
+            raise ValueError("set_positions_async needs a C-contiguous array of the handle's dtype (no implicit copy)")
+        self._chk(self.L.clm_set_positions_async(self.h, int(which), x.ctypes.data_as(C.c_void_p), int(x.shape[0])))
+
     def set_foreign(self, which, x):
         """particles owned by other ranks that are within the stencil reach of this rank's slab (None / empty: none)."""
         if x is None or int(x.shape[0]) == 0:
@@ -273,9 +285,10 @@ class Handle:
             raise ValueError("outputs of one call must be all host or all device arrays")
         return (RESET if reset else 0) | (OUT_DEVICE if any(dev) else 0) | (PROFILE if profile else 0)
 
-    def map_lj(self, c6, c12, energy, forces=None, reset=True, profile=False):
+    def map_lj(self, c6, c12, energy, forces=None, reset=True, profile=False, async_=False):
+        """async_=True (pipelined frames): host outputs must be pinned; they are valid after synchronize()."""
         p = np.array([c6, c12], dtype=self.dtype)
-        fl = self._flags(reset, (energy, forces), profile)
+        fl = self._flags(reset, (energy, forces), profile) | (ASYNC if async_ else 0)
         self._chk(self.L.clm_map_lj(self.h, p.ctypes.data_as(C.c_void_p), fl, _addr(energy)[0], _addr(forces)[0]))
 
     def map_coulomb(self, k, wx, wy, energy, forces=None, reset=True, profile=False):

@@ -32,7 +32,8 @@ template <class T> int Engine<T>::init(int dim_, int device_) {
     CLM_CK(dscal.ensure(DS_COUNT));
     CLM_CK(d_res.ensure(1));
     CLM_CK(d_minres.ensure(2));
-    CLM_CK(cudaMallocHost((void**)&h_dscal, DS_COUNT * sizeof(int)));
+    CLM_CK(cudaHostAlloc((void**)&h_dscal, DS_COUNT * sizeof(int), cudaHostAllocMapped));
+    CLM_CK(cudaHostGetDevicePointer((void**)&h_dscal_dev, h_dscal, 0));
     CLM_CK(cudaMallocHost((void**)&h_res, sizeof(ResultBlock) + 2 * sizeof(MinResult)));
     std::memset(&stats, 0, sizeof(stats));
     stats.n_sm = n_sm;
@@ -42,7 +43,11 @@ template <class T> int Engine<T>::init(int dim_, int device_) {
 template <class T> Engine<T>::~Engine() {
     cudaSetDevice(device);
     if (own_stream) cudaStreamSynchronize(own_stream);
-    for (auto& s : sets) { s.pos.release(); s.fpos.release(); s.rec.release(); s.rec_n3.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
+    if (copy_in) { cudaStreamSynchronize(copy_in); cudaStreamDestroy(copy_in); }
+    if (copy_out) { cudaStreamSynchronize(copy_out); cudaStreamDestroy(copy_out); }
+    for (cudaEvent_t e : {ev_h2d, ev_posfree, ev_done, ev_out[0], ev_out[1]}) if (e) cudaEventDestroy(e);
+    d_forces_alt.release(); d_eout.release();
+    for (auto& s : sets) { s.pos.release(); s.pos_alt.release(); s.fpos.release(); s.rec.release(); s.rec_n3.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
     dscal.release(); tiles.release(); d_res.release();
     d_hcount.release(); nl.release(); d_hsum.release(); d_rbins.release(); d_forces.release(); d_facc.release(); d_minmax.release(); d_minpart.release(); d_minres.release();
     custom_store_free(custom_store);
@@ -112,6 +117,28 @@ template <class T> int Engine<T>::set_positions(int set, const void* xyz, int64_
     if (n) CLM_CK(cudaMemcpyAsync(s.pos.p, xyz, (size_t)n * dim * sizeof(T), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
     s.n = n;
     if (set == 1) two_sets = (n > 0) || (xyz != nullptr);   // (NULL, 0) removes the second set; an empty y set gives no pairs
+    dirty = true;
+    return CLM_OK;
+}
+
+// pipelined frames: the coordinates of the NEXT frame are copied from PINNED host memory on the copy-in stream into the
+// buffer the frame in flight is not using; the next cell-list build waits for the copy, nothing else does
+template <class T> int Engine<T>::set_positions_async(int set, const void* xyz, int64_t n) {
+    if (set != 0 && set != 1) return fail(CLM_ERR_ARGUMENT, "set must be 0 (x) or 1 (y)");
+    if (n <= 0 || !xyz) return fail(CLM_ERR_ARGUMENT, "clm_set_positions_async needs a non-empty pinned host array");
+    if (n > (int64_t)(TagT<float>::MASK)) return fail(CLM_ERR_UNSUPPORTED, "more than 2^30 particles in one set");
+    CLM_CK(cudaSetDevice(device));
+    if (int rc = pipeline_init()) return rc;
+    DevSet<T>& s = sets[set];
+    std::swap(s.pos, s.pos_alt);
+    CLM_CK(s.pos.ensure((size_t)n * dim));
+    // the build that read this buffer two frames ago has finished once the latest enqueued build has (same stream)
+    CLM_CK(cudaStreamWaitEvent(copy_in, ev_posfree, 0));
+    if (!(dbg & 4)) CLM_CK(cudaMemcpyAsync(s.pos.p, xyz, (size_t)n * dim * sizeof(T), cudaMemcpyHostToDevice, copy_in));
+    CLM_CK(cudaEventRecord(ev_h2d, copy_in));
+    pending_h2d = true;
+    s.n = n;
+    if (set == 1) two_sets = true;
     dirty = true;
     return CLM_OK;
 }
@@ -201,11 +228,11 @@ template <class T> int Engine<T>::build_enqueue() {
     const int nsets = two_sets ? 2 : 1;
     for (int s = 0; s < nsets; ++s)
         if (sets[s].n + sets[s].n_foreign > 0x7fffffffLL / 28 || sets[s].n + sets[s].n_foreign > (int64_t)TagT<float>::MASK) return fail(CLM_ERR_UNSUPPORTED, "too many particles for 32-bit record indices");
+    if (pending_h2d) { if (!(dbg & 1)) CLM_CK(cudaStreamWaitEvent(stream, ev_h2d, 0)); pending_h2d = false; }
     CLM_CK(cudaEventRecord(ev_b0, stream));
-    // device scalars
-    for (int k = 0; k < DS_COUNT; ++k) h_dscal[k] = 0;
-    h_dscal[DS_NAN] = h_dscal[DS_OOB] = h_dscal[DS_SET_STRIDE + DS_NAN] = h_dscal[DS_SET_STRIDE + DS_OOB] = IDX_NONE;
-    CLM_CK(cudaMemcpyAsync(dscal.p, h_dscal, DS_COUNT * sizeof(int), cudaMemcpyHostToDevice, stream));
+    // device scalars (a kernel, not a copy: see k_dscal_init)
+    k_dscal_init<<<1, 32, 0, stream>>>(dscal.p);
+    CLM_CK(cudaGetLastError());
     if (nonperiodic) {
         // Box(limits(x[,y]), cutoff): sides = extent + 2.1*cutoff, origin = minimum coordinates
         // (CellOperations.jl:290-324, Box.jl:38, :374-377); limits by a device reduction
@@ -308,9 +335,7 @@ template <class T> int Engine<T>::build_enqueue() {
         img_factor = std::min(std::max(vbox / std::max(vcell, 1e-300), 1.0), (dim == 3) ? 8.0 : 4.0);
     }
     {
-        for (int k = 0; k < DS_COUNT; ++k) h_dscal[k] = 0;
-        h_dscal[DS_NAN] = h_dscal[DS_OOB] = h_dscal[DS_SET_STRIDE + DS_NAN] = h_dscal[DS_SET_STRIDE + DS_OOB] = IDX_NONE;
-        CLM_CK(cudaMemcpyAsync(dscal.p, h_dscal, DS_COUNT * sizeof(int), cudaMemcpyHostToDevice, stream));
+        if (nonperiodic) { k_dscal_init<<<1, 32, 0, stream>>>(dscal.p); CLM_CK(cudaGetLastError()); }   // the limits pass used the flags
         for (int s = 0; s < nsets; ++s) {
             DevSet<T>& S = sets[s];
             const size_t want = std::max<size_t>((size_t)((double)(S.n + S.n_foreign) * img_factor * 1.25) + 4096, (size_t)std::max<int64_t>(S.n_tot, 1));
@@ -319,7 +344,11 @@ template <class T> int Engine<T>::build_enqueue() {
             CLM_CK(S.cell_start.ensure((size_t)ncp + 2));
             CLM_CK(S.counters.ensure((size_t)(2 * ncp + nref)));
             S.cell_count = S.counters.p; S.cell_nact = S.counters.p + ncp; S.ref_real = S.counters.p + 2 * ncp;
-            CLM_CK(cudaMemsetAsync(S.counters.p, 0, (size_t)(2 * ncp + nref) * sizeof(int), stream));
+            {   // one zero fill of [cell_count | cell_nact | ref_real] (a kernel: see k_dscal_init)
+                const long long nz = 2 * ncp + nref;
+                k_zero_ints<<<(int)std::min<long long>((nz / 4 + 255) / 256 + 1, (long long)n_sm * 8), 256, 0, stream>>>(S.counters.p, nz);
+                CLM_CK(cudaGetLastError());
+            }
             int* ds = dscal.p + s * DS_SET_STRIDE;
             const int64_t nall = S.n + S.n_foreign;
             const int nb = (int)((nall + 255) / 256);
@@ -353,9 +382,11 @@ template <class T> int Engine<T>::build_enqueue() {
             stats.launches += 1;
         }
         CLM_CK(cudaEventRecord(ev_b1, stream));
+        if (ev_posfree) CLM_CK(cudaEventRecord(ev_posfree, stream));   // pipelined frames: the coordinate buffer has been read
         // the one host round trip of the build (validation flags, record counts, tile count) is only ENQUEUED here; the
         // caller queues its map kernels behind it and then waits for this event, so the GPU never idles on the host
-        CLM_CK(cudaMemcpyAsync(h_dscal, dscal.p, DS_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        k_dscal_publish<<<1, 32, 0, stream>>>(dscal.p, h_dscal_dev);
+        CLM_CK(cudaGetLastError());
         CLM_CK(cudaEventRecord(ev_built, stream));
     }
     validate_pending = true;
@@ -411,8 +442,9 @@ template <class T> int Engine<T>::prepare_map(int flags) {
     else if (int rc = build_enqueue()) return rc;
     profile_sweep = (flags & CLM_PROFILE) != 0;
     if (flags & CLM_PROFILE) CLM_CK(cudaEventRecord(ev0, stream));
-    CLM_CK(cudaMemsetAsync(d_res.p, 0, sizeof(ResultBlock), stream));
-    CLM_CK(cudaMemsetAsync(dscal.p + DS_WORK, 0, sizeof(int), stream));
+    static_assert(sizeof(ResultBlock) % 8 == 0 && sizeof(ResultBlock) / 8 <= 32, "k_map_begin zeroes the result block with one warp");
+    k_map_begin<<<1, 32, 0, stream>>>(reinterpret_cast<unsigned long long*>(d_res.p), (int)(sizeof(ResultBlock) / 8), dscal.p + DS_WORK);
+    CLM_CK(cudaGetLastError());
     return CLM_OK;
 }
 template <class T> int Engine<T>::finish_map(int flags) {
@@ -481,8 +513,9 @@ template <class T> int Engine<T>::forces_begin(void* forces_out, int flags, Forc
     fo.dim = dim; fo.rotated = geom.rotated;
     for (int k = 0; k < 9; ++k) fo.inv_rot[k] = geom.inv_rot[k];
     if (flags & CLM_OUT_DEVICE) { fo.forces = (T*)forces_out; fo.accumulate = (flags & CLM_RESET) ? 0 : 1; return CLM_OK; }
-    CLM_CK(d_forces.ensure((size_t)std::max<int64_t>(sets[0].n, 1) * dim));
-    fo.forces = d_forces.p; fo.accumulate = 0;
+    DBuf<T>& stage = ((flags & CLM_ASYNC) && (frame & 1)) ? d_forces_alt : d_forces;   // pipelined frames: staging by frame parity
+    CLM_CK(stage.ensure((size_t)std::max<int64_t>(sets[0].n, 1) * dim));
+    fo.forces = stage.p; fo.accumulate = 0;
     return CLM_OK;
 }
 template <class T> int Engine<T>::forces_end(void* forces_out, int flags) { return part_end(forces_out, flags, dim); }
@@ -514,6 +547,7 @@ template <class T> int Engine<T>::set_option(const char* name, int64_t v) {
     if (!name) return fail(CLM_ERR_ARGUMENT, "option name is NULL");
     const std::string s(name);
     if (s == "sub") { if (v < 0 || v > LF_MAX) return fail(CLM_ERR_ARGUMENT, "sub must be in 0..7"); opt_sub = (int)v; dirty = true; return CLM_OK; }
+    if (s == "dbg") { dbg = (int)v; return CLM_OK; }
     if (s == "n3") { opt_n3 = (v < 0) ? -1 : (v ? 1 : 0); return CLM_OK; }
     if (s == "blocks_per_sm") { if (v < 0) return fail(CLM_ERR_ARGUMENT, "blocks_per_sm must be >= 0"); opt_bps = (int)v; return CLM_OK; }
     return fail(CLM_ERR_ARGUMENT, "unknown option " + s);
@@ -599,6 +633,7 @@ int clm_synchronize(clm_handle* h) { H_OR_FAIL; return h->e->synchronize(); }
 int clm_set_box(clm_handle* h, int ct, const void* uc, int is_matrix, const void* cutoff, int lcell) { H_OR_FAIL; return h->e->set_box(ct, uc, is_matrix, cutoff, lcell); }
 int clm_get_box(clm_handle* h, clm_box_info* o) { H_OR_FAIL; return h->e->get_box(o); }
 int clm_set_positions(clm_handle* h, int set, const void* xyz, int64_t n, int on_device) { H_OR_FAIL; return h->e->set_positions(set, xyz, n, on_device); }
+int clm_set_positions_async(clm_handle* h, int set, const void* xyz, int64_t n) { H_OR_FAIL; return h->e->set_positions_async(set, xyz, n); }
 int clm_build(clm_handle* h) { H_OR_FAIL; return h->e->build(); }
 int clm_set_foreign(clm_handle* h, int set, const void* xyz, int64_t n, int on_device) { H_OR_FAIL; return h->e->set_foreign(set, xyz, n, on_device); }
 int clm_cell_coords(clm_handle* h, const void* xyz, int64_t n, int on_device, int axis, int32_t* out) { H_OR_FAIL; return h->e->cell_coords(xyz, n, on_device, axis, out); }

@@ -27,6 +27,30 @@ constexpr int IDX_NONE = 0x7fffffff;
 enum { DS_NAN = 0, DS_OOB = 1, DS_NTOT = 2, DS_NTILES = 3, DS_WORK = 4, DS_NCELLS_REAL = 5, DS_COUNT = 16 };
 constexpr int DS_SET_STRIDE_DEV = 6;   // the scalar block of the second set starts at dscal + 6
 
+// The device scalars are initialised and published by two one-warp kernels, not by cudaMemcpyAsync: a small copy on the
+// compute stream queues on the same DMA engines as the megabyte copies of pipelined frames (positions in, forces out)
+// and stalled the stream behind them (0.16 ms per step on the 1M-particle system).  h_pub is MAPPED pinned host memory.
+static __global__ void k_dscal_init(int* __restrict__ dscal) {
+    const int k = threadIdx.x;
+    if (k < DS_COUNT) dscal[k] = (k == DS_NAN || k == DS_OOB || k == DS_SET_STRIDE_DEV + DS_NAN || k == DS_SET_STRIDE_DEV + DS_OOB) ? IDX_NONE : 0;
+}
+// zero fills as kernels for the same reason (cudaMemsetAsync may be served by a DMA engine)
+static __global__ void __launch_bounds__(256) k_zero_ints(int* __restrict__ p, long long n) {
+    const long long n4 = n >> 2;
+    int4* p4 = reinterpret_cast<int4*>(p);
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n4; k += (long long)gridDim.x * blockDim.x) p4[k] = make_int4(0, 0, 0, 0);
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) p[(n4 << 2) + threadIdx.x] = 0;
+}
+static __global__ void k_map_begin(unsigned long long* __restrict__ res_words, int nwords, int* __restrict__ work) {
+    if (threadIdx.x < nwords) res_words[threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) *work = 0;
+}
+static __global__ void k_dscal_publish(const int* __restrict__ dscal, volatile int* __restrict__ h_pub) {
+    const int k = threadIdx.x;
+    if (k < DS_COUNT) h_pub[k] = dscal[k];
+    __threadfence_system();
+}
+
 // p = rotation * (M * frac(M \ x)), every operation rounded separately in T
 // (CellLists.jl:944-945; CellOperations.jl:56-66, :91-94).  Non-periodic: coordinates are used as given.
 template <class T, int DIM> __device__ __forceinline__ void place_particle(const GeomT<T>& g, const T* x, T p[3]) {

@@ -29,6 +29,7 @@ struct EngineBase {
     virtual int set_box(int cell_type, const void* uc, int is_matrix, const void* cutoff, int lcell) = 0;
     virtual int get_box(clm_box_info* out) = 0;
     virtual int set_positions(int set, const void* xyz, int64_t n, int on_device) = 0;
+    virtual int set_positions_async(int set, const void* xyz, int64_t n) = 0;
     virtual int set_foreign(int set, const void* xyz, int64_t n, int on_device) = 0;
     virtual int cell_coords(const void* xyz, int64_t n, int on_device, int axis, int32_t* out) = 0;
     virtual int select_layers(const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b, int64_t capacity, int32_t* counts) = 0;
@@ -76,6 +77,7 @@ template <class U> struct DBuf {
 
 template <class T> struct DevSet {
     DBuf<T> pos;             // caller's coordinates, AoS n x dim (owning copy, like ParticleSystemPositions)
+    DBuf<T> pos_alt;         // pipelined frames: the buffer the NEXT frame's coordinates are copied into while this one is binned
     int64_t n = 0;
     DBuf<T> fpos;            // foreign particles of a slab-decomposed system (owned by other ranks), AoS
     int64_t n_foreign = 0;
@@ -103,7 +105,8 @@ template <class T> struct Engine : EngineBase {
     DevSet<T> sets[2];
     DBuf<int> dscal;
     DBuf<Tile> tiles;
-    int* h_dscal = nullptr;          // pinned
+    int* h_dscal = nullptr;          // pinned, mapped: written by k_dscal_publish
+    int* h_dscal_dev = nullptr;      // its device-side address
     DBuf<ResultBlock> d_res;
     ResultBlock* h_res = nullptr;    // pinned
     DBuf<unsigned long long> d_hcount, nl;
@@ -131,13 +134,16 @@ template <class T> struct Engine : EngineBase {
     ~Engine() override;
     int set_stream(void* s) override { stream = s ? (cudaStream_t)s : own_stream; return CLM_OK; }
     int synchronize() override {
+        if (copy_in) CLM_CK(cudaStreamSynchronize(copy_in));
         CLM_CK(cudaStreamSynchronize(stream));
+        if (copy_out) { CLM_CK(cudaStreamSynchronize(copy_out)); out_pending[0] = out_pending[1] = false; }
         const int v = build_validate();
         return (v == CLM_RETRY_INTERNAL) ? fail(CLM_ERR_CAPACITY, "the record capacity of the last enqueued cell-list build was too small: repeat the call") : v;
     }
     int set_box(int cell_type, const void* uc, int is_matrix, const void* cutoff, int lcell) override;
     int get_box(clm_box_info* out) override;
     int set_positions(int set, const void* xyz, int64_t n, int on_device) override;
+    int set_positions_async(int set, const void* xyz, int64_t n) override;
     int set_foreign(int set, const void* xyz, int64_t n, int on_device) override;
     int cell_coords(const void* xyz, int64_t n, int on_device, int axis, int32_t* out) override;
     int select_layers(const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b, int64_t capacity, int32_t* counts) override;
@@ -252,6 +258,56 @@ template <class T> struct Engine : EngineBase {
         return CLM_OK;
     }
     int last_grid = 0;
+
+    // ---- pipelined frames (clm_set_positions_async + CLM_ASYNC maps): independent frames of a trajectory overlap their
+    //      host->device copy, compute and device->host copy on three streams; buffers are double-buffered by frame parity
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_posfree = nullptr, ev_done = nullptr, ev_out[2] = {nullptr, nullptr};
+    bool pending_h2d = false, out_pending[2] = {false, false};
+    int frame = 0;
+    int dbg = 0;   // debugging switches of the pipelined path (clm_set_option "dbg"): 1 no wait for the copy-in, 2 no force copy-out, 4 no copy-in
+    DBuf<T> d_forces_alt, d_eout;
+    int pipeline_init() {
+        if (copy_in) return CLM_OK;
+        CLM_CK(cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking));
+        CLM_CK(cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking));
+        CLM_CK(cudaEventCreateWithFlags(&ev_h2d, cudaEventDisableTiming));
+        CLM_CK(cudaEventCreateWithFlags(&ev_posfree, cudaEventDisableTiming));
+        CLM_CK(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+        CLM_CK(cudaEventCreateWithFlags(&ev_out[0], cudaEventDisableTiming));
+        CLM_CK(cudaEventCreateWithFlags(&ev_out[1], cudaEventDisableTiming));
+        CLM_CK(d_eout.ensure(2));
+        return CLM_OK;
+    }
+    // a map called with CLM_ASYNC: the previous frame's build is validated here (its scalars arrived long ago), this
+    // frame's outputs go to the buffers of its parity once the copy-out of the frame before the previous one has drained
+    int async_begin(int flags) {
+        if ((flags & CLM_OUT_DEVICE) || !(flags & CLM_RESET)) return fail(CLM_ERR_ARGUMENT, "CLM_ASYNC needs host outputs and CLM_RESET");
+        if (int rc = pipeline_init()) return rc;
+        const int v = build_validate();
+        if (v == CLM_RETRY_INTERNAL) return fail(CLM_ERR_CAPACITY, "the record capacity of the previous asynchronous frame was too small (it has been grown): repeat that frame");
+        if (v) return v;
+        const int p = frame & 1;
+        if (out_pending[p]) CLM_CK(cudaStreamWaitEvent(stream, ev_out[p], 0));
+        return CLM_OK;
+    }
+    // energy (scaled) -> the frame's device scalar; forces staging + scalar -> caller's PINNED host memory on the copy-out stream
+    int async_end(void* e_host, void* f_host, size_t force_count, double escale) {
+        const int p = frame & 1;
+        if (e_host) {
+            k_store_real<T><<<1, 32, 0, stream>>>(d_eout.p + p, &d_res.p->f[RB_ENERGY], 1, escale, 0);
+            CLM_CK(cudaGetLastError());
+            stats.launches += 1;
+        }
+        CLM_CK(cudaEventRecord(ev_done, stream));
+        CLM_CK(cudaStreamWaitEvent(copy_out, ev_done, 0));
+        if (f_host && force_count && !(dbg & 2)) CLM_CK(cudaMemcpyAsync(f_host, (p ? d_forces_alt.p : d_forces.p), force_count * sizeof(T), cudaMemcpyDeviceToHost, copy_out));
+        if (e_host) CLM_CK(cudaMemcpyAsync(e_host, d_eout.p + p, sizeof(T), cudaMemcpyDeviceToHost, copy_out));
+        CLM_CK(cudaEventRecord(ev_out[p], copy_out));
+        out_pending[p] = true;
+        frame += 1;
+        return CLM_OK;
+    }
 };
 
 }  // namespace clm

@@ -10,6 +10,8 @@ template <class T> int Engine<T>::map_lj(const void* p, int flags, void* e, void
     double scale = 1.0;
     const bool norm = FLJ<T, true, true>::can_normalise(c[0], c[1]);
     const bool n3 = f && n3_usable();
+    const bool async = (flags & CLM_ASYNC) != 0;
+    if (async) { if (int rc = async_begin(flags)) return rc; }
     for (;;) {   // repeated only when the build's record-capacity estimate was too small (build_validate)
     if (n3) n3_request();
     if (int rc = prepare_map(flags)) return rc;
@@ -52,11 +54,13 @@ template <class T> int Engine<T>::map_lj(const void* p, int flags, void* e, void
         std::memset(&fn.fo, 0, sizeof(fn.fo));
         if (int rc = launch_reduce(fn, 0)) return rc;
     }
+    if (async) break;   // validated when the next frame is enqueued (or by clm_synchronize)
     const int v = build_validate();
     if (v == CLM_RETRY_INTERNAL) continue;
     if (v) return v;
     break;
     }
+    if (async) return async_end(e, f, f ? (size_t)sets[0].n * dim : 0, scale);
     if (!(flags & CLM_OUT_DEVICE)) { if (int rc = fetch_results()) return rc; }
     if (int rc = store_real(e, &d_res.p->f[RB_ENERGY], &h_res->f[RB_ENERGY], 1, scale, flags)) return rc;
     if (f) { if (int rc = forces_end(f, flags)) return rc; }

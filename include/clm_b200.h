@@ -68,7 +68,11 @@ enum clm_flags {
     CLM_OUT_DEVICE = 2, /* ARRAY arguments of the call (outputs, and per-particle inputs such as weights and
                            velocities) are device pointers; scalars and bin edges stay host pointers.  The call only
                            enqueues work on the handle's stream (no host synchronisation) */
-    CLM_PROFILE = 4     /* record CUDA-event timings of this call into clm_stats */
+    CLM_PROFILE = 4,    /* record CUDA-event timings of this call into clm_stats */
+    CLM_ASYNC = 8       /* pipelined frames (clm_map_lj; needs CLM_RESET and PINNED host outputs): the call only enqueues; the
+                           outputs are written by a device->host copy on a separate stream and are valid after
+                           clm_synchronize().  With clm_set_positions_async the copy-in of frame k+1, the compute of frame
+                           k and the copy-out of frame k-1 overlap (frames of a trajectory are independent) */
 };
 
 /* Box record (src/internals/Box.jl:84-96); values widened to double (exact for float). */
@@ -121,6 +125,11 @@ CLM_API int clm_get_box(clm_handle* h, clm_box_info* out);
  * (set = 1, aos_xyz = NULL, n = 0) removes the second set; a non-NULL pointer with n = 0 is an EMPTY
  * second set (no pairs). */
 CLM_API int clm_set_positions(clm_handle* h, int set, const void* aos_xyz, int64_t n, int on_device);
+/* pipelined frames: the same update from PINNED host memory, enqueued on the handle's copy-in stream into the buffer the
+ * frame in flight is not using; returns at once (the caller must not touch the array until the next clm_synchronize,
+ * or until two more frames have been enqueued).  The reference's counterpart is the per-frame
+ * `sys.xpositions .= frame; pairwise!(f, sys)` loop of a trajectory analysis (docs/src/ParticleSystem/updating.md). */
+CLM_API int clm_set_positions_async(clm_handle* h, int set, const void* aos_xyz_pinned, int64_t n);
 
 /* ---- slab decomposition across GPUs (no counterpart in the reference, which is single-process) ----
  * One handle per rank.  A rank owns the particles whose reference cell along dimension 1 falls in its slab and
