@@ -103,7 +103,7 @@ template <class T, int DIM> __device__ __forceinline__ void place_particle(const
 // reference-cell pair from the SAME home cell as the reference and therefore evaluates the same periodic
 // image of every pair (bit-identical d2).  Returns false when the point is outside the grid (or NaN/Inf).
 template <class T, int DIM>
-__device__ __forceinline__ bool cell_of(const GeomT<T>& g, const T p[3], bool real, int& dev_lin, int& ref_lin) {
+__device__ __forceinline__ bool cell_of(const GeomT<T>& g, const T p[3], bool real, int& dev_lin, int& ref_lin, int* ref_fast = nullptr) {
     dev_lin = 0; ref_lin = 0;
 #pragma unroll
     for (int k = 0; k < DIM; ++k) {
@@ -118,6 +118,7 @@ __device__ __forceinline__ bool cell_of(const GeomT<T>& g, const T p[3], bool re
         }
         if (c < 0 || c >= g.nc[k]) return false;
         ref_lin = ref_lin * g.nc[k] + c;
+        if (k == DIM - 1 && ref_fast) *ref_fast = c;   // reference cell along the row of the device grid
         dev_lin = dev_lin * (g.nc[k] * g.sub + ((k == DIM - 1) ? 1 : 0)) + c * g.sub + sc;   // row pitch nx + 1
     }
     return true;
@@ -147,12 +148,12 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
         const T* src = (ip < n_own) ? pos + (size_t)ip * DIM : fpos + (size_t)(ip - n_own) * DIM;   // owned particles, then foreign ones
 #pragma unroll
         for (int k = 0; k < DIM; ++k) { x[k] = src[k]; bad |= (x[k] != x[k]); }
-        int lin = 0, rlin = 0;
+        int lin = 0, rlin = 0, cfast = 0;
         if (bad) {
             if (!SCATTER) atomicMin(&dscal[DS_NAN], ip);     // _validate_coordinates, CellOperations.jl:6-21
         } else {
             place_particle<T, DIM>(g, x, p);
-            if (!cell_of<T, DIM>(g, p, true, lin, rlin)) { if (!SCATTER) atomicMin(&dscal[DS_OOB], ip); bad = true; }
+            if (!cell_of<T, DIM>(g, p, true, lin, rlin, &cfast)) { if (!SCATTER) atomicMin(&dscal[DS_OOB], ip); bad = true; }
         }
         if (!bad) {
             // cell_cursor: the per-cell histogram in the count pass; the per-cell write cursor (pre-loaded with the
@@ -164,8 +165,10 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
                 ref_real[rlin] = 1;
             } else if (slot < rec_cap) {
                 strec(&rec[slot], p[0], p[1], p[2], (typename TG::type)ip | TG::HOME | foreign);
-                // slot-tagged twin of the record array (clm_sweep_n3.cuh): 4th word = slot of the particle's real record
-                if (rec_n3) strec(&rec_n3[slot], p[0], p[1], p[2], (typename TG::type)(unsigned)slot);
+                // slot-tagged twin of the record array (clm_sweep_n3.cuh): 4th word = slot of the particle's real record |
+                // HOME | parity of the reference cell along the row (bit 29)
+                // (triclinic cells: the particle index instead of the slot -- the reference's index_i < index_j rule)
+                if (rec_n3) strec(&rec_n3[slot], p[0], p[1], p[2], (typename TG::type)((unsigned)(g.cell_type == CLM_TRICLINIC_CT ? ip : slot) | 0x40000000u | ((unsigned)(cfast & 1) << 29)));
             }
             real_slot = slot;
             // replicate_particle! (Box.jl:556-566): images x + aligned_cell*idx, idx in {-1,0,1}^N \ {0}, kept iff inside the
@@ -221,15 +224,15 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
             in = in && (g.cb_min[k] <= q[k]) && (q[k] < g.cb_max[k]);
         }
         if (!in) continue;
-        int lq, rq;
-        if (!cell_of<T, DIM>(g, q, false, lq, rq)) continue;
+        int lq, rq, qfast = 0;
+        if (!cell_of<T, DIM>(g, q, false, lq, rq, &qfast)) continue;
         const typename TG::type foreign = (ips >= n_own) ? TG::FOREIGN : (typename TG::type)0;
         const int qslot = atomicAdd(&cell_cursor[lq], 1);
         if (SCATTER && qslot < rec_cap) {
             const bool home = ref_real[rq] != 0;
             if (home && !foreign) cell_nact[lq] = 1;
             strec(&rec[qslot], q[0], q[1], q[2], (typename TG::type)ips | TG::GHOST | foreign | (home ? TG::HOME : (typename TG::type)0));
-            if (rec_n3) strec(&rec_n3[qslot], q[0], q[1], q[2], (typename TG::type)((unsigned)rslot | 0x80000000u));   // image -> its original's slot | GHOST
+            if (rec_n3) strec(&rec_n3[qslot], q[0], q[1], q[2], (typename TG::type)((unsigned)(g.cell_type == CLM_TRICLINIC_CT ? ips : rslot) | 0x80000000u | (home ? 0x40000000u : 0u) | ((unsigned)(qfast & 1) << 29)));   // image -> its original's slot | GHOST
         }
     }
 }

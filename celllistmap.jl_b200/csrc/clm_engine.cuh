@@ -82,7 +82,7 @@ template <class T> struct DevSet {
     DBuf<T> fpos;            // foreign particles of a slab-decomposed system (owned by other ranks), AoS
     int64_t n_foreign = 0;
     DBuf<RecT<T>> rec;       // cell-sorted records, real + image particles
-    DBuf<RecT<T>> rec_n3;    // slot-tagged twin of rec (4th word = slot of the particle's real record | GHOST), written by the
+    DBuf<RecT<T>> rec_n3;    // slot-tagged twin of rec (4th word = slot of the particle's real record | GHOST | HOME | cell parity), written by the
                              // scatter pass once a Newton's-third-law force map has been asked for (clm_sweep_n3.cuh)
     int64_t n_tot = 0, n_cells_real = 0;
     DBuf<int> cell_start;    // row pitch nfast + 1: [row * pitch + x] = first record of cell x, entry nfast = end of the row (after the scatter pass)
@@ -242,16 +242,16 @@ template <class T> struct Engine : EngineBase {
         grid = std::max<int64_t>(1, std::min<int64_t>(grid, (tiles_upper + (SWEEP_THREADS / 32) - 1) / (SWEEP_THREADS / 32)));
         DevSet<T>& S = sets[0];
         const size_t old_cap = d_facc.cap;
-        CLM_CK(d_facc.ensure(S.rec.cap * 4));
+        CLM_CK(d_facc.ensure(std::max<size_t>(S.rec.cap, (size_t)S.n) * 4));
         if (d_facc.cap != old_cap) CLM_CK(cudaMemsetAsync(d_facc.p, 0, d_facc.cap * sizeof(T), stream));
         SweepArgs<T> a = make_args();
         a.rec_j = S.rec_n3.p;
         if (profile_sweep) CLM_CK(cudaEventRecord(ev2, stream));
-        kern<<<(unsigned)grid, SWEEP_THREADS, smem, stream>>>(a, f, S.rec.p, d_facc.p);
+        kern<<<(unsigned)grid, SWEEP_THREADS, smem, stream>>>(a, f, d_facc.p);
         CLM_CK(cudaGetLastError());
         if (profile_sweep) CLM_CK(cudaEventRecord(ev3, stream));
         const int nb = (int)std::min<int64_t>((int64_t)n_sm * 8, (int64_t)(S.rec.cap + 255) / 256);
-        k_force_finish<T><<<std::max(nb, 1), 256, 0, stream>>>(S.rec.p, d_facc.p, dscal.p, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), out, dim, scale, accumulate, geom.rotated, geom);
+        k_force_finish<T, MODE == MODE_TRI><<<std::max(nb, 1), 256, 0, stream>>>(S.rec.p, d_facc.p, dscal.p, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), (int)S.n, out, dim, scale, accumulate, geom.rotated, geom);
         CLM_CK(cudaGetLastError());
         stats.launches += 2;
         last_grid = (int)grid;

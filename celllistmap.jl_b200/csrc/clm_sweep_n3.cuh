@@ -28,13 +28,14 @@
 namespace clm {
 
 static_assert(TILE_I == 8, "the reduce-scatter of the i-side accumulators is written for 8 particles per tile");
-constexpr uint32_t N3_GHOST = 0x80000000u, N3_SLOT = 0x7fffffffu;   // rec_n3 4th word: slot of the real record | GHOST
-constexpr int N3_KEYED_CAP = 128;                   // records of the keyed ("direct") part staged per pass
-constexpr int N3_KBUF = N3_KEYED_CAP + 32;          // keys: one per keyed slot + the carried partial chunk
-constexpr int N3_IBUF_BYTES = 8 * 4 * 8 + 8 * 16 + N3_KBUF * 4;   // per warp: TILE_I x (x, y, z, w) of T (<= double), TILE_I x int4, keys
+// rec_n3 4th word: slot of the particle's REAL record (an image points at its original) | flags.  PAR = parity of the
+// record's reference cell along the row (the key of the record-order rules follows from it, see k_sweep_n3)
+constexpr uint32_t N3_GHOST = 0x80000000u, N3_HOME = 0x40000000u, N3_SLOT = 0x1fffffffu;
+constexpr int N3_PAR_SHIFT = 29;
 
-// per-warp staging buffer: with ~80 registers per thread 6 CTAs are resident per SM whatever the buffer size up to
-// 8 KB, so the buffer is sized for the whole forward part of a typical tile in one pass
+// per-warp shared memory: [mbarrier | i-side keys | i-side positions | staging buffer (| side-array staging buffer)].
+// With 80-96 registers per thread 5-6 CTAs are resident per SM whatever the buffer size up to 8 KB, so the buffer is
+// sized for the whole partner sequence of a typical tile in one pass
 #ifndef CLM_N3_STAGE_BYTES_F32
 #define CLM_N3_STAGE_BYTES_F32 8192
 #endif
@@ -45,12 +46,11 @@ template <class T, bool AUX> struct N3Cap {
     static constexpr int SB = AUX ? 6144 : ((sizeof(T) == 4) ? CLM_N3_STAGE_BYTES_F32 : CLM_N3_STAGE_BYTES_F64);
     static constexpr int REC = (int)sizeof(RecT<T>);
     static constexpr int SLOTS = SB / REC;
-    static constexpr int FWD = SLOTS - 32 - STAGE_PAD;   // staged per pass: the carried partial chunk (< 32) and the padding share the buffer
-    static constexpr int MBAR_OFF = (SWEEP_THREADS / 32) * SB;
-    static constexpr int ABUF_OFF = MBAR_OFF + 64;
-    static constexpr int IBUF_OFF = ABUF_OFF + (AUX ? (SWEEP_THREADS / 32) * SB : 0);
+    static constexpr int CAPP = SLOTS - 64;      // staged per pass: the carried partial chunk (< 32) and the padding (< 32) share the buffer
+    static constexpr int IKEY_OFF = 128, IPOS_OFF = 256, BUF_OFF = 512, ABUF_OFF = BUF_OFF + SB;
+    static constexpr int WSTRIDE = BUF_OFF + SB * (AUX ? 2 : 1);
 };
-template <class T, bool AUX> struct N3Smem { static constexpr int value = N3Cap<T, AUX>::IBUF_OFF + (SWEEP_THREADS / 32) * N3_IBUF_BYTES; };
+template <class T, bool AUX> struct N3Smem { static constexpr int value = (SWEEP_THREADS / 32) * N3Cap<T, AUX>::WSTRIDE; };
 
 __device__ __forceinline__ void red_add3(float* p, float x, float y, float z) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(0.f) : "memory");
@@ -60,6 +60,9 @@ __device__ __forceinline__ void red_add3(double* p, double x, double y, double z
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p + 1), "d"(y) : "memory");
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p + 2), "d"(z) : "memory");
 }
+// true unless all three are +0 (a lane that saw no pair holds exact +0s; -0 only costs a redundant reduction)
+__device__ __forceinline__ bool any_nonzero(float x, float y, float z) { return (__float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z)) != 0u; }
+__device__ __forceinline__ bool any_nonzero(double x, double y, double z) { return x != 0.0 || y != 0.0 || z != 0.0; }
 // slot word of a staged rec_n3 record
 __device__ __forceinline__ uint32_t slotword(const RecT<float>& r) { return r.tag; }
 __device__ __forceinline__ uint32_t slotword(const RecT<double>& r) { return (uint32_t)r.tag; }
@@ -129,35 +132,49 @@ enum { N3_PLAIN = 0, N3_KEYED = 1, N3_GENERAL = 2, N3_TRI = 3 };
 #endif
 template <class T, bool AUX> struct N3MinBlocks { static constexpr int value = (sizeof(T) == 4) ? (AUX ? 4 : CLM_N3_MINB_F32) : (AUX ? 3 : CLM_N3_MINB_F64); };
 
+// Per tile (TILE_I consecutive records of one row, particles i):
+//   1. lane r classifies stencil row r and fetches its record range; rows of the tile's own REFERENCE row split into
+//      the KEYED part D (the reference cells rbase, rbase + 1 the tile's particles live in: the record-order rules
+//      apply) and the forward part F (plain forward rule).  The partner sequence of the tile is S = [D rows | F rows].
+//   2. S is bulk-copied (TMA 1-D copies, one or two per row) behind the partners that wait at buf[0 .. nl), culled
+//      against the bounding box of the tile and compacted in place; nk = number of keyed partners at the front.
+//   3. whole chunks of 32 partners are swept (one partner per lane, TILE_I warp steps per chunk); the partial chunk at
+//      the end is carried to the next pass; the last pass pads it and sweeps it too.
+// The key of a keyed partner (its reference cell along the row) is rbase + (parity bit of its record ^ parity of
+// rbase): no key array.  A tile that spans more than two reference cells (sparse rows only) is processed in several
+// trips of the rbase loop, each with the particles i of two reference cells.
 template <class T, int MODE, class F>
 __global__ void __launch_bounds__(SWEEP_THREADS, N3MinBlocks<T, F::AUX>::value)
-k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, const RecT<T>* __restrict__ rec_tag, T* __restrict__ facc) {
+k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, T* __restrict__ facc) {
     typedef TagT<T> TG;
     typedef typename TG::type tag_t;
     typedef N3Cap<T, F::AUX> CP;
     extern __shared__ __align__(128) unsigned char dsm_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int lf = a.lf, sub = a.sub, hww = 2 * lf + 1;
-    const unsigned smagic = a.sub_magic;
-    auto div_sub = [&](int v) { return (sub == 1) ? v : (int)__umulhi((unsigned)v, smagic); };
-    const int nrows_st = (a.nz == 1) ? hww : hww * hww;
+    const int lane = threadIdx.x & 31;
+    // one base address per warp; everything else sits at a compile-time offset from it
+    unsigned char* const wb = dsm_raw + (threadIdx.x >> 5) * CP::WSTRIDE;
+    // [TILE_I] i-side keys.  MODE_HALF: x = (reference cell - rbase) << 30 | own slot (an image particle: | 0x3fffffff, so that
+    // no partner of its own cell passes), y = image flag; MODE_TRI: x = particle index.  A partner's key is built the same way
+    // (cell 2 = beyond the keyed part; image partner: slot bits 0x3fffffff) and a pair counts iff key_j > key_i (unsigned).
+    int2* const ikey = reinterpret_cast<int2*>(wb + CP::IKEY_OFF);
+    Vec4S<T>* const ipos = reinterpret_cast<Vec4S<T>*>(wb + CP::IPOS_OFF);  // [TILE_I]: x, y, z, functor weight
+    RecT<T>* const buf = reinterpret_cast<RecT<T>*>(wb + CP::BUF_OFF);
+    RecT<T>* const abuf = reinterpret_cast<RecT<T>*>(wb + CP::ABUF_OFF);
     constexpr uint32_t REC = (uint32_t)sizeof(RecT<T>);
-    RecT<T>* const buf = reinterpret_cast<RecT<T>*>(dsm_raw + warp * CP::SB);
-    RecT<T>* const abuf = reinterpret_cast<RecT<T>*>(dsm_raw + CP::ABUF_OFF + warp * CP::SB);
-    unsigned char* const ibraw = dsm_raw + CP::IBUF_OFF + warp * N3_IBUF_BYTES;
-    Vec4S<T>* const ipos = reinterpret_cast<Vec4S<T>*>(ibraw);             // [TILE_I]: x, y, z, functor weight
-    int4* const ikey = reinterpret_cast<int4*>(ibraw + TILE_I * 4 * 8);     // [TILE_I]: reference cell x, own slot, image flag, slot of the real record
-    int* const kbuf = reinterpret_cast<int*>(ibraw + TILE_I * 4 * 8 + TILE_I * 16);   // [N3_KBUF]: reference cell x of the keyed partners
-    const uint32_t abuf_addr = smem_u32(abuf), buf_addr = smem_u32(buf);
-    const uint32_t mbar = smem_u32(dsm_raw + CP::MBAR_OFF + warp * 8);
+    const uint32_t mbar = smem_u32(wb), buf_addr = smem_u32(buf), abuf_addr = smem_u32(abuf);
     uint32_t parity = 0;
     if (lane == 0) { mbar_init(mbar, 1); fence_proxy_async(); }
     __syncwarp();
     if (a.dscal[DS_NTOT] > a.rec_cap_i) return;   // overflowed build: the host repeats build + map
+    const int lf = a.lf, sub = a.sub, hww = 2 * lf + 1;
+    const unsigned smagic = a.sub_magic;
+    auto div_sub = [&](int v) { return (sub == 1) ? v : (int)__umulhi((unsigned)v, smagic); };
+    const int nrows_st = (a.nz == 1) ? hww : hww * hww;
     double e_acc = 0.0;
     const int ntiles = a.dscal[DS_NTILES];
     const T rc2 = a.rc2;
     const unsigned lt = (1u << lane) - 1u;
+    const RecT<T>* const rec = a.rec_j;           // slot-tagged records (rec_n3)
     int t_next = 0;
     if (lane == 0) t_next = atomicAdd(&a.dscal[DS_WORK], 1);
     for (;;) {
@@ -168,226 +185,214 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
         const int islot = lane & (TILE_I - 1);
         const bool valid = islot < tl.cnt;
         const int ki = tl.k0 + (valid ? islot : 0);
-        const RecT<T> ri = ldrec(rec_tag + ki);                      // coordinates + tag (HOME / GHOST / FOREIGN)
-        const bool ghost_i = (ri.tag & TG::GHOST) != 0;
-        const bool active = valid && ((ri.tag & TG::FOREIGN) == 0) && ((MODE == MODE_HALF) ? ((ri.tag & TG::HOME) != 0) : !ghost_i);
-        T blo[3], bhi[3];
-        {
-            const T inf = CUDART_INF_T<T>();
-            blo[0] = tile_min(active ? ri.x : inf); blo[1] = tile_min(active ? ri.y : inf); blo[2] = tile_min(active ? ri.z : inf);
-            bhi[0] = tile_max(active ? ri.x : -inf); bhi[1] = tile_max(active ? ri.y : -inf); bhi[2] = tile_max(active ? ri.z : -inf);
-        }
-        const int iy = tl.yz & 0xffff, iz = tl.yz >> 16, tile_row = iz * a.ny + iy;
+        const RecT<T> ri = ldrec(rec + ki);
+        const uint32_t swi = slotword(ri);
+        const bool ghost_i = (swi & N3_GHOST) != 0u;
+        const bool active0 = valid && ((MODE == MODE_HALF) ? ((swi & N3_HOME) != 0u) : !ghost_i);
+        const int iy = tl.yz & 0xffff, iz = tl.yz >> 16;
         const int cxa = tl.cx & 0xffff, cxb = tl.cx >> 16;
-        int rfx_i = 0;
+        int rfx_i = 0, rfa = 0, rfb = 0;
         if (MODE == MODE_HALF) {
-            const int* cs = a.cell_start_i + (size_t)tile_row * (a.nx + 1);
+            const int* cs = a.cell_start_i + (size_t)(iz * a.ny + iy) * (a.nx + 1);
             int cx = cxa;
             while (cx < cxb && cs[cx + 1] <= ki) ++cx;
-            rfx_i = div_sub(cx);
+            rfx_i = div_sub(cx); rfa = div_sub(cxa); rfb = div_sub(cxb);
         }
         const int ry_i = div_sub(iy), rz_i = div_sub(iz);
-        const bool any_ghost_i = __ballot_sync(0xffffffffu, active && ghost_i) != 0u;
-        const int slot_i = (int)(slotword(ldrec(a.rec_j + ki)) & N3_SLOT);   // slot of i's real record (own slot for a real particle)
-        __syncwarp();   // every lane is done with the previous tile's i-side data
-        if (lane < TILE_I) {
-            Vec4S<T> v;
-            v.x = active ? ri.x : huge_coord<T>(); v.y = ri.y; v.z = ri.z; v.w = (F::AUX && active) ? f.wi(ki) : T(0);
-            ipos[lane] = v;
-            ikey[lane] = make_int4(rfx_i, ki, ghost_i ? 1 : 0, slot_i);
-        }
-        __syncwarp();
         T fi[TILE_I][3];
 #pragma unroll
         for (int i = 0; i < TILE_I; ++i) fi[i][0] = fi[i][1] = fi[i][2] = T(0);
         T e_tile = T(0);
-        // keyed ("direct") part along the row (MODE_HALF): the reference cells rfa .. rfb the tile touches
-        const int rfa = div_sub(cxa), rfb = div_sub(cxb);
-        const int xlo_dir = rfa * sub, xhi_dir = min((rfb + 1) * sub, a.nx);
-        // the partner list of the tile: survivors of the cull wait at buf[0 .. nl); the first nkey of them carry keys
-        int nl = 0, nkey = 0;
 
-        // ---- one chunk = 32 partners, one per lane; one warp step per particle i of the tile ---------------------
-        // PLAIN: forward partners of a tile without image particles i (every pair counts); KEYED: chunks that hold keyed
-        // partners; GENERAL: tiles with image particles i; TRI: triclinic rule
-        auto chunk = [&](auto kind_tag, const int s) {
-            constexpr int KIND = decltype(kind_tag)::value;
-            const RecT<T> rj = ldrec_s(buf + s);
-            T wj = T(0);
-            if constexpr (F::AUX) wj = ldrec_s(abuf + s).x;
-            const uint32_t sw = slotword(rj);
-            const bool gj = (sw & N3_GHOST) != 0u;
-            const int slot_j = (int)(sw & N3_SLOT);
-            int K1 = 0x7fffffff;
-            const int K2 = (MODE == MODE_TRI) ? slot_j : (gj ? 0x7fffffff : slot_j);
-            if (KIND == N3_KEYED || KIND == N3_GENERAL) { if (s < nkey) K1 = kbuf[s]; }
-            T fjx = T(0), fjy = T(0), fjz = T(0);
-#pragma unroll
-            for (int i = 0; i < TILE_I; ++i) {
-                const Vec4S<T> pi = ldvec4_s(ipos + i);
-                const T dx = pi.x - rj.x, dy = pi.y - rj.y, dz = pi.z - rj.z;
-                const T d2 = xfma(dz, dz, xfma(dy, dy, dx * dx));
-                bool ok = true;
-                if (KIND == N3_KEYED) { const int4 ik = ikey[i]; ok = (K1 > ik.x) || (K1 == ik.x && K2 > ik.y); }
-                else if (KIND == N3_GENERAL) { const int4 ik = ikey[i]; ok = ik.z ? (K1 > ik.x && !gj) : ((K1 > ik.x) || (K1 == ik.x && K2 > ik.y)); }
-                else if (KIND == N3_TRI) { const int4 ik = ikey[i]; ok = K2 > ik.w; }
-                const bool hit = ok && (d2 <= rc2);
-                const T sc = f.fs(hit, d2, e_tile, pi.w, wj);
-                fi[i][0] = xfma(sc, dx, fi[i][0]); fi[i][1] = xfma(sc, dy, fi[i][1]); fi[i][2] = xfma(sc, dz, fi[i][2]);
-                fjx = xfma(-sc, dx, fjx); fjy = xfma(-sc, dy, fjy); fjz = xfma(-sc, dz, fjz);
+#pragma unroll 1
+        for (int rbase = rfa; rbase <= rfb; rbase += 2) {
+            const bool active = active0 && (MODE != MODE_HALF || (unsigned)(rfx_i - rbase) < 2u);
+            T blo[3], bhi[3];
+            {
+                const T inf = CUDART_INF_T<T>();
+                blo[0] = tile_min(active ? ri.x : inf); blo[1] = tile_min(active ? ri.y : inf); blo[2] = tile_min(active ? ri.z : inf);
+                bhi[0] = tile_max(active ? ri.x : -inf); bhi[1] = tile_max(active ? ri.y : -inf); bhi[2] = tile_max(active ? ri.z : -inf);
             }
-            if (fjx != T(0) || fjy != T(0) || fjz != T(0)) red_add3(facc + (size_t)slot_j * 4, fjx, fjy, fjz);
-        };
+            const bool any_ghost_i = (MODE == MODE_HALF) && (__ballot_sync(0xffffffffu, active && ghost_i) != 0u);
+            __syncwarp();   // every lane is done with the i-side data of the previous trip / tile
+            if (lane < TILE_I) {
+                Vec4S<T> v;
+                v.x = active ? ri.x : huge_coord<T>(); v.y = ri.y; v.z = ri.z; v.w = (F::AUX && active) ? f.wi(ki) : T(0);
+                ipos[lane] = v;
+                if (MODE == MODE_TRI) ikey[lane] = make_int2((int)(swi & N3_SLOT), 0);
+                else ikey[lane] = make_int2((int)(((unsigned)(rfx_i - rbase) << 30) | (ghost_i ? 0x3fffffffu : (unsigned)ki)), ghost_i ? 1 : 0);
+            }
+            __syncwarp();
+            // keyed part along the row (MODE_HALF): device cells [xD0, xD1) = reference cells rbase .. min(rbase + 1, rfb)
+            const int xD0 = rbase * sub, xD1 = min((min(rbase + 1, rfb) + 1) * sub, a.nx);
+            const uint32_t rpar = (uint32_t)(rbase & 1);
+            int nl = 0, nk = 0;   // partners waiting at buf[0 .. nl); the first nk of them are keyed
 
-        for (int rb = 0; rb < nrows_st; rb += 32) {
-            // ---- lane r classifies stencil row r (same rules as k_sweep) -------------------------------------------
-            const int r = rb + lane;
-            int j0 = 0, j1 = 0, rowbase = 0, dj0 = 0, dj1 = 0, bnd1 = 0x7fffffff;
-            if (r < nrows_st) {
-                const int dz = a.rdz[r], dy = a.rdy[r];
-                const int z2 = iz + dz, y2 = iy + dy;
-                const int w = a.hw[(dz + lf) * hww + dy + lf];
-                bool use = (z2 >= 0 && z2 < a.nz && y2 >= 0 && y2 < a.ny && w >= 0);
-                int rel = 1;
-                if (MODE == MODE_HALF && use) {
-                    const int rz_j = div_sub(z2), ry_j = div_sub(y2);
-                    rel = (rz_j != rz_i) ? (rz_j - rz_i) : (ry_j - ry_i);
-                    use = rel >= 0;
+            // ---- one chunk = 32 partners, one per lane; one warp step per particle i of the tile ------------------
+            auto chunk = [&](auto kind_tag, const int s) {
+                constexpr int KIND = decltype(kind_tag)::value;
+                const RecT<T> rj = ldrec_s(buf + s);
+                T wj = T(0);
+                if constexpr (F::AUX) wj = ldrec_s(abuf + s).x;
+                const uint32_t sw = slotword(rj);
+                const bool gj = (sw & N3_GHOST) != 0u;
+                const int slot_j = (int)(sw & N3_SLOT);
+                // key of the partner: see ikey
+                unsigned KJ = 0u;
+                if (MODE == MODE_TRI) KJ = (unsigned)slot_j;
+                else if (KIND == N3_KEYED || KIND == N3_GENERAL)
+                    KJ = ((s < nk) ? ((((sw >> N3_PAR_SHIFT) & 1u) ^ rpar) << 30) : 0x80000000u) | (gj ? 0x3fffffffu : (unsigned)slot_j);
+                T fjx = T(0), fjy = T(0), fjz = T(0);
+#pragma unroll
+                for (int i = 0; i < TILE_I; ++i) {
+                    const Vec4S<T> pi = ldvec4_s(ipos + i);
+                    const T dx = pi.x - rj.x, dy = pi.y - rj.y, dz = pi.z - rj.z;
+                    const T d2 = xfma(dz, dz, xfma(dy, dy, dx * dx));
+                    bool ok = true;
+                    if (KIND == N3_KEYED || KIND == N3_TRI) ok = KJ > (unsigned)ikey[i].x;
+                    else if (KIND == N3_GENERAL) { const int2 ik = ikey[i]; ok = (KJ > (unsigned)ik.x) && !(ik.y && gj); }
+                    const bool hit = ok && (d2 <= rc2);
+                    const T sc = f.fs(hit, d2, e_tile, pi.w, wj);
+                    fi[i][0] = xfma(sc, dx, fi[i][0]); fi[i][1] = xfma(sc, dy, fi[i][1]); fi[i][2] = xfma(sc, dz, fi[i][2]);
+                    fjx = xfma(-sc, dx, fjx); fjy = xfma(-sc, dy, fjy); fjz = xfma(-sc, dz, fjz);
                 }
-                if (use) {
-                    rowbase = (z2 * a.ny + y2) * (a.nx + 1);
-                    const int xa = max(cxa - w, 0), xb = min(cxb + w, a.nx - 1);
-                    j0 = a.cell_start_j[rowbase + xa];
-                    j1 = a.cell_start_j[rowbase + xb + 1];
-                    if (MODE == MODE_HALF && rel == 0) {
-                        const int* csj = a.cell_start_j + rowbase;
-                        const int tsplit = csj[xhi_dir];
-                        dj0 = max(j0, csj[xlo_dir]);
-                        dj1 = min(j1, tsplit);
-                        j0 = max(j0, tsplit);
-                        if (rfb > rfa) bnd1 = csj[(rfa + 1) * sub];   // first record of the tile's second reference cell in this row
+                if (any_nonzero(fjx, fjy, fjz)) red_add3(facc + (size_t)slot_j * 4, fjx, fjy, fjz);
+            };
+            // one cull step: 32 staged records, survivors compacted in place behind buf[ns)
+            auto cull_step = [&](const RecT<T>* q, int& ns) -> unsigned {
+                const RecT<T> rq = ldrec_s(q);
+                RecT<T> aq = rq;
+                if constexpr (F::AUX) aq = ldrec_s(abuf + (q - buf));
+                const T ex = fmax(fmax(blo[0] - rq.x, rq.x - bhi[0]), T(0));
+                const T ey = fmax(fmax(blo[1] - rq.y, rq.y - bhi[1]), T(0));
+                const T ez = fmax(fmax(blo[2] - rq.z, rq.z - bhi[2]), T(0));
+                const T dd = xfma(ez, ez, xfma(ey, ey, ex * ex));
+                const bool keep = (dd <= rc2);
+                const unsigned m = __ballot_sync(0xffffffffu, keep);   // every lane has read its slot: in-place writes are safe
+                if (keep) {
+                    const int pos = ns + __popc(m & lt);
+                    strec(buf + pos, rq.x, rq.y, rq.z, rq.tag);
+                    if constexpr (F::AUX) strec(abuf + pos, aq.x, aq.y, aq.z, aq.tag);
+                }
+                return m;
+            };
+
+#pragma unroll 1
+            for (int rb = 0; rb < nrows_st; rb += 32) {
+                // ---- lane r classifies stencil row r (same rules as k_sweep) ---------------------------------------
+                const int r = rb + lane;
+                int j0 = 0, j1 = 0, d0 = 0, d1 = 0;
+                if (r < nrows_st) {
+                    const int dz = a.rdz[r], dy = a.rdy[r];
+                    const int z2 = iz + dz, y2 = iy + dy;
+                    const int w = a.hw[(dz + lf) * hww + dy + lf];
+                    bool use = ((unsigned)z2 < (unsigned)a.nz) && ((unsigned)y2 < (unsigned)a.ny) && (w >= 0);
+                    int rel = 1;
+                    if (MODE == MODE_HALF && use) {
+                        const int rz_j = div_sub(z2), ry_j = div_sub(y2);
+                        rel = (rz_j != rz_i) ? (rz_j - rz_i) : (ry_j - ry_i);
+                        use = rel >= 0;
+                    }
+                    if (use) {
+                        const int* csj = a.cell_start_j + (size_t)(z2 * a.ny + y2) * (a.nx + 1);
+                        j0 = csj[max(cxa - w, 0)];
+                        j1 = csj[min(cxb + w, a.nx - 1) + 1];
+                        if (MODE == MODE_HALF && rel == 0) {
+                            const int sD1 = csj[xD1];
+                            d0 = max(j0, csj[xD0]);
+                            d1 = min(j1, sD1);
+                            j0 = max(j0, sD1);
+                        }
                     }
                 }
-            }
-            const int dlen = (MODE == MODE_HALF) ? max(dj1 - dj0, 0) : 0, flen = max(j1 - j0, 0);
-            // prefixes of the segment lengths: where each row's records go in the staged sequence of its part
-            int dincl = dlen, fincl = flen;
+                const int dlen = (MODE == MODE_HALF) ? max(d1 - d0, 0) : 0, flen = max(j1 - j0, 0);
+                int dincl = dlen, fincl = flen;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, fincl, o);
-                if (lane >= o) fincl += v;
-                if (MODE == MODE_HALF) { const int u = __shfl_up_sync(0xffffffffu, dincl, o); if (lane >= o) dincl += u; }
-            }
-            const int dtotal = (MODE == MODE_HALF) ? __shfl_sync(0xffffffffu, dincl, 31) : 0, ftotal = __shfl_sync(0xffffffffu, fincl, 31);
-            // ---- passes: the keyed ("direct") part first, then the forward part; each pass stages at most CAPP records
-            //      behind the partners that wait at buf[0 .. nl), culls them against the tile's bounding box, compacts in
-            //      place and sweeps the whole chunks of the list; the partial chunk at its end is carried to the next pass.
-            //      The last forward pass of the batch sweeps everything. ----
-            bool keyed = dtotal > 0;
-            int c0 = 0;
-            for (;;) {
-                const int total = keyed ? dtotal : ftotal, capp = keyed ? N3_KEYED_CAP : CP::FWD;
-                if (keyed && c0 >= total) { keyed = false; c0 = 0; continue; }
-                const int len = keyed ? dlen : flen, off = keyed ? (dincl - dlen) : (fincl - flen), seg0 = keyed ? dj0 : j0;
-                const int cn = min(total - c0, capp);
-                const int lo = max(off, c0), hi = min(off + len, c0 + cn);
-                if (cn > 0) {
-                    if (lane == 0) { fence_proxy_async(); mbar_expect_tx(mbar, (uint32_t)cn * REC * (F::AUX ? 2u : 1u)); }
-                    __syncwarp();
-                    if (hi > lo) {
-                        bulk_g2s(buf_addr + (uint32_t)(nl + lo - c0) * REC, a.rec_j + (seg0 + (lo - off)), (uint32_t)(hi - lo) * REC, mbar);
-                        if constexpr (F::AUX) bulk_g2s(abuf_addr + (uint32_t)(nl + lo - c0) * REC, f.aux_j() + (seg0 + (lo - off)), (uint32_t)(hi - lo) * REC, mbar);
-                    }
-                    if (MODE == MODE_HALF && keyed) {
-                        // keys of the staged records, row by row: reference cell (along the row) = rfa + the number of reference-cell
-                        // starts of that row at or before the record's slot in the global array
-                        unsigned md = __ballot_sync(0xffffffffu, hi > lo);
-                        while (md) {
-                            const int src = __ffs(md) - 1;
-                            md &= md - 1;
-                            const int slo = __shfl_sync(0xffffffffu, lo, src), shi = __shfl_sync(0xffffffffu, hi, src);
-                            const int sbase = __shfl_sync(0xffffffffu, seg0 - off, src), sb1 = __shfl_sync(0xffffffffu, bnd1, src);
-                            const int srb = __shfl_sync(0xffffffffu, rowbase, src);
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, fincl, o);
+                    if (lane >= o) fincl += v;
+                    if (MODE == MODE_HALF) { const int u = __shfl_up_sync(0xffffffffu, dincl, o); if (lane >= o) dincl += u; }
+                }
+                const int tD = (MODE == MODE_HALF) ? __shfl_sync(0xffffffffu, dincl, 31) : 0;
+                const int total = tD + __shfl_sync(0xffffffffu, fincl, 31);
+                // where this lane's segments sit in S, and what they read: (global record index - offset in S)
+                const int offD = dincl - dlen, offF = tD + fincl - flen;
+                const int srcD = d0 - offD, srcF = j0 - offF;
+
+                // ---- passes over S --------------------------------------------------------------------------------
 #pragma unroll 1
-                            for (int p = slo + lane; p < shi; p += 32) {
-                                const int jc = sbase + p;
-                                int key = rfa + ((jc >= sb1) ? 1 : 0);
-                                if (rfb > rfa + 1) {   // a sparse row: the tile spans more than two reference cells
-#pragma unroll 1
-                                    for (int rc = rfa + 2; rc <= rfb; ++rc) key += (jc >= a.cell_start_j[srb + rc * sub]) ? 1 : 0;
-                                }
-                                kbuf[nl + p - c0] = key;
+                for (int c0 = 0; c0 < total;) {
+                    const int cn = min(total - c0, CP::CAPP - nl);
+                    {
+                        if (lane == 0) { fence_proxy_async(); mbar_expect_tx(mbar, (uint32_t)cn * REC * (F::AUX ? 2u : 1u)); }
+                        __syncwarp();
+                        const int wdst = nl - c0;   // S offset -> buffer slot
+#pragma unroll
+                        for (int part = (MODE == MODE_HALF ? 0 : 1); part < 2; ++part) {
+                            const int off = part ? offF : offD, len = part ? flen : dlen, src = part ? srcF : srcD;
+                            const int lo = max(off, c0), hi = min(off + len, c0 + cn);
+                            if (hi > lo) {
+                                bulk_g2s(buf_addr + (uint32_t)(wdst + lo) * REC, rec + (src + lo), (uint32_t)(hi - lo) * REC, mbar);
+                                if constexpr (F::AUX) bulk_g2s(abuf_addr + (uint32_t)(wdst + lo) * REC, f.aux_j() + (src + lo), (uint32_t)(hi - lo) * REC, mbar);
                             }
                         }
+                        mbar_wait(mbar, parity);
+                        parity ^= 1u;
+                        __syncwarp();
                     }
-                    mbar_wait(mbar, parity);
-                    parity ^= 1u;
+                    // far-away dummies round the staged records up to whole cull steps
+                    if (cn + lane < ((cn + 31) & ~31)) strec(buf + nl + cn + lane, -huge_coord<T>(), T(0), T(0), (tag_t)0);
                     __syncwarp();
-                }
-                if (cn + lane < ((cn + 31) & ~31)) strec(buf + nl + cn + lane, -huge_coord<T>(), T(0), T(0), (tag_t)0);
-                __syncwarp();
-                int ns = nl;
-                {
-                    const RecT<T>* q = buf + nl + lane;
+                    int ns = nl;
+                    {
+                        const RecT<T>* q = buf + nl + lane;
+                        int k0 = 0;
+                        if (MODE == MODE_HALF) {
+                            const int kend = min(tD - c0, cn);   // staged records [0, kend) of this pass are keyed
 #pragma unroll 1
-                    for (int k0 = 0; k0 < cn; k0 += 32, q += 32) {
-                        const RecT<T> rq = ldrec_s(q);
-                        RecT<T> aq = rq;
-                        if constexpr (F::AUX) aq = ldrec_s(abuf + (q - buf));
-                        int key = 0;
-                        if (MODE == MODE_HALF && keyed) key = kbuf[nl + k0 + lane];
-                        const T ex = fmax(fmax(blo[0] - rq.x, rq.x - bhi[0]), T(0));
-                        const T ey = fmax(fmax(blo[1] - rq.y, rq.y - bhi[1]), T(0));
-                        const T ez = fmax(fmax(blo[2] - rq.z, rq.z - bhi[2]), T(0));
-                        const T dd = xfma(ez, ez, xfma(ey, ey, ex * ex));
-                        const bool keep = (dd <= rc2);
-                        const unsigned m = __ballot_sync(0xffffffffu, keep);   // every lane has read its slot: in-place writes are safe
-                        if (keep) {
-                            const int pos = ns + __popc(m & lt);
-                            strec(buf + pos, rq.x, rq.y, rq.z, rq.tag);
-                            if constexpr (F::AUX) strec(abuf + pos, aq.x, aq.y, aq.z, aq.tag);
-                            if (MODE == MODE_HALF && keyed) kbuf[pos] = key;
+                            for (; k0 < kend; k0 += 32, q += 32) {
+                                const unsigned m = cull_step(q, ns);
+                                const int left = kend - k0;
+                                nk = ns + __popc(m & ((left >= 32) ? 0xffffffffu : ((1u << left) - 1u)));
+                                ns += __popc(m);
+                            }
                         }
-                        ns += __popc(m);
-                    }
-                }
-                if (keyed) nkey = ns;      // the keyed part comes first: every waiting partner is keyed
-                const bool last = !keyed && (c0 + cn >= total);
-                int nfull = ns >> 5;
-                if (last && (ns & 31)) {   // pad the partial chunk with far-away dummies and sweep it too
-                    if ((ns & 31) + lane < 32) strec(buf + ns + lane, -huge_coord<T>(), T(0), T(0), (tag_t)0);
-                    nfull += 1;
-                    ns = nfull * 32;
-                }
-                __syncwarp();
 #pragma unroll 1
-                for (int ch = 0; ch < nfull; ++ch) {
-                    const int s = ch * 32 + lane;
-                    if (MODE == MODE_TRI) chunk(std::integral_constant<int, N3_TRI>{}, s);
-                    else if (any_ghost_i) chunk(std::integral_constant<int, N3_GENERAL>{}, s);
-                    else if (ch * 32 < nkey) chunk(std::integral_constant<int, N3_KEYED>{}, s);
-                    else chunk(std::integral_constant<int, N3_PLAIN>{}, s);
-                }
-                const int rem = ns & 31;
-                if (nfull > 0 && rem > 0) {
-                    // carry the partial chunk to the front
-                    const RecT<T> rq = ldrec_s(buf + nfull * 32 + lane);
-                    RecT<T> aq = rq;
-                    if constexpr (F::AUX) aq = ldrec_s(abuf + nfull * 32 + lane);
-                    int key = 0;
-                    if (MODE == MODE_HALF && keyed) key = kbuf[nfull * 32 + lane];
-                    __syncwarp();
-                    if (lane < rem) {
-                        strec(buf + lane, rq.x, rq.y, rq.z, rq.tag);
-                        if constexpr (F::AUX) strec(abuf + lane, aq.x, aq.y, aq.z, aq.tag);
-                        if (MODE == MODE_HALF && keyed) kbuf[lane] = key;
+                        for (; k0 < cn; k0 += 32, q += 32) ns += __popc(cull_step(q, ns));
                     }
+                    c0 += cn;
+                    const bool last = (c0 >= total);
+                    int nfull = ns >> 5;
+                    if (last && (ns & 31)) {   // pad the partial chunk with far-away dummies and sweep it too
+                        if ((ns & 31) + lane < 32) strec(buf + ns + lane, -huge_coord<T>(), T(0), T(0), (tag_t)0);
+                        nfull += 1;
+                        ns = nfull * 32;
+                    }
+                    __syncwarp();
+#pragma unroll 1
+                    for (int ch = 0; ch < nfull; ++ch) {
+                        const int s = ch * 32 + lane;
+                        if (MODE == MODE_TRI) chunk(std::integral_constant<int, N3_TRI>{}, s);
+                        else if (any_ghost_i) chunk(std::integral_constant<int, N3_GENERAL>{}, s);
+                        else if (ch * 32 < nk) chunk(std::integral_constant<int, N3_KEYED>{}, s);
+                        else chunk(std::integral_constant<int, N3_PLAIN>{}, s);
+                    }
+                    const int rem = ns & 31;
+                    if (nfull > 0 && rem > 0) {
+                        // carry the partial chunk to the front
+                        const RecT<T> rq = ldrec_s(buf + nfull * 32 + lane);
+                        RecT<T> aq = rq;
+                        if constexpr (F::AUX) aq = ldrec_s(abuf + nfull * 32 + lane);
+                        __syncwarp();
+                        if (lane < rem) {
+                            strec(buf + lane, rq.x, rq.y, rq.z, rq.tag);
+                            if constexpr (F::AUX) strec(abuf + lane, aq.x, aq.y, aq.z, aq.tag);
+                        }
+                    }
+                    nk = max(nk - nfull * 32, 0);
+                    nl = rem;
+                    __syncwarp();
                 }
-                if (nfull > 0) nkey = keyed ? rem : 0;
-                nl = rem;
-                __syncwarp();
-                c0 += cn;
-                if (last) break;
             }
         }
 
@@ -412,8 +417,8 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
                 v[0] += __shfl_xor_sync(0xffffffffu, v[0], o); v[1] += __shfl_xor_sync(0xffffffffu, v[1], o); v[2] += __shfl_xor_sync(0xffffffffu, v[2], o);
             }
             const int g = lane >> 2;
-            const int slot_g = __shfl_sync(0xffffffffu, slot_i, g);
-            const bool act_g = __shfl_sync(0xffffffffu, active ? 1 : 0, g) != 0;
+            const int slot_g = (int)(__shfl_sync(0xffffffffu, swi, g) & N3_SLOT);
+            const bool act_g = __shfl_sync(0xffffffffu, active0 ? 1 : 0, g) != 0;
             if ((lane & 3) == 0 && act_g && (v[0] != T(0) || v[1] != T(0) || v[2] != T(0))) red_add3(facc + (size_t)slot_g * 4, v[0], v[1], v[2]);
         }
         e_acc += (double)e_tile;
@@ -425,18 +430,25 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
     }
 }
 
-// record-ordered accumulator rows -> the caller's per-particle force array (particle order), and back to zero:
-// out[idx] = (accumulate ? out[idx] : 0) + scale * R^-1 f.  Every particle has exactly one real record.
-template <class T>
+// accumulator rows -> the caller's per-particle force array (particle order), and back to zero:
+// out[idx] = (accumulate ? out[idx] : 0) + scale * R^-1 f.  BY_INDEX = false: rows in record order (every particle has exactly
+// one real record; image rows are never written: images add into their original's row); true: rows in particle order
+// (triclinic cells, whose exactly-once rule compares particle indices).
+template <class T, bool BY_INDEX>
 __global__ void __launch_bounds__(256)
-k_force_finish(const RecT<T>* __restrict__ rec_tag, T* __restrict__ facc, const int* __restrict__ dscal, int rec_cap, T* __restrict__ out, int dim,
+k_force_finish(const RecT<T>* __restrict__ rec_tag, T* __restrict__ facc, const int* __restrict__ dscal, int rec_cap, int n, T* __restrict__ out, int dim,
                T scale, int accumulate, int rotated, const __grid_constant__ GeomT<T> g) {
     typedef TagT<T> TG;
     const int ntot = dscal[DS_NTOT];
     if (ntot > rec_cap) return;   // overflowed build
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < ntot; k += gridDim.x * blockDim.x) {
-        const typename TG::type tag = rec_tag[k].tag;
-        if (tag & (TG::GHOST | TG::FOREIGN)) continue;   // image rows are never written: images add into their original's row
+    const int nrows = BY_INDEX ? n : ntot;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nrows; k += gridDim.x * blockDim.x) {
+        size_t idx = (size_t)k;
+        if (!BY_INDEX) {
+            const typename TG::type tag = rec_tag[k].tag;
+            if (tag & (TG::GHOST | TG::FOREIGN)) continue;
+            idx = (size_t)(tag & TG::MASK);
+        }
         T* row = facc + (size_t)k * 4;
         T fx = row[0] * scale, fy = row[1] * scale, fz = row[2] * scale;
         row[0] = T(0); row[1] = T(0); row[2] = T(0);
@@ -446,7 +458,7 @@ k_force_finish(const RecT<T>* __restrict__ rec_tag, T* __restrict__ facc, const 
             const T s = g.inv_rot[6] * fx + g.inv_rot[7] * fy + g.inv_rot[8] * fz;
             fx = p; fy = q; fz = s;
         }
-        T* o = out + (size_t)(tag & TG::MASK) * dim;
+        T* o = out + idx * dim;
         if (accumulate) { o[0] += fx; o[1] += fy; if (dim == 3) o[2] += fz; }
         else { o[0] = fx; o[1] = fy; if (dim == 3) o[2] = fz; }
     }
