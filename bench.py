@@ -136,13 +136,14 @@ def load_peaks():
 
 
 # ----------------------------------------------------------------------------------------------------------
-def cpu_port_run(w, dtype, reps, threads=None):
+def cpu_port_run(w, dtype, reps, threads):
     """the oracle (CPU restatement of the reference's algorithm incl. projection filter and batch-private outputs)
-    on the host cores: full workload, `reps` repetitions of build + map; returns (median seconds, pairs, threads)."""
+    on the host cores: full workload, `reps` repetitions of build + map; returns (median seconds, pairs, threads, energy,
+    forces of the last repetition)."""
     from oracle import oracle as om
-    nt = threads or om.lib().ora_num_threads()
+    nt = threads
     x = np.ascontiguousarray(w["x"], dtype=dtype)
-    times, npairs = [], None
+    times, e, f = [], None, None
     for _ in range(reps):
         t0 = time.perf_counter()
         o = om.Oracle(x, w["cutoff"], unitcell=w["unitcell"].astype(dtype), dtype=dtype)   # UpdateCellList!
@@ -151,22 +152,35 @@ def cpu_port_run(w, dtype, reps, threads=None):
         del o
     o = om.Oracle(x, w["cutoff"], unitcell=w["unitcell"].astype(dtype), dtype=dtype)
     npairs = o.sum_d_d2(nbatches=nt)[2]
-    return statistics.median(times), npairs, nt
+    return statistics.median(times), npairs, nt, e, f
 
 
 def run_reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference is pure Julia and no Julia
-    toolchain exists here or on the GPU box, so this is the oracle port with all host threads."""
+    toolchain exists here or on the GPU box, so this is the oracle port with all host threads (the thread count is
+    taken from the CPU affinity mask: torchrun's OMP_NUM_THREADS=1 is overridden before the OpenMP runtime loads).
+    N = 1: the full 1M-particle C2 workload.  N > 1 (the GPU arm runs the slab-decomposed C5 system, 8M particles per
+    GPU): a bounded sample of that system -- the same density, cutoff and generator at 2M particles -- because the metric
+    is a throughput (in-cutoff pair evaluations per second) and one 64M-particle CPU step takes about a minute."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    nt = host_threads()
     dtype = np.float32
-    nside = args.cpu_nside
-    w = W.c2_argon(nside, dtype)
     from oracle import oracle as om
     nt = om.lib().ora_num_threads()
-    x = w["x"]
-    uc = w["unitcell"]
+    if args.gpus > 1:
+        import bench_multi
+        nside = 126
+        x, uc = bench_multi.slab_lattice(0, 1, nside, nside, dtype)
+        w = dict(x=x, unitcell=uc, cutoff=12.0, c6=W.ARGON_C6, c12=W.ARGON_C12)
+        workload = ("C5 sample: LJ energy+forces, argon-density particles, cubic PBC, cutoff 12 A (BASELINE.json configs[4]): "
+                    f"{nside}^3 = {nside ** 3} particles of the generator the GPU arm shards over {args.gpus} GPUs")
+    else:
+        nside = args.cpu_nside
+        w = W.c2_argon(nside, dtype)
+        workload = "C2: LJ energy+forces, 1M argon-density particles, cubic PBC, cutoff 12 A (BASELINE.json configs[1])"
+    x, uc = w["x"], w["unitcell"]
 
     def step():
         o = om.Oracle(x, w["cutoff"], unitcell=uc, dtype=dtype)
@@ -181,17 +195,132 @@ def run_reference_arm(args):
     dt = time.perf_counter() - t0
     npairs = o.sum_d_d2(nbatches=nt)[2]
     value = npairs * args.steps / dt
-    sample = f"{nside}^3 = {nside ** 3} argon-density particles (same generator/density/cutoff as the GPU arm), build + LJ energy+forces per step"
+    sample = (f"{nside}^3 = {nside ** 3} argon-density particles (same generator/density/cutoff as the GPU arm), build + LJ energy+forces per step, "
+              f"{nt} OpenMP threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2: LJ energy+forces, argon-density particles, cubic PBC, cutoff 12 A", "n_particles": nside ** 3,
+        "config": {"workload": workload, "n_particles": nside ** 3,
                    "note": "CPU restatement of CellListMap.jl (C++/OpenMP oracle port, not Julia: no Julia toolchain on the box)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nt, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------
+def c5_single_gpu(clm, torch, local, stream, flush_buf, nside, nx, steps=5):
+    """the C5 particle system (argon-density lattice, nx x nside x nside sites, Float32) on ONE GPU through a plain handle:
+    the denominators of the weak-scaling (8M particles per GPU) and strong-scaling (64M particles) figures of the N > 1 runs"""
+    import bench_multi
+    dev = torch.device("cuda", local)
+    x_dev, uc = bench_multi.slab_lattice_torch(0, 1, nside, nx, np.float32, dev)
+    n = x_dev.shape[0]
+    h = clm.Handle(3, np.float32, device=local)
+    h.set_stream(stream.cuda_stream)
+    h.set_box(clm._capi.ORTHORHOMBIC, uc, 12.0, 1)
+    e_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+    f_dev = torch.zeros((n, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.stream(stream):
+        h.set_positions(0, x_dev)
+        h.build()
+        sd, sd2, npairs = np.zeros(1, np.float32), np.zeros(1, np.float32), np.zeros(1, np.int64)
+        h.map_sum_d_d2(sd, sd2, npairs)
+        for _ in range(3):
+            h.set_positions(0, x_dev)
+            h.map_lj(W.ARGON_C6, W.ARGON_C12, e_dev, f_dev)
+        evs = []
+        for _ in range(steps):
+            flush_buf.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            h.set_positions(0, x_dev)
+            h.map_lj(W.ARGON_C6, W.ARGON_C12, e_dev, f_dev)
+            b.record(stream)
+            evs.append((a, b))
+        torch.cuda.synchronize()
+        ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+        sw, bd = [], []
+        for _ in range(3):
+            h.set_positions(0, x_dev)
+            h.map_lj(W.ARGON_C6, W.ARGON_C12, e_dev, f_dev, profile=True)
+            st = h.stats()
+            sw.append(st.sweep_ms)
+            bd.append(st.build_ms)
+    out = {"n_particles": int(n), "in_cutoff_pairs": int(npairs[0]), "ms_per_step": ms, "sweep_kernel_ms": statistics.mean(sw), "build_ms": statistics.mean(bd),
+           "value": int(npairs[0]) / (ms * 1e-3), "energy": float(e_dev[0]), "step": "update positions (D2D) + UpdateCellList! + pairwise!(LJ energy+forces), device-resident"}
+    h.close()
+    del x_dev, f_dev
+    torch.cuda.empty_cache()
+    return out
+
+
+def other_configs(clm, torch, local, fp64_peak_tf):
+    """BASELINE.json configs 3 and 4 at full size (parity-test configurations: extra keys, not the metric): device time of
+    the map (CUDA events around the sweep, build separately) and the end-to-end call with HOST arrays in and out; the work
+    model of the roofline is SURVEY.md's 8 flops per reference-stencil candidate + F_f per in-cutoff pair, candidates from
+    the uniform density (27 (9) reference cells around every particle) against the FP64 FMA peak measured live."""
+    out = {}
+
+    def timed(fn, h, reps):
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        st = h.stats()
+        return 1e3 * statistics.median(ts), st.build_ms, st.sweep_ms
+
+    w = W.c3_triclinic_cross(1_000_000, 1_000_000)
+    h = clm.Handle(3, np.float64, device=local)
+    h.set_box(clm._capi.TRICLINIC, w["unitcell"], w["cutoff"], 1)
+    i, j, d = np.zeros(1, np.int64), np.zeros(1, np.int64), np.zeros(1)
+    sd, sd2, npr = np.zeros(1), np.zeros(1), np.zeros(1, np.int64)
+
+    def c3_e2e():
+        h.set_positions(0, w["x"])
+        h.set_positions(1, w["y"])
+        h.map_mindist(i, j, d, profile=True)
+
+    c3_e2e()
+    h.map_sum_d_d2(sd, sd2, npr)
+    t, b, s = timed(c3_e2e, h, 5)
+    box = h.get_box()
+    vcell = float(np.prod([box.cell_size[k] for k in range(3)]))
+    cand = 1_000_000 * 27.0 * vcell * (1_000_000 / abs(np.linalg.det(w["unitcell"].astype(np.float64))))   # x particles x (27 cells x density of y)
+    flops = 8.0 * cand + 2.0 * int(npr[0])
+    out["c3_triclinic_cross_mindist_f64"] = {
+        "config": "configs[2] at 1M x 1M particles (the 2M-particle system), triclinic cell, cutoff 12 A, Float64", "pairs": int(npr[0]),
+        "sweep_kernel_ms": s, "build_ms": b, "e2e_ms": t, "value": int(npr[0]) / ((s + b) * 1e-3), "e2e_value": int(npr[0]) / (t * 1e-3),
+        "roofline": {"bound": "fp64", "achieved": flops / (s * 1e-3) / 1e12, "peak": fp64_peak_tf, "unit": "TFLOP/s", "frac": flops / (s * 1e-3) / 1e12 / fp64_peak_tf,
+                     "algorithmic_flops_per_launch": flops, "work_model": "8 flops x 27 reference cells of candidates per x particle + 2 per in-cutoff pair"}}
+    h.close()
+    for dim in (3, 2):
+        w = W.c4_galaxies(4_000_000, dim)
+        h = clm.Handle(dim, np.float64, device=local)
+        h.set_box(clm._capi.ORTHORHOMBIC, w["unitcell"], w["cutoff"], 1)
+        c, sm = np.zeros(5, np.int64), np.zeros(5)
+
+        def c4_e2e():
+            h.set_positions(0, w["x"])
+            h.map_pairvel(w["v"], None, w["rbins"], c, sm, profile=True)
+
+        c4_e2e()
+        t, b, s = timed(c4_e2e, h, 3)
+        npairs = int(c.sum())
+        box = h.get_box()
+        vcell = float(np.prod([box.cell_size[k] for k in range(dim)]))
+        n = w["x"].shape[0]
+        cand = 0.5 * n * (3 ** dim) * vcell * (n / float(w["L"]) ** dim)
+        flops = 8.0 * cand + 12.0 * npairs
+        out[f"c4_pairwise_velocities_{dim}d_f64"] = {
+            "config": f"configs[3]: mean pairwise velocity histogram, 4M galaxies, {dim}-D, cutoff 5, 5 bins, Float64", "pairs": npairs,
+            "sweep_kernel_ms": s, "build_ms": b, "e2e_ms": t, "value": npairs / ((s + b) * 1e-3), "e2e_value": npairs / (t * 1e-3),
+            "roofline": {"bound": "fp64", "achieved": flops / (s * 1e-3) / 1e12, "peak": fp64_peak_tf, "unit": "TFLOP/s", "frac": flops / (s * 1e-3) / 1e12 / fp64_peak_tf,
+                         "algorithmic_flops_per_launch": flops, "work_model": f"8 flops x half of {3 ** dim} reference cells of candidates per particle + 12 per in-cutoff pair"}}
+        h.close()
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -205,6 +334,8 @@ def main():
     ap.add_argument("--cpu-nside", type=int, default=100, help="size of the CPU arm / cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-f64", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="N = 1: skip the extra keys (C5 on one GPU, configs 3 and 4)")
+    ap.add_argument("--no-64m", action="store_true", help="skip the 64M-particle single-GPU run (strong-scaling denominator)")
     ap.add_argument("--no-nl", action="store_true", help="N > 1: skip the neighbour-list build timing")
     ap.add_argument("--workload", default="auto")
     ap.add_argument("--multi-nside", type=int, default=400, help="N > 1: lattice sites along y and z")
@@ -214,6 +345,7 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return run_reference_arm(args)
+    nthreads = host_threads()   # before anything loads an OpenMP runtime
 
     import torch
     import torch.distributed as dist
@@ -259,12 +391,13 @@ def main():
             h.map_lj(w["c6"], w["c12"], e_dev, f_dev, reset=True, profile=profile)   # pairwise!: UpdateCellList! + map
 
         with torch.cuda.stream(stream):
-            # pair count and reference-stencil candidates (work model), outside the timed region
+            # pair count, at-cutoff band and reference-stencil candidates (work model), outside the timed region
             h.set_positions(0, x_dev)
             h.build()
             sd, sd2, npairs = np.zeros(1, dtype), np.zeros(1, dtype), np.zeros(1, np.int64)
             h.map_sum_d_d2(sd, sd2, npairs)
             P_in = int(npairs[0])
+            band = int(h.stats().n_cutoff_band)
             for _ in range(warmup):
                 step_dev()
             stream.synchronize()
@@ -286,37 +419,63 @@ def main():
             launches = (h.stats().launches - l0) / steps
             clocks = sampler.stop() if sampler else None
             # kernel-level durations (CUDA events around the sweep launch / the build) from a separate short profiled loop
-            sweep_ms, build_ms = [], []
+            sweep_ms, build_ms, map_ms = [], [], []
             for _ in range(10):
                 flush_buf.zero_()
                 step_dev(profile=True)
                 st = h.stats()
                 sweep_ms.append(st.sweep_ms)
                 build_ms.append(st.build_ms)
+                map_ms.append(st.map_ms)
             dev_ms = sum(evs) / steps
-            # ---- end-to-end arm: HOST buffers through the C ABI, H2D + D2H inside the timed region ----
-            x_pin = torch.from_numpy(w["x"]).pin_memory()
-            f_pin = torch.zeros((n, 3), dtype=tdt).pin_memory()
-            x_host, f_host, e_host = x_pin.numpy(), f_pin.numpy(), np.zeros(1, dtype)
+            f_gpu = f_dev.cpu().numpy()
+            e_gpu = float(e_dev[0])
+            # ---- end-to-end arms: HOST buffers through the C ABI, H2D + D2H inside the timed region ----
+            # (a) synchronous calls: clm_set_positions + clm_map_lj return with the outputs in host memory
+            x_pin = [torch.from_numpy(w["x"]).pin_memory() for _ in range(2)]
+            f_pin = [torch.zeros((n, 3), dtype=tdt).pin_memory() for _ in range(2)]
+            e_pin = [torch.zeros(1, dtype=tdt).pin_memory() for _ in range(2)]
 
-            def step_e2e():
-                h.set_positions(0, x_host)                  # H2D from pinned host memory
-                h.map_lj(w["c6"], w["c12"], e_host, f_host, reset=True)   # forces + energy D2H, synchronous on return
+            def step_sync(k):
+                h.set_positions(0, x_pin[k & 1].numpy())    # H2D from pinned host memory
+                h.map_lj(w["c6"], w["c12"], e_pin[k & 1].numpy(), f_pin[k & 1].numpy(), reset=True)   # forces + energy D2H, synchronous on return
 
-            for _ in range(3):
-                step_e2e()
+            for k in range(3):
+                step_sync(k)
+            nsync = max(5, steps // 4)
             e2e = []
-            for _ in range(steps):
+            for k in range(nsync):
                 flush_buf.zero_()
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
-                step_e2e()
+                step_sync(k)
                 torch.cuda.synchronize()
                 e2e.append(time.perf_counter() - t0)
-            e2e_ms = 1e3 * sum(e2e) / steps
-        res = dict(P_in=P_in, n=n, dev_ms=dev_ms, sweep_ms=statistics.mean(sweep_ms), build_ms=statistics.mean(build_ms),
-                   e2e_ms=e2e_ms, launches=launches, clocks=clocks, w=w, energy=float(e_host[0]),
-                   h2d=int(x_host.nbytes), d2h=int(f_host.nbytes + e_host.nbytes), stats=h.stats())
+            e2e_sync_ms = 1e3 * sum(e2e) / len(e2e)
+            # (b) pipelined frames (clm_set_positions_async + CLM_ASYNC): the frames of a trajectory are independent, so the
+            # copy-in of frame k+1, the compute of frame k and the copy-out of frame k-1 overlap on three streams.  EVERY frame's
+            # positions are copied from pinned host memory and its forces + energy copied back, all inside the timed region;
+            # the L2 flush runs on the compute stream between frames (inside the timed region too).
+            def step_pipe(k):
+                h.set_positions_async(0, x_pin[k & 1].numpy())
+                h.map_lj(w["c6"], w["c12"], e_pin[k & 1].numpy(), f_pin[k & 1].numpy(), async_=True)
+
+            for k in range(4):
+                step_pipe(k)
+            h.synchronize()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for k in range(steps):
+                flush_buf.zero_()
+                step_pipe(k)
+            h.synchronize()
+            torch.cuda.synchronize()
+            e2e_ms = 1e3 * (time.perf_counter() - t0) / steps
+            e_pipe = float(e_pin[(steps - 1) & 1][0])
+            f_pipe_ok = bool(np.array_equal(f_pin[(steps - 1) & 1].numpy(), f_pin[steps & 1].numpy()))
+        res = dict(P_in=P_in, band=band, n=n, dev_ms=dev_ms, sweep_ms=statistics.mean(sweep_ms), build_ms=statistics.mean(build_ms), map_ms=statistics.mean(map_ms),
+                   e2e_ms=e2e_ms, e2e_sync_ms=e2e_sync_ms, launches=launches, clocks=clocks, w=w, energy=e_gpu, forces=f_gpu, energy_pipe=e_pipe,
+                   h2d=int(x_pin[0].numpy().nbytes), d2h=int(f_pin[0].numpy().nbytes + e_pin[0].numpy().nbytes), stats=h.stats(), frames_equal=f_pipe_ok)
         h.close()
         return res
 
@@ -344,6 +503,7 @@ def main():
             hh.neighborlist_count()
             td.append(time.perf_counter() - t0)
         return {"config": "configs[0]: 10k random 3-D particles, orthorhombic unit cube, cutoff 0.1, Float64", "pairs": int(len(lst)),
+                "at_cutoff_band_pairs": int(nb.n_cutoff_band),
                 "e2e_ms": 1e3 * statistics.median(te), "device_resident_ms": 1e3 * statistics.median(td),
                 "reference_published_ms": 7.978, "reference_source": "src/API/neighborlist.jl:204-207 (serial Julia, unstated CPU)"}
 
@@ -362,41 +522,66 @@ def main():
     achieved_tf = F_alg / (r32["sweep_ms"] * 1e-3) / 1e12
     # algorithmic HBM bytes of the same launch: records in (16 B / particle incl. images) + forces out (12 B / particle)
     B_alg = 16.0 * r32["stats"].n_total[0] + 12.0 * r32["n"]
+    kernel_name = "k_sweep_n3<float, MODE_HALF, N3LJ<float,true,true>>"
+    traffic, traffic_note = measured_traffic("k_sweep_n3_f32")
     line = {
         "metric": METRIC, "value": r32["P_in"] / (r32["dev_ms"] * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r32["dev_ms"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C2: LJ energy+forces, 1M argon-density particles, cubic PBC, cutoff 12 A (BASELINE.json configs[1])",
-                   "n_particles": r32["n"], "in_cutoff_pairs": r32["P_in"], "reference_stencil_candidates": C_st,
+                   "n_particles": r32["n"], "in_cutoff_pairs": r32["P_in"], "at_cutoff_band_pairs": r32["band"], "reference_stencil_candidates": C_st,
                    "step": "update positions (D2D) + UpdateCellList! + pairwise!(LJ energy+forces)",
                    "l2": "flushed between timed steps (256 MiB memset, untimed); per-step CUDA events on the launching stream"},
         "clocks": r32["clocks"],
         "e2e": {"value": r32["P_in"] / (r32["e2e_ms"] * 1e-3), "unit": UNIT, "ms_per_step": r32["e2e_ms"],
-                "h2d_bytes_per_step": r32["h2d"], "d2h_bytes_per_step": r32["d2h"]},
+                "h2d_bytes_per_step": r32["h2d"], "d2h_bytes_per_step": r32["d2h"],
+                "mode": "pipelined frames through the C ABI (clm_set_positions_async + clm_map_lj with CLM_ASYNC): every frame's positions are copied from "
+                        "pinned host memory and its forces + energy copied back inside the timed region; copy-in of frame k+1, compute of frame k and "
+                        "copy-out of frame k-1 overlap; L2 flush between frames on the compute stream, inside the timed region; wall clock over all steps",
+                "frames_equal": r32["frames_equal"], "energy": r32["energy_pipe"]},
+        "e2e_sync": {"value": r32["P_in"] / (r32["e2e_sync_ms"] * 1e-3), "unit": UNIT, "ms_per_step": r32["e2e_sync_ms"],
+                     "mode": "one synchronous clm_set_positions + clm_map_lj per step (outputs in host memory on return): the latency of a dependent step"},
         "gpu_launches": r32["launches"] * args.steps,
-        "roofline": {"bound": "fp32", "kernel": "k_sweep<float, MODE_ALL, FLJ<float,true,true>>", "achieved": achieved_tf, "peak": fp32_peak_tf,
+        "roofline": {"bound": "fp32", "kernel": kernel_name, "achieved": achieved_tf, "peak": fp32_peak_tf,
                      "unit": "TFLOP/s", "frac": achieved_tf / fp32_peak_tf,
-                     "traffic": 22.57e6, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload (profiles/r1_final_kernels.txt; the 12 MB of forces stay in the 126 MB L2)",
+                     "traffic": traffic, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on this workload: " + traffic_note,
                      "algorithmic_flops_per_launch": F_alg, "kernel_ms": r32["sweep_ms"], "build_ms": r32["build_ms"],
                      "peak_source": "FP32 FMA peak measured live by clm_measure_fma_peak (register-resident FMA loop, all SMs); "
                                     f"nominal {fp32_nominal_tf:.1f} TFLOP/s = 148 SM x 128 lanes x 2 x sm_max_mhz from {peaks_src}; no tensor cores on this path",
                      "fp64_peak_measured": fp64_peak_tf,
                      "hbm": {"algorithmic_bytes_per_launch": B_alg, "achieved_gbs": B_alg / (r32["sweep_ms"] * 1e-3) / 1e9,
                              "peak_gbs": peaks.get("hbm_gbs")}},
-        "breakdown_ms": {"step": r32["dev_ms"], "build": r32["build_ms"], "sweep_kernel": r32["sweep_ms"]},
+        "breakdown_ms": {"step": r32["dev_ms"], "build": r32["build_ms"], "sweep_kernel": r32["sweep_ms"], "map_call_device": r32["map_ms"]},
+        "source_hash": src_hash(),
     }
     if r64:
+        F64_alg = FLOPS_PER_CANDIDATE * C_st + FLOPS_PER_PAIR_LJ * r64["P_in"]
         line["f64"] = {"value": r64["P_in"] / (r64["dev_ms"] * 1e-3), "unit": UNIT, "ms_per_step": r64["dev_ms"],
                        "sweep_kernel_ms": r64["sweep_ms"], "build_ms": r64["build_ms"],
-                       "e2e_value": r64["P_in"] / (r64["e2e_ms"] * 1e-3), "in_cutoff_pairs": r64["P_in"]}
+                       "e2e_value": r64["P_in"] / (r64["e2e_ms"] * 1e-3), "e2e_sync_value": r64["P_in"] / (r64["e2e_sync_ms"] * 1e-3), "in_cutoff_pairs": r64["P_in"],
+                       "roofline_frac_fp64": F64_alg / (r64["sweep_ms"] * 1e-3) / 1e12 / fp64_peak_tf}
     line["neighborlist_build"] = neighborlist_ms()
+    if not args.no_extras:
+        line["c5_1gpu"] = {"8M": c5_single_gpu(clm, torch, local, stream, flush_buf, args.multi_nside, args.multi_nx_per_rank)}
+        if not args.no_64m:
+            line["c5_1gpu"]["64M"] = c5_single_gpu(clm, torch, local, stream, flush_buf, args.multi_nside, args.multi_nx_per_rank * 8, steps=3)
+        line["other_configs"] = other_configs(clm, torch, local, fp64_peak_tf)
     if not args.no_cpu_baseline:
+        from oracle import oracle as om
+        nt = om.lib().ora_num_threads()
         wc = W.c2_argon(args.cpu_nside, np.float32)
-        t, npairs, nt = cpu_port_run(wc, np.float32, 3)
+        t, npairs, nt, e_o, f_o = cpu_port_run(wc, np.float32, 3, nt)
         line["cpu_baseline"] = {"value": npairs / t, "unit": UNIT, "cores": nt, "kind": "port",
                                 "sample": f"full workload ({args.cpu_nside}^3 particles), median of 3 x (build + LJ energy+forces), "
                                           "C++/OpenMP restatement of the reference (projection filter, batch-private outputs)",
-                                "seconds_per_step": t}
+                                "seconds_per_step": t, "host_threads_available": nthreads}
+        if args.cpu_nside == args.nside:
+            # parity of the timed GPU result against the CPU restatement run in the same precision on the same input
+            fo = np.asarray(f_o, np.float64)
+            line["parity"] = {"pairs_equal": bool(npairs == r32["P_in"]), "energy_rel_err": abs(r32["energy"] - e_o) / abs(e_o),
+                              "force_max_rel_err": float(np.abs(r32["forces"].astype(np.float64) - fo).max() / np.abs(fo).max()),
+                              "against": "oracle (C++ restatement of the reference) in Float32 on the same input; north_star tolerance 1e-5",
+                              "at_cutoff_band_pairs": r32["band"]}
     print(json.dumps(line))
 
 

@@ -39,10 +39,53 @@ def slab_lattice(rank, world, nside, nx_per_rank, dtype):
     return np.ascontiguousarray(x.astype(dtype)), unitcell
 
 
+def _splitmix64_torch(seed, k):
+    """splitmix64 output for the 1-based counters k (int64 tensor, two's-complement arithmetic = the uint64 arithmetic of
+    workloads.splitmix64; logical right shifts emulated by masking the sign extension)."""
+    def shr(z, s):
+        return (z >> s) & ((1 << (64 - s)) - 1)
+
+    def i64(v):
+        v &= (1 << 64) - 1
+        return v - (1 << 64) if v >= (1 << 63) else v
+    z = i64(seed) + i64(0x9E3779B97F4A7C15) * k
+    z = (z ^ shr(z, 30)) * i64(0xBF58476D1CE4E5B9)
+    z = (z ^ shr(z, 27)) * i64(0x94D049BB133111EB)
+    return z ^ shr(z, 31)
+
+
+def slab_lattice_torch(rank, world, nside, nx_per_rank, dtype, device):
+    """slab_lattice generated on `device` with torch (bit-identical values and order): the 64M-particle single-GPU case
+    takes a second instead of a minute of numpy."""
+    a = W.ARGON_RHO ** (-1.0 / 3.0)
+    nx_tot = world * nx_per_rank
+    ix = torch.arange(rank * nx_per_rank, (rank + 1) * nx_per_rank, dtype=torch.int64, device=device)
+    g = torch.arange(nside, dtype=torch.int64, device=device)
+    I, J, K = torch.meshgrid(ix, g, g, indexing="ij")
+    I, J, K = I.reshape(-1), J.reshape(-1), K.reshape(-1)
+    site = (I * nside + J) * nside + K
+    n = site.shape[0]
+    x = torch.empty((n, 3), dtype=torch.float64, device=device)
+    for c, idx in enumerate((I, J, K)):
+        z = _splitmix64_torch(W.SEED, site * 3 + (c + 1))
+        u = ((z >> 11) & ((1 << 53) - 1)).to(torch.float64) * 2.0 ** -53
+        x[:, c] = idx.to(torch.float64) * a + (u - 0.5) * (0.5 * a) + 0.25 * a
+    del I, J, K, site
+    # workloads.shuffle_perm: stable argsort of the uint64 stream (sign bit flipped for the signed sort)
+    keys = _splitmix64_torch(W.SEED + 1 + rank, torch.arange(1, n + 1, dtype=torch.int64, device=device)) ^ (-(1 << 63))
+    perm = torch.sort(keys, stable=True).indices
+    del keys
+    tdt = torch.float32 if np.dtype(dtype) == np.float32 else torch.float64
+    x = x[perm].to(tdt).contiguous()
+    unitcell = np.array([a * nx_tot, a * nside, a * nside], dtype)
+    return x, unitcell
+
+
 def run(args, rank, world, local):
     import celllistmap_b200 as clm  # noqa: F401
     from celllistmap_b200 import slab
     import bench
+    bench.host_threads()   # torchrun exports OMP_NUM_THREADS=1: the CPU baseline leg uses every core of the affinity mask
     dev = torch.device("cuda", local)
     dtype = np.float32
     nside = args.multi_nside
@@ -198,6 +241,31 @@ def run(args, rank, world, local):
         if not args.no_nl:
             line["neighborlist_build"] = {"config": "the same slab-decomposed system, cutoff 12 A: halo exchange + cell-list build + emission, per-rank lists left on the device",
                                           "pairs": int(tn_sum[1]), "ms_max_over_ranks": float(tn_max[0])}
+        # strong-scaling denominator: the SAME global system (all ranks' planes) on rank 0's GPU alone, through a plain handle
+        # (the other ranks wait at the barrier below)
+        if not args.no_64m:
+            one = bench.c5_single_gpu(clm, torch, local, stream, flush_buf, nside, nx_per_rank * world, steps=3)
+            key = "strong_scaling_64M" if one["n_particles"] == 64_000_000 else "strong_scaling"
+            line[key] = {"n_particles": one["n_particles"], "ms_per_step_1gpu": one["ms_per_step"], "ms_per_step_ngpu": ms, "n_gpus": world,
+                         "speedup": one["ms_per_step"] / ms, "sweep_kernel_ms_1gpu": one["sweep_kernel_ms"], "build_ms_1gpu": one["build_ms"],
+                         "energy_1gpu": one["energy"], "energy_ngpu": float(e_host), "energy_rel_diff": abs(one["energy"] - float(e_host)) / abs(float(e_host)),
+                         "note": "same particle system, device-resident steps; the 1-GPU step has no halo exchange and no all_reduce"}
+        if not args.no_cpu_baseline:
+            # the CPU restatement on a bounded sample of the same system (2M particles of the same generator), all host threads
+            from oracle import oracle as om
+            import time
+            nt = om.lib().ora_num_threads()
+            xs, ucs = slab_lattice(0, 1, 126, 126, dtype)
+            ts = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                o = om.Oracle(xs, cutoff, unitcell=ucs, dtype=dtype)
+                o.lj(W.ARGON_C6, W.ARGON_C12, forces=True, nbatches=nt)
+                ts.append(time.perf_counter() - t0)
+            npc = o.sum_d_d2(nbatches=nt)[2]
+            line["cpu_baseline"] = {"value": npc / min(ts), "unit": bench.UNIT, "cores": nt, "kind": "port",
+                                    "sample": "126^3 = 2 000 376 particles of the same generator / density / cutoff (bounded sample of the sharded system), "
+                                              "best of 2 x (build + LJ energy+forces), C++/OpenMP restatement of the reference", "seconds_per_step": min(ts)}
         print(json.dumps(line))
     s.close()
     dist.barrier()

@@ -47,7 +47,7 @@ template <class T> Engine<T>::~Engine() {
     if (copy_out) { cudaStreamSynchronize(copy_out); cudaStreamDestroy(copy_out); }
     for (cudaEvent_t e : {ev_h2d, ev_posfree, ev_done, ev_out[0], ev_out[1]}) if (e) cudaEventDestroy(e);
     d_forces_alt.release(); d_eout.release();
-    for (auto& s : sets) { s.pos.release(); s.pos_alt.release(); s.fpos.release(); s.rec.release(); s.rec_n3.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
+    for (auto& s : sets) { s.pos.release(); s.pos_alt.release(); s.fpos.release(); s.rec.release(); s.rec_n3.release(); s.ghost_r.release(); s.place_p.release(); s.ghost_q.release(); s.place_r.release(); s.slot_of.release(); s.ghost_i.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
     dscal.release(); tiles.release(); d_res.release();
     d_hcount.release(); nl.release(); d_hsum.release(); d_rbins.release(); d_forces.release(); d_facc.release(); d_minmax.release(); d_minpart.release(); d_minres.release();
     custom_store_free(custom_store);
@@ -110,7 +110,7 @@ template <class T> int Engine<T>::set_positions(int set, const void* xyz, int64_
     if (set != 0 && set != 1) return fail(CLM_ERR_ARGUMENT, "set must be 0 (x) or 1 (y)");
     if (n < 0) return fail(CLM_ERR_ARGUMENT, "negative particle count");
     if (n > 0 && !xyz) return fail(CLM_ERR_ARGUMENT, "positions pointer is NULL");
-    if (n > (int64_t)(TagT<float>::MASK)) return fail(CLM_ERR_UNSUPPORTED, "more than 2^30 particles in one set");
+    if (n > (int64_t)(TagT<float>::MASK)) return fail(CLM_ERR_UNSUPPORTED, "more than 2^29 particles in one set");
     CLM_CK(cudaSetDevice(device));
     DevSet<T>& s = sets[set];
     CLM_CK(s.pos.ensure((size_t)n * dim));
@@ -126,7 +126,7 @@ template <class T> int Engine<T>::set_positions(int set, const void* xyz, int64_
 template <class T> int Engine<T>::set_positions_async(int set, const void* xyz, int64_t n) {
     if (set != 0 && set != 1) return fail(CLM_ERR_ARGUMENT, "set must be 0 (x) or 1 (y)");
     if (n <= 0 || !xyz) return fail(CLM_ERR_ARGUMENT, "clm_set_positions_async needs a non-empty pinned host array");
-    if (n > (int64_t)(TagT<float>::MASK)) return fail(CLM_ERR_UNSUPPORTED, "more than 2^30 particles in one set");
+    if (n > (int64_t)(TagT<float>::MASK)) return fail(CLM_ERR_UNSUPPORTED, "more than 2^29 particles in one set");
     CLM_CK(cudaSetDevice(device));
     if (int rc = pipeline_init()) return rc;
     DevSet<T>& s = sets[set];
@@ -340,7 +340,8 @@ template <class T> int Engine<T>::build_enqueue() {
             DevSet<T>& S = sets[s];
             const size_t want = std::max<size_t>((size_t)((double)(S.n + S.n_foreign) * img_factor * 1.25) + 4096, (size_t)std::max<int64_t>(S.n_tot, 1));
             CLM_CK(S.rec.ensure(want));
-            if (want_n3 && s == 0) CLM_CK(S.rec_n3.ensure(S.rec.cap));
+            const bool n3 = want_n3 && s == 0;
+            if (n3) CLM_CK(S.rec_n3.ensure(S.rec.cap));
             CLM_CK(S.cell_start.ensure((size_t)ncp + 2));
             CLM_CK(S.counters.ensure((size_t)(2 * ncp + nref)));
             S.cell_count = S.counters.p; S.cell_nact = S.counters.p + ncp; S.ref_real = S.counters.p + 2 * ncp;
@@ -352,20 +353,30 @@ template <class T> int Engine<T>::build_enqueue() {
             int* ds = dscal.p + s * DS_SET_STRIDE;
             const int64_t nall = S.n + S.n_foreign;
             const int nb = (int)((nall + 255) / 256);
+            const int rec_cap = (int)std::min<size_t>(S.rec.cap, 0x7fffffff);
+            const int ghost_cap = (int)std::max<int64_t>((int64_t)rec_cap - nall, 0);   // more images than this overflow the record capacity too
             if (nall > 0) {
-                if (dim == 3) k_bin<T, 3, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, nullptr, 0, ds);
-                else k_bin<T, 2, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, nullptr, 0, ds);
+                CLM_CK(S.place_p.ensure((size_t)nall));
+                CLM_CK(S.place_r.ensure((size_t)nall));
+                CLM_CK(S.ghost_q.ensure((size_t)std::max(ghost_cap, 1)));
+                CLM_CK(S.ghost_i.ensure((size_t)std::max(ghost_cap, 1)));
+                CLM_CK(S.ghost_r.ensure((size_t)std::max(ghost_cap, 1)));
+                CLM_CK(S.slot_of.ensure((size_t)nall));
+                // count pass: wrap, cells, images, per-cell histogram; everything the placement needs is cached
+                if (dim == 3) k_bin<T, 3><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, S.place_p.p, S.place_r.p, S.ghost_q.p, S.ghost_i.p, S.ghost_r.p, ghost_cap, dscal.p + DS_NGHOST + s, ds);
+                else k_bin<T, 2><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, S.place_p.p, S.place_r.p, S.ghost_q.p, S.ghost_i.p, S.ghost_r.p, ghost_cap, dscal.p + DS_NGHOST + s, ds);
                 CLM_CK(cudaGetLastError());
                 stats.launches += 1;
             }
-            // per-row starts, written one slot up: the scatter pass uses cell_start[c + 1] as the cursor of cell c, which
-            // leaves the row's exclusive starts behind once every record is placed (no second counter array)
             k_row_starts<<<(int)((nrows * 32 + 255) / 256), 256, 0, stream>>>(S.cell_count, S.cell_start.p, nfast, (int)nrows, ds + DS_NTOT);
             CLM_CK(cudaGetLastError());
             stats.launches += 1;
             if (nall > 0) {
-                if (dim == 3) k_bin<T, 3, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, (want_n3 && s == 0) ? S.rec_n3.p : nullptr, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), ds);
-                else k_bin<T, 2, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, (want_n3 && s == 0) ? S.rec_n3.p : nullptr, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), ds);
+                // placement pass: slot = first record of the cell + cached rank (no wrap, no atomics)
+                const int64_t nthreads = nall + ghost_cap;
+                k_place<T><<<(int)((nthreads + 255) / 256), 256, 0, stream>>>(S.place_p.p, S.place_r.p, (int)nall, (int)S.n, S.ghost_q.p, S.ghost_i.p, S.ghost_r.p, dscal.p + DS_NGHOST + s, ghost_cap,
+                                                                             S.cell_start.p, S.cell_nact, S.ref_real, S.rec.p, n3 ? S.rec_n3.p : nullptr, S.slot_of.p, rec_cap,
+                                                                             box.cell_type == CLM_TRICLINIC ? 1 : 0);
                 CLM_CK(cudaGetLastError());
                 stats.launches += 1;
             }

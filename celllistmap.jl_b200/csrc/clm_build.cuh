@@ -4,12 +4,15 @@
 //
 // The reference builds an array of heap-allocated per-cell vectors; here the list is ONE
 // counting sort into a cell-sorted packed record array:
-//   k_bin<count>  : wrap + rotate each particle, enumerate its 3^N-1 lattice images, keep those inside
-//                   the computing box, histogram real+image particles per cell (global atomics)
+//   k_bin         : the only pass over the caller's coordinates: wrap + rotate each particle, enumerate its 3^N-1
+//                   lattice images, keep those inside the computing box, histogram real + image particles per cell
+//                   (global atomics; the value an atomic returns is the particle's rank inside its cell), cache
+//                   (position, cell, rank) per particle and append the images to a list
 //   k_row_starts  : one warp per ROW of device cells: prefix of the row's counts; the row's base comes from one
 //                   atomicAdd on the record counter, so rows are contiguous but placed in arbitrary order -- the
 //                   sweep only ever reads record ranges inside one row.  Replaces a 3-kernel global scan.
-//   k_bin<scatter>: same traversal, records scattered to the per-cell atomic cursor
+//   k_place       : record slot = first record of the cell + cached rank: a pure gather/scatter pass (no second wrap,
+//                   no second round of atomics)
 //   k_row_tiles   : one warp per row: the row's active record range cut into tiles, appended to the tile array with
 //                   one atomicAdd per row (tile order is irrelevant: tiles are dealt out by a work counter)
 // Every per-cell array is laid out with a row pitch of nx + 1 entries: cell_start[row * (nx + 1) + x] is the first
@@ -24,7 +27,7 @@ namespace clm {
 
 constexpr int IDX_NONE = 0x7fffffff;
 // device scalar block (ints)
-enum { DS_NAN = 0, DS_OOB = 1, DS_NTOT = 2, DS_NTILES = 3, DS_WORK = 4, DS_NCELLS_REAL = 5, DS_COUNT = 16 };
+enum { DS_NAN = 0, DS_OOB = 1, DS_NTOT = 2, DS_NTILES = 3, DS_WORK = 4, DS_NCELLS_REAL = 5, DS_NGHOST = 12 /* + set */, DS_COUNT = 16 };
 constexpr int DS_SET_STRIDE_DEV = 6;   // the scalar block of the second set starts at dscal + 6
 
 // The device scalars are initialised and published by two one-warp kernels, not by cudaMemcpyAsync: a small copy on the
@@ -124,24 +127,31 @@ __device__ __forceinline__ bool cell_of(const GeomT<T>& g, const T p[3], bool re
     return true;
 }
 
-// Count pass (SCATTER = false): per-cell histogram of real + image particles.  Scatter pass: records to the
-// atomic per-cell cursor.  cell_nact[c] flags cells holding a record that can act as particle i of a
-// pair: real particles, and images living in a REFERENCE cell that holds a real particle (the reference sweeps
-// exactly those cells, self.jl:56-57); ref_real[] flags reference cells with a real particle.
+// cell_nact[c] flags cells holding a record that can act as particle i of a pair: real particles, and images living
+// in a REFERENCE cell that holds a real particle (the reference sweeps exactly those cells, self.jl:56-57); ref_real[]
+// flags reference cells with a real particle.
 __device__ __forceinline__ float shfl_t(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ double shfl_t(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-template <class T, int DIM, bool SCATTER>
+// Count pass of the counting sort, and the ONLY pass that touches the caller's coordinates: the wrapped position, the
+// device cell and the rank inside the cell (the value the histogram atomic returns) of every particle are cached
+// (place_p / place_r), and every image that lands inside the computing box is appended to a list (ghost_q / ghost_i)
+// with its cell and rank.  The placement pass (k_place) then only adds the cell's first record to the rank: no second
+// wrap (six IEEE divisions per particle), no second round of atomics.
+//   place_p[ip] = (p, device cell)            place_r[ip] = rank | parity of the reference cell along the row << 30, -1: invalid
+//   ghost_q[g]  = (q, device cell)            ghost_i[g]  = (rank | parity << 30, particle, reference cell, device cell of the original)
+//                                             ghost_r[g]  = rank of the original inside its cell
+template <class T, int DIM>
 __global__ void __launch_bounds__(256)
-k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __restrict__ fpos, int n, int n_own, int* __restrict__ cell_cursor,
-      int* __restrict__ cell_nact, int* __restrict__ ref_real, RecT<T>* __restrict__ rec, RecT<T>* __restrict__ rec_n3, int rec_cap, int* __restrict__ dscal) {
+k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __restrict__ fpos, int n, int n_own, int* __restrict__ cell_count,
+      int* __restrict__ cell_nact, int* __restrict__ ref_real, RecT<T>* __restrict__ place_p, int* __restrict__ place_r,
+      RecT<T>* __restrict__ ghost_q, int4* __restrict__ ghost_i, int* __restrict__ ghost_r, int ghost_cap, int* __restrict__ nghost, int* __restrict__ dscal) {
     typedef TagT<T> TG;
     const int ip = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
-    constexpr int NIMG = (DIM == 3) ? 27 : 9;
     constexpr int CENTER = (DIM == 3) ? 13 : 4;
     T p[3] = {T(0), T(0), T(0)};
     unsigned okmask = 0u;      // candidate images of this lane's particle (none for invalid / interior / non-periodic)
-    int real_slot = 0;         // scatter pass: where this lane's real record went
+    int lin_own = 0, rank_own = 0;
     if (ip < n) {
         T x[DIM];
         bool bad = false;
@@ -150,27 +160,18 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
         for (int k = 0; k < DIM; ++k) { x[k] = src[k]; bad |= (x[k] != x[k]); }
         int lin = 0, rlin = 0, cfast = 0;
         if (bad) {
-            if (!SCATTER) atomicMin(&dscal[DS_NAN], ip);     // _validate_coordinates, CellOperations.jl:6-21
+            atomicMin(&dscal[DS_NAN], ip);     // _validate_coordinates, CellOperations.jl:6-21
         } else {
             place_particle<T, DIM>(g, x, p);
-            if (!cell_of<T, DIM>(g, p, true, lin, rlin, &cfast)) { if (!SCATTER) atomicMin(&dscal[DS_OOB], ip); bad = true; }
+            if (!cell_of<T, DIM>(g, p, true, lin, rlin, &cfast)) { atomicMin(&dscal[DS_OOB], ip); bad = true; }
         }
+        int rank = -1;
         if (!bad) {
-            // cell_cursor: the per-cell histogram in the count pass; the per-cell write cursor (pre-loaded with the
-            // exclusive starts) in the scatter pass
-            const typename TG::type foreign = (ip >= n_own) ? TG::FOREIGN : (typename TG::type)0;
-            const int slot = atomicAdd(&cell_cursor[lin], 1);
-            if (!SCATTER) {
-                if (!foreign) cell_nact[lin] = 1;   // flags: plain stores, every writer stores the same value
-                ref_real[rlin] = 1;
-            } else if (slot < rec_cap) {
-                strec(&rec[slot], p[0], p[1], p[2], (typename TG::type)ip | TG::HOME | foreign);
-                // slot-tagged twin of the record array (clm_sweep_n3.cuh): 4th word = slot of the particle's real record |
-                // HOME | parity of the reference cell along the row (bit 29)
-                // (triclinic cells: the particle index instead of the slot -- the reference's index_i < index_j rule)
-                if (rec_n3) strec(&rec_n3[slot], p[0], p[1], p[2], (typename TG::type)((unsigned)(g.cell_type == CLM_TRICLINIC_CT ? ip : slot) | 0x40000000u | ((unsigned)(cfast & 1) << 29)));
-            }
-            real_slot = slot;
+            rank = atomicAdd(&cell_count[lin], 1) | ((cfast & 1) << 30);
+            lin_own = lin; rank_own = rank & 0x3fffffff;
+            if (ip < n_own) cell_nact[lin] = 1;   // flags: plain stores, every writer stores the same value
+            ref_real[rlin] = 1;
+            strec(&place_p[ip], p[0], p[1], p[2], (typename TG::type)(unsigned)lin);
             // replicate_particle! (Box.jl:556-566): images x + aligned_cell*idx, idx in {-1,0,1}^N \ {0}, kept iff inside the
             // computing box [cb_min, cb_max).  Orthorhombic cells: the shift of image index (i1,i2,i3) is (i1*L1, i2*L2, i3*L3)
             // exactly, so which indices can land inside the computing box is decided per dimension.
@@ -193,6 +194,7 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
                 okmask &= ~(1u << CENTER);
             }
         }
+        place_r[ip] = rank;
     }
     // The (particle, image) candidates of the WARP are dealt evenly to its lanes: a warp next to a cell face holds a
     // handful of candidates in a few lanes, and would otherwise run as many divergent iterations as its busiest lane.
@@ -211,37 +213,85 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
         const int k_th = w - __shfl_sync(0xffffffffu, excl, s);
         const unsigned m = __shfl_sync(0xffffffffu, okmask, s);
         const int ips = __shfl_sync(0xffffffffu, ip, s);
-        const int rslot = __shfl_sync(0xffffffffu, real_slot, s);
+        const int lin_s = __shfl_sync(0xffffffffu, lin_own, s), rank_s = __shfl_sync(0xffffffffu, rank_own, s);
         const T px = shfl_t(p[0], s), py = shfl_t(p[1], s), pz = shfl_t(p[2], s);
-        if (w >= total) continue;
-        const int img = (int)__fns(m, 0u, k_th + 1);
-        const T ps[3] = {px, py, pz};
+        bool in = (w < total);
         T q[3] = {T(0), T(0), T(0)};
-        bool in = true;
+        int lq = 0, rq = 0, qfast = 0;
+        if (in) {
+            const int img = (int)__fns(m, 0u, k_th + 1);
+            const T ps[3] = {px, py, pz};
 #pragma unroll
-        for (int k = 0; k < DIM; ++k) {
-            q[k] = xadd(ps[k], g.shift[img][k]);
-            in = in && (g.cb_min[k] <= q[k]) && (q[k] < g.cb_max[k]);
+            for (int k = 0; k < DIM; ++k) {
+                q[k] = xadd(ps[k], g.shift[img][k]);
+                in = in && (g.cb_min[k] <= q[k]) && (q[k] < g.cb_max[k]);
+            }
+            if (in) in = cell_of<T, DIM>(g, q, false, lq, rq, &qfast);
         }
-        if (!in) continue;
-        int lq, rq, qfast = 0;
-        if (!cell_of<T, DIM>(g, q, false, lq, rq, &qfast)) continue;
-        const typename TG::type foreign = (ips >= n_own) ? TG::FOREIGN : (typename TG::type)0;
-        const int qslot = atomicAdd(&cell_cursor[lq], 1);
-        if (SCATTER && qslot < rec_cap) {
-            const bool home = ref_real[rq] != 0;
-            if (home && !foreign) cell_nact[lq] = 1;
-            strec(&rec[qslot], q[0], q[1], q[2], (typename TG::type)ips | TG::GHOST | foreign | (home ? TG::HOME : (typename TG::type)0));
-            if (rec_n3) strec(&rec_n3[qslot], q[0], q[1], q[2], (typename TG::type)((unsigned)(g.cell_type == CLM_TRICLINIC_CT ? ips : rslot) | 0x80000000u | (home ? 0x40000000u : 0u) | ((unsigned)(qfast & 1) << 29)));   // image -> its original's slot | GHOST
+        // append the images found by this warp step to the ghost list: one atomic per warp step
+        const unsigned mv = __ballot_sync(0xffffffffu, in);
+        if (mv == 0u) continue;
+        int gbase = 0;
+        if (lane == 0) gbase = atomicAdd(nghost, __popc(mv));
+        gbase = __shfl_sync(0xffffffffu, gbase, 0);
+        if (in) {
+            const int rank = atomicAdd(&cell_count[lq], 1) | ((qfast & 1) << 30);
+            const int gslot = gbase + __popc(mv & ((1u << lane) - 1u));
+            if (gslot < ghost_cap) {
+                strec(&ghost_q[gslot], q[0], q[1], q[2], (typename TG::type)(unsigned)lq);
+                ghost_i[gslot] = make_int4(rank, ips, rq, lin_s);
+                ghost_r[gslot] = rank_s;
+            }
+        }
+    }
+}
+
+// Placement pass: record slot = first record of the cell + cached rank.  Threads [0, n): the particles themselves;
+// threads [n, n + ghost_cap): the image list.  Writes the cell-sorted records, slot_of[particle] = slot of the particle's
+// real record, flags the cells that hold an image able to act as particle i and -- when the Newton's-third-law force sweep
+// wants it (rec_n3 != nullptr, clm_sweep_n3.cuh) -- the slot-tagged twin of the records: 4th word = slot of the particle's
+// REAL record (an image points at its original; by_index: the particle index, triclinic cells) | GHOST | HOME | parity of
+// the reference cell along the row << 29.
+template <class T>
+__global__ void __launch_bounds__(256)
+k_place(const RecT<T>* __restrict__ place_p, const int* __restrict__ place_r, int n, int n_own, const RecT<T>* __restrict__ ghost_q,
+        const int4* __restrict__ ghost_i, const int* __restrict__ ghost_r, const int* __restrict__ nghost, int ghost_cap, const int* __restrict__ cell_start,
+        int* __restrict__ cell_nact, const int* __restrict__ ref_real, RecT<T>* __restrict__ rec, RecT<T>* __restrict__ rec_n3, int* __restrict__ slot_of,
+        int rec_cap, int by_index) {
+    typedef TagT<T> TG;
+    typedef typename TG::type tag_t;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr int RANK = 0x3fffffff;
+    if (t < n) {
+        const int r = place_r[t];
+        if (r < 0) return;
+        const RecT<T> P = ldrec(place_p + t);
+        const int slot = cell_start[(int)P.tag] + (r & RANK);
+        slot_of[t] = slot;
+        if (slot >= rec_cap) return;
+        strec(&rec[slot], P.x, P.y, P.z, (tag_t)t | TG::HOME | ((t >= n_own) ? TG::FOREIGN : (tag_t)0));
+        if (rec_n3) strec(&rec_n3[slot], P.x, P.y, P.z, (tag_t)((unsigned)(by_index ? t : slot) | 0x40000000u | (((unsigned)r >> 30) << 29)));
+    } else {
+        const int gidx = t - n;
+        if (gidx >= min(*nghost, ghost_cap)) return;
+        const RecT<T> Q = ldrec(ghost_q + gidx);
+        const int4 e = ghost_i[gidx];
+        const int lq = (int)Q.tag, ips = e.y;
+        const int slot = cell_start[lq] + (e.x & RANK);
+        const bool home = ref_real[e.z] != 0, foreign = ips >= n_own;
+        if (home && !foreign) cell_nact[lq] = 1;
+        if (slot >= rec_cap) return;
+        strec(&rec[slot], Q.x, Q.y, Q.z, (tag_t)ips | TG::GHOST | (foreign ? TG::FOREIGN : (tag_t)0) | (home ? TG::HOME : (tag_t)0));
+        if (rec_n3) {
+            const int rslot = cell_start[e.w] + ghost_r[gidx];   // slot of the original
+            strec(&rec_n3[slot], Q.x, Q.y, Q.z, (tag_t)((unsigned)(by_index ? ips : rslot) | 0x80000000u | (home ? 0x40000000u : 0u) | (((unsigned)e.x >> 30) << 29)));
         }
     }
 }
 
 // ---- row starts ------------------------------------------------------------------------------------------
-// One warp per row of device cells.  cs = cell_start + 1 is the cursor array of the scatter pass: the cursor of cell x
-// of a row is cs[row * px + x], pre-loaded with the cell's first record; once every record is placed it holds the
-// cell's END, i.e. cell_start[row * px + x + 1] = start of cell x + 1, and cell_start[row * px] (never incremented)
-// stays the start of the row: no second counter array.
+// One warp per row of device cells: cell_start[row * px + x] = first record of cell x, entry nx = end of the row.  The
+// row's base comes from one atomicAdd on the record counter.
 static __global__ void __launch_bounds__(256)
 k_row_starts(const int* __restrict__ cell_count, int* __restrict__ cell_start, int nx, int nrows, int* __restrict__ ntot) {
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -256,16 +306,16 @@ k_row_starts(const int* __restrict__ cell_count, int* __restrict__ cell_start, i
     int base = 0;
     if (lane == 0) base = (total > 0) ? atomicAdd(ntot, total) : 0;
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (lane == 0) cs[0] = base;
     for (int c0 = 0; c0 < nx; c0 += 32) {
         const int c = c0 + lane;
         const int v = (c < nx) ? cnt[c] : 0;
         int inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        if (c < nx) cs[c + 1] = base + inc - v;    // cursor of cell c = its first record
+        if (c < nx) cs[c] = base + inc - v;
         base += __shfl_sync(0xffffffffu, inc, 31);
     }
+    if (lane == 0) cs[nx] = base;
 }
 
 // ---- tiles ------------------------------------------------------------------------------------------------

@@ -77,13 +77,17 @@ template <class U> struct DBuf {
 
 template <class T> struct DevSet {
     DBuf<T> pos;             // caller's coordinates, AoS n x dim (owning copy, like ParticleSystemPositions)
+    // build scratch (clm_build.cuh): wrapped position + device cell and rank inside the cell of every particle (count pass ->
+    // placement pass), the image list, and the slot of every particle's real record (force gather of the N3 sweep)
+    DBuf<RecT<T>> place_p, ghost_q;
+    DBuf<RecT<T>> rec_n3;    // slot-tagged twin of rec for the Newton's-third-law force sweep (k_place), written on request
+    DBuf<int> place_r, slot_of, ghost_r;
+    DBuf<int4> ghost_i;
     DBuf<T> pos_alt;         // pipelined frames: the buffer the NEXT frame's coordinates are copied into while this one is binned
     int64_t n = 0;
     DBuf<T> fpos;            // foreign particles of a slab-decomposed system (owned by other ranks), AoS
     int64_t n_foreign = 0;
     DBuf<RecT<T>> rec;       // cell-sorted records, real + image particles
-    DBuf<RecT<T>> rec_n3;    // slot-tagged twin of rec (4th word = slot of the particle's real record | GHOST | HOME | cell parity), written by the
-                             // scatter pass once a Newton's-third-law force map has been asked for (clm_sweep_n3.cuh)
     int64_t n_tot = 0, n_cells_real = 0;
     DBuf<int> cell_start;    // row pitch nfast + 1: [row * pitch + x] = first record of cell x, entry nfast = end of the row (after the scatter pass)
     DBuf<int> counters;      // one memset: [cell_count | cell_nact | ref_real]
@@ -250,8 +254,7 @@ template <class T> struct Engine : EngineBase {
         kern<<<(unsigned)grid, SWEEP_THREADS, smem, stream>>>(a, f, d_facc.p);
         CLM_CK(cudaGetLastError());
         if (profile_sweep) CLM_CK(cudaEventRecord(ev3, stream));
-        const int nb = (int)std::min<int64_t>((int64_t)n_sm * 8, (int64_t)(S.rec.cap + 255) / 256);
-        k_force_finish<T, MODE == MODE_TRI><<<std::max(nb, 1), 256, 0, stream>>>(S.rec.p, d_facc.p, dscal.p, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), (int)S.n, out, dim, scale, accumulate, geom.rotated, geom);
+        k_force_finish<T><<<(int)((S.n + 255) / 256), 256, 0, stream>>>((MODE == MODE_TRI) ? nullptr : S.slot_of.p, d_facc.p, dscal.p, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), (int)S.n, out, dim, scale, accumulate, geom.rotated, geom);
         CLM_CK(cudaGetLastError());
         stats.launches += 2;
         last_grid = (int)grid;

@@ -13,15 +13,19 @@
 // consecutive records of a row, so a warp's flush touches a few 128-byte lines even when the caller's particle
 // numbering is random (tools/red_microbench.cu: 3.7e11 coalesced vs 1.9e11 random lane-REDs/s with 1 M slots, 3.0e11
 // vs 6.1e10 with 8 M).  For that the build writes a second record array (rec_n3) whose 4th word is the slot of the
-// particle's REAL record (an image points at its original) | GHOST: images add straight into their original's row and
-// k_force_finish gathers the real rows into the caller's particle order (scale, inverse rotation, reset/accumulate).
+// particle's REAL record (an image points at its original) | GHOST | HOME | cell parity: images add straight into their
+// original's row and k_force_finish gathers the rows into the caller's particle order through slot_of[] (scale, inverse
+// rotation, reset/accumulate).  (Measured alternative: no twin array, the row of a partner gathered from slot_of[index]
+// by every lane of every chunk -- the uncoalesced 4-byte gathers cost 0.045 ms of the 0.465 ms sweep; the twin array
+// costs 0.006 ms of the build.)
 //
 // Exactly-once rules, identical pair sets to k_sweep<MODE_HALF / MODE_TRI> (which are bit-exact against the oracle):
 //   MODE_HALF  forward reference rows / cells: every record, except image-image pairs; partners in the reference cells
 //              the tile itself touches ("direct" part) carry their reference cell index as a key: later cell -> forward
 //              rule, same cell -> real i only, image partner or later record slot.
-//   MODE_TRI   full stencil, i real, slot of i's real record < slot of j's real record (any strict total order on the
-//              particles selects one of the two symmetric evaluations; the reference uses the particle index).
+//   MODE_TRI   full stencil, i real, index_i < index_j: the reference's rule, so that of the two symmetric image pairs of
+//              a pair the same one is evaluated (their Float32 coordinates round differently).  For triclinic cells the
+//              4th word of rec_n3 holds the particle INDEX and the accumulator rows are in particle order.
 #pragma once
 #include "clm_sweep.cuh"
 
@@ -430,38 +434,38 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
     }
 }
 
-// accumulator rows -> the caller's per-particle force array (particle order), and back to zero:
-// out[idx] = (accumulate ? out[idx] : 0) + scale * R^-1 f.  BY_INDEX = false: rows in record order (every particle has exactly
-// one real record; image rows are never written: images add into their original's row); true: rows in particle order
+// accumulator rows -> the caller's per-particle force array, and back to zero:
+// out[idx] = (accumulate ? out[idx] : 0) + scale * R^-1 f(row of idx).  One thread per PARTICLE: the output is written in
+// particle order (coalesced) and the particle's row is gathered through slot_of[idx] (k_place) -- rows are in record
+// order, image rows are never written (images add into their original's row).  slot_of == nullptr: rows in particle order
 // (triclinic cells, whose exactly-once rule compares particle indices).
-template <class T, bool BY_INDEX>
+template <class T> struct Row4;
+template <> struct Row4<float> { typedef float4 type; };
+template <> struct Row4<double> { typedef double4 type; };
+template <class T>
 __global__ void __launch_bounds__(256)
-k_force_finish(const RecT<T>* __restrict__ rec_tag, T* __restrict__ facc, const int* __restrict__ dscal, int rec_cap, int n, T* __restrict__ out, int dim,
+k_force_finish(const int* __restrict__ slot_of, T* __restrict__ facc, const int* __restrict__ dscal, int rec_cap, int n, T* __restrict__ out, int dim,
                T scale, int accumulate, int rotated, const __grid_constant__ GeomT<T> g) {
-    typedef TagT<T> TG;
-    const int ntot = dscal[DS_NTOT];
-    if (ntot > rec_cap) return;   // overflowed build
-    const int nrows = BY_INDEX ? n : ntot;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nrows; k += gridDim.x * blockDim.x) {
-        size_t idx = (size_t)k;
-        if (!BY_INDEX) {
-            const typename TG::type tag = rec_tag[k].tag;
-            if (tag & (TG::GHOST | TG::FOREIGN)) continue;
-            idx = (size_t)(tag & TG::MASK);
-        }
-        T* row = facc + (size_t)k * 4;
-        T fx = row[0] * scale, fy = row[1] * scale, fz = row[2] * scale;
-        row[0] = T(0); row[1] = T(0); row[2] = T(0);
-        if (rotated) {
-            const T p = g.inv_rot[0] * fx + g.inv_rot[1] * fy + g.inv_rot[2] * fz;
-            const T q = g.inv_rot[3] * fx + g.inv_rot[4] * fy + g.inv_rot[5] * fz;
-            const T s = g.inv_rot[6] * fx + g.inv_rot[7] * fy + g.inv_rot[8] * fz;
-            fx = p; fy = q; fz = s;
-        }
-        T* o = out + idx * dim;
-        if (accumulate) { o[0] += fx; o[1] += fy; if (dim == 3) o[2] += fz; }
-        else { o[0] = fx; o[1] = fy; if (dim == 3) o[2] = fz; }
+    typedef typename Row4<T>::type row_t;
+    if (dscal[DS_NTOT] > rec_cap) return;   // overflowed build
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int k = slot_of ? slot_of[idx] : idx;
+    if (k >= rec_cap) return;
+    row_t* row = reinterpret_cast<row_t*>(facc) + k;
+    const row_t v = *row;
+    row_t z; z.x = T(0); z.y = T(0); z.z = T(0); z.w = T(0);
+    *row = z;
+    T fx = v.x * scale, fy = v.y * scale, fz = v.z * scale;
+    if (rotated) {
+        const T p = g.inv_rot[0] * fx + g.inv_rot[1] * fy + g.inv_rot[2] * fz;
+        const T q = g.inv_rot[3] * fx + g.inv_rot[4] * fy + g.inv_rot[5] * fz;
+        const T s = g.inv_rot[6] * fx + g.inv_rot[7] * fy + g.inv_rot[8] * fz;
+        fx = p; fy = q; fz = s;
     }
+    T* o = out + (size_t)idx * dim;
+    if (accumulate) { o[0] += fx; o[1] += fy; if (dim == 3) o[2] += fz; }
+    else { o[0] = fx; o[1] = fy; if (dim == 3) o[2] = fz; }
 }
 
 }  // namespace clm
