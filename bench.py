@@ -206,7 +206,7 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nt, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line, default=lambda o: o.item() if hasattr(o, "item") else str(o)))
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -216,6 +216,7 @@ def c5_single_gpu(clm, torch, local, stream, flush_buf, nside, nx, steps=5):
     import bench_multi
     dev = torch.device("cuda", local)
     x_dev, uc = bench_multi.slab_lattice_torch(0, 1, nside, nx, np.float32, dev)
+    torch.cuda.synchronize()   # generated on torch's default stream, consumed on the bench stream
     n = x_dev.shape[0]
     h = clm.Handle(3, np.float32, device=local)
     h.set_stream(stream.cuda_stream)
@@ -582,7 +583,7 @@ def main():
                               "force_max_rel_err": float(np.abs(r32["forces"].astype(np.float64) - fo).max() / np.abs(fo).max()),
                               "against": "oracle (C++ restatement of the reference) in Float32 on the same input; north_star tolerance 1e-5",
                               "at_cutoff_band_pairs": r32["band"]}
-    print(json.dumps(line))
+    print(json.dumps(line, default=lambda o: o.item() if hasattr(o, "item") else str(o)))
 
 
 if __name__ == "__main__":

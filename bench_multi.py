@@ -266,7 +266,7 @@ def run(args, rank, world, local):
             line["cpu_baseline"] = {"value": npc / min(ts), "unit": bench.UNIT, "cores": nt, "kind": "port",
                                     "sample": "126^3 = 2 000 376 particles of the same generator / density / cutoff (bounded sample of the sharded system), "
                                               "best of 2 x (build + LJ energy+forces), C++/OpenMP restatement of the reference", "seconds_per_step": min(ts)}
-        print(json.dumps(line))
+        print(json.dumps(line, default=lambda o: o.item() if hasattr(o, "item") else str(o)))
     s.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -100,7 +100,7 @@ def lib():
     L.clm_measure_fma_peak.argtypes = [ci, ci, C.POINTER(C.c_double)]
     L.clm_set_foreign.argtypes = [vp, ci, vp, i64, ci]
     L.clm_cell_coords.argtypes = [vp, vp, i64, ci, ci, vp]
-    L.clm_select_layers.argtypes = [vp, vp, i64, ci, C.POINTER(C.c_int32), ci, vp, vp, i64, vp]
+    L.clm_select_layers.argtypes = [vp, vp, i64, ci, C.POINTER(C.c_int32), ci, vp, vp, i64, vp, vp, vp]
     L.clm_custom_compile.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(CustomInfo)]
     L.clm_custom_log.restype = C.c_char_p
     L.clm_custom_log.argtypes = [vp]
@@ -255,11 +255,12 @@ class Handle:
         self._chk(self.L.clm_cell_coords(self.h, _addr(x)[0], n, 0, int(axis), _addr(out)[0]))
         return out
 
-    def select_layers(self, x, axis, ranges, merge, out_a, out_b, counts):
+    def select_layers(self, x, axis, ranges, merge, out_a, out_b, counts, idx_a=None, idx_b=None):
         """one-pass face selection (torch CUDA tensors; enqueue only): see clm_select_layers."""
         r = (C.c_int32 * 4)(*[int(v) for v in ranges])
         self._chk(self.L.clm_select_layers(self.h, _addr(x)[0], int(x.shape[0]), int(axis), r, 1 if merge else 0,
-                                           _addr(out_a)[0], _addr(out_b)[0], int(out_a.shape[0]), _addr(counts)[0]))
+                                           _addr(out_a)[0], _addr(out_b)[0], int(out_a.shape[0]), _addr(counts)[0],
+                                           _addr(idx_a)[0], _addr(idx_b)[0]))
 
     def build(self):
         self._chk(self.L.clm_build(self.h))

@@ -47,7 +47,7 @@ template <class T> Engine<T>::~Engine() {
     if (copy_out) { cudaStreamSynchronize(copy_out); cudaStreamDestroy(copy_out); }
     for (cudaEvent_t e : {ev_h2d, ev_posfree, ev_done, ev_out[0], ev_out[1]}) if (e) cudaEventDestroy(e);
     d_forces_alt.release(); d_eout.release();
-    for (auto& s : sets) { s.pos.release(); s.pos_alt.release(); s.fpos.release(); s.rec.release(); s.rec_n3.release(); s.ghost_r.release(); s.place_p.release(); s.ghost_q.release(); s.place_r.release(); s.slot_of.release(); s.ghost_i.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
+    for (auto& s : sets) { s.pos.release(); s.pos_alt.release(); s.fpos.release(); s.rec.release(); s.rec_n3.release(); s.ghost_r.release(); s.order.release(); s.place_p.release(); s.ghost_q.release(); s.place_r.release(); s.slot_of.release(); s.ghost_i.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
     dscal.release(); tiles.release(); d_res.release();
     d_hcount.release(); nl.release(); d_hsum.release(); d_rbins.release(); d_forces.release(); d_facc.release(); d_minmax.release(); d_minpart.release(); d_minres.release();
     custom_store_free(custom_store);
@@ -191,7 +191,7 @@ template <class T> int Engine<T>::cell_coords(const void* xyz, int64_t n, int on
 
 // one-pass face selection for the halo exchange (all pointers on the device, enqueue only)
 template <class T> int Engine<T>::select_layers(const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b,
-                                                int64_t capacity, int32_t* counts) {
+                                                int64_t capacity, int32_t* counts, int32_t* idx_a, int32_t* idx_b) {
     if (!box_set) return fail(CLM_ERR_STATE, "clm_set_box must be called first");
     if (axis < 0 || axis >= dim || !ranges || !counts || (n > 0 && (!xyz || !out_a || !out_b))) return fail(CLM_ERR_ARGUMENT, "bad argument");
     if (n <= 0) return CLM_OK;
@@ -201,8 +201,8 @@ template <class T> int Engine<T>::select_layers(const void* xyz, int64_t n, int 
     const int nb = (int)((n + 255) / 256);
     const int4 r = make_int4(ranges[0], ranges[1], ranges[2], ranges[3]);
     const int cap = (int)std::min<int64_t>(capacity, 0x7fffffff);
-    if (dim == 3) k_select_layers<T, 3><<<nb, 256, 0, stream>>>(g, (const T*)xyz, (int)n, axis, r, merge, (T*)out_a, (T*)out_b, cap, (int*)counts);
-    else k_select_layers<T, 2><<<nb, 256, 0, stream>>>(g, (const T*)xyz, (int)n, axis, r, merge, (T*)out_a, (T*)out_b, cap, (int*)counts);
+    if (dim == 3) k_select_layers<T, 3><<<nb, 256, 0, stream>>>(g, (const T*)xyz, (int)n, axis, r, merge, (T*)out_a, (T*)out_b, cap, (int*)counts, (int*)idx_a, (int*)idx_b);
+    else k_select_layers<T, 2><<<nb, 256, 0, stream>>>(g, (const T*)xyz, (int)n, axis, r, merge, (T*)out_a, (T*)out_b, cap, (int*)counts, (int*)idx_a, (int*)idx_b);
     CLM_CK(cudaGetLastError());
     stats.launches += 1;
     return CLM_OK;
@@ -372,13 +372,17 @@ template <class T> int Engine<T>::build_enqueue() {
             CLM_CK(cudaGetLastError());
             stats.launches += 1;
             if (nall > 0) {
-                // placement pass: slot = first record of the cell + cached rank (no wrap, no atomics)
+                // placement: order[slot] = id (the only scattered store), then the records in slot order (coalesced)
                 const int64_t nthreads = nall + ghost_cap;
-                k_place<T><<<(int)((nthreads + 255) / 256), 256, 0, stream>>>(S.place_p.p, S.place_r.p, (int)nall, (int)S.n, S.ghost_q.p, S.ghost_i.p, S.ghost_r.p, dscal.p + DS_NGHOST + s, ghost_cap,
-                                                                             S.cell_start.p, S.cell_nact, S.ref_real, S.rec.p, n3 ? S.rec_n3.p : nullptr, S.slot_of.p, rec_cap,
-                                                                             box.cell_type == CLM_TRICLINIC ? 1 : 0);
+                const int by_index = box.cell_type == CLM_TRICLINIC ? 1 : 0;
+                CLM_CK(S.order.ensure(S.rec.cap));
+                k_order<T><<<(int)((nthreads + 255) / 256), 256, 0, stream>>>(S.place_p.p, S.place_r.p, (int)nall, (int)S.n, S.ghost_q.p, S.ghost_i.p, S.ghost_r.p, dscal.p + DS_NGHOST + s, ghost_cap,
+                                                                             S.cell_start.p, S.cell_nact, S.ref_real, S.order.p, S.slot_of.p, rec_cap, by_index);
                 CLM_CK(cudaGetLastError());
-                stats.launches += 1;
+                k_gather<T><<<(int)(((int64_t)rec_cap + 255) / 256), 256, 0, stream>>>(S.place_p.p, (int)nall, (int)S.n, S.ghost_q.p, S.ghost_i.p, S.order.p, ds + DS_NTOT, S.rec.p,
+                                                                                      n3 ? S.rec_n3.p : nullptr, rec_cap, by_index);
+                CLM_CK(cudaGetLastError());
+                stats.launches += 2;
             }
         }
         tiles_upper = (int64_t)(sets[0].rec.cap / tile_i) + nrows + 1;
@@ -648,7 +652,7 @@ int clm_set_positions_async(clm_handle* h, int set, const void* xyz, int64_t n) 
 int clm_build(clm_handle* h) { H_OR_FAIL; return h->e->build(); }
 int clm_set_foreign(clm_handle* h, int set, const void* xyz, int64_t n, int on_device) { H_OR_FAIL; return h->e->set_foreign(set, xyz, n, on_device); }
 int clm_cell_coords(clm_handle* h, const void* xyz, int64_t n, int on_device, int axis, int32_t* out) { H_OR_FAIL; return h->e->cell_coords(xyz, n, on_device, axis, out); }
-int clm_select_layers(clm_handle* h, const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b, int64_t capacity, int32_t* counts) { H_OR_FAIL; return h->e->select_layers(xyz, n, axis, ranges, merge, out_a, out_b, capacity, counts); }
+int clm_select_layers(clm_handle* h, const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b, int64_t capacity, int32_t* counts, int32_t* idx_a, int32_t* idx_b) { H_OR_FAIL; return h->e->select_layers(xyz, n, axis, ranges, merge, out_a, out_b, capacity, counts, idx_a, idx_b); }
 int clm_map_lj(clm_handle* h, const void* p, int flags, void* e, void* f) { H_OR_FAIL; return h->e->map_lj(p, flags, e, f); }
 int clm_map_coulomb(clm_handle* h, const void* wx, const void* wy, const void* k, int flags, void* e, void* f) { H_OR_FAIL; return h->e->map_coulomb(wx, wy, k, flags, e, f); }
 int clm_map_dist_hist(clm_handle* h, const void* width, int nbins, int flags, int64_t* counts) { H_OR_FAIL; return h->e->map_dist_hist(width, nbins, flags, counts); }

@@ -11,8 +11,9 @@
 //   k_row_starts  : one warp per ROW of device cells: prefix of the row's counts; the row's base comes from one
 //                   atomicAdd on the record counter, so rows are contiguous but placed in arbitrary order -- the
 //                   sweep only ever reads record ranges inside one row.  Replaces a 3-kernel global scan.
-//   k_place       : record slot = first record of the cell + cached rank: a pure gather/scatter pass (no second wrap,
-//                   no second round of atomics)
+//   k_order       : record slot = first record of the cell + cached rank; order[slot] = particle / image id: the only
+//                   scattered store of the build (4 bytes per record)
+//   k_gather      : one thread per record slot: position gathered through order[], cell-sorted records written coalesced
 //   k_row_tiles   : one warp per row: the row's active record range cut into tiles, appended to the tile array with
 //                   one atomicAdd per row (tile order is irrelevant: tiles are dealt out by a work counter)
 // Every per-cell array is laid out with a row pitch of nx + 1 entries: cell_start[row * (nx + 1) + x] is the first
@@ -136,8 +137,8 @@ __device__ __forceinline__ double shfl_t(double v, int src) { return __shfl_sync
 // Count pass of the counting sort, and the ONLY pass that touches the caller's coordinates: the wrapped position, the
 // device cell and the rank inside the cell (the value the histogram atomic returns) of every particle are cached
 // (place_p / place_r), and every image that lands inside the computing box is appended to a list (ghost_q / ghost_i)
-// with its cell and rank.  The placement pass (k_place) then only adds the cell's first record to the rank: no second
-// wrap (six IEEE divisions per particle), no second round of atomics.
+// with its cell and rank.  The placement (k_order, k_gather) then only adds the cell's first record to the rank: no
+// second wrap (six IEEE divisions per particle), no second round of atomics.
 //   place_p[ip] = (p, device cell)            place_r[ip] = rank | parity of the reference cell along the row << 30, -1: invalid
 //   ghost_q[g]  = (q, device cell)            ghost_i[g]  = (rank | parity << 30, particle, reference cell, device cell of the original)
 //                                             ghost_r[g]  = rank of the original inside its cell
@@ -246,46 +247,66 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
     }
 }
 
-// Placement pass: record slot = first record of the cell + cached rank.  Threads [0, n): the particles themselves;
-// threads [n, n + ghost_cap): the image list.  Writes the cell-sorted records, slot_of[particle] = slot of the particle's
-// real record, flags the cells that hold an image able to act as particle i and -- when the Newton's-third-law force sweep
-// wants it (rec_n3 != nullptr, clm_sweep_n3.cuh) -- the slot-tagged twin of the records: 4th word = slot of the particle's
-// REAL record (an image points at its original; by_index: the particle index, triclinic cells) | GHOST | HOME | parity of
-// the reference cell along the row << 29.
+// Placement, two kernels, so that the only SCATTERED traffic is one 4-byte store per record (scattered 16-byte record
+// stores are partial-sector writes: beyond the L2 capacity every one of them costs a DRAM read-modify-write):
+//   k_order  (particle / image order, coalesced reads): slot = first record of the cell + cached rank;
+//            order[slot] = id | parity << 30 (id < n: particle, else image n + g); slot_of[particle] = slot; an image's tag
+//            words are finished here (HOME flag of its reference cell, slot of its original) and left in ghost_i.
+//   k_gather (record order, coalesced writes): the record's position is gathered through order[] and the cell-sorted
+//            records are written -- and, when the Newton's-third-law force sweep wants it (rec_n3 != nullptr,
+//            clm_sweep_n3.cuh), their slot-tagged twin: 4th word = slot of the particle's REAL record (an image points at
+//            its original; by_index: the particle index, triclinic cells) | GHOST | HOME | parity of the reference cell
+//            along the row << 29.
 template <class T>
 __global__ void __launch_bounds__(256)
-k_place(const RecT<T>* __restrict__ place_p, const int* __restrict__ place_r, int n, int n_own, const RecT<T>* __restrict__ ghost_q,
-        const int4* __restrict__ ghost_i, const int* __restrict__ ghost_r, const int* __restrict__ nghost, int ghost_cap, const int* __restrict__ cell_start,
-        int* __restrict__ cell_nact, const int* __restrict__ ref_real, RecT<T>* __restrict__ rec, RecT<T>* __restrict__ rec_n3, int* __restrict__ slot_of,
-        int rec_cap, int by_index) {
-    typedef TagT<T> TG;
-    typedef typename TG::type tag_t;
+k_order(const RecT<T>* __restrict__ place_p, const int* __restrict__ place_r, int n, int n_own, const RecT<T>* __restrict__ ghost_q,
+        int4* __restrict__ ghost_i, const int* __restrict__ ghost_r, const int* __restrict__ nghost, int ghost_cap, const int* __restrict__ cell_start,
+        int* __restrict__ cell_nact, const int* __restrict__ ref_real, int* __restrict__ order, int* __restrict__ slot_of, int rec_cap, int by_index) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     constexpr int RANK = 0x3fffffff;
     if (t < n) {
         const int r = place_r[t];
         if (r < 0) return;
-        const RecT<T> P = ldrec(place_p + t);
-        const int slot = cell_start[(int)P.tag] + (r & RANK);
+        const int slot = cell_start[(int)place_p[t].tag] + (r & RANK);
         slot_of[t] = slot;
-        if (slot >= rec_cap) return;
-        strec(&rec[slot], P.x, P.y, P.z, (tag_t)t | TG::HOME | ((t >= n_own) ? TG::FOREIGN : (tag_t)0));
-        if (rec_n3) strec(&rec_n3[slot], P.x, P.y, P.z, (tag_t)((unsigned)(by_index ? t : slot) | 0x40000000u | (((unsigned)r >> 30) << 29)));
+        if (slot < rec_cap) order[slot] = t | (r & 0x40000000);
     } else {
         const int gidx = t - n;
         if (gidx >= min(*nghost, ghost_cap)) return;
-        const RecT<T> Q = ldrec(ghost_q + gidx);
         const int4 e = ghost_i[gidx];
-        const int lq = (int)Q.tag, ips = e.y;
+        const int lq = (int)ghost_q[gidx].tag, ips = e.y;
         const int slot = cell_start[lq] + (e.x & RANK);
         const bool home = ref_real[e.z] != 0, foreign = ips >= n_own;
         if (home && !foreign) cell_nact[lq] = 1;
-        if (slot >= rec_cap) return;
-        strec(&rec[slot], Q.x, Q.y, Q.z, (tag_t)ips | TG::GHOST | (foreign ? TG::FOREIGN : (tag_t)0) | (home ? TG::HOME : (tag_t)0));
-        if (rec_n3) {
-            const int rslot = cell_start[e.w] + ghost_r[gidx];   // slot of the original
-            strec(&rec_n3[slot], Q.x, Q.y, Q.z, (tag_t)((unsigned)(by_index ? ips : rslot) | 0x80000000u | (home ? 0x40000000u : 0u) | (((unsigned)e.x >> 30) << 29)));
-        }
+        const int rslot = cell_start[e.w] + ghost_r[gidx];   // slot of the original
+        // .x: flag bits of the record's tag (GHOST is implied), .y: particle, .z: 4th word of the slot-tagged twin
+        ghost_i[gidx] = make_int4((home ? 2 : 0) | (foreign ? 1 : 0), ips,
+                                  (int)((unsigned)(by_index ? ips : rslot) | 0x80000000u | (home ? 0x40000000u : 0u) | ((((unsigned)e.x >> 30) & 1u) << 29)), 0);
+        if (slot < rec_cap) order[slot] = t | (e.x & 0x40000000);
+    }
+}
+template <class T>
+__global__ void __launch_bounds__(256)
+k_gather(const RecT<T>* __restrict__ place_p, int n, int n_own, const RecT<T>* __restrict__ ghost_q, const int4* __restrict__ ghost_i,
+         const int* __restrict__ order, const int* __restrict__ ntot, RecT<T>* __restrict__ rec, RecT<T>* __restrict__ rec_n3, int rec_cap, int by_index) {
+    typedef TagT<T> TG;
+    typedef typename TG::type tag_t;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    // an overflowed build (more records than the capacity estimate) is repeated by the host: its order[] has holes (the
+    // images beyond the capacity were dropped), so nothing is gathered
+    if (*ntot > rec_cap || k >= *ntot) return;
+    const int o = order[k];
+    const int id = o & 0x3fffffff;
+    const unsigned par = ((unsigned)o >> 30) & 1u;
+    if (id < n) {
+        const RecT<T> P = ldrec(place_p + id);
+        strec(&rec[k], P.x, P.y, P.z, (tag_t)id | TG::HOME | ((id >= n_own) ? TG::FOREIGN : (tag_t)0));
+        if (rec_n3) strec(&rec_n3[k], P.x, P.y, P.z, (tag_t)((unsigned)(by_index ? id : k) | 0x40000000u | (par << 29)));
+    } else {
+        const RecT<T> Q = ldrec(ghost_q + (id - n));
+        const int4 e = ghost_i[id - n];
+        strec(&rec[k], Q.x, Q.y, Q.z, (tag_t)e.y | TG::GHOST | ((e.x & 1) ? TG::FOREIGN : (tag_t)0) | ((e.x & 2) ? TG::HOME : (tag_t)0));
+        if (rec_n3) strec(&rec_n3[k], Q.x, Q.y, Q.z, (tag_t)(unsigned)e.z);
     }
 }
 
@@ -388,7 +409,7 @@ k_cell_coord(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, int 
 template <class T, int DIM>
 __global__ void __launch_bounds__(256)
 k_select_layers(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, int n, int axis, int4 r, int merge,
-                T* __restrict__ out_a, T* __restrict__ out_b, int capacity, int* __restrict__ counts) {
+                T* __restrict__ out_a, T* __restrict__ out_b, int capacity, int* __restrict__ counts, int* __restrict__ idx_a, int* __restrict__ idx_b) {
     const int ip = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     bool in_a = false, in_b = false;
     T x[DIM];
@@ -405,7 +426,7 @@ k_select_layers(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, i
         in_b = (c >= r.z && c < r.w);
         if (merge) { in_a = in_a || in_b; in_b = false; }
     }
-    auto append = [&](bool take, T* out, int* counter) {
+    auto append = [&](bool take, T* out, int* counter, int* idx_out) {
         const unsigned m = __ballot_sync(0xffffffffu, take);
         if (m == 0u) return;
         const int leader = __ffs(m) - 1;
@@ -416,10 +437,11 @@ k_select_layers(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, i
         if (take && slot < capacity) {
 #pragma unroll
             for (int k = 0; k < DIM; ++k) out[(size_t)slot * DIM + k] = x[k];
+            if (idx_out) idx_out[slot] = ip;   // source row: the caller gathers the particles' side data (ids, weights, ...) with it
         }
     };
-    append(in_a, out_a, counts);
-    append(in_b, out_b, counts + 1);
+    append(in_a, out_a, counts, idx_a);
+    append(in_b, out_b, counts + 1, idx_b);
 }
 
 // per-block min/max of the coordinates (limits(), CellOperations.jl:262-324): out[b][0..2] = min, [3..5] = max

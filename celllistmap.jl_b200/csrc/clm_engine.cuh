@@ -32,7 +32,7 @@ struct EngineBase {
     virtual int set_positions_async(int set, const void* xyz, int64_t n) = 0;
     virtual int set_foreign(int set, const void* xyz, int64_t n, int on_device) = 0;
     virtual int cell_coords(const void* xyz, int64_t n, int on_device, int axis, int32_t* out) = 0;
-    virtual int select_layers(const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b, int64_t capacity, int32_t* counts) = 0;
+    virtual int select_layers(const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b, int64_t capacity, int32_t* counts, int32_t* idx_a, int32_t* idx_b) = 0;
     virtual int build() = 0;
     virtual int map_lj(const void* p, int flags, void* e, void* f) = 0;
     virtual int map_coulomb(const void* wx, const void* wy, const void* k, int flags, void* e, void* f) = 0;
@@ -81,7 +81,7 @@ template <class T> struct DevSet {
     // placement pass), the image list, and the slot of every particle's real record (force gather of the N3 sweep)
     DBuf<RecT<T>> place_p, ghost_q;
     DBuf<RecT<T>> rec_n3;    // slot-tagged twin of rec for the Newton's-third-law force sweep (k_place), written on request
-    DBuf<int> place_r, slot_of, ghost_r;
+    DBuf<int> place_r, slot_of, ghost_r, order;
     DBuf<int4> ghost_i;
     DBuf<T> pos_alt;         // pipelined frames: the buffer the NEXT frame's coordinates are copied into while this one is binned
     int64_t n = 0;
@@ -150,7 +150,7 @@ template <class T> struct Engine : EngineBase {
     int set_positions_async(int set, const void* xyz, int64_t n) override;
     int set_foreign(int set, const void* xyz, int64_t n, int on_device) override;
     int cell_coords(const void* xyz, int64_t n, int on_device, int axis, int32_t* out) override;
-    int select_layers(const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b, int64_t capacity, int32_t* counts) override;
+    int select_layers(const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b, int64_t capacity, int32_t* counts, int32_t* idx_a, int32_t* idx_b) override;
     int build() override;
     int build_enqueue();
     int build_validate();
@@ -256,7 +256,12 @@ template <class T> struct Engine : EngineBase {
         if (profile_sweep) CLM_CK(cudaEventRecord(ev3, stream));
         k_force_finish<T><<<(int)((S.n + 255) / 256), 256, 0, stream>>>((MODE == MODE_TRI) ? nullptr : S.slot_of.p, d_facc.p, dscal.p, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), (int)S.n, out, dim, scale, accumulate, geom.rotated, geom);
         CLM_CK(cudaGetLastError());
-        stats.launches += 2;
+        {   // rows in particle order (triclinic): n rows; record order: the records of the current list
+            const int nrows_cap = (int)std::min<size_t>((MODE == MODE_TRI) ? std::max<size_t>(S.rec.cap, (size_t)S.n) : S.rec.cap, 0x7fffffff);
+            k_zero_rows<T><<<n_sm * 4, 256, 0, stream>>>(d_facc.p, (MODE == MODE_TRI) ? nullptr : dscal.p, (MODE == MODE_TRI) ? (int)S.n : nrows_cap);
+            CLM_CK(cudaGetLastError());
+        }
+        stats.launches += 3;
         last_grid = (int)grid;
         return CLM_OK;
     }

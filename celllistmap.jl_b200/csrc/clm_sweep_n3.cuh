@@ -434,7 +434,7 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
     }
 }
 
-// accumulator rows -> the caller's per-particle force array, and back to zero:
+// accumulator rows -> the caller's per-particle force array:
 // out[idx] = (accumulate ? out[idx] : 0) + scale * R^-1 f(row of idx).  One thread per PARTICLE: the output is written in
 // particle order (coalesced) and the particle's row is gathered through slot_of[idx] (k_place) -- rows are in record
 // order, image rows are never written (images add into their original's row).  slot_of == nullptr: rows in particle order
@@ -442,6 +442,15 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
 template <class T> struct Row4;
 template <> struct Row4<float> { typedef float4 type; };
 template <> struct Row4<double> { typedef double4 type; };
+// the accumulator rows back to zero for the next map: one coalesced fill (scattered 16-byte zero stores from the gather
+// above would be partial-sector writes)
+template <class T>
+__global__ void __launch_bounds__(256) k_zero_rows(T* __restrict__ facc, const int* __restrict__ dscal, int rec_cap) {
+    typedef typename Row4<T>::type row_t;
+    const int ntot = dscal ? min(dscal[DS_NTOT], rec_cap) : rec_cap;   // dscal == nullptr: rec_cap rows
+    row_t z; z.x = T(0); z.y = T(0); z.z = T(0); z.w = T(0);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < ntot; k += gridDim.x * blockDim.x) reinterpret_cast<row_t*>(facc)[k] = z;
+}
 template <class T>
 __global__ void __launch_bounds__(256)
 k_force_finish(const int* __restrict__ slot_of, T* __restrict__ facc, const int* __restrict__ dscal, int rec_cap, int n, T* __restrict__ out, int dim,
@@ -452,10 +461,7 @@ k_force_finish(const int* __restrict__ slot_of, T* __restrict__ facc, const int*
     if (idx >= n) return;
     const int k = slot_of ? slot_of[idx] : idx;
     if (k >= rec_cap) return;
-    row_t* row = reinterpret_cast<row_t*>(facc) + k;
-    const row_t v = *row;
-    row_t z; z.x = T(0); z.y = T(0); z.z = T(0); z.w = T(0);
-    *row = z;
+    const row_t v = *(reinterpret_cast<const row_t*>(facc) + k);   // the rows are zeroed afterwards by one coalesced fill (k_zero_rows)
     T fx = v.x * scale, fy = v.y * scale, fz = v.z * scale;
     if (rotated) {
         const T p = g.inv_rot[0] * fx + g.inv_rot[1] * fy + g.inv_rot[2] * fz;

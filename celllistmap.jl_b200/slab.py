@@ -43,8 +43,15 @@ class SlabPlan:
 
     def face_masks(self, c, rank):
         """(to_lower, to_upper): which owned particles (cell layers c) the lower / upper neighbour needs."""
+        lo, hi = self.face_ranges(rank)[0], self.face_ranges(rank)[3]
+        return (c >= lo) & (c < lo + self.lcell), (c >= self.face_ranges(rank)[2]) & (c < hi)
+
+    def face_ranges(self, rank):
+        """(lo, lo + lcell, hi - lcell, hi'): the cell layers of the lower and the upper face.  The last rank's upper face
+        is closed at bounds[world]: a real particle can round into layer lcell + n_inner (the build's border nudge keeps it
+        there), it belongs to the last rank and rank 0 needs it as a periodic partner."""
         lo, hi = self.bounds[rank], self.bounds[rank + 1]
-        return (c >= lo) & (c < lo + self.lcell), (c >= hi - self.lcell) & (c < hi)
+        return lo, lo + self.lcell, hi - self.lcell, hi + (1 if rank == self.world - 1 else 0)
 
     def neighbours(self, rank):
         return (rank - 1) % self.world, (rank + 1) % self.world
@@ -127,6 +134,8 @@ class SlabSystem:
         self._lcell = lcell
         self._n_global = None
         self._cap = None              # capacity of the fixed-size halo messages (set by the first, exact exchange)
+        self.force_fast = False       # tests: take the single-sync exchange over gloo too (messages staged through the host)
+        self.fast_exchanges = 0       # how many updates went through the single-sync exchange
         self.n_owned = 0
         self.n_foreign = 0
         self.ids = None
@@ -165,12 +174,18 @@ class SlabSystem:
             sub = int(np.floor(max(per_cell / 4.0, 1.0) ** (1.0 / self.dim) + 0.35))
             self.h.set_option("sub", max(1, min(sub, 7 // self._lcell)))
         got = None
-        if ids is None and aux is None and self.world > 1 and self._cap is not None and dist.get_backend(self.group) != "gloo":
-            got = self._exchange_fast(x)
-        if got is None:
+        ids_t = None if ids is None else torch.as_tensor(ids).to(self.device)
+        if self.world > 1 and self._cap is not None and (self.force_fast or dist.get_backend(self.group) != "gloo"):
+            got = self._exchange_fast(x, ids_t, aux)
+        if got is not None:
+            self.fast_exchanges += 1
+            got, self.foreign_ids, aux_f = got
+            self.ids = ids_t
+            self.aux = None if aux is None else torch.cat([aux, aux_f], dim=0).contiguous()
+        else:
             c = self.cell_layers(x).to(torch.int64)
             to_lower, to_upper = self.plan.face_masks(c, self.rank)
-            payloads = [x] + ([] if ids is None else [torch.as_tensor(ids).to(self.device)]) + ([] if aux is None else [aux])
+            payloads = [x] + ([] if ids is None else [ids_t]) + ([] if aux is None else [aux])
             res = exchange_halo(payloads, to_lower, to_upper, self.plan, self.rank, self.group)
             got = res[0].contiguous()
             self.ids = None if ids is None else payloads[1]
@@ -183,8 +198,6 @@ class SlabSystem:
                                  dtype=torch.int64, device=self.device if dist.get_backend(self.group) != "gloo" else "cpu")
                 dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
                 self._alloc_fast(int(int(m) * 1.5) + 1024)
-        else:
-            self.ids = self.foreign_ids = self.aux = None
         self.x_owned, self.x_foreign = x, got
         self.n_foreign = int(got.shape[0])
         self.h.set_positions(0, x)
@@ -198,37 +211,70 @@ class SlabSystem:
         self._cap = cap
         self._send = [torch.empty((cap, self.dim), dtype=t, device=d) for _ in range(2)]
         self._recv = [torch.empty((cap, self.dim), dtype=t, device=d) for _ in range(2)]
+        self._idx = [torch.zeros(cap, dtype=torch.int32, device=d) for _ in range(2)]
         self._cnt = torch.zeros(2, dtype=torch.int32, device=d)
         self._rcnt = torch.zeros(2, dtype=torch.int32, device=d)
+        self._side = {}               # receive buffers of the side payloads (ids, aux), keyed by (dtype, columns)
 
-    def _exchange_fast(self, x):
+    def _side_recv(self, p, k):
+        key = (k, p.dtype, tuple(p.shape[1:]))
+        if key not in self._side:
+            self._side[key] = [torch.empty((self._cap,) + tuple(p.shape[1:]), dtype=p.dtype, device=self.device) for _ in range(2)]
+        return self._side[key]
+
+    def _exchange_fast(self, x, ids=None, aux=None):
         """halo exchange with ONE host synchronisation: the engine selects both faces in one pass into fixed-capacity
-        buffers, the buffers and their fill counts travel in one batch of NCCL send/recv, and only the received counts
-        are read back.  Returns None (caller falls back to the exact path) when a face outgrew the capacity."""
-        lo, hi = self.plan.bounds[self.rank], self.plan.bounds[self.rank + 1]
+        buffers (and returns the source rows, with which the side payloads -- global ids, weights, velocities -- are
+        gathered into messages of the same order), the buffers and their fill counts travel in one batch of send/recv, an
+        all-reduced overflow flag makes the fallback decision COLLECTIVE, and only then the counts are read back.  Returns
+        (foreign positions, foreign ids, foreign aux), or None on EVERY rank when a face of ANY rank outgrew the capacity
+        (the caller then takes the exact path, which re-sizes the messages)."""
         lower, upper = self.plan.neighbours(self.rank)
         merge = self.world == 2
+        cap = self._cap
         self._cnt.zero_()
-        self.h.select_layers(x, 0, (lo, lo + self._lcell, hi - self._lcell, hi), merge, self._send[0], self._send[1], self._cnt)
+        self.h.select_layers(x, 0, self.plan.face_ranges(self.rank), merge, self._send[0], self._send[1], self._cnt, self._idx[0], self._idx[1])
         g = self.group
-        if merge:     # both faces go to the one peer as a single list
-            ops = [dist.P2POp(dist.isend, self._send[0], upper, g), dist.P2POp(dist.isend, self._cnt[0:1], upper, g),
-                   dist.P2POp(dist.irecv, self._recv[0], upper, g), dist.P2POp(dist.irecv, self._rcnt[0:1], upper, g)]
-        else:         # my lower face -> lower neighbour, my upper face -> upper neighbour; theirs come back
-            ops = [dist.P2POp(dist.isend, self._send[0], lower, g), dist.P2POp(dist.isend, self._cnt[0:1], lower, g),
-                   dist.P2POp(dist.isend, self._send[1], upper, g), dist.P2POp(dist.isend, self._cnt[1:2], upper, g),
-                   dist.P2POp(dist.irecv, self._recv[0], upper, g), dist.P2POp(dist.irecv, self._rcnt[0:1], upper, g),
-                   dist.P2POp(dist.irecv, self._recv[1], lower, g), dist.P2POp(dist.irecv, self._rcnt[1:2], lower, g)]
+        stage = dist.get_backend(g) == "gloo"        # CPU tests force this path over gloo: messages staged through the host
+        side = [p for p in (ids, aux) if p is not None]
+        # rows beyond the fill count gather row 0 (the index buffers start zeroed and only ever hold valid rows): harmless
+        side_send = [[p.index_select(0, self._idx[f].long().clamp_(0, max(p.shape[0] - 1, 0))) if p.shape[0] else p.new_zeros((cap,) + tuple(p.shape[1:])) for f in range(2)] for p in side]
+        side_recv = [self._side_recv(p, k) for k, p in enumerate(side)]
+        faces = [(0, upper, 0)] if merge else [(0, lower, 1), (1, upper, 0)]   # (my face f, peer, the peer's slot in my receive buffers)
+        msgs = []      # (send tensor, recv tensor, peer)
+        for f, peer, rslot in faces:
+            msgs.append((self._send[f], self._recv[rslot], peer))
+            msgs.append((self._cnt[f:f + 1], self._rcnt[rslot:rslot + 1], peer))
+            for ss, rr in zip(side_send, side_recv):
+                msgs.append((ss[f], rr[rslot], peer))
+        if stage:
+            host = [(a.cpu(), torch.empty(b.shape, dtype=b.dtype), b, peer) for a, b, peer in msgs]
+            ops = [dist.P2POp(dist.isend, a, peer, g) for a, _, _, peer in host] + [dist.P2POp(dist.irecv, r, peer, g) for _, r, _, peer in host]
+        else:
+            ops = [dist.P2POp(dist.isend, a, peer, g) for a, _, peer in msgs] + [dist.P2POp(dist.irecv, b, peer, g) for _, b, peer in msgs]
         for w in dist.batch_isend_irecv(ops):
             w.wait()
-        counts = torch.cat([self._cnt, self._rcnt]).cpu().tolist()      # the one synchronisation
-        if max(counts) > self._cap:
-            # a face outgrew the fixed-size messages (the density near a slab face rose by > 50 % since the first
-            # exchange): the rows beyond the capacity were not sent.  Every rank would have to agree on a fallback, which
-            # costs a collective per step; instead this is an error the caller resolves with reset_halo_capacity().
-            raise RuntimeError(f"halo capacity exceeded on rank {self.rank}: {max(counts)} rows > {self._cap}; call reset_halo_capacity() on every rank")
+        if stage:
+            for _, r, b, _ in host:
+                b.copy_(r)
+        # the overflow decision is collective: every rank learns whether ANY face of ANY rank outgrew its message
+        allc = torch.cat([self._cnt, self._rcnt])
+        flag = (allc.max() > cap).to(torch.int32).reshape(1)
+        flag = flag.cpu() if stage else flag
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=g)
+        counts = torch.cat([allc, flag.to(allc.device)]).cpu().tolist()      # the one synchronisation
+        if counts[4]:
+            return None
         n_up, n_lo = counts[2], (0 if merge else counts[3])
-        return torch.cat([self._recv[0][:n_up], self._recv[1][:n_lo]], dim=0) if n_lo else self._recv[0][:n_up]
+        cat = (lambda r: torch.cat([r[0][:n_up], r[1][:n_lo]], dim=0) if n_lo else r[0][:n_up])
+        out = [cat(self._recv)] + [cat(r) for r in side_recv]
+        k = 1
+        f_ids = f_aux = None
+        if ids is not None:
+            f_ids = out[k]; k += 1
+        if aux is not None:
+            f_aux = out[k]
+        return out[0], f_ids, f_aux
 
     def reset_halo_capacity(self):
         """the next update() takes the exact (collective) exchange again and re-sizes the fixed-capacity messages."""

@@ -145,9 +145,11 @@ CLM_API int clm_cell_coords(clm_handle* h, const void* aos_xyz, int64_t n, int o
 /* one-pass face selection for the halo exchange; every pointer except `ranges` is a DEVICE pointer and the call only
  * enqueues.  Particles whose cell layer along `axis` is in [ranges[0], ranges[1]) are appended (AoS rows of T) to out_a,
  * those in [ranges[2], ranges[3]) to out_b; merge != 0: either range -> out_a, each particle once.  counts_dev[0..1] must be
- * zeroed by the caller and receive the list lengths; rows beyond `capacity` are counted but not written. */
+ * zeroed by the caller and receive the list lengths; rows beyond `capacity` are counted but not written.  idx_a / idx_b
+ * (device, `capacity` entries each, or NULL) receive the 0-based source row of every appended particle, so that the caller can
+ * gather the particles' side data (global ids, weights, velocities) into messages of the same order. */
 CLM_API int clm_select_layers(clm_handle* h, const void* aos_xyz, int64_t n, int axis, const int32_t ranges[4], int merge,
-                              void* out_a, void* out_b, int64_t capacity, int32_t* counts_dev);
+                              void* out_a, void* out_b, int64_t capacity, int32_t* counts_dev, int32_t* idx_a, int32_t* idx_b);
 
 /* ---- UpdateCellList!  src/internals/CellLists.jl:727-927 ---------------------------------- */
 /* validates coordinates (NaN -> CLM_ERR_INVALID_COORDINATES with the 1-based index in the message),

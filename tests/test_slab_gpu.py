@@ -1,6 +1,7 @@
 """Slab-decomposed path on the GPU: 2 and 3 ranks sharing cuda:0 (gloo plumbing, halo staged through the host), results
 against the CPU oracle / the single-handle run: neighbour lists bit-exact (union over ranks), counts exact, LJ forces
-and energy within tolerance.  On a multi-GPU box bench.py exercises the same code over NCCL."""
+and energy within tolerance; every case also through the single-sync ("fast") halo exchange, and -- when the box has two
+GPUs -- over NCCL, one rank per GPU (the path bench.py times at N > 1)."""
 import os
 import socket
 
@@ -33,14 +34,20 @@ struct WeightedCount {   // scalar: sum par0 w_i w_j; per particle: sum_j w_j
 """
 
 
-def _worker(rank, world, port, case, q):
+def _worker(rank, world, port, case, q, fast=False, backend="gloo"):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ndev = torch.cuda.device_count()
+    dev = rank if backend == "nccl" else 0
+    assert dev < ndev
+    torch.cuda.set_device(dev)
+    if backend == "nccl":
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
+    else:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        torch.cuda.set_device(0)
         import celllistmap_b200  # noqa: F401
         from celllistmap_b200 import slab
         dtype = np.float64 if case in ("list", "aux") else np.float32
@@ -53,6 +60,10 @@ def _worker(rank, world, port, case, q):
             xo, ids = s.partition(w["x"])
             own = ids.cpu().numpy() - 1
             s.update(xo, ids, aux=wts[own])
+            if fast:      # second update through the single-sync exchange (fixed-capacity messages sized by the first one)
+                s.force_fast = True
+                s.update(xo, ids, aux=wts[own])
+                assert s.fast_exchanges == 1
             f = torch.zeros((s.n_owned, 3), dtype=torch.float64, device="cuda")
             e = s.map_coulomb(-9.8, f)
             sc, pp, _, _ = s.map_custom(CUSTOM_SRC, "WeightedCount", params=(2.0,))
@@ -70,6 +81,10 @@ def _worker(rank, world, port, case, q):
         s = slab.SlabSystem(w["unitcell"], w["cutoff"], dtype=dtype)
         xo, ids = s.partition(w["x"])
         s.update(xo, ids)
+        if fast:
+            s.force_fast = True
+            s.update(xo, ids)
+            assert s.fast_exchanges == 1
         if case == "list":
             rec = s.neighborlist()
             sd, sd2, n = s.sum_d_d2()
@@ -84,11 +99,11 @@ def _worker(rank, world, port, case, q):
         dist.destroy_process_group()
 
 
-def _run(world, case):
+def _run(world, case, fast=False, backend="gloo"):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, case, q, fast, backend)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
@@ -98,9 +113,19 @@ def _run(world, case):
     return res
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_slab_neighborlist_bit_exact(oracle_mod, world):
-    res = _run(world, "list")
+MODES = [(2, False, "gloo"), (3, False, "gloo"), (2, True, "gloo"), (3, True, "gloo"), (2, True, "nccl")]
+
+
+def _skip_unless_possible(world, backend):
+    import torch
+    if backend == "nccl" and torch.cuda.device_count() < world:
+        pytest.skip("the NCCL variant needs one GPU per rank (run with gpurun --gpus 2; output kept under profiles/)")
+
+
+@pytest.mark.parametrize("world,fast,backend", MODES)
+def test_slab_neighborlist_bit_exact(oracle_mod, world, fast, backend):
+    _skip_unless_possible(world, backend)
+    res = _run(world, "list", fast, backend)
     w = W.c1_neighborlist(6000)
     o = oracle_mod.Oracle(w["x"], w["cutoff"], unitcell=w["unitcell"])
     wi, wj, wd = o.neighborlist()
@@ -114,9 +139,10 @@ def test_slab_neighborlist_bit_exact(oracle_mod, world):
         assert r[5] == o.dist_hist(w["cutoff"] / 10, 10).tolist()  # all_reduced histogram
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_slab_lj_forces(oracle_mod, world):
-    res = _run(world, "lj")
+@pytest.mark.parametrize("world,fast,backend", MODES)
+def test_slab_lj_forces(oracle_mod, world, fast, backend):
+    _skip_unless_possible(world, backend)
+    res = _run(world, "lj", fast, backend)
     w = W.c2_argon(24, np.float32)
     we, wf = oracle_mod.Oracle(w["x"].astype(np.float64), w["cutoff"], unitcell=w["unitcell"].astype(np.float64)).lj(w["c6"], w["c12"], forces=True)
     f = np.zeros_like(wf)
@@ -137,11 +163,14 @@ def test_slab_lj_forces(oracle_mod, world):
     assert err_same <= 1e-5
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_slab_side_arrays(oracle_mod, world):
+@pytest.mark.parametrize("world,fast,backend", MODES)
+def test_slab_side_arrays(oracle_mod, world, fast, backend):
     """Coulomb energy + forces, a user pair function, the minimum distance and the pair-velocity histogram of a
-    slab-decomposed system equal the single-process results (side arrays exchanged with the halo)."""
-    res = _run(world, "aux")
+    slab-decomposed system equal the single-process results (side arrays exchanged with the halo).  fast: through the
+    single-sync exchange (clm_select_layers + fixed-capacity messages + collective overflow flag), which carries the global
+    ids and the side arrays too; backend nccl: the path the multi-GPU bench times."""
+    _skip_unless_possible(world, backend)
+    res = _run(world, "aux", fast, backend)
     w = W.c1_neighborlist(5000)
     rng = np.random.default_rng(9)
     wts, vel = 0.5 + rng.random(5000), rng.random((5000, 3))
