@@ -473,10 +473,12 @@ def main():
             torch.cuda.synchronize()
             e2e_ms = 1e3 * (time.perf_counter() - t0) / steps
             e_pipe = float(e_pin[(steps - 1) & 1][0])
-            f_pipe_ok = bool(np.array_equal(f_pin[(steps - 1) & 1].numpy(), f_pin[steps & 1].numpy()))
+            # the last two frames carry the same positions: their forces agree to the rounding of the order-free reductions
+            fa, fb = f_pin[(steps - 1) & 1].numpy().astype(np.float64), f_pin[steps & 1].numpy().astype(np.float64)
+            f_pipe_diff = float(np.abs(fa - fb).max() / np.abs(fa).max())
         res = dict(P_in=P_in, band=band, n=n, dev_ms=dev_ms, sweep_ms=statistics.mean(sweep_ms), build_ms=statistics.mean(build_ms), map_ms=statistics.mean(map_ms),
                    e2e_ms=e2e_ms, e2e_sync_ms=e2e_sync_ms, launches=launches, clocks=clocks, w=w, energy=e_gpu, forces=f_gpu, energy_pipe=e_pipe,
-                   h2d=int(x_pin[0].numpy().nbytes), d2h=int(f_pin[0].numpy().nbytes + e_pin[0].numpy().nbytes), stats=h.stats(), frames_equal=f_pipe_ok)
+                   h2d=int(x_pin[0].numpy().nbytes), d2h=int(f_pin[0].numpy().nbytes + e_pin[0].numpy().nbytes), stats=h.stats(), frames_diff=f_pipe_diff)
         h.close()
         return res
 
@@ -539,7 +541,7 @@ def main():
                 "mode": "pipelined frames through the C ABI (clm_set_positions_async + clm_map_lj with CLM_ASYNC): every frame's positions are copied from "
                         "pinned host memory and its forces + energy copied back inside the timed region; copy-in of frame k+1, compute of frame k and "
                         "copy-out of frame k-1 overlap; L2 flush between frames on the compute stream, inside the timed region; wall clock over all steps",
-                "frames_equal": r32["frames_equal"], "energy": r32["energy_pipe"]},
+                "last_two_frames_force_max_rel_diff": r32["frames_diff"], "energy": r32["energy_pipe"]},
         "e2e_sync": {"value": r32["P_in"] / (r32["e2e_sync_ms"] * 1e-3), "unit": UNIT, "ms_per_step": r32["e2e_sync_ms"],
                      "mode": "one synchronous clm_set_positions + clm_map_lj per step (outputs in host memory on return): the latency of a dependent step"},
         "gpu_launches": r32["launches"] * args.steps,
@@ -577,11 +579,17 @@ def main():
                                           "C++/OpenMP restatement of the reference (projection filter, batch-private outputs)",
                                 "seconds_per_step": t, "host_threads_available": nthreads}
         if args.cpu_nside == args.nside:
-            # parity of the timed GPU result against the CPU restatement run in the same precision on the same input
+            # parity of the timed GPU result against the CPU restatement on the same input: forces against the oracle run in
+            # the same precision (Float32 input -> Float32 arithmetic in the reference), the energy against the oracle in
+            # Float64 (the reference's Float32 sum of 7.7e7 signed terms is itself only good to ~1e-2)
             fo = np.asarray(f_o, np.float64)
-            line["parity"] = {"pairs_equal": bool(npairs == r32["P_in"]), "energy_rel_err": abs(r32["energy"] - e_o) / abs(e_o),
+            o64 = om.Oracle(wc["x"].astype(np.float64), wc["cutoff"], unitcell=wc["unitcell"].astype(np.float64))
+            e64 = float(o64.lj(wc["c6"], wc["c12"], forces=False, nbatches=nt))
+            del o64
+            line["parity"] = {"pairs_equal": bool(npairs == r32["P_in"]), "energy_rel_err": abs(r32["energy"] - e64) / abs(e64),
                               "force_max_rel_err": float(np.abs(r32["forces"].astype(np.float64) - fo).max() / np.abs(fo).max()),
-                              "against": "oracle (C++ restatement of the reference) in Float32 on the same input; north_star tolerance 1e-5",
+                              "against": "forces: oracle (C++ restatement of the reference) in Float32 on the same input; energy: the oracle in Float64; "
+                                         "north_star tolerance 1e-5", "oracle_f32_energy_rel_err": abs(float(e_o) - e64) / abs(e64),
                               "at_cutoff_band_pairs": r32["band"]}
     print(json.dumps(line, default=lambda o: o.item() if hasattr(o, "item") else str(o)))
 

@@ -26,6 +26,7 @@ SYMBOLS = [
     "clm_map_mindist", "clm_map_sum_d_d2", "clm_neighborlist", "clm_neighborlist_copy", "clm_get_stats",
     "clm_set_option", "clm_version", "clm_measure_fma_peak", "clm_set_foreign", "clm_cell_coords", "clm_select_layers",
     "clm_custom_compile", "clm_custom_log", "clm_map_custom", "clm_custom_check",
+    "clm_comm_unique_id", "clm_comm_init", "clm_comm_destroy", "clm_slab_range", "clm_slab_update", "clm_comm_allreduce_sum", "clm_slab_info",
 ]
 
 
@@ -65,6 +66,15 @@ class ClmError(RuntimeError):
 _LIB = None
 
 
+def comm_unique_id():
+    """128-byte NCCL unique id (rank 0 creates it; every rank passes it to Handle.comm_init)"""
+    buf = (C.c_char * 128)()
+    rc = lib().clm_comm_unique_id(C.cast(buf, C.c_void_p))
+    if rc:
+        raise ClmError(rc, lib().clm_last_error(None).decode())
+    return bytes(buf)
+
+
 def lib():
     global _LIB
     if _LIB is not None:
@@ -86,6 +96,13 @@ def lib():
     L.clm_get_box.argtypes = [vp, C.POINTER(BoxInfo)]
     L.clm_set_positions.argtypes = [vp, ci, vp, i64, ci]
     L.clm_set_positions_async.argtypes = [vp, ci, vp, i64]
+    L.clm_comm_unique_id.argtypes = [vp]
+    L.clm_comm_init.argtypes = [vp, vp, ci, ci]
+    L.clm_comm_destroy.argtypes = [vp]
+    L.clm_slab_range.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    L.clm_slab_update.argtypes = [vp, vp, i64, ci]
+    L.clm_comm_allreduce_sum.argtypes = [vp, vp, i64, ci, ci]
+    L.clm_slab_info.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.clm_build.argtypes = [vp]
     L.clm_map_lj.argtypes = [vp, vp, ci, vp, vp]
     L.clm_map_coulomb.argtypes = [vp, vp, vp, vp, ci, vp, vp]
@@ -261,6 +278,39 @@ class Handle:
         self._chk(self.L.clm_select_layers(self.h, _addr(x)[0], int(x.shape[0]), int(axis), r, 1 if merge else 0,
                                            _addr(out_a)[0], _addr(out_b)[0], int(out_a.shape[0]), _addr(counts)[0],
                                            _addr(idx_a)[0], _addr(idx_b)[0]))
+
+    # ---- slab decomposition over NCCL behind the C ABI (clm_comm.cu) ----
+    def comm_init(self, unique_id, rank, world):
+        """unique_id: the 128 bytes of comm_unique_id() (called on rank 0 and handed to every rank)."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._chk(self.L.clm_comm_init(self.h, C.cast(buf, C.c_void_p), int(rank), int(world)))
+
+    def comm_destroy(self):
+        self._chk(self.L.clm_comm_destroy(self.h))
+
+    def slab_range(self):
+        lo, hi = C.c_int32(0), C.c_int32(0)
+        self._chk(self.L.clm_slab_range(self.h, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def slab_update(self, x):
+        if not _is_torch(x):
+            x = np.ascontiguousarray(x, dtype=self.dtype)
+        p, dev = _addr(x)
+        self._chk(self.L.clm_slab_update(self.h, p, int(x.shape[0]), 1 if dev else 0))
+
+    def comm_allreduce_sum(self, buf):
+        """in-place sum over the ranks of a numpy array (host) or torch CUDA tensor of the handle's real type, int64 or float64"""
+        dt = np.dtype(str(buf.dtype).replace("torch.", ""))
+        kind = 0 if dt == self.dtype else (1 if dt == np.int64 else (2 if dt == np.float64 else -1))
+        p, dev = _addr(buf)
+        n = int(buf.numel()) if _is_torch(buf) else int(buf.size)
+        self._chk(self.L.clm_comm_allreduce_sum(self.h, p, n, kind, 1 if dev else 0))
+
+    def slab_info(self):
+        a, b, r, w = C.c_int64(0), C.c_int64(0), C.c_int32(0), C.c_int32(0)
+        self._chk(self.L.clm_slab_info(self.h, C.byref(a), C.byref(b), C.byref(r), C.byref(w)))
+        return a.value, b.value, r.value, w.value
 
     def build(self):
         self._chk(self.L.clm_build(self.h))

@@ -41,13 +41,14 @@ template <class T> int Engine<T>::init(int dim_, int device_) {
 }
 
 template <class T> Engine<T>::~Engine() {
+    comm_destroy();
     cudaSetDevice(device);
     if (own_stream) cudaStreamSynchronize(own_stream);
     if (copy_in) { cudaStreamSynchronize(copy_in); cudaStreamDestroy(copy_in); }
     if (copy_out) { cudaStreamSynchronize(copy_out); cudaStreamDestroy(copy_out); }
     for (cudaEvent_t e : {ev_h2d, ev_posfree, ev_done, ev_out[0], ev_out[1]}) if (e) cudaEventDestroy(e);
     d_forces_alt.release(); d_eout.release();
-    for (auto& s : sets) { s.pos.release(); s.pos_alt.release(); s.fpos.release(); s.rec.release(); s.rec_n3.release(); s.ghost_r.release(); s.order.release(); s.place_p.release(); s.ghost_q.release(); s.place_r.release(); s.slot_of.release(); s.ghost_i.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
+    for (auto& s : sets) { s.pos.release(); s.pos_alt.release(); s.fpos.release(); s.rec.release(); s.rec_n3.release(); s.order.release(); s.place_p.release(); s.ghost_q.release(); s.slot_of.release(); s.ghost_i.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
     dscal.release(); tiles.release(); d_res.release();
     d_hcount.release(); nl.release(); d_hsum.release(); d_rbins.release(); d_forces.release(); d_facc.release(); d_minmax.release(); d_minpart.release(); d_minres.release();
     custom_store_free(custom_store);
@@ -70,7 +71,7 @@ template <class T> int Engine<T>::set_box(int cell_type, const void* uc, int is_
     const T rc = *(const T*)cutoff;
     dirty = true;
     if (cell_type == CLM_NONPERIODIC) {
-        nonperiodic = true; np_cutoff = rc; np_lcell = lcell; box_set = false;
+        nonperiodic = true; np_cutoff = rc; np_lcell = lcell; box_set = false; np_have_limits = false;
         return CLM_OK;
     }
     if (cell_type != CLM_ORTHORHOMBIC && cell_type != CLM_TRICLINIC) return fail(CLM_ERR_ARGUMENT, "unknown cell type");
@@ -233,27 +234,41 @@ template <class T> int Engine<T>::build_enqueue() {
     // device scalars (a kernel, not a copy: see k_dscal_init)
     k_dscal_init<<<1, 32, 0, stream>>>(dscal.p);
     CLM_CK(cudaGetLastError());
-    if (nonperiodic) {
+    const bool np_reuse = nonperiodic && box_set && np_have_limits && !np_force_limits;
+    if (nonperiodic && !np_reuse) {
         // Box(limits(x[,y]), cutoff): sides = extent + 2.1*cutoff, origin = minimum coordinates
-        // (CellOperations.jl:290-324, Box.jl:38, :374-377); limits by a device reduction
+        // (CellOperations.jl:290-324, Box.jl:38, :374-377); limits by a device reduction, ONE host round trip for both
+        // sets and the NaN flags
         T lo[3], hi[3];
         for (int k = 0; k < 3; ++k) { lo[k] = std::numeric_limits<T>::max(); hi[k] = std::numeric_limits<T>::lowest(); }
+        int nblk[2] = {0, 0};
+        for (int s = 0; s < nsets; ++s) nblk[s] = sets[s].n > 0 ? (int)std::min<int64_t>(1024, (sets[s].n + 255) / 256) : 0;
+        CLM_CK(d_minmax.ensure((size_t)std::max(nblk[0] + nblk[1], 1) * 6));
+        h_stage.resize((size_t)std::max(nblk[0] + nblk[1], 1) * 6 * sizeof(T));
         for (int s = 0; s < nsets; ++s) {
-            const int64_t n = sets[s].n;
+            if (!nblk[s]) continue;
+            T* out = d_minmax.p + (size_t)(s ? nblk[0] : 0) * 6;
+            if (dim == 3) k_minmax<T, 3><<<nblk[s], 256, 0, stream>>>(sets[s].pos.p, (int)sets[s].n, out, dscal.p + s * DS_SET_STRIDE);
+            else k_minmax<T, 2><<<nblk[s], 256, 0, stream>>>(sets[s].pos.p, (int)sets[s].n, out, dscal.p + s * DS_SET_STRIDE);
+            CLM_CK(cudaGetLastError());
+            stats.launches += 1;
+        }
+        if (nblk[0] + nblk[1]) CLM_CK(cudaMemcpyAsync(h_stage.data(), d_minmax.p, (size_t)(nblk[0] + nblk[1]) * 6 * sizeof(T), cudaMemcpyDeviceToHost, stream));
+        k_dscal_publish<<<1, 32, 0, stream>>>(dscal.p, h_dscal_dev);
+        CLM_CK(cudaGetLastError());
+        CLM_CK(cudaStreamSynchronize(stream));
+        // a NaN coordinate poisons the limits: report it as the reference does (validation runs first there)
+        for (int s = 0; s < nsets; ++s)
+            if (h_dscal[s * DS_SET_STRIDE + DS_NAN] != IDX_NONE)
+                return fail(CLM_ERR_INVALID_COORDINATES, "Invalid coordinates found (NaN) for particle of index " + std::to_string(h_dscal[s * DS_SET_STRIDE + DS_NAN] + 1) + (s ? " of the second set" : ""));
+        const T* h = reinterpret_cast<const T*>(h_stage.data());
+        for (int s = 0; s < nsets; ++s) {
             T slo[3] = {T(0), T(0), T(0)}, shi[3] = {T(0), T(0), T(0)};   // empty set: zero limits (_minmax, CellOperations.jl:263-265)
-            if (n > 0) {
-                const int nb = (int)std::min<int64_t>(1024, (n + 255) / 256);
-                CLM_CK(d_minmax.ensure((size_t)nb * 6));
-                if (dim == 3) k_minmax<T, 3><<<nb, 256, 0, stream>>>(sets[s].pos.p, (int)n, d_minmax.p, dscal.p + s * DS_SET_STRIDE);
-                else k_minmax<T, 2><<<nb, 256, 0, stream>>>(sets[s].pos.p, (int)n, d_minmax.p, dscal.p + s * DS_SET_STRIDE);
-                CLM_CK(cudaGetLastError());
-                stats.launches += 1;
-                std::vector<T> h((size_t)nb * 6);
-                CLM_CK(cudaMemcpyAsync(h.data(), d_minmax.p, h.size() * sizeof(T), cudaMemcpyDeviceToHost, stream));
-                CLM_CK(cudaStreamSynchronize(stream));
+            if (nblk[s]) {
                 for (int k = 0; k < 3; ++k) { slo[k] = std::numeric_limits<T>::max(); shi[k] = std::numeric_limits<T>::lowest(); }
-                for (int b = 0; b < nb; ++b)
-                    for (int k = 0; k < dim; ++k) { slo[k] = std::min(slo[k], h[(size_t)b * 6 + k]); shi[k] = std::max(shi[k], h[(size_t)b * 6 + 3 + k]); }
+                const T* hs = h + (size_t)(s ? nblk[0] : 0) * 6;
+                for (int b = 0; b < nblk[s]; ++b)
+                    for (int k = 0; k < dim; ++k) { slo[k] = std::min(slo[k], hs[(size_t)b * 6 + k]); shi[k] = std::max(shi[k], hs[(size_t)b * 6 + 3 + k]); }
             }
             for (int k = 0; k < dim; ++k) { lo[k] = std::min(lo[k], slo[k]); hi[k] = std::max(hi[k], shi[k]); }
         }
@@ -262,18 +277,21 @@ template <class T> int Engine<T>::build_enqueue() {
         const T pad = T(210) * np_cutoff / T(100);
         for (int k = 0; k < dim; ++k) { cell[k][k] = (hi[k] - lo[k]) + pad; origin[k] = lo[k]; }
         box_set = false;
-        // a NaN coordinate poisons the limits: report it as the reference does (validation runs first there)
-        CLM_CK(cudaMemcpyAsync(h_dscal, dscal.p, DS_COUNT * sizeof(int), cudaMemcpyDeviceToHost, stream));
-        CLM_CK(cudaStreamSynchronize(stream));
-        for (int s = 0; s < nsets; ++s)
-            if (h_dscal[s * DS_SET_STRIDE + DS_NAN] != IDX_NONE)
-                return fail(CLM_ERR_INVALID_COORDINATES, "Invalid coordinates found (NaN) for particle of index " + std::to_string(h_dscal[s * DS_SET_STRIDE + DS_NAN] + 1) + (s ? " of the second set" : ""));
         int rcode = make_box(box, dim, CLM_NONPERIODIC, cell, np_cutoff, np_lcell, origin, err);
         if (rcode != CLM_OK) return rcode;
         box_set = true;
+        for (int k = 0; k < 3; ++k) { np_lo[k] = (k < dim) ? lo[k] : T(0); np_hi[k] = (k < dim) ? hi[k] : T(0); }
+        np_have_limits = true;
+        np_force_limits = false;
+        k_dscal_init<<<1, 32, 0, stream>>>(dscal.p);    // the limits pass used the flags
+        CLM_CK(cudaGetLastError());
     }
     if (!box_set) return fail(CLM_ERR_STATE, "clm_set_box must be called before clm_build");
     fill_geom(box, geom);
+    if (np_reuse) {   // the box of the previous build is kept while every particle stays inside the limits it was made from
+        geom.np_check = 1;
+        for (int k = 0; k < 3; ++k) { geom.np_lo[k] = np_lo[k]; geom.np_hi[k] = np_hi[k]; }
+    }
     double nref_total = 1;
     for (int k = 0; k < dim; ++k) nref_total *= (double)box.nc[k];
     if (nref_total > 2.0e9) return fail(CLM_ERR_UNSUPPORTED, "more than 2e9 computing cells: increase the cutoff or use lcell = 1");
@@ -302,7 +320,7 @@ template <class T> int Engine<T>::build_enqueue() {
     ncells = (int64_t)nfast * nmid * nslow;
     nrows = ncells / nfast;
     const int64_t ncp = nrows * (nfast + 1);   // per-cell arrays have a row pitch of nfast + 1 (clm_build.cuh)
-    if (ncp + 2 > 0x7fffffff) return fail(CLM_ERR_UNSUPPORTED, "device cell grid too large");
+    if (ncp + 2 > 0x3fffffff) return fail(CLM_ERR_UNSUPPORTED, "device cell grid too large");   // cell indices travel in 30 bits (clm_build.cuh)
     // stencil rows: a row offset (dslow, dmid) is at least d_perp away; partners can only sit within
     // sqrt(cutoff^2 - d_perp^2) along the row (1e-4 relative slack covers coordinate rounding at cell borders)
     {
@@ -335,13 +353,17 @@ template <class T> int Engine<T>::build_enqueue() {
         img_factor = std::min(std::max(vbox / std::max(vcell, 1e-300), 1.0), (dim == 3) ? 8.0 : 4.0);
     }
     {
-        if (nonperiodic) { k_dscal_init<<<1, 32, 0, stream>>>(dscal.p); CLM_CK(cudaGetLastError()); }   // the limits pass used the flags
         for (int s = 0; s < nsets; ++s) {
             DevSet<T>& S = sets[s];
             const size_t want = std::max<size_t>((size_t)((double)(S.n + S.n_foreign) * img_factor * 1.25) + 4096, (size_t)std::max<int64_t>(S.n_tot, 1));
             CLM_CK(S.rec.ensure(want));
             const bool n3 = want_n3 && s == 0;
-            if (n3) CLM_CK(S.rec_n3.ensure(S.rec.cap));
+            if (n3) {
+                CLM_CK(S.rec_n3.ensure(S.rec.cap));
+                const size_t old_cap = d_facc.cap;
+                CLM_CK(d_facc.ensure(S.rec.cap * 4));
+                if (d_facc.cap != old_cap) CLM_CK(cudaMemsetAsync(d_facc.p, 0, d_facc.cap * sizeof(T), stream));
+            }
             CLM_CK(S.cell_start.ensure((size_t)ncp + 2));
             CLM_CK(S.counters.ensure((size_t)(2 * ncp + nref)));
             S.cell_count = S.counters.p; S.cell_nact = S.counters.p + ncp; S.ref_real = S.counters.p + 2 * ncp;
@@ -357,14 +379,12 @@ template <class T> int Engine<T>::build_enqueue() {
             const int ghost_cap = (int)std::max<int64_t>((int64_t)rec_cap - nall, 0);   // more images than this overflow the record capacity too
             if (nall > 0) {
                 CLM_CK(S.place_p.ensure((size_t)nall));
-                CLM_CK(S.place_r.ensure((size_t)nall));
                 CLM_CK(S.ghost_q.ensure((size_t)std::max(ghost_cap, 1)));
                 CLM_CK(S.ghost_i.ensure((size_t)std::max(ghost_cap, 1)));
-                CLM_CK(S.ghost_r.ensure((size_t)std::max(ghost_cap, 1)));
                 CLM_CK(S.slot_of.ensure((size_t)nall));
                 // count pass: wrap, cells, images, per-cell histogram; everything the placement needs is cached
-                if (dim == 3) k_bin<T, 3><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, S.place_p.p, S.place_r.p, S.ghost_q.p, S.ghost_i.p, S.ghost_r.p, ghost_cap, dscal.p + DS_NGHOST + s, ds);
-                else k_bin<T, 2><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, S.place_p.p, S.place_r.p, S.ghost_q.p, S.ghost_i.p, S.ghost_r.p, ghost_cap, dscal.p + DS_NGHOST + s, ds);
+                if (dim == 3) k_bin<T, 3><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, S.place_p.p, S.ghost_q.p, S.ghost_i.p, ghost_cap, dscal.p + DS_NGHOST + s, ds);
+                else k_bin<T, 2><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, S.place_p.p, S.ghost_q.p, S.ghost_i.p, ghost_cap, dscal.p + DS_NGHOST + s, ds);
                 CLM_CK(cudaGetLastError());
                 stats.launches += 1;
             }
@@ -376,11 +396,11 @@ template <class T> int Engine<T>::build_enqueue() {
                 const int64_t nthreads = nall + ghost_cap;
                 const int by_index = box.cell_type == CLM_TRICLINIC ? 1 : 0;
                 CLM_CK(S.order.ensure(S.rec.cap));
-                k_order<T><<<(int)((nthreads + 255) / 256), 256, 0, stream>>>(S.place_p.p, S.place_r.p, (int)nall, (int)S.n, S.ghost_q.p, S.ghost_i.p, S.ghost_r.p, dscal.p + DS_NGHOST + s, ghost_cap,
-                                                                             S.cell_start.p, S.cell_nact, S.ref_real, S.order.p, S.slot_of.p, rec_cap, by_index);
+                k_order<T><<<(int)((nthreads + 255) / 256), 256, 0, stream>>>(S.place_p.p, (int)nall, (int)S.n, S.ghost_q.p, S.ghost_i.p, dscal.p + DS_NGHOST + s, ghost_cap,
+                                                                             S.cell_start.p + 1, S.cell_nact, S.ref_real, S.order.p, S.slot_of.p, rec_cap);
                 CLM_CK(cudaGetLastError());
-                k_gather<T><<<(int)(((int64_t)rec_cap + 255) / 256), 256, 0, stream>>>(S.place_p.p, (int)nall, (int)S.n, S.ghost_q.p, S.ghost_i.p, S.order.p, ds + DS_NTOT, S.rec.p,
-                                                                                      n3 ? S.rec_n3.p : nullptr, rec_cap, by_index);
+                k_gather<T><<<(int)(((int64_t)rec_cap + 255) / 256), 256, 0, stream>>>(S.place_p.p, (int)nall, (int)S.n, S.ghost_q.p, S.ghost_i.p, S.ref_real, S.slot_of.p, S.order.p, ds + DS_NTOT,
+                                                                                      S.rec.p, n3 ? S.rec_n3.p : nullptr, rec_cap, by_index, n3 ? d_facc.p : nullptr);
                 CLM_CK(cudaGetLastError());
                 stats.launches += 2;
             }
@@ -407,6 +427,7 @@ template <class T> int Engine<T>::build_enqueue() {
     validate_pending = true;
     dirty = false;
     have_n3 = want_n3;
+    facc_clean = want_n3;   // k_gather zeroed the accumulator rows of the new list
     return CLM_OK;
 }
 
@@ -418,18 +439,25 @@ template <class T> int Engine<T>::build_validate() {
     CLM_CK(cudaEventSynchronize(ev_built));
     const int nsets = two_sets ? 2 : 1;
     bool overflow = false;
+    bool nofit = nonperiodic && h_dscal[DS_NOFIT] != 0;
     for (int s = 0; s < nsets; ++s) {
         const int* hs = h_dscal + s * DS_SET_STRIDE;
         if (hs[DS_NAN] != IDX_NONE) {
             dirty = true;
             return fail(CLM_ERR_INVALID_COORDINATES, "Invalid coordinates found (NaN) for particle of index " + std::to_string(hs[DS_NAN] + 1) + (s ? " of the second set" : ""));
         }
+        if (nofit) continue;   // the reused non-periodic box does not hold the new coordinates: rebuilt below
         if (hs[DS_OOB] != IDX_NONE) {
             dirty = true;
             return fail(CLM_ERR_INVALID_COORDINATES, "Invalid coordinates found: particle of index " + std::to_string(hs[DS_OOB] + 1) + " falls outside the computing grid (non-finite coordinate?)");
         }
         sets[s].n_tot = hs[DS_NTOT];
         if ((size_t)sets[s].n_tot > sets[s].rec.cap) overflow = true;
+    }
+    if (nofit) {   // _limits_fit_in_box failed: new limits, new box, build again
+        dirty = true;
+        np_force_limits = true;
+        return CLM_RETRY_INTERNAL;
     }
     if (overflow) {
         dirty = true;
@@ -632,7 +660,7 @@ int clm_create(clm_handle** out, int dim, int dtype, int device, int ngpus) {
     *out = nullptr;
     if (dim != 2 && dim != 3) { clm::g_create_error = "Dimension must be 2 or 3."; return CLM_ERR_DIMENSION; }
     if (dtype != CLM_F32 && dtype != CLM_F64) { clm::g_create_error = "dtype must be CLM_F32 or CLM_F64"; return CLM_ERR_ARGUMENT; }
-    if (ngpus != 1) { clm::g_create_error = "one handle drives one GPU; multi-GPU slabs use one handle per rank (clm_slab_*)"; return CLM_ERR_UNSUPPORTED; }
+    if (ngpus != 1) { clm::g_create_error = "one handle drives one GPU; multi-GPU slabs use one handle per rank (clm_comm_init + clm_slab_update)"; return CLM_ERR_UNSUPPORTED; }
     EngineBase* e = nullptr;
     int rc;
     if (dtype == CLM_F32) { auto* p = new (std::nothrow) clm::Engine<float>(); e = p; rc = p ? p->init(dim, device) : CLM_ERR_CUDA; }
@@ -670,5 +698,12 @@ int clm_map_custom(clm_handle* h, int32_t id, const void* params, int nparams, c
     H_OR_FAIL;
     return h->e->map_custom(id, params, nparams, aux_x, aux_y, nbins, flags, scalars_out, part_out, hist_counts, hist_sums);
 }
+int clm_comm_unique_id(void* id128) { std::string e; const int rc = clm::comm_unique_id(id128, e); if (rc) clm::g_create_error = e; return rc; }
+int clm_comm_init(clm_handle* h, const void* id128, int rank, int world) { H_OR_FAIL; return h->e->comm_init(id128, rank, world); }
+int clm_comm_destroy(clm_handle* h) { H_OR_FAIL; return h->e->comm_destroy(); }
+int clm_slab_range(clm_handle* h, int32_t* lo, int32_t* hi) { H_OR_FAIL; return h->e->slab_range(lo, hi); }
+int clm_slab_update(clm_handle* h, const void* xyz, int64_t n, int on_device) { H_OR_FAIL; return h->e->slab_update(xyz, n, on_device); }
+int clm_comm_allreduce_sum(clm_handle* h, void* buf, int64_t count, int kind, int on_device) { H_OR_FAIL; return h->e->comm_allreduce_sum(buf, count, kind, on_device); }
+int clm_slab_info(clm_handle* h, int64_t* n_owned, int64_t* n_foreign, int32_t* rank, int32_t* world) { H_OR_FAIL; return h->e->slab_info(n_owned, n_foreign, rank, world); }
 int clm_custom_check(const char* source, const char* name, int dtype, char* log, int64_t log_capacity) { return clm::custom_check(source, name, dtype, log, log_capacity); }
 }

@@ -28,7 +28,7 @@ namespace clm {
 
 constexpr int IDX_NONE = 0x7fffffff;
 // device scalar block (ints)
-enum { DS_NAN = 0, DS_OOB = 1, DS_NTOT = 2, DS_NTILES = 3, DS_WORK = 4, DS_NCELLS_REAL = 5, DS_NGHOST = 12 /* + set */, DS_COUNT = 16 };
+enum { DS_NAN = 0, DS_OOB = 1, DS_NTOT = 2, DS_NTILES = 3, DS_WORK = 4, DS_NCELLS_REAL = 5, DS_NGHOST = 12 /* + set */, DS_NOFIT = 14, DS_COUNT = 16 };
 constexpr int DS_SET_STRIDE_DEV = 6;   // the scalar block of the second set starts at dscal + 6
 
 // The device scalars are initialised and published by two one-warp kernels, not by cudaMemcpyAsync: a small copy on the
@@ -44,6 +44,10 @@ static __global__ void __launch_bounds__(256) k_zero_ints(int* __restrict__ p, l
     int4* p4 = reinterpret_cast<int4*>(p);
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n4; k += (long long)gridDim.x * blockDim.x) p4[k] = make_int4(0, 0, 0, 0);
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) p[(n4 << 2) + threadIdx.x] = 0;
+}
+// out[0] = max(cnt[0], cnt[1]) (halo face counts: the value the ranks all-reduce, clm_comm.cu)
+static __global__ void k_max2(const int* __restrict__ cnt, int* __restrict__ out) {
+    if (threadIdx.x == 0) out[0] = max(cnt[0], cnt[1]);
 }
 static __global__ void k_map_begin(unsigned long long* __restrict__ res_words, int nwords, int* __restrict__ work) {
     if (threadIdx.x < nwords) res_words[threadIdx.x] = 0ull;
@@ -139,20 +143,20 @@ __device__ __forceinline__ double shfl_t(double v, int src) { return __shfl_sync
 // (place_p / place_r), and every image that lands inside the computing box is appended to a list (ghost_q / ghost_i)
 // with its cell and rank.  The placement (k_order, k_gather) then only adds the cell's first record to the rank: no
 // second wrap (six IEEE divisions per particle), no second round of atomics.
-//   place_p[ip] = (p, device cell)            place_r[ip] = rank | parity of the reference cell along the row << 30, -1: invalid
-//   ghost_q[g]  = (q, device cell)            ghost_i[g]  = (rank | parity << 30, particle, reference cell, device cell of the original)
-//                                             ghost_r[g]  = rank of the original inside its cell
+//   place_p[ip] = (p, device cell | parity of the reference cell along the row << 30; 0xffffffff: invalid particle)
+//   ghost_q[g]  = (q, device cell | parity << 30)          ghost_i[g]  = (particle, reference cell)
+// The histogram atomics return nothing (RED): the slot inside the cell is handed out by k_order, a light kernel that can
+// afford to wait for its atomics.
 template <class T, int DIM>
 __global__ void __launch_bounds__(256)
 k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __restrict__ fpos, int n, int n_own, int* __restrict__ cell_count,
-      int* __restrict__ cell_nact, int* __restrict__ ref_real, RecT<T>* __restrict__ place_p, int* __restrict__ place_r,
-      RecT<T>* __restrict__ ghost_q, int4* __restrict__ ghost_i, int* __restrict__ ghost_r, int ghost_cap, int* __restrict__ nghost, int* __restrict__ dscal) {
+      int* __restrict__ cell_nact, int* __restrict__ ref_real, RecT<T>* __restrict__ place_p,
+      RecT<T>* __restrict__ ghost_q, int2* __restrict__ ghost_i, int ghost_cap, int* __restrict__ nghost, int* __restrict__ dscal) {
     typedef TagT<T> TG;
     const int ip = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     constexpr int CENTER = (DIM == 3) ? 13 : 4;
     T p[3] = {T(0), T(0), T(0)};
     unsigned okmask = 0u;      // candidate images of this lane's particle (none for invalid / interior / non-periodic)
-    int lin_own = 0, rank_own = 0;
     if (ip < n) {
         T x[DIM];
         bool bad = false;
@@ -160,19 +164,24 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
 #pragma unroll
         for (int k = 0; k < DIM; ++k) { x[k] = src[k]; bad |= (x[k] != x[k]); }
         int lin = 0, rlin = 0, cfast = 0;
+        if (g.np_check && !bad) {
+            bool fit = true;
+#pragma unroll
+            for (int k = 0; k < DIM; ++k) fit = fit && (x[k] >= g.np_lo[k]) && (x[k] <= g.np_hi[k]);
+            if (!fit) dscal[DS_NOFIT] = 1;     // the reused box does not hold this particle: the host recomputes the limits
+        }
         if (bad) {
             atomicMin(&dscal[DS_NAN], ip);     // _validate_coordinates, CellOperations.jl:6-21
         } else {
             place_particle<T, DIM>(g, x, p);
             if (!cell_of<T, DIM>(g, p, true, lin, rlin, &cfast)) { atomicMin(&dscal[DS_OOB], ip); bad = true; }
         }
-        int rank = -1;
+        if (bad) strec(&place_p[ip], T(0), T(0), T(0), (typename TG::type)0xffffffffu);
         if (!bad) {
-            rank = atomicAdd(&cell_count[lin], 1) | ((cfast & 1) << 30);
-            lin_own = lin; rank_own = rank & 0x3fffffff;
+            atomicAdd(&cell_count[lin], 1);
             if (ip < n_own) cell_nact[lin] = 1;   // flags: plain stores, every writer stores the same value
             ref_real[rlin] = 1;
-            strec(&place_p[ip], p[0], p[1], p[2], (typename TG::type)(unsigned)lin);
+            strec(&place_p[ip], p[0], p[1], p[2], (typename TG::type)((unsigned)lin | ((unsigned)(cfast & 1) << 30)));
             // replicate_particle! (Box.jl:556-566): images x + aligned_cell*idx, idx in {-1,0,1}^N \ {0}, kept iff inside the
             // computing box [cb_min, cb_max).  Orthorhombic cells: the shift of image index (i1,i2,i3) is (i1*L1, i2*L2, i3*L3)
             // exactly, so which indices can land inside the computing box is decided per dimension.
@@ -195,7 +204,6 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
                 okmask &= ~(1u << CENTER);
             }
         }
-        place_r[ip] = rank;
     }
     // The (particle, image) candidates of the WARP are dealt evenly to its lanes: a warp next to a cell face holds a
     // handful of candidates in a few lanes, and would otherwise run as many divergent iterations as its busiest lane.
@@ -214,7 +222,6 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
         const int k_th = w - __shfl_sync(0xffffffffu, excl, s);
         const unsigned m = __shfl_sync(0xffffffffu, okmask, s);
         const int ips = __shfl_sync(0xffffffffu, ip, s);
-        const int lin_s = __shfl_sync(0xffffffffu, lin_own, s), rank_s = __shfl_sync(0xffffffffu, rank_own, s);
         const T px = shfl_t(p[0], s), py = shfl_t(p[1], s), pz = shfl_t(p[2], s);
         bool in = (w < total);
         T q[3] = {T(0), T(0), T(0)};
@@ -236,12 +243,11 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
         if (lane == 0) gbase = atomicAdd(nghost, __popc(mv));
         gbase = __shfl_sync(0xffffffffu, gbase, 0);
         if (in) {
-            const int rank = atomicAdd(&cell_count[lq], 1) | ((qfast & 1) << 30);
+            atomicAdd(&cell_count[lq], 1);
             const int gslot = gbase + __popc(mv & ((1u << lane) - 1u));
             if (gslot < ghost_cap) {
-                strec(&ghost_q[gslot], q[0], q[1], q[2], (typename TG::type)(unsigned)lq);
-                ghost_i[gslot] = make_int4(rank, ips, rq, lin_s);
-                ghost_r[gslot] = rank_s;
+                strec(&ghost_q[gslot], q[0], q[1], q[2], (typename TG::type)((unsigned)lq | ((unsigned)(qfast & 1) << 30)));
+                ghost_i[gslot] = make_int2(ips, rq);
             }
         }
     }
@@ -249,52 +255,52 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
 
 // Placement, two kernels, so that the only SCATTERED traffic is one 4-byte store per record (scattered 16-byte record
 // stores are partial-sector writes: beyond the L2 capacity every one of them costs a DRAM read-modify-write):
-//   k_order  (particle / image order, coalesced reads): slot = first record of the cell + cached rank;
-//            order[slot] = id | parity << 30 (id < n: particle, else image n + g); slot_of[particle] = slot; an image's tag
-//            words are finished here (HOME flag of its reference cell, slot of its original) and left in ghost_i.
+//   k_order  (particle / image order, coalesced reads): slot = atomic cursor of the cell (cell_start[c + 1], pre-loaded
+//            with the cell's first record by k_row_starts: once every record is placed it holds the cell's END = the
+//            start of cell c + 1); order[slot] = id | parity << 30 (id < n: particle, else image n + g);
+//            slot_of[particle] = slot; flags the cells that hold an image able to act as particle i.
 //   k_gather (record order, coalesced writes): the record's position is gathered through order[] and the cell-sorted
 //            records are written -- and, when the Newton's-third-law force sweep wants it (rec_n3 != nullptr,
 //            clm_sweep_n3.cuh), their slot-tagged twin: 4th word = slot of the particle's REAL record (an image points at
-//            its original; by_index: the particle index, triclinic cells) | GHOST | HOME | parity of the reference cell
-//            along the row << 29.
+//            its original: slot_of[particle]; by_index: the particle index, triclinic cells) | GHOST | HOME | parity of
+//            the reference cell along the row << 29.
+constexpr unsigned PLACE_BAD = 0xffffffffu, PLACE_LIN = 0x3fffffffu;
 template <class T>
 __global__ void __launch_bounds__(256)
-k_order(const RecT<T>* __restrict__ place_p, const int* __restrict__ place_r, int n, int n_own, const RecT<T>* __restrict__ ghost_q,
-        int4* __restrict__ ghost_i, const int* __restrict__ ghost_r, const int* __restrict__ nghost, int ghost_cap, const int* __restrict__ cell_start,
-        int* __restrict__ cell_nact, const int* __restrict__ ref_real, int* __restrict__ order, int* __restrict__ slot_of, int rec_cap, int by_index) {
+k_order(const RecT<T>* __restrict__ place_p, int n, int n_own, const RecT<T>* __restrict__ ghost_q, const int2* __restrict__ ghost_i,
+        const int* __restrict__ nghost, int ghost_cap, int* __restrict__ cell_cursor, int* __restrict__ cell_nact, const int* __restrict__ ref_real,
+        int* __restrict__ order, int* __restrict__ slot_of, int rec_cap) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    constexpr int RANK = 0x3fffffff;
     if (t < n) {
-        const int r = place_r[t];
-        if (r < 0) return;
-        const int slot = cell_start[(int)place_p[t].tag] + (r & RANK);
+        const unsigned w = (unsigned)place_p[t].tag;
+        if (w == PLACE_BAD) return;
+        const int slot = atomicAdd(&cell_cursor[w & PLACE_LIN], 1);
         slot_of[t] = slot;
-        if (slot < rec_cap) order[slot] = t | (r & 0x40000000);
+        if (slot < rec_cap) order[slot] = t | (int)(w & 0x40000000u);
     } else {
         const int gidx = t - n;
         if (gidx >= min(*nghost, ghost_cap)) return;
-        const int4 e = ghost_i[gidx];
-        const int lq = (int)ghost_q[gidx].tag, ips = e.y;
-        const int slot = cell_start[lq] + (e.x & RANK);
-        const bool home = ref_real[e.z] != 0, foreign = ips >= n_own;
-        if (home && !foreign) cell_nact[lq] = 1;
-        const int rslot = cell_start[e.w] + ghost_r[gidx];   // slot of the original
-        // .x: flag bits of the record's tag (GHOST is implied), .y: particle, .z: 4th word of the slot-tagged twin
-        ghost_i[gidx] = make_int4((home ? 2 : 0) | (foreign ? 1 : 0), ips,
-                                  (int)((unsigned)(by_index ? ips : rslot) | 0x80000000u | (home ? 0x40000000u : 0u) | ((((unsigned)e.x >> 30) & 1u) << 29)), 0);
-        if (slot < rec_cap) order[slot] = t | (e.x & 0x40000000);
+        const unsigned w = (unsigned)ghost_q[gidx].tag;
+        const int2 e = ghost_i[gidx];
+        const int lq = (int)(w & PLACE_LIN);
+        const int slot = atomicAdd(&cell_cursor[lq], 1);
+        if (ref_real[e.y] != 0 && e.x < n_own) cell_nact[lq] = 1;
+        if (slot < rec_cap) order[slot] = t | (int)(w & 0x40000000u);
     }
 }
 template <class T>
 __global__ void __launch_bounds__(256)
-k_gather(const RecT<T>* __restrict__ place_p, int n, int n_own, const RecT<T>* __restrict__ ghost_q, const int4* __restrict__ ghost_i,
-         const int* __restrict__ order, const int* __restrict__ ntot, RecT<T>* __restrict__ rec, RecT<T>* __restrict__ rec_n3, int rec_cap, int by_index) {
+k_gather(const RecT<T>* __restrict__ place_p, int n, int n_own, const RecT<T>* __restrict__ ghost_q, const int2* __restrict__ ghost_i,
+         const int* __restrict__ ref_real, const int* __restrict__ slot_of, const int* __restrict__ order, const int* __restrict__ ntot,
+         RecT<T>* __restrict__ rec, RecT<T>* __restrict__ rec_n3, int rec_cap, int by_index, T* __restrict__ facc) {
     typedef TagT<T> TG;
     typedef typename TG::type tag_t;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     // an overflowed build (more records than the capacity estimate) is repeated by the host: its order[] has holes (the
     // images beyond the capacity were dropped), so nothing is gathered
     if (*ntot > rec_cap || k >= *ntot) return;
+    // the force accumulator row of this slot starts the next Newton's-third-law sweep at zero (coalesced, in passing)
+    if (facc) strec(reinterpret_cast<RecT<T>*>(facc) + k, T(0), T(0), T(0), (tag_t)0);
     const int o = order[k];
     const int id = o & 0x3fffffff;
     const unsigned par = ((unsigned)o >> 30) & 1u;
@@ -304,15 +310,18 @@ k_gather(const RecT<T>* __restrict__ place_p, int n, int n_own, const RecT<T>* _
         if (rec_n3) strec(&rec_n3[k], P.x, P.y, P.z, (tag_t)((unsigned)(by_index ? id : k) | 0x40000000u | (par << 29)));
     } else {
         const RecT<T> Q = ldrec(ghost_q + (id - n));
-        const int4 e = ghost_i[id - n];
-        strec(&rec[k], Q.x, Q.y, Q.z, (tag_t)e.y | TG::GHOST | ((e.x & 1) ? TG::FOREIGN : (tag_t)0) | ((e.x & 2) ? TG::HOME : (tag_t)0));
-        if (rec_n3) strec(&rec_n3[k], Q.x, Q.y, Q.z, (tag_t)(unsigned)e.z);
+        const int2 e = ghost_i[id - n];
+        const bool home = ref_real[e.y] != 0, foreign = e.x >= n_own;
+        strec(&rec[k], Q.x, Q.y, Q.z, (tag_t)e.x | TG::GHOST | (foreign ? TG::FOREIGN : (tag_t)0) | (home ? TG::HOME : (tag_t)0));
+        if (rec_n3) strec(&rec_n3[k], Q.x, Q.y, Q.z, (tag_t)((unsigned)(by_index ? e.x : slot_of[e.x]) | 0x80000000u | (home ? 0x40000000u : 0u) | (par << 29)));
     }
 }
 
 // ---- row starts ------------------------------------------------------------------------------------------
-// One warp per row of device cells: cell_start[row * px + x] = first record of cell x, entry nx = end of the row.  The
-// row's base comes from one atomicAdd on the record counter.
+// One warp per row of device cells.  cs = cell_start + 1 is the cursor array of k_order: the cursor of cell x of a row is
+// cs[row * px + x], pre-loaded with the cell's first record; once every record is placed it holds the cell's END, i.e.
+// cell_start[row * px + x + 1] = start of cell x + 1, and cell_start[row * px] (never incremented) stays the start of
+// the row: no second counter array.  The row's base comes from one atomicAdd on the record counter.
 static __global__ void __launch_bounds__(256)
 k_row_starts(const int* __restrict__ cell_count, int* __restrict__ cell_start, int nx, int nrows, int* __restrict__ ntot) {
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -327,16 +336,16 @@ k_row_starts(const int* __restrict__ cell_count, int* __restrict__ cell_start, i
     int base = 0;
     if (lane == 0) base = (total > 0) ? atomicAdd(ntot, total) : 0;
     base = __shfl_sync(0xffffffffu, base, 0);
+    if (lane == 0) cs[0] = base;
     for (int c0 = 0; c0 < nx; c0 += 32) {
         const int c = c0 + lane;
         const int v = (c < nx) ? cnt[c] : 0;
         int inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        if (c < nx) cs[c] = base + inc - v;
+        if (c < nx) cs[c + 1] = base + inc - v;    // cursor of cell c = its first record
         base += __shfl_sync(0xffffffffu, inc, 31);
     }
-    if (lane == 0) cs[nx] = base;
 }
 
 // ---- tiles ------------------------------------------------------------------------------------------------

@@ -99,6 +99,10 @@ template <class T> struct GeomT {
     int dim;
     int cell_type;  // clm_cell_type
     int rotated;    // 1 iff rotation != identity (triclinic)
+    // non-periodic systems that REUSE the box of the previous build (_limits_fit_in_box, src/internals/ParticleSystem.jl:165-174):
+    // the coordinate limits that box was made from; a particle outside them flags DS_NOFIT and the build is redone with new limits
+    int np_check;
+    T np_lo[3], np_hi[3];
 };
 
 struct Tile {       // 16 bytes

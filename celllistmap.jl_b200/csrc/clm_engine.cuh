@@ -32,6 +32,12 @@ struct EngineBase {
     virtual int set_positions_async(int set, const void* xyz, int64_t n) = 0;
     virtual int set_foreign(int set, const void* xyz, int64_t n, int on_device) = 0;
     virtual int cell_coords(const void* xyz, int64_t n, int on_device, int axis, int32_t* out) = 0;
+    virtual int comm_init(const void* id, int rank, int world) = 0;
+    virtual int comm_destroy() = 0;
+    virtual int slab_range(int32_t* lo, int32_t* hi) = 0;
+    virtual int slab_update(const void* xyz, int64_t n, int on_device) = 0;
+    virtual int comm_allreduce_sum(void* buf, int64_t count, int kind, int on_device) = 0;
+    virtual int slab_info(int64_t* n_owned, int64_t* n_foreign, int32_t* rank, int32_t* world) = 0;
     virtual int select_layers(const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b, int64_t capacity, int32_t* counts, int32_t* idx_a, int32_t* idx_b) = 0;
     virtual int build() = 0;
     virtual int map_lj(const void* p, int flags, void* e, void* f) = 0;
@@ -81,8 +87,8 @@ template <class T> struct DevSet {
     // placement pass), the image list, and the slot of every particle's real record (force gather of the N3 sweep)
     DBuf<RecT<T>> place_p, ghost_q;
     DBuf<RecT<T>> rec_n3;    // slot-tagged twin of rec for the Newton's-third-law force sweep (k_place), written on request
-    DBuf<int> place_r, slot_of, ghost_r, order;
-    DBuf<int4> ghost_i;
+    DBuf<int> slot_of, order;
+    DBuf<int2> ghost_i;
     DBuf<T> pos_alt;         // pipelined frames: the buffer the NEXT frame's coordinates are copied into while this one is binned
     int64_t n = 0;
     DBuf<T> fpos;            // foreign particles of a slab-decomposed system (owned by other ranks), AoS
@@ -106,6 +112,10 @@ template <class T> struct Engine : EngineBase {
     bool box_set = false, nonperiodic = false, two_sets = false, dirty = true;
     T np_cutoff = 0;
     int np_lcell = 1;
+    // non-periodic: the limits the current box was made from; the next build reuses the box while every particle stays inside
+    // them (checked on the device, no host round trip) -- the reference's _limits_fit_in_box
+    bool np_have_limits = false, np_force_limits = false;
+    T np_lo[3] = {T(0), T(0), T(0)}, np_hi[3] = {T(0), T(0), T(0)};
     DevSet<T> sets[2];
     DBuf<int> dscal;
     DBuf<Tile> tiles;
@@ -131,6 +141,7 @@ template <class T> struct Engine : EngineBase {
     // (faster, but a pair that crosses the periodic boundary is evaluated from two different image pairs: 5.6e-5 in
     // Float32 on the 1M-particle C2 system), -1 = by precision: Float32 -> 1, Float64 -> 0 (full shell: 1e-13, 10 % faster)
     int opt_n3 = -1;
+    bool facc_clean = false;                 // the accumulator rows are zero (set by the build, cleared by a sweep)
     bool want_n3 = false, have_n3 = false;   // slot-tagged records requested / present in the current cell list
     DBuf<T> d_facc;                       // record-ordered force accumulator rows (4 x T per record slot), all zero between maps
 
@@ -151,6 +162,14 @@ template <class T> struct Engine : EngineBase {
     int set_foreign(int set, const void* xyz, int64_t n, int on_device) override;
     int cell_coords(const void* xyz, int64_t n, int on_device, int axis, int32_t* out) override;
     int select_layers(const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b, int64_t capacity, int32_t* counts, int32_t* idx_a, int32_t* idx_b) override;
+    // slab decomposition over NCCL (clm_comm.cu)
+    void* comm_state = nullptr;
+    int comm_init(const void* id, int rank, int world) override;
+    int comm_destroy() override;
+    int slab_range(int32_t* lo, int32_t* hi) override;
+    int slab_update(const void* xyz, int64_t n, int on_device) override;
+    int comm_allreduce_sum(void* buf, int64_t count, int kind, int on_device) override;
+    int slab_info(int64_t* n_owned, int64_t* n_foreign, int32_t* rank, int32_t* world) override;
     int build() override;
     int build_enqueue();
     int build_validate();
@@ -245,9 +264,13 @@ template <class T> struct Engine : EngineBase {
         int64_t grid = (int64_t)n_sm * bps;
         grid = std::max<int64_t>(1, std::min<int64_t>(grid, (tiles_upper + (SWEEP_THREADS / 32) - 1) / (SWEEP_THREADS / 32)));
         DevSet<T>& S = sets[0];
-        const size_t old_cap = d_facc.cap;
-        CLM_CK(d_facc.ensure(std::max<size_t>(S.rec.cap, (size_t)S.n) * 4));
-        if (d_facc.cap != old_cap) CLM_CK(cudaMemsetAsync(d_facc.p, 0, d_facc.cap * sizeof(T), stream));
+        const int nrows_cap = (int)std::min<size_t>(S.rec.cap, 0x7fffffff);
+        if (!facc_clean) {   // a second map on the same cell list: the rows of the previous sweep are cleared by a coalesced fill
+            k_zero_rows<T><<<n_sm * 4, 256, 0, stream>>>(d_facc.p, dscal.p, nrows_cap);
+            CLM_CK(cudaGetLastError());
+            stats.launches += 1;
+        }
+        facc_clean = false;
         SweepArgs<T> a = make_args();
         a.rec_j = S.rec_n3.p;
         if (profile_sweep) CLM_CK(cudaEventRecord(ev2, stream));
@@ -256,12 +279,7 @@ template <class T> struct Engine : EngineBase {
         if (profile_sweep) CLM_CK(cudaEventRecord(ev3, stream));
         k_force_finish<T><<<(int)((S.n + 255) / 256), 256, 0, stream>>>((MODE == MODE_TRI) ? nullptr : S.slot_of.p, d_facc.p, dscal.p, (int)std::min<size_t>(S.rec.cap, 0x7fffffff), (int)S.n, out, dim, scale, accumulate, geom.rotated, geom);
         CLM_CK(cudaGetLastError());
-        {   // rows in particle order (triclinic): n rows; record order: the records of the current list
-            const int nrows_cap = (int)std::min<size_t>((MODE == MODE_TRI) ? std::max<size_t>(S.rec.cap, (size_t)S.n) : S.rec.cap, 0x7fffffff);
-            k_zero_rows<T><<<n_sm * 4, 256, 0, stream>>>(d_facc.p, (MODE == MODE_TRI) ? nullptr : dscal.p, (MODE == MODE_TRI) ? (int)S.n : nrows_cap);
-            CLM_CK(cudaGetLastError());
-        }
-        stats.launches += 3;
+        stats.launches += 2;
         last_grid = (int)grid;
         return CLM_OK;
     }
@@ -317,5 +335,7 @@ template <class T> struct Engine : EngineBase {
         return CLM_OK;
     }
 };
+
+int comm_unique_id(void* out, std::string& err);
 
 }  // namespace clm

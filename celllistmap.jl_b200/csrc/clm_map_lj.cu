@@ -21,15 +21,14 @@ template <class T> int Engine<T>::map_lj(const void* p, int flags, void* e, void
         if (int rc = forces_begin(f, flags, fo)) return rc;
         const int mode = sweep_mode();
         int rc;
-        if (norm) {
-            N3LJ<T, true, true> fn;
+        // energy_out == NULL: the pair loop drops the energy arithmetic (one FADD of ~23 instructions per pair step)
+        auto run = [&](auto fn) {
             fn.set(c[0], c[1]);
-            rc = (mode == MODE_TRI) ? launch_n3<MODE_TRI>(fn, fo.forces, fo.accumulate, fn.fscale) : launch_n3<MODE_HALF>(fn, fo.forces, fo.accumulate, fn.fscale);
-        } else {
-            N3LJ<T, false, true> fn;
-            fn.set(c[0], c[1]);
-            rc = (mode == MODE_TRI) ? launch_n3<MODE_TRI>(fn, fo.forces, fo.accumulate, T(1)) : launch_n3<MODE_HALF>(fn, fo.forces, fo.accumulate, T(1));
-        }
+            const T fsc = norm ? fn.fscale : T(1);
+            return (mode == MODE_TRI) ? launch_n3<MODE_TRI>(fn, fo.forces, fo.accumulate, fsc) : launch_n3<MODE_HALF>(fn, fo.forces, fo.accumulate, fsc);
+        };
+        if (norm) rc = e ? run(N3LJ<T, true, true>()) : run(N3LJ<T, true, false>());
+        else rc = e ? run(N3LJ<T, false, true>()) : run(N3LJ<T, false, false>());
         if (rc) return rc;
         scale = 1.0;
     } else if (f) {

@@ -447,7 +447,7 @@ template <> struct Row4<double> { typedef double4 type; };
 template <class T>
 __global__ void __launch_bounds__(256) k_zero_rows(T* __restrict__ facc, const int* __restrict__ dscal, int rec_cap) {
     typedef typename Row4<T>::type row_t;
-    const int ntot = dscal ? min(dscal[DS_NTOT], rec_cap) : rec_cap;   // dscal == nullptr: rec_cap rows
+    const int ntot = min(dscal[DS_NTOT], rec_cap);
     row_t z; z.x = T(0); z.y = T(0); z.z = T(0); z.w = T(0);
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < ntot; k += gridDim.x * blockDim.x) reinterpret_cast<row_t*>(facc)[k] = z;
 }
@@ -461,7 +461,7 @@ k_force_finish(const int* __restrict__ slot_of, T* __restrict__ facc, const int*
     if (idx >= n) return;
     const int k = slot_of ? slot_of[idx] : idx;
     if (k >= rec_cap) return;
-    const row_t v = *(reinterpret_cast<const row_t*>(facc) + k);   // the rows are zeroed afterwards by one coalesced fill (k_zero_rows)
+    const row_t v = *(reinterpret_cast<const row_t*>(facc) + k);   // the rows are zeroed by the next build (k_gather) or by k_zero_rows
     T fx = v.x * scale, fy = v.y * scale, fz = v.z * scale;
     if (rotated) {
         const T p = g.inv_rot[0] * fx + g.inv_rot[1] * fy + g.inv_rot[2] * fz;

@@ -179,15 +179,19 @@ end
 function pairwise!(f::CoulombEnergy, sys::ParticleSystem{N,T}; show_progress=false, reset=true) where {N,T}
     _sync!(sys)
     e = Ref(reset ? zero(T) : T(sys.output)); k = Ref(T(f.k))
-    wy = isnothing(f.weights_y) ? C_NULL : pointer(f.weights_y)
-    _check(sys.handle, ccall((:clm_map_coulomb, libclm), Cint, (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Ref{T}, Cint, Ref{T}, Ptr{Cvoid}), sys.handle, f.weights, wy, k, _flags(reset), e, C_NULL))
+    GC.@preserve f begin   # pointer(f.weights_y) is only valid while the array is rooted
+        wy = isnothing(f.weights_y) ? Ptr{T}(C_NULL) : pointer(f.weights_y)
+        _check(sys.handle, ccall((:clm_map_coulomb, libclm), Cint, (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Ref{T}, Cint, Ref{T}, Ptr{Cvoid}), sys.handle, f.weights, wy, k, _flags(reset), e, C_NULL))
+    end
     return sys.output = e[]
 end
 function pairwise!(f::CoulombEnergyAndForces, sys::ParticleSystem{N,T}; show_progress=false, reset=true) where {N,T}
     _sync!(sys)
     e = Ref(reset ? zero(T) : T(sys.output.energy)); k = Ref(T(f.k))
-    wy = isnothing(f.weights_y) ? C_NULL : pointer(f.weights_y)
-    _check(sys.handle, ccall((:clm_map_coulomb, libclm), Cint, (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Ref{T}, Cint, Ref{T}, Ptr{SVector{N,T}}), sys.handle, f.weights, wy, k, _flags(reset), e, sys.output.forces))
+    GC.@preserve f begin
+        wy = isnothing(f.weights_y) ? Ptr{T}(C_NULL) : pointer(f.weights_y)
+        _check(sys.handle, ccall((:clm_map_coulomb, libclm), Cint, (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Ref{T}, Cint, Ref{T}, Ptr{SVector{N,T}}), sys.handle, f.weights, wy, k, _flags(reset), e, sys.output.forces))
+    end
     sys.output.energy = e[]
     return sys.output
 end
@@ -199,9 +203,11 @@ end
 function pairwise!(f::PairwiseVelocities, sys::ParticleSystem{N,T}; show_progress=false, reset=true) where {N,T}
     _sync!(sys)                              # output = (counts::Vector{Int}, sums::Vector{T}); velocities::Vector{SVector{N,T}}
     counts, sums = sys.output
-    vy = isnothing(f.velocities_y) ? C_NULL : pointer(f.velocities_y)
-    _check(sys.handle, ccall((:clm_map_pairvel, libclm), Cint, (Ptr{Cvoid}, Ptr{SVector{N,T}}, Ptr{SVector{N,T}}, Ptr{T}, Cint, Cint, Ptr{Int64}, Ptr{T}),
-                             sys.handle, f.velocities, vy, f.rbins, length(f.rbins) - 1, _flags(reset), counts, sums))
+    GC.@preserve f begin
+        vy = isnothing(f.velocities_y) ? Ptr{SVector{N,T}}(C_NULL) : pointer(f.velocities_y)
+        _check(sys.handle, ccall((:clm_map_pairvel, libclm), Cint, (Ptr{Cvoid}, Ptr{SVector{N,T}}, Ptr{SVector{N,T}}, Ptr{T}, Cint, Cint, Ptr{Int64}, Ptr{T}),
+                                 sys.handle, f.velocities, vy, f.rbins, length(f.rbins) - 1, _flags(reset), counts, sums))
+    end
     return sys.output
 end
 function pairwise!(::MinimumDistanceMap, sys::ParticleSystem{N,T}; show_progress=false, reset=true) where {N,T}

@@ -151,6 +151,26 @@ CLM_API int clm_cell_coords(clm_handle* h, const void* aos_xyz, int64_t n, int o
 CLM_API int clm_select_layers(clm_handle* h, const void* aos_xyz, int64_t n, int axis, const int32_t ranges[4], int merge,
                               void* out_a, void* out_b, int64_t capacity, int32_t* counts_dev, int32_t* idx_a, int32_t* idx_b);
 
+/* ---- the same decomposition driven by the library itself over NCCL (csrc/clm_comm.cu) ----------------------------------------
+ * For hosts without their own communication layer (a Julia or C driver with one process / task per GPU): the slab plan, the halo
+ * exchange (ncclSend / ncclRecv on the handle's stream) and the reduction of scalar / histogram results (ncclAllReduce) sit
+ * behind these entry points; libnccl.so.2 is opened at run time (CLM_ERR_COMM when it cannot be).  Orthorhombic self-set
+ * systems.  Sequence: rank 0 calls clm_comm_unique_id and hands the 128 bytes to every rank by its own means; every rank:
+ * clm_create (its device) -> clm_set_box (the GLOBAL box) -> clm_comm_init -> [clm_slab_range: which reference-cell layers
+ * along dimension 1 it owns, to partition a global array with clm_cell_coords] -> per step: clm_slab_update(owned particles)
+ * -> any clm_map_* (per-particle outputs cover the owned particles; a rank's neighbour list holds the pairs it evaluated,
+ * partner indices > n_owned are halo particles) -> clm_comm_allreduce_sum on the scalar / histogram results.
+ * clm_slab_update costs one host synchronisation (the received counts); when a halo message outgrows its fixed capacity,
+ * EVERY rank learns it from an all-reduced maximum, grows its buffers and repeats the exchange (no rank-local error path). */
+CLM_API int clm_comm_unique_id(void* id_out_128_bytes);
+CLM_API int clm_comm_init(clm_handle* h, const void* id_128_bytes, int rank, int world);
+CLM_API int clm_comm_destroy(clm_handle* h);
+CLM_API int clm_slab_range(clm_handle* h, int32_t* layer_lo, int32_t* layer_hi);     /* this rank owns layers [lo, hi) */
+CLM_API int clm_slab_update(clm_handle* h, const void* aos_xyz_owned, int64_t n, int on_device);
+/* in-place sum over the ranks; kind 0 = the handle's real type, 1 = int64, 2 = double */
+CLM_API int clm_comm_allreduce_sum(clm_handle* h, void* buf, int64_t count, int kind, int on_device);
+CLM_API int clm_slab_info(clm_handle* h, int64_t* n_owned, int64_t* n_foreign, int32_t* rank, int32_t* world);
+
 /* ---- UpdateCellList!  src/internals/CellLists.jl:727-927 ---------------------------------- */
 /* validates coordinates (NaN -> CLM_ERR_INVALID_COORDINATES with the 1-based index in the message),
  * wraps, bins real + image particles, counting-sorts them by cell.  No-op if nothing changed. */

@@ -609,3 +609,50 @@ def test_pipelined_frames_equal_synchronous(clm, dtype):
         assert abs(float(es[k][0]) - float(we[0])) <= tol * abs(float(we[0])), k
         assert np.abs(fs[k].numpy() - wf).max() <= tol * np.abs(wf).max(), k
     h.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# non-periodic systems reuse the box of the previous build while the new coordinates stay inside the limits it was made
+# from (_limits_fit_in_box, src/internals/ParticleSystem.jl:165-174; checked on the device, no host round trip) and get
+# a new box when they do not: the neighbour list is the oracle's either way
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("two_sets", [False, True])
+def test_nonperiodic_box_reuse_and_regrow(clm, oracle_mod, dtype, two_sets):
+    rng = np.random.default_rng(77)
+    x0 = rng.random((3000, 3)).astype(dtype)
+    y0 = rng.random((2000, 3)).astype(dtype) if two_sets else None
+    nb = clm.InPlaceNeighborList(x=x0, y=y0, cutoff=0.08)
+    key = lambda lst: sorted(zip(lst["i"].tolist(), lst["j"].tolist(), lst["d"].tolist()))
+
+    def check(x, y):
+        lst = nb.neighborlist()
+        i, j, d = oracle_mod.Oracle(x, 0.08, y=y, dtype=dtype).neighborlist()
+        if two_sets:
+            want = sorted(zip(i.tolist(), j.tolist(), d.tolist()))
+            got = key(lst)
+        else:
+            want = sorted(zip(np.minimum(i, j).tolist(), np.maximum(i, j).tolist(), d.tolist()))
+            got = sorted(zip(np.minimum(lst["i"], lst["j"]).tolist(), np.maximum(lst["i"], lst["j"]).tolist(), lst["d"].tolist()))
+        assert got == want
+
+    check(x0, y0)
+    box0 = nb.sys._h.get_box()
+    # (a) the coordinates contract towards the centre: they fit, the box is kept
+    x1 = (0.5 + 0.8 * (x0 - 0.5)).astype(dtype)
+    y1 = None if y0 is None else (0.5 + 0.8 * (y0 - 0.5)).astype(dtype)
+    clm.update(nb, xpositions=x1, ypositions=y1)
+    check(x1, y1)
+    box1 = nb.sys._h.get_box()
+    assert list(box1.nc) == list(box0.nc) and list(box1.origin) == list(box0.origin)
+    # (b) they expand beyond the old limits: new limits, new box (one retry inside the call)
+    x2 = (0.5 + 1.7 * (x0 - 0.5)).astype(dtype)
+    y2 = None if y0 is None else (0.5 + 1.7 * (y0 - 0.5)).astype(dtype)
+    clm.update(nb, xpositions=x2, ypositions=y2)
+    check(x2, y2)
+    box2 = nb.sys._h.get_box()
+    assert list(box2.origin) != list(box0.origin)
+    # (c) a single stray particle is enough
+    x3 = x2.copy()
+    x3[17] += dtype(5.0)
+    clm.update(nb, xpositions=x3, ypositions=y2)
+    check(x3, y2)

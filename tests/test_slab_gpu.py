@@ -198,3 +198,72 @@ def test_slab_side_arrays(oracle_mod, world, fast, backend):
         assert np.abs(np.array(r[8]) - ws).max() <= 1e-10 * np.abs(ws).max()
     assert np.abs(f - wf).max() <= 1e-9 * np.abs(wf).max()
     assert np.abs(pp - want_pp).max() <= 1e-10 * want_pp.max()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the same decomposition driven by the library itself over NCCL (clm_comm_init / clm_slab_update / clm_comm_allreduce_sum):
+# what a Julia or C host without its own communication layer calls.  One GPU per rank; world = 1 runs on any box.
+def _capi_worker(rank, world, uid, q):
+    import torch
+    torch.cuda.set_device(rank)
+    import celllistmap_b200 as clm
+    w = W.c2_argon(24, np.float32)
+    h = clm.Handle(3, np.float32, device=rank)
+    h.set_box(clm._capi.ORTHORHOMBIC, w["unitcell"], w["cutoff"], 1)
+    h.comm_init(uid, rank, world)
+    lo, hi = h.slab_range()
+    c = h.cell_coords(w["x"], 0)
+    c = c.cpu().numpy() if hasattr(c, "cpu") else np.asarray(c)
+    top = hi + (1 if rank == world - 1 else 0)      # the last rank also owns the rounding layer at the top
+    mine = np.nonzero((c >= lo) & (c < top))[0]
+    for step in range(2):                           # second step: warm halo capacity
+        h.slab_update(w["x"][mine])
+        e, f = np.zeros(1, np.float32), np.zeros((len(mine), 3), np.float32)
+        h.map_lj(w["c6"], w["c12"], e, f)
+        sd, sd2, npairs = np.zeros(1, np.float32), np.zeros(1, np.float32), np.zeros(1, np.int64)
+        h.map_sum_d_d2(sd, sd2, npairs)
+        e64 = e.astype(np.float64)
+        h.comm_allreduce_sum(e64)
+        h.comm_allreduce_sum(npairs)
+    n_own, n_for, r, wd = h.slab_info()
+    assert (r, wd, n_own) == (rank, world, len(mine))
+    q.put((rank, mine.tolist(), f.tolist(), float(e64[0]), int(npairs[0]), n_for))
+    h.comm_destroy()
+    h.close()
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_slab_through_the_c_abi_over_nccl(oracle_mod, world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("one GPU per rank (run with gpurun --gpus 2; output kept under profiles/)")
+    import celllistmap_b200 as clm
+    uid = clm._capi.comm_unique_id()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_capi_worker, args=(r, world, uid, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    w = W.c2_argon(24, np.float32)
+    o64 = oracle_mod.Oracle(w["x"].astype(np.float64), w["cutoff"], unitcell=w["unitcell"].astype(np.float64))
+    we, wf = o64.lj(w["c6"], w["c12"], forces=True)
+    wn = o64.sum_d_d2()[2]
+    f32 = oracle_mod.Oracle(w["x"], w["cutoff"], unitcell=w["unitcell"], dtype=np.float32).lj(w["c6"], w["c12"], forces=True)[1]
+    f = np.zeros_like(wf)
+    seen = np.zeros(len(wf), bool)
+    for r in res:
+        ids = np.array(r[1])
+        assert not seen[ids].any()
+        seen[ids] = True
+        f[ids] = np.array(r[2])
+        assert abs(r[3] - we) <= 1e-5 * abs(we)
+        assert r[4] == wn
+        assert (r[5] > 0) == (world > 1)
+    assert seen.all()
+    from parity_util import force_report
+    err_same, _, _ = force_report(f"C-ABI slab LJ {world} rank(s) f32", f, f32, wf)
+    assert err_same <= 1e-5

@@ -22,14 +22,14 @@ for dtype in [d for d, k in ((np.float32, "f32"), (np.float64, "f64")) if which 
     x_dev = torch.from_numpy(w["x"]).cuda()
     e_dev = torch.zeros(1, dtype=tdt, device="cuda")
     f_dev = torch.zeros((n, 3), dtype=tdt, device="cuda")
-    for n3 in (1, 0):
+    for n3 in (1, 0, 2):     # 2: the Newton's-third-law sweep without the energy (energy_out = NULL)
         h = clm.Handle(3, dtype)
-        h.set_option("n3", n3)
+        h.set_option("n3", min(n3, 1))
         h.set_box(clm._capi.ORTHORHOMBIC, w["unitcell"], w["cutoff"], 1)
         ts, bs, ms = [], [], []
         for it in range(12):
             h.set_positions(0, x_dev)
-            h.map_lj(w["c6"], w["c12"], e_dev, f_dev, reset=True, profile=True)
+            h.map_lj(w["c6"], w["c12"], None if n3 == 2 else e_dev, f_dev, reset=True, profile=True)
             st = h.stats()
             if it >= 4:
                 ts.append(st.sweep_ms); bs.append(st.build_ms); ms.append(st.map_ms)
