@@ -50,7 +50,8 @@ class Stats(C.Structure):
 
 
 class CustomInfo(C.Structure):
-    _fields_ = [("nscalar", C.c_int32), ("npart", C.c_int32), ("naux", C.c_int32), ("hist", C.c_int32)]
+    _fields_ = [("nscalar", C.c_int32), ("npart", C.c_int32), ("naux", C.c_int32), ("hist", C.c_int32),
+                ("scalar_min_mask", C.c_int32), ("scalar_max_mask", C.c_int32)]
 
 
 class ClmError(RuntimeError):

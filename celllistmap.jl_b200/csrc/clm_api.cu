@@ -48,7 +48,7 @@ template <class T> Engine<T>::~Engine() {
     if (copy_out) { cudaStreamSynchronize(copy_out); cudaStreamDestroy(copy_out); }
     for (cudaEvent_t e : {ev_h2d, ev_posfree, ev_done, ev_out[0], ev_out[1]}) if (e) cudaEventDestroy(e);
     d_forces_alt.release(); d_eout.release();
-    for (auto& s : sets) { s.pos.release(); s.pos_alt.release(); s.fpos.release(); s.rec.release(); s.rec_n3.release(); s.order.release(); s.place_p.release(); s.ghost_q.release(); s.slot_of.release(); s.ghost_i.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
+    for (auto& s : sets) { s.pos.release(); s.pos_alt.release(); s.fpos.release(); s.rec.release(); s.rec_n3.release(); s.slot_of.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
     dscal.release(); tiles.release(); d_res.release();
     d_hcount.release(); nl.release(); d_hsum.release(); d_rbins.release(); d_forces.release(); d_facc.release(); d_minmax.release(); d_minpart.release(); d_minres.release();
     custom_store_free(custom_store);
@@ -320,7 +320,7 @@ template <class T> int Engine<T>::build_enqueue() {
     ncells = (int64_t)nfast * nmid * nslow;
     nrows = ncells / nfast;
     const int64_t ncp = nrows * (nfast + 1);   // per-cell arrays have a row pitch of nfast + 1 (clm_build.cuh)
-    if (ncp + 2 > 0x3fffffff) return fail(CLM_ERR_UNSUPPORTED, "device cell grid too large");   // cell indices travel in 30 bits (clm_build.cuh)
+    if (ncp + 2 > 0x7fffffff) return fail(CLM_ERR_UNSUPPORTED, "device cell grid too large");
     // stencil rows: a row offset (dslow, dmid) is at least d_perp away; partners can only sit within
     // sqrt(cutoff^2 - d_perp^2) along the row (1e-4 relative slack covers coordinate rounding at cell borders)
     {
@@ -376,33 +376,32 @@ template <class T> int Engine<T>::build_enqueue() {
             const int64_t nall = S.n + S.n_foreign;
             const int nb = (int)((nall + 255) / 256);
             const int rec_cap = (int)std::min<size_t>(S.rec.cap, 0x7fffffff);
-            const int ghost_cap = (int)std::max<int64_t>((int64_t)rec_cap - nall, 0);   // more images than this overflow the record capacity too
             if (nall > 0) {
-                CLM_CK(S.place_p.ensure((size_t)nall));
-                CLM_CK(S.ghost_q.ensure((size_t)std::max(ghost_cap, 1)));
-                CLM_CK(S.ghost_i.ensure((size_t)std::max(ghost_cap, 1)));
                 CLM_CK(S.slot_of.ensure((size_t)nall));
-                // count pass: wrap, cells, images, per-cell histogram; everything the placement needs is cached
-                if (dim == 3) k_bin<T, 3><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, S.place_p.p, S.ghost_q.p, S.ghost_i.p, ghost_cap, dscal.p + DS_NGHOST + s, ds);
-                else k_bin<T, 2><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, S.place_p.p, S.ghost_q.p, S.ghost_i.p, ghost_cap, dscal.p + DS_NGHOST + s, ds);
+                if (dim == 3) k_bin<T, 3, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, nullptr, 0, ds);
+                else k_bin<T, 2, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, nullptr, 0, ds);
                 CLM_CK(cudaGetLastError());
                 stats.launches += 1;
             }
+            // per-row starts, written one slot up: the scatter pass uses cell_start[c + 1] as the cursor of cell c, which
+            // leaves the row's exclusive starts behind once every record is placed (no second counter array)
             k_row_starts<<<(int)((nrows * 32 + 255) / 256), 256, 0, stream>>>(S.cell_count, S.cell_start.p, nfast, (int)nrows, ds + DS_NTOT);
             CLM_CK(cudaGetLastError());
             stats.launches += 1;
             if (nall > 0) {
-                // placement: order[slot] = id (the only scattered store), then the records in slot order (coalesced)
-                const int64_t nthreads = nall + ghost_cap;
-                const int by_index = box.cell_type == CLM_TRICLINIC ? 1 : 0;
-                CLM_CK(S.order.ensure(S.rec.cap));
-                k_order<T><<<(int)((nthreads + 255) / 256), 256, 0, stream>>>(S.place_p.p, (int)nall, (int)S.n, S.ghost_q.p, S.ghost_i.p, dscal.p + DS_NGHOST + s, ghost_cap,
-                                                                             S.cell_start.p + 1, S.cell_nact, S.ref_real, S.order.p, S.slot_of.p, rec_cap);
+                if (dim == 3) k_bin<T, 3, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, S.slot_of.p, rec_cap, ds);
+                else k_bin<T, 2, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, S.slot_of.p, rec_cap, ds);
                 CLM_CK(cudaGetLastError());
-                k_gather<T><<<(int)(((int64_t)rec_cap + 255) / 256), 256, 0, stream>>>(S.place_p.p, (int)nall, (int)S.n, S.ghost_q.p, S.ghost_i.p, S.ref_real, S.slot_of.p, S.order.p, ds + DS_NTOT,
-                                                                                      S.rec.p, n3 ? S.rec_n3.p : nullptr, rec_cap, by_index, n3 ? d_facc.p : nullptr);
-                CLM_CK(cudaGetLastError());
-                stats.launches += 2;
+                stats.launches += 1;
+                if (n3) {
+                    // slot-tagged twin of the records + zeroed accumulator rows: one coalesced pass in record order
+                    const int by_index = box.cell_type == CLM_TRICLINIC ? 1 : 0;
+                    const int nbt = (int)(((int64_t)rec_cap + 255) / 256);
+                    if (dim == 3) k_twin<T, 3><<<nbt, 256, 0, stream>>>(geom, S.rec.p, S.slot_of.p, ds + DS_NTOT, rec_cap, S.rec_n3.p, d_facc.p, by_index);
+                    else k_twin<T, 2><<<nbt, 256, 0, stream>>>(geom, S.rec.p, S.slot_of.p, ds + DS_NTOT, rec_cap, S.rec_n3.p, d_facc.p, by_index);
+                    CLM_CK(cudaGetLastError());
+                    stats.launches += 1;
+                }
             }
         }
         tiles_upper = (int64_t)(sets[0].rec.cap / tile_i) + nrows + 1;

@@ -4,18 +4,20 @@
 //
 // The reference builds an array of heap-allocated per-cell vectors; here the list is ONE
 // counting sort into a cell-sorted packed record array:
-//   k_bin         : the only pass over the caller's coordinates: wrap + rotate each particle, enumerate its 3^N-1
-//                   lattice images, keep those inside the computing box, histogram real + image particles per cell
-//                   (global atomics; the value an atomic returns is the particle's rank inside its cell), cache
-//                   (position, cell, rank) per particle and append the images to a list
+//   k_bin<count>  : wrap + rotate each particle, enumerate its 3^N-1 lattice images, keep those inside
+//                   the computing box, histogram real+image particles per cell (global atomics)
 //   k_row_starts  : one warp per ROW of device cells: prefix of the row's counts; the row's base comes from one
 //                   atomicAdd on the record counter, so rows are contiguous but placed in arbitrary order -- the
 //                   sweep only ever reads record ranges inside one row.  Replaces a 3-kernel global scan.
-//   k_order       : record slot = first record of the cell + cached rank; order[slot] = particle / image id: the only
-//                   scattered store of the build (4 bytes per record)
-//   k_gather      : one thread per record slot: position gathered through order[], cell-sorted records written coalesced
+//   k_bin<scatter>: same traversal, records scattered to the per-cell atomic cursor; slot_of[particle] = its slot
 //   k_row_tiles   : one warp per row: the row's active record range cut into tiles, appended to the tile array with
 //                   one atomicAdd per row (tile order is irrelevant: tiles are dealt out by a work counter)
+//   k_twin        : (on request) the slot-tagged twin of the records for the Newton's-third-law force sweep, one
+//                   coalesced pass in record order
+// Round 2 also built the alternative the round-1 review asked for -- ONE wrapping pass that caches (position, cell) per
+// particle, then a placement without divisions (first scattered like the records, then as a 4-byte order[] scatter + a
+// coalesced gather) -- and measured it slower at every size: the wrap's instructions are not what
+// bounds the build, its random memory streams are, and the cached variant adds streams.
 // Every per-cell array is laid out with a row pitch of nx + 1 entries: cell_start[row * (nx + 1) + x] is the first
 // record of cell x of the row and entry nx is the end of the row.
 // All of it is HBM/latency bound integer + a few dozen flops per particle: no tensor cores.
@@ -132,26 +134,17 @@ __device__ __forceinline__ bool cell_of(const GeomT<T>& g, const T p[3], bool re
     return true;
 }
 
-// cell_nact[c] flags cells holding a record that can act as particle i of a pair: real particles, and images living
-// in a REFERENCE cell that holds a real particle (the reference sweeps exactly those cells, self.jl:56-57); ref_real[]
-// flags reference cells with a real particle.
+// Count pass (SCATTER = false): per-cell histogram of real + image particles.  Scatter pass: records to the
+// atomic per-cell cursor.  cell_nact[c] flags cells holding a record that can act as particle i of a
+// pair: real particles, and images living in a REFERENCE cell that holds a real particle (the reference sweeps
+// exactly those cells, self.jl:56-57); ref_real[] flags reference cells with a real particle.
 __device__ __forceinline__ float shfl_t(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ double shfl_t(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
-// Count pass of the counting sort, and the ONLY pass that touches the caller's coordinates: the wrapped position, the
-// device cell and the rank inside the cell (the value the histogram atomic returns) of every particle are cached
-// (place_p / place_r), and every image that lands inside the computing box is appended to a list (ghost_q / ghost_i)
-// with its cell and rank.  The placement (k_order, k_gather) then only adds the cell's first record to the rank: no
-// second wrap (six IEEE divisions per particle), no second round of atomics.
-//   place_p[ip] = (p, device cell | parity of the reference cell along the row << 30; 0xffffffff: invalid particle)
-//   ghost_q[g]  = (q, device cell | parity << 30)          ghost_i[g]  = (particle, reference cell)
-// The histogram atomics return nothing (RED): the slot inside the cell is handed out by k_order, a light kernel that can
-// afford to wait for its atomics.
-template <class T, int DIM>
+template <class T, int DIM, bool SCATTER>
 __global__ void __launch_bounds__(256)
-k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __restrict__ fpos, int n, int n_own, int* __restrict__ cell_count,
-      int* __restrict__ cell_nact, int* __restrict__ ref_real, RecT<T>* __restrict__ place_p,
-      RecT<T>* __restrict__ ghost_q, int2* __restrict__ ghost_i, int ghost_cap, int* __restrict__ nghost, int* __restrict__ dscal) {
+k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __restrict__ fpos, int n, int n_own, int* __restrict__ cell_cursor,
+      int* __restrict__ cell_nact, int* __restrict__ ref_real, RecT<T>* __restrict__ rec, int* __restrict__ slot_of, int rec_cap, int* __restrict__ dscal) {
     typedef TagT<T> TG;
     const int ip = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     constexpr int CENTER = (DIM == 3) ? 13 : 4;
@@ -164,24 +157,30 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
 #pragma unroll
         for (int k = 0; k < DIM; ++k) { x[k] = src[k]; bad |= (x[k] != x[k]); }
         int lin = 0, rlin = 0, cfast = 0;
-        if (g.np_check && !bad) {
+        if (!SCATTER && g.np_check && !bad) {
             bool fit = true;
 #pragma unroll
             for (int k = 0; k < DIM; ++k) fit = fit && (x[k] >= g.np_lo[k]) && (x[k] <= g.np_hi[k]);
             if (!fit) dscal[DS_NOFIT] = 1;     // the reused box does not hold this particle: the host recomputes the limits
         }
         if (bad) {
-            atomicMin(&dscal[DS_NAN], ip);     // _validate_coordinates, CellOperations.jl:6-21
+            if (!SCATTER) atomicMin(&dscal[DS_NAN], ip);     // _validate_coordinates, CellOperations.jl:6-21
         } else {
             place_particle<T, DIM>(g, x, p);
-            if (!cell_of<T, DIM>(g, p, true, lin, rlin, &cfast)) { atomicMin(&dscal[DS_OOB], ip); bad = true; }
+            if (!cell_of<T, DIM>(g, p, true, lin, rlin, &cfast)) { if (!SCATTER) atomicMin(&dscal[DS_OOB], ip); bad = true; }
         }
-        if (bad) strec(&place_p[ip], T(0), T(0), T(0), (typename TG::type)0xffffffffu);
         if (!bad) {
-            atomicAdd(&cell_count[lin], 1);
-            if (ip < n_own) cell_nact[lin] = 1;   // flags: plain stores, every writer stores the same value
-            ref_real[rlin] = 1;
-            strec(&place_p[ip], p[0], p[1], p[2], (typename TG::type)((unsigned)lin | ((unsigned)(cfast & 1) << 30)));
+            // cell_cursor: the per-cell histogram in the count pass; the per-cell write cursor (pre-loaded with the
+            // exclusive starts) in the scatter pass
+            const typename TG::type foreign = (ip >= n_own) ? TG::FOREIGN : (typename TG::type)0;
+            const int slot = atomicAdd(&cell_cursor[lin], 1);
+            if (!SCATTER) {
+                if (!foreign) cell_nact[lin] = 1;   // flags: plain stores, every writer stores the same value
+                ref_real[rlin] = 1;
+            } else if (slot < rec_cap) {
+                strec(&rec[slot], p[0], p[1], p[2], (typename TG::type)ip | TG::HOME | foreign);
+            }
+            if (SCATTER) slot_of[ip] = slot;     // slot of the particle's real record (force gather of the N3 sweep, k_twin)
             // replicate_particle! (Box.jl:556-566): images x + aligned_cell*idx, idx in {-1,0,1}^N \ {0}, kept iff inside the
             // computing box [cb_min, cb_max).  Orthorhombic cells: the shift of image index (i1,i2,i3) is (i1*L1, i2*L2, i3*L3)
             // exactly, so which indices can land inside the computing box is decided per dimension.
@@ -223,105 +222,34 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
         const unsigned m = __shfl_sync(0xffffffffu, okmask, s);
         const int ips = __shfl_sync(0xffffffffu, ip, s);
         const T px = shfl_t(p[0], s), py = shfl_t(p[1], s), pz = shfl_t(p[2], s);
-        bool in = (w < total);
+        if (w >= total) continue;
+        const int img = (int)__fns(m, 0u, k_th + 1);
+        const T ps[3] = {px, py, pz};
         T q[3] = {T(0), T(0), T(0)};
-        int lq = 0, rq = 0, qfast = 0;
-        if (in) {
-            const int img = (int)__fns(m, 0u, k_th + 1);
-            const T ps[3] = {px, py, pz};
+        bool in = true;
 #pragma unroll
-            for (int k = 0; k < DIM; ++k) {
-                q[k] = xadd(ps[k], g.shift[img][k]);
-                in = in && (g.cb_min[k] <= q[k]) && (q[k] < g.cb_max[k]);
-            }
-            if (in) in = cell_of<T, DIM>(g, q, false, lq, rq, &qfast);
+        for (int k = 0; k < DIM; ++k) {
+            q[k] = xadd(ps[k], g.shift[img][k]);
+            in = in && (g.cb_min[k] <= q[k]) && (q[k] < g.cb_max[k]);
         }
-        // append the images found by this warp step to the ghost list: one atomic per warp step
-        const unsigned mv = __ballot_sync(0xffffffffu, in);
-        if (mv == 0u) continue;
-        int gbase = 0;
-        if (lane == 0) gbase = atomicAdd(nghost, __popc(mv));
-        gbase = __shfl_sync(0xffffffffu, gbase, 0);
-        if (in) {
-            atomicAdd(&cell_count[lq], 1);
-            const int gslot = gbase + __popc(mv & ((1u << lane) - 1u));
-            if (gslot < ghost_cap) {
-                strec(&ghost_q[gslot], q[0], q[1], q[2], (typename TG::type)((unsigned)lq | ((unsigned)(qfast & 1) << 30)));
-                ghost_i[gslot] = make_int2(ips, rq);
-            }
+        if (!in) continue;
+        int lq, rq;
+        if (!cell_of<T, DIM>(g, q, false, lq, rq)) continue;
+        const typename TG::type foreign = (ips >= n_own) ? TG::FOREIGN : (typename TG::type)0;
+        const int qslot = atomicAdd(&cell_cursor[lq], 1);
+        if (SCATTER && qslot < rec_cap) {
+            const bool home = ref_real[rq] != 0;
+            if (home && !foreign) cell_nact[lq] = 1;
+            strec(&rec[qslot], q[0], q[1], q[2], (typename TG::type)ips | TG::GHOST | foreign | (home ? TG::HOME : (typename TG::type)0));
         }
-    }
-}
-
-// Placement, two kernels, so that the only SCATTERED traffic is one 4-byte store per record (scattered 16-byte record
-// stores are partial-sector writes: beyond the L2 capacity every one of them costs a DRAM read-modify-write):
-//   k_order  (particle / image order, coalesced reads): slot = atomic cursor of the cell (cell_start[c + 1], pre-loaded
-//            with the cell's first record by k_row_starts: once every record is placed it holds the cell's END = the
-//            start of cell c + 1); order[slot] = id | parity << 30 (id < n: particle, else image n + g);
-//            slot_of[particle] = slot; flags the cells that hold an image able to act as particle i.
-//   k_gather (record order, coalesced writes): the record's position is gathered through order[] and the cell-sorted
-//            records are written -- and, when the Newton's-third-law force sweep wants it (rec_n3 != nullptr,
-//            clm_sweep_n3.cuh), their slot-tagged twin: 4th word = slot of the particle's REAL record (an image points at
-//            its original: slot_of[particle]; by_index: the particle index, triclinic cells) | GHOST | HOME | parity of
-//            the reference cell along the row << 29.
-constexpr unsigned PLACE_BAD = 0xffffffffu, PLACE_LIN = 0x3fffffffu;
-template <class T>
-__global__ void __launch_bounds__(256)
-k_order(const RecT<T>* __restrict__ place_p, int n, int n_own, const RecT<T>* __restrict__ ghost_q, const int2* __restrict__ ghost_i,
-        const int* __restrict__ nghost, int ghost_cap, int* __restrict__ cell_cursor, int* __restrict__ cell_nact, const int* __restrict__ ref_real,
-        int* __restrict__ order, int* __restrict__ slot_of, int rec_cap) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n) {
-        const unsigned w = (unsigned)place_p[t].tag;
-        if (w == PLACE_BAD) return;
-        const int slot = atomicAdd(&cell_cursor[w & PLACE_LIN], 1);
-        slot_of[t] = slot;
-        if (slot < rec_cap) order[slot] = t | (int)(w & 0x40000000u);
-    } else {
-        const int gidx = t - n;
-        if (gidx >= min(*nghost, ghost_cap)) return;
-        const unsigned w = (unsigned)ghost_q[gidx].tag;
-        const int2 e = ghost_i[gidx];
-        const int lq = (int)(w & PLACE_LIN);
-        const int slot = atomicAdd(&cell_cursor[lq], 1);
-        if (ref_real[e.y] != 0 && e.x < n_own) cell_nact[lq] = 1;
-        if (slot < rec_cap) order[slot] = t | (int)(w & 0x40000000u);
-    }
-}
-template <class T>
-__global__ void __launch_bounds__(256)
-k_gather(const RecT<T>* __restrict__ place_p, int n, int n_own, const RecT<T>* __restrict__ ghost_q, const int2* __restrict__ ghost_i,
-         const int* __restrict__ ref_real, const int* __restrict__ slot_of, const int* __restrict__ order, const int* __restrict__ ntot,
-         RecT<T>* __restrict__ rec, RecT<T>* __restrict__ rec_n3, int rec_cap, int by_index, T* __restrict__ facc) {
-    typedef TagT<T> TG;
-    typedef typename TG::type tag_t;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    // an overflowed build (more records than the capacity estimate) is repeated by the host: its order[] has holes (the
-    // images beyond the capacity were dropped), so nothing is gathered
-    if (*ntot > rec_cap || k >= *ntot) return;
-    // the force accumulator row of this slot starts the next Newton's-third-law sweep at zero (coalesced, in passing)
-    if (facc) strec(reinterpret_cast<RecT<T>*>(facc) + k, T(0), T(0), T(0), (tag_t)0);
-    const int o = order[k];
-    const int id = o & 0x3fffffff;
-    const unsigned par = ((unsigned)o >> 30) & 1u;
-    if (id < n) {
-        const RecT<T> P = ldrec(place_p + id);
-        strec(&rec[k], P.x, P.y, P.z, (tag_t)id | TG::HOME | ((id >= n_own) ? TG::FOREIGN : (tag_t)0));
-        if (rec_n3) strec(&rec_n3[k], P.x, P.y, P.z, (tag_t)((unsigned)(by_index ? id : k) | 0x40000000u | (par << 29)));
-    } else {
-        const RecT<T> Q = ldrec(ghost_q + (id - n));
-        const int2 e = ghost_i[id - n];
-        const bool home = ref_real[e.y] != 0, foreign = e.x >= n_own;
-        strec(&rec[k], Q.x, Q.y, Q.z, (tag_t)e.x | TG::GHOST | (foreign ? TG::FOREIGN : (tag_t)0) | (home ? TG::HOME : (tag_t)0));
-        if (rec_n3) strec(&rec_n3[k], Q.x, Q.y, Q.z, (tag_t)((unsigned)(by_index ? e.x : slot_of[e.x]) | 0x80000000u | (home ? 0x40000000u : 0u) | (par << 29)));
     }
 }
 
 // ---- row starts ------------------------------------------------------------------------------------------
-// One warp per row of device cells.  cs = cell_start + 1 is the cursor array of k_order: the cursor of cell x of a row is
-// cs[row * px + x], pre-loaded with the cell's first record; once every record is placed it holds the cell's END, i.e.
-// cell_start[row * px + x + 1] = start of cell x + 1, and cell_start[row * px] (never incremented) stays the start of
-// the row: no second counter array.  The row's base comes from one atomicAdd on the record counter.
+// One warp per row of device cells.  cs = cell_start + 1 is the cursor array of the scatter pass: the cursor of cell x
+// of a row is cs[row * px + x], pre-loaded with the cell's first record; once every record is placed it holds the
+// cell's END, i.e. cell_start[row * px + x + 1] = start of cell x + 1, and cell_start[row * px] (never incremented)
+// stays the start of the row: no second counter array.
 static __global__ void __launch_bounds__(256)
 k_row_starts(const int* __restrict__ cell_count, int* __restrict__ cell_start, int nx, int nrows, int* __restrict__ ntot) {
     const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -346,6 +274,37 @@ k_row_starts(const int* __restrict__ cell_count, int* __restrict__ cell_start, i
         if (c < nx) cs[c + 1] = base + inc - v;    // cursor of cell c = its first record
         base += __shfl_sync(0xffffffffu, inc, 31);
     }
+}
+
+// ---- slot-tagged twin of the records (on request: Newton's-third-law force sweep, clm_sweep_n3.cuh) ---------------------
+// One coalesced pass in record order: rec_n3[k] = (position of rec[k], slot of the particle's REAL record -- an image
+// points at its original through slot_of[]; by_index: the particle index, triclinic cells -- | GHOST | HOME | parity of
+// the record's reference cell along the row << 29), and the force accumulator row of the slot is zeroed in passing.  The
+// reference cell along the row is recomputed from the stored coordinate with the arithmetic of cell_of (one IEEE
+// division): cheaper than a second scattered store stream in k_bin, which is a DRAM read-modify-write per record once the
+// arrays outgrow the L2.
+template <class T, int DIM>
+__global__ void __launch_bounds__(256)
+k_twin(const __grid_constant__ GeomT<T> g, const RecT<T>* __restrict__ rec, const int* __restrict__ slot_of, const int* __restrict__ ntot, int rec_cap,
+       RecT<T>* __restrict__ rec_n3, T* __restrict__ facc, int by_index) {
+    typedef TagT<T> TG;
+    typedef typename TG::type tag_t;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (*ntot > rec_cap || k >= *ntot) return;   // overflowed build: repeated by the host
+    const RecT<T> r = ldrec(rec + k);
+    const bool ghost = (r.tag & TG::GHOST) != 0;
+    const int idx = (int)(r.tag & TG::MASK);
+    constexpr int kf = DIM - 1;                  // the row of the device grid runs along the last reference dimension
+    const T pf = (kf == 0) ? r.x : ((kf == 1) ? r.y : r.z);
+    int c = (int)floor(xdiv(xsub(pf, g.cb_min[kf]), g.cs[kf]));
+    if (!ghost) {                                // border nudge of real particles (cell_of)
+        if (c == g.lcell - 1) c += 1;
+        if (c == g.nc[kf] - g.lcell) c -= 1;
+    }
+    const unsigned word = (unsigned)(by_index ? idx : (ghost ? slot_of[idx] : k)) | (ghost ? 0x80000000u : 0u) | ((r.tag & TG::HOME) ? 0x40000000u : 0u) |
+                          ((unsigned)(c & 1) << 29);
+    strec(&rec_n3[k], r.x, r.y, r.z, (tag_t)word);
+    strec(reinterpret_cast<RecT<T>*>(facc) + k, T(0), T(0), T(0), (tag_t)0);
 }
 
 // ---- tiles ------------------------------------------------------------------------------------------------

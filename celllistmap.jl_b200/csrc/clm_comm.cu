@@ -132,28 +132,31 @@ template <class T> int Engine<T>::slab_update(const void* xyz, int64_t n, int on
     if (int rc = set_positions(0, xyz, n, on_device)) return rc;
     if (c->world == 1) { c->n_foreign = 0; return set_foreign(0, nullptr, 0, 1); }
     CLM_CK(cudaSetDevice(device));
-    if (c->cap == 0 && opt_sub == 0) {
-        // the engine sizes its device grid from the particle density; a rank only sees its slab, so it is told the global
-        // density once (same rule as Engine::build_enqueue: ~4 particles per device cell)
+    const int lcell = box.lcell, world = c->world, lower = (c->rank + world - 1) % world, upper = (c->rank + 1) % world;
+    const bool merge = world == 2;      // both faces go to the one peer: one message, every particle once
+    if (c->cap == 0) {
+        // first call, one collective: the global particle count.  (1) The engine sizes its device grid from the particle
+        // density; a rank only sees its slab, so it is told the global density (same rule as Engine::build_enqueue: ~4
+        // particles per device cell).  (2) The capacity of the halo messages must be the SAME on every rank (a send and its
+        // matching receive carry cap rows): it follows from the global count -- a face holds about lcell / (layers per
+        // rank) of a rank's share; 50 % slack -- and grows collectively (below) when a face outgrows it.
         CLM_CK(c->own.ensure(4));
         long long hn = (long long)n;
         CLM_CK(cudaMemcpyAsync(c->own.p, &hn, sizeof(hn), cudaMemcpyHostToDevice, stream));
         CLM_NCCL(g_nccl.AllReduce(c->own.p, c->own.p, 1, NCCL_INT64, NCCL_SUM, c->comm, stream));
         CLM_CK(cudaMemcpyAsync(&hn, c->own.p, sizeof(hn), cudaMemcpyDeviceToHost, stream));
         CLM_CK(cudaStreamSynchronize(stream));
-        double inner = 1;
-        for (int k = 0; k < dim; ++k) inner *= (double)std::max<int64_t>(1, box.nc[k] - 2 * box.lcell - 1);
-        const int sub = (int)std::floor(std::pow(std::max((double)hn / inner / 4.0, 1.0), 1.0 / dim) + 0.35);
-        opt_sub = std::max(1, std::min(sub, LF_MAX / box.lcell));
+        if (opt_sub == 0) {
+            double inner = 1;
+            for (int k = 0; k < dim; ++k) inner *= (double)std::max<int64_t>(1, box.nc[k] - 2 * box.lcell - 1);
+            const int sub = (int)std::floor(std::pow(std::max((double)hn / inner / 4.0, 1.0), 1.0 / dim) + 0.35);
+            opt_sub = std::max(1, std::min(sub, LF_MAX / box.lcell));
+        }
+        const int layers = std::max(1, ((int)box.nc[0] - 2 * lcell - 1) / world);
+        const double frac = std::min(1.0, (double)lcell / layers * (merge ? 2.0 : 1.0));
+        c->cap = (int64_t)((double)hn / world * frac * 1.5) + 1024;
     }
-    const int lcell = box.lcell, world = c->world, lower = (c->rank + world - 1) % world, upper = (c->rank + 1) % world;
-    const bool merge = world == 2;      // both faces go to the one peer: one message, every particle once
     const T* x_dev = sets[0].pos.p;     // the engine's own copy of the owned particles
-    if (c->cap == 0) {
-        // first call: the two faces hold about lcell / (hi - lo) of the particles each; 50 % slack
-        const double frac = (double)lcell / std::max(1, c->hi - c->lo) * (merge ? 2.0 : 1.0);
-        c->cap = (int64_t)((double)n * std::min(1.0, frac) * 1.5) + 1024;
-    }
     const int dt = sizeof(T) == 4 ? NCCL_FLOAT32 : NCCL_FLOAT64;
     for (int attempt = 0; attempt < 4; ++attempt) {
         for (int k = 0; k < 2; ++k) { CLM_CK(c->send[k].ensure((size_t)c->cap * dim)); CLM_CK(c->recv[k].ensure((size_t)c->cap * dim)); }

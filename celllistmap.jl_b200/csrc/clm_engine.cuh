@@ -83,12 +83,8 @@ template <class U> struct DBuf {
 
 template <class T> struct DevSet {
     DBuf<T> pos;             // caller's coordinates, AoS n x dim (owning copy, like ParticleSystemPositions)
-    // build scratch (clm_build.cuh): wrapped position + device cell and rank inside the cell of every particle (count pass ->
-    // placement pass), the image list, and the slot of every particle's real record (force gather of the N3 sweep)
-    DBuf<RecT<T>> place_p, ghost_q;
-    DBuf<RecT<T>> rec_n3;    // slot-tagged twin of rec for the Newton's-third-law force sweep (k_place), written on request
-    DBuf<int> slot_of, order;
-    DBuf<int2> ghost_i;
+    DBuf<RecT<T>> rec_n3;    // slot-tagged twin of rec for the Newton's-third-law force sweep (k_twin), written on request
+    DBuf<int> slot_of;       // particle -> slot of its real record (scatter pass of the build)
     DBuf<T> pos_alt;         // pipelined frames: the buffer the NEXT frame's coordinates are copied into while this one is binned
     int64_t n = 0;
     DBuf<T> fpos;            // foreign particles of a slab-decomposed system (owned by other ranks), AoS

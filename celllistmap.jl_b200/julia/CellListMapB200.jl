@@ -217,7 +217,7 @@ function pairwise!(::MinimumDistanceMap, sys::ParticleSystem{N,T}; show_progress
     return sys.output = MinimumDistance{T}(i[], j[], d[])
 end
 # ---- user pair functions: CUDA C++ source compiled at run time (clm_custom_compile / clm_map_custom) ----------------
-struct ClmCustomInfo; nscalar::Int32; npart::Int32; naux::Int32; hist::Int32; end
+struct ClmCustomInfo; nscalar::Int32; npart::Int32; naux::Int32; hist::Int32; scalar_min_mask::Int32; scalar_max_mask::Int32; end
 """A user pair function: `source` defines a stateless struct `name` (interface: include/clm_b200.h).  `params` (<= 16)
 reach the functor as par[]; `aux`/`aux_y` are per-particle side arrays (Vector{T} or Vector{SVector{NAUX,T}})."""
 mutable struct CustomPairFunction

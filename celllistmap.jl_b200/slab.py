@@ -384,3 +384,81 @@ class SlabSystem:
 
     def close(self):
         self.h.close()
+
+
+class SlabSystem2:
+    """One rank's share of a slab-decomposed TWO-set system (cross.jl:8-25: every pair (x_i, y_j) once, i over the first set).
+
+    A rank owns the x particles of its slab -- they are the particles i of its sweep -- and holds the y particles of its slab
+    plus the `lcell` outermost layers of both neighbours (the halo of the y set).  The y set is the PARTNER set: none of its
+    particles ever acts as particle i, so the halo needs no foreign flag and every pair is evaluated exactly once, by the
+    owner of x_i, on bit-identical coordinates.  Per-x outputs stay with their owners; scalars, histograms and minima are
+    reduced over the ranks.  Orthorhombic cells."""
+
+    def __init__(self, unitcell, cutoff, dtype=np.float64, lcell=1, dim=3, device=None, group=None):
+        self.s = SlabSystem(unitcell, cutoff, dtype=dtype, lcell=lcell, dim=dim, device=device, group=group)
+        self.h, self.plan, self.rank, self.world, self.group = self.s.h, self.s.plan, self.s.rank, self.s.world, self.s.group
+        self.device, self.dtype, self.tdtype, self.dim = self.s.device, self.s.dtype, self.s.tdtype, dim
+        self._inner_cells, self._lcell, self._n_global = self.s._inner_cells, lcell, None
+
+    def partition(self, x_global, ids=None):
+        return self.s.partition(x_global, ids)
+
+    def update(self, x_owned, y_owned, x_ids=None, y_ids=None, y_aux=None):
+        """x_owned / y_owned: the particles of either set whose cell layer is in this rank's slab (partition()).  The y halo is
+        exchanged here; `y_ids` / `y_aux` (global ids, per-particle side data of the y set) travel with it."""
+        x = torch.as_tensor(x_owned).to(self.device, self.tdtype).contiguous()
+        y = torch.as_tensor(y_owned).to(self.device, self.tdtype).contiguous()
+        if self._n_global is None:
+            n = torch.tensor([max(x.shape[0], y.shape[0])], dtype=torch.int64, device=self.device)
+            if self.world > 1:
+                n = n.cpu() if dist.get_backend(self.group) == "gloo" else n
+                dist.all_reduce(n, group=self.group)
+            self._n_global = int(n)
+            sub = int(np.floor(max(self._n_global / self._inner_cells / 4.0, 1.0) ** (1.0 / self.dim) + 0.35))
+            self.h.set_option("sub", max(1, min(sub, 7 // self._lcell)))
+        c = self.s.cell_layers(y).to(torch.int64)
+        to_lower, to_upper = self.plan.face_masks(c, self.rank)
+        payloads = [y] + ([] if y_ids is None else [torch.as_tensor(y_ids).to(self.device)]) + \
+                   ([] if y_aux is None else [torch.as_tensor(y_aux).to(self.device, self.tdtype).reshape(y.shape[0], -1).contiguous()])
+        res = exchange_halo(payloads, to_lower, to_upper, self.plan, self.rank, self.group)
+        self.n_x, self.n_y_owned, self.n_y_halo = int(x.shape[0]), int(y.shape[0]), int(res[0].shape[0])
+        self.x_ids = None if x_ids is None else torch.as_tensor(x_ids).to(self.device)
+        self.y_ids = None if y_ids is None else torch.cat([payloads[1], res[1]])
+        self.y_aux = None if y_aux is None else torch.cat([payloads[-1], res[-1]], dim=0).contiguous()
+        self.h.set_positions(0, x)
+        self.h.set_positions(1, torch.cat([y, res[0]], dim=0).contiguous())
+        return self
+
+    def mindist(self):
+        """(i, j, d) of the closest cross pair of the GLOBAL system (global ids when update() was given ids)."""
+        i, j = np.zeros(1, np.int64), np.zeros(1, np.int64)
+        d = np.full(1, np.inf, self.dtype)
+        self.h.map_mindist(i, j, d, reset=True)
+        if i[0] > 0 and self.x_ids is not None and self.y_ids is not None:
+            i[0], j[0] = int(self.x_ids[i[0] - 1]), int(self.y_ids[j[0] - 1])
+        cand = [(float(d[0]), int(i[0]), int(j[0]))]
+        if self.world > 1:
+            allc = [None] * self.world
+            dist.all_gather_object(allc, cand[0], group=self.group)
+            cand = [c for c in allc if c[1] > 0] or [cand[0]]
+        best = min(cand, key=lambda c: (c[0], c[1], c[2]))
+        return best[1], best[2], best[0]
+
+    def neighborlist(self):
+        """this rank's part of the cross neighbour list (i: x ids, j: y ids; global when update() was given ids)."""
+        n = self.h.neighborlist_count()
+        rec = np.zeros(n, dtype=_capi.nl_dtype(self.dtype))
+        if n:
+            self.h.neighborlist_copy(rec)
+        if self.x_ids is not None and self.y_ids is not None:
+            xi, yi = self.x_ids.cpu().numpy(), self.y_ids.cpu().numpy()
+            rec["i"] = xi[rec["i"] - 1]
+            rec["j"] = yi[rec["j"] - 1]
+        return rec
+
+    def sum_d_d2(self):
+        return self.s.sum_d_d2()
+
+    def close(self):
+        self.h.close()

@@ -211,6 +211,9 @@ CLM_API int clm_map_sum_d_d2(clm_handle* h, int flags, void* sum_d, void* sum_d2
  *         static constexpr int NPART   = 3;   // per-particle output components, output[i] += ...        (0..4)
  *         static constexpr int NAUX    = 1;   // per-particle input components (masses, charges, ...)    (0..4)
  *         static constexpr int HIST    = 0;   // 1: histogram output, counts[bin] += 1; sums[bin] += v
+ *         static constexpr unsigned SCALAR_MIN = 0, SCALAR_MAX = 0;   // optional bit masks over the scalar outputs 0..3: reduced
+ *                                             // with min / max instead of + (a custom reducer!, src/API/parallel_custom.jl:196-214);
+ *                                             // written with out.min_scalar(k, v) / out.max_scalar(k, v); +-Inf when no pair was seen
  *         template <class T, class Out>
  *         __device__ void operator()(const clm::NeighborPair<T>& p, const T* par, Out& out) const {
  *             // p.i, p.j (1-based), p.x[3], p.y[3] (y - x = minimum-image vector), p.d2, p.d(), p.ai[], p.aj[]
@@ -224,7 +227,7 @@ CLM_API int clm_map_sum_d_d2(clm_handle* h, int flags, void* sum_d, void* sum_d2
  * symmetric under the exchange of the two particles, as in the reference, where the orientation of (i, j) is unspecified.
  * Errors: CLM_ERR_ARGUMENT with the NVRTC log in clm_last_error() / clm_custom_log() when the source does not compile,
  * CLM_ERR_UNSUPPORTED when libnvrtc cannot be opened. */
-typedef struct clm_custom_info { int32_t nscalar, npart, naux, hist; } clm_custom_info;
+typedef struct clm_custom_info { int32_t nscalar, npart, naux, hist, scalar_min_mask, scalar_max_mask; } clm_custom_info;
 CLM_API int clm_custom_compile(clm_handle* h, const char* source, const char* functor_name, int32_t* functor_id, clm_custom_info* info_out);
 CLM_API const char* clm_custom_log(clm_handle* h); /* NVRTC log of the last compilation of this handle */
 /* params: nparams (<= 16) values of T handed to the functor as par[]; aux_x / aux_y: n x NAUX side arrays of the two sets

@@ -207,3 +207,77 @@ def test_custom_errors(clm):
         clm.pairwise(clm.CustomPairFunction(SCALAR_SRC, "InvDist", aux=np.ones(len(x))), sys)
     with pytest.raises(TypeError):
         clm.pairwise(lambda pair, out: out, sys)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# custom reducers (src/API/parallel_custom.jl:196-214): scalar outputs reduced with min / max instead of +
+MINMAX_SRC = """
+struct Extremes {   // 0: smallest d2, 1: largest w_i w_j d, 2: pair count (a + output next to the two reducers)
+    static constexpr int NSCALAR = 3, NPART = 0, NAUX = 1, HIST = 0;
+    static constexpr unsigned SCALAR_MIN = 1u, SCALAR_MAX = 2u;
+    template <class T, class Out>
+    __device__ void operator()(const clm::NeighborPair<T>& p, const T* par, Out& out) const {
+        out.min_scalar(0, p.d2);
+        out.max_scalar(1, p.ai[0] * p.aj[0] * p.d());
+        out.add_scalar(2, T(1));
+    }
+};
+"""
+MINMAX_PART_SRC = """
+struct NearestAndCount {   // per particle: neighbour count; scalar 0: smallest d over all pairs (full-shell mode)
+    static constexpr int NSCALAR = 1, NPART = 1, NAUX = 0, HIST = 0;
+    static constexpr unsigned SCALAR_MIN = 1u;
+    template <class T, class Out>
+    __device__ void operator()(const clm::NeighborPair<T>& p, const T* par, Out& out) const {
+        out.min_scalar(0, p.d());
+        out.add_i(0, T(1));
+    }
+};
+"""
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("kind", ["ortho", "triclinic", "nonperiodic"])
+@pytest.mark.parametrize("two", [False, True])
+def test_custom_min_max_reducers(clm, oracle_mod, dtype, kind, two):
+    rng = np.random.default_rng(5)
+    x, uc = random_system(rng, 3000, 3, kind, dtype)
+    y = random_system(rng, 2500, 3, kind, dtype)[0] if two else None
+    wx = (0.5 + rng.random(len(x))).astype(dtype)
+    wy = (0.5 + rng.random(len(y))).astype(dtype) if two else None
+    sys = clm.ParticleSystem(xpositions=x, ypositions=y, unitcell=uc, cutoff=1.3, output=clm.CustomOutput(scalars=np.zeros(3, dtype)))
+    f = clm.CustomPairFunction(MINMAX_SRC, "Extremes", aux=wx, aux_y=wy)
+    out = clm.pairwise(f, sys)
+    i, j, d = oracle_mod.Oracle(x, 1.3, unitcell=uc, y=y, dtype=dtype).neighborlist()
+    wj = (wy if two else wx)[j - 1]
+    # the minimum of the exact d2 values is exact; d2 = d*d up to the square root's rounding
+    assert abs(float(out.scalars[0]) - float(d.min()) ** 2) <= 4 * np.finfo(dtype).eps * float(d.min()) ** 2
+    want_max = (wx[i - 1].astype(np.float64) * wj.astype(np.float64) * d.astype(np.float64)).max()
+    assert abs(float(out.scalars[1]) - want_max) <= RTOL[np.dtype(dtype)] * want_max
+    assert out.scalars[2] == len(d)
+    # reset = false: the values found in the output take part in the reduction (min / max), the + output accumulates
+    sys.output.scalars[:] = [dtype(1e-9), dtype(1e9), dtype(5)]
+    out2 = clm.pairwise(f, sys, reset=False)
+    assert out2.scalars[0] == dtype(1e-9) and out2.scalars[1] == dtype(1e9) and out2.scalars[2] == len(d) + 5
+    # no pair at all: the identities
+    far = (x[:1] + dtype(3.0)).astype(dtype)
+    if two:
+        sys0 = clm.ParticleSystem(xpositions=x[:1], ypositions=far, unitcell=uc, cutoff=1.3, output=clm.CustomOutput(scalars=np.zeros(3, dtype)))
+        f0 = clm.CustomPairFunction(MINMAX_SRC, "Extremes", aux=wx[:1], aux_y=wx[:1])
+    else:
+        sys0 = clm.ParticleSystem(xpositions=np.concatenate([x[:1], far]), unitcell=uc, cutoff=1.3, output=clm.CustomOutput(scalars=np.zeros(3, dtype)))
+        f0 = clm.CustomPairFunction(MINMAX_SRC, "Extremes", aux=wx[:2])
+    o0 = clm.pairwise(f0, sys0)
+    assert o0.scalars[0] == np.inf and o0.scalars[1] == -np.inf and o0.scalars[2] == 0
+
+
+def test_custom_min_reducer_with_per_particle_output(clm, oracle_mod):
+    rng = np.random.default_rng(6)
+    x, uc = random_system(rng, 2500, 3, "ortho", np.float64)
+    n = len(x)
+    sys = clm.ParticleSystem(xpositions=x, unitcell=uc, cutoff=1.2, output=clm.CustomOutput(scalars=np.zeros(1), per_particle=np.zeros((n, 1))))
+    out = clm.pairwise(clm.CustomPairFunction(MINMAX_PART_SRC, "NearestAndCount"), sys)
+    i, j, d = oracle_mod.Oracle(x, 1.2, unitcell=uc).neighborlist()
+    assert out.scalars[0] == d.min()          # not halved: only + outputs of the full-shell mode are
+    cnt = np.bincount(np.concatenate([i, j]) - 1, minlength=n)
+    assert np.array_equal(out.per_particle[:, 0], cnt)

@@ -50,7 +50,21 @@ def _worker(rank, world, port, case, q, fast=False, backend="gloo"):
     try:
         import celllistmap_b200  # noqa: F401
         from celllistmap_b200 import slab
-        dtype = np.float64 if case in ("list", "aux") else np.float32
+        dtype = np.float64 if case in ("list", "aux", "cross") else np.float32
+        if case == "cross":
+            # two-set system: x particles sharded by slab, the y set (partners only) with its halo
+            rng = np.random.default_rng(21)
+            x, y = rng.random((4000, 3)), rng.random((3000, 3))
+            s2 = slab.SlabSystem2(np.ones(3), 0.1, dtype=np.float64)
+            xo, xi = s2.partition(x)
+            yo, yi = s2.partition(y)
+            s2.update(xo, yo, xi, yi)
+            rec = s2.neighborlist()
+            mi, mj, md = s2.mindist()
+            sd, sd2, n = s2.sum_d_d2()
+            q.put((rank, rec["i"].tolist(), rec["j"].tolist(), rec["d"].tolist(), n, (mi, mj, md), s2.n_y_halo))
+            s2.close()
+            return
         if case == "aux":
             # side arrays travel with the halo: Coulomb weights, pair velocities, a user pair function
             w = W.c1_neighborlist(5000)
@@ -244,9 +258,14 @@ def test_slab_through_the_c_abi_over_nccl(oracle_mod, world):
     procs = [ctx.Process(target=_capi_worker, args=(r, world, uid, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in range(world)]
+    try:
+        res = [q.get(timeout=150) for _ in range(world)]
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():
+                p.kill()
     for p in procs:
-        p.join(timeout=120)
         assert p.exitcode == 0
     w = W.c2_argon(24, np.float32)
     o64 = oracle_mod.Oracle(w["x"].astype(np.float64), w["cutoff"], unitcell=w["unitcell"].astype(np.float64))
@@ -267,3 +286,23 @@ def test_slab_through_the_c_abi_over_nccl(oracle_mod, world):
     from parity_util import force_report
     err_same, _, _ = force_report(f"C-ABI slab LJ {world} rank(s) f32", f, f32, wf)
     assert err_same <= 1e-5
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_two_set_system(oracle_mod, world):
+    """cross-set slabs (src/internals/cross.jl:8-25): the union of the per-rank cross lists is the reference list bit for
+    bit, the global minimum distance and pair count are the single-process ones."""
+    res = _run(world, "cross")
+    rng = np.random.default_rng(21)
+    x, y = rng.random((4000, 3)), rng.random((3000, 3))
+    o = oracle_mod.Oracle(x, 0.1, unitcell=np.ones(3), y=y)
+    wi, wj, wd = o.neighborlist()
+    gi = np.concatenate([np.array(r[1], np.int64) for r in res])
+    gj = np.concatenate([np.array(r[2], np.int64) for r in res])
+    gd = np.concatenate([np.array(r[3], np.float64) for r in res])
+    assert sorted(zip(gi.tolist(), gj.tolist(), gd.tolist())) == sorted(zip(wi.tolist(), wj.tolist(), wd.tolist()))
+    k = int(np.argmin(wd))
+    for r in res:
+        assert r[4] == len(wi)
+        assert r[5][2] == wd[k] and (r[5][0], r[5][1]) == (int(wi[k]), int(wj[k]))
+        assert r[6] > 0
