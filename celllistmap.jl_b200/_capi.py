@@ -24,7 +24,7 @@ SYMBOLS = [
     "clm_create", "clm_destroy", "clm_last_error", "clm_set_stream", "clm_synchronize", "clm_set_box", "clm_get_box",
     "clm_set_positions", "clm_set_positions_async", "clm_build", "clm_map_lj", "clm_map_coulomb", "clm_map_dist_hist", "clm_map_pairvel",
     "clm_map_mindist", "clm_map_sum_d_d2", "clm_neighborlist", "clm_neighborlist_copy", "clm_get_stats",
-    "clm_set_option", "clm_version", "clm_measure_fma_peak", "clm_set_foreign", "clm_cell_coords", "clm_select_layers",
+    "clm_set_option", "clm_version", "clm_measure_fma_peak", "clm_set_foreign", "clm_set_foreign_mask", "clm_cell_coords", "clm_select_layers",
     "clm_custom_compile", "clm_custom_log", "clm_map_custom", "clm_custom_check",
     "clm_comm_unique_id", "clm_comm_init", "clm_comm_destroy", "clm_slab_range", "clm_slab_update", "clm_comm_allreduce_sum", "clm_slab_info",
 ]
@@ -117,6 +117,7 @@ def lib():
     L.clm_set_option.argtypes = [vp, C.c_char_p, i64]
     L.clm_measure_fma_peak.argtypes = [ci, ci, C.POINTER(C.c_double)]
     L.clm_set_foreign.argtypes = [vp, ci, vp, i64, ci]
+    L.clm_set_foreign_mask.argtypes = [vp, ci, vp, i64, ci]
     L.clm_cell_coords.argtypes = [vp, vp, i64, ci, ci, vp]
     L.clm_select_layers.argtypes = [vp, vp, i64, ci, C.POINTER(C.c_int32), ci, vp, vp, i64, vp, vp, vp]
     L.clm_custom_compile.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(CustomInfo)]
@@ -259,6 +260,20 @@ class Handle:
             x = np.ascontiguousarray(x, dtype=self.dtype)
         p, dev = _addr(x)
         self._chk(self.L.clm_set_foreign(self.h, int(which), p, int(x.shape[0]), 1 if dev else 0))
+
+    def set_foreign_mask(self, which, mask):
+        """rows of set_positions(which, ...) that belong to other ranks (uint8, one per row; None removes the mask)."""
+        if mask is None:
+            self._chk(self.L.clm_set_foreign_mask(self.h, int(which), None, 0, 0))
+            return
+        if _is_torch(mask):
+            import torch
+            mask = mask.to(torch.uint8).contiguous()
+        else:
+            mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        p, dev = _addr(mask)
+        self._chk(self.L.clm_set_foreign_mask(self.h, int(which), p, int(mask.shape[0]), 1 if dev else 0))
+        self._keep_mask = mask
 
     def cell_coords(self, x, axis, out=None):
         """0-based reference-cell index along `axis` of every row of x (numpy in -> numpy out, torch CUDA in -> torch out)."""

@@ -48,7 +48,7 @@ template <class T> Engine<T>::~Engine() {
     if (copy_out) { cudaStreamSynchronize(copy_out); cudaStreamDestroy(copy_out); }
     for (cudaEvent_t e : {ev_h2d, ev_posfree, ev_done, ev_out[0], ev_out[1]}) if (e) cudaEventDestroy(e);
     d_forces_alt.release(); d_eout.release();
-    for (auto& s : sets) { s.pos.release(); s.pos_alt.release(); s.fpos.release(); s.rec.release(); s.rec_n3.release(); s.slot_of.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
+    for (auto& s : sets) { s.pos.release(); s.pos_alt.release(); s.fpos.release(); s.rec.release(); s.rec_n3.release(); s.slot_of.release(); s.fmask.release(); s.cell_start.release(); s.counters.release(); s.aux.release(); }
     dscal.release(); tiles.release(); d_res.release();
     d_hcount.release(); nl.release(); d_hsum.release(); d_rbins.release(); d_forces.release(); d_facc.release(); d_minmax.release(); d_minpart.release(); d_minres.release();
     custom_store_free(custom_store);
@@ -154,6 +154,22 @@ template <class T> int Engine<T>::set_foreign(int set, const void* xyz, int64_t 
     CLM_CK(s.fpos.ensure((size_t)std::max<int64_t>(n, 1) * dim));
     if (n) CLM_CK(cudaMemcpyAsync(s.fpos.p, xyz, (size_t)n * dim * sizeof(T), on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
     s.n_foreign = n;
+    dirty = true;
+    return CLM_OK;
+}
+
+// rows of the set's own coordinate array that belong to other ranks (see include/clm_b200.h)
+template <class T> int Engine<T>::set_foreign_mask(int set, const uint8_t* mask, int64_t n, int on_device) {
+    if (set != 0 && set != 1) return fail(CLM_ERR_ARGUMENT, "set must be 0 (x) or 1 (y)");
+    if (n < 0 || (n > 0 && !mask)) return fail(CLM_ERR_ARGUMENT, "bad foreign mask");
+    CLM_CK(cudaSetDevice(device));
+    DevSet<T>& s = sets[set];
+    if (n) {
+        CLM_CK(s.fmask.ensure((size_t)n));
+        CLM_CK(cudaMemcpyAsync(s.fmask.p, mask, (size_t)n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+        if (!on_device) CLM_CK(cudaStreamSynchronize(stream));   // the caller's array may be pageable and short-lived
+    }
+    s.n_mask = n;
     dirty = true;
     return CLM_OK;
 }
@@ -353,6 +369,14 @@ template <class T> int Engine<T>::build_enqueue() {
         img_factor = std::min(std::max(vbox / std::max(vcell, 1e-300), 1.0), (dim == 3) ? 8.0 : 4.0);
     }
     {
+        // tile array: sized from the record capacity of set 0 (its capacity is settled first)
+        {
+            DevSet<T>& S0 = sets[0];
+            const size_t want0 = std::max<size_t>((size_t)((double)(S0.n + S0.n_foreign) * img_factor * 1.25) + 4096, (size_t)std::max<int64_t>(S0.n_tot, 1));
+            CLM_CK(S0.rec.ensure(want0));
+            tiles_upper = (int64_t)(S0.rec.cap / tile_i) + nrows + 1;
+            CLM_CK(tiles.ensure((size_t)tiles_upper));
+        }
         for (int s = 0; s < nsets; ++s) {
             DevSet<T>& S = sets[s];
             const size_t want = std::max<size_t>((size_t)((double)(S.n + S.n_foreign) * img_factor * 1.25) + 4096, (size_t)std::max<int64_t>(S.n_tot, 1));
@@ -376,21 +400,29 @@ template <class T> int Engine<T>::build_enqueue() {
             const int64_t nall = S.n + S.n_foreign;
             const int nb = (int)((nall + 255) / 256);
             const int rec_cap = (int)std::min<size_t>(S.rec.cap, 0x7fffffff);
+            if (S.n_mask != 0 && S.n_mask != S.n) return fail(CLM_ERR_ARGUMENT, "clm_set_foreign_mask: the mask must have one byte per row of clm_set_positions");
+            const uint8_t* fm = S.n_mask ? S.fmask.p : nullptr;
             if (nall > 0) {
                 CLM_CK(S.slot_of.ensure((size_t)nall));
-                if (dim == 3) k_bin<T, 3, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, nullptr, 0, ds);
-                else k_bin<T, 2, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, nullptr, 0, ds);
+                if (dim == 3) k_bin<T, 3, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, nullptr, 0, ds, fm);
+                else k_bin<T, 2, false><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_count, S.cell_nact, S.ref_real, nullptr, nullptr, 0, ds, fm);
                 CLM_CK(cudaGetLastError());
                 stats.launches += 1;
             }
-            // per-row starts, written one slot up: the scatter pass uses cell_start[c + 1] as the cursor of cell c, which
-            // leaves the row's exclusive starts behind once every record is placed (no second counter array)
-            k_row_starts<<<(int)((nrows * 32 + 255) / 256), 256, 0, stream>>>(S.cell_count, S.cell_start.p, nfast, (int)nrows, ds + DS_NTOT);
-            CLM_CK(cudaGetLastError());
-            stats.launches += 1;
+            // per-row starts (written one slot up: the scatter pass uses cell_start[c + 1] as the cursor of cell c, which leaves
+            // the row's exclusive starts behind once every record is placed) + the tiles of set 0 + the real-cell count
+            {
+                const int make_tiles = (s == 0) ? 1 : 0;
+                const int nbr = (int)std::max<int64_t>(((int64_t)nrows * 32 + 255) / 256, 1);
+                const int tcap = (int)std::min<int64_t>(tiles_upper, 0x7fffffff);
+                if (dim == 3) k_rows<3><<<nbr, 256, 0, stream>>>(S.cell_count, S.cell_nact, S.ref_real, S.cell_start.p, nfast, nmid, (int)nrows, sub, (int)box.nc[1], (int)box.nc[2], (int)nref, make_tiles, tile_i, tiles.p, tcap, ds);
+                else k_rows<2><<<nbr, 256, 0, stream>>>(S.cell_count, S.cell_nact, S.ref_real, S.cell_start.p, nfast, nmid, (int)nrows, sub, 1, (int)box.nc[1], (int)nref, make_tiles, tile_i, tiles.p, tcap, ds);
+                CLM_CK(cudaGetLastError());
+                stats.launches += 1;
+            }
             if (nall > 0) {
-                if (dim == 3) k_bin<T, 3, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, S.slot_of.p, rec_cap, ds);
-                else k_bin<T, 2, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, S.slot_of.p, rec_cap, ds);
+                if (dim == 3) k_bin<T, 3, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, S.slot_of.p, rec_cap, ds, fm);
+                else k_bin<T, 2, true><<<nb, 256, 0, stream>>>(geom, S.pos.p, S.fpos.p, (int)nall, (int)S.n, S.cell_start.p + 1, S.cell_nact, S.ref_real, S.rec.p, S.slot_of.p, rec_cap, ds, fm);
                 CLM_CK(cudaGetLastError());
                 stats.launches += 1;
                 if (n3) {
@@ -403,17 +435,6 @@ template <class T> int Engine<T>::build_enqueue() {
                     stats.launches += 1;
                 }
             }
-        }
-        tiles_upper = (int64_t)(sets[0].rec.cap / tile_i) + nrows + 1;
-        CLM_CK(tiles.ensure((size_t)tiles_upper));
-        for (int s = 0; s < nsets; ++s) {
-            // set 0: tiles + real-cell count; set 1 (the partner set of a two-set system): real-cell count only
-            const int rows = (s == 0) ? (int)nrows : 0;
-            const int nb = (int)std::max<int64_t>(((int64_t)rows * 32 + 255) / 256, std::min<int64_t>(256, (nref + 255) / 256));
-            k_row_tiles<<<nb, 256, 0, stream>>>(sets[s].cell_nact, sets[s].cell_start.p, nfast, nmid, rows, tile_i, tiles.p, (int)std::min<int64_t>(tiles_upper, 0x7fffffff), dscal.p + s * DS_SET_STRIDE,
-                                               sets[s].ref_real, (int)nref);
-            CLM_CK(cudaGetLastError());
-            stats.launches += 1;
         }
         CLM_CK(cudaEventRecord(ev_b1, stream));
         if (ev_posfree) CLM_CK(cudaEventRecord(ev_posfree, stream));   // pipelined frames: the coordinate buffer has been read
@@ -678,6 +699,7 @@ int clm_set_positions(clm_handle* h, int set, const void* xyz, int64_t n, int on
 int clm_set_positions_async(clm_handle* h, int set, const void* xyz, int64_t n) { H_OR_FAIL; return h->e->set_positions_async(set, xyz, n); }
 int clm_build(clm_handle* h) { H_OR_FAIL; return h->e->build(); }
 int clm_set_foreign(clm_handle* h, int set, const void* xyz, int64_t n, int on_device) { H_OR_FAIL; return h->e->set_foreign(set, xyz, n, on_device); }
+int clm_set_foreign_mask(clm_handle* h, int set, const uint8_t* mask, int64_t n, int on_device) { H_OR_FAIL; return h->e->set_foreign_mask(set, mask, n, on_device); }
 int clm_cell_coords(clm_handle* h, const void* xyz, int64_t n, int on_device, int axis, int32_t* out) { H_OR_FAIL; return h->e->cell_coords(xyz, n, on_device, axis, out); }
 int clm_select_layers(clm_handle* h, const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b, int64_t capacity, int32_t* counts, int32_t* idx_a, int32_t* idx_b) { H_OR_FAIL; return h->e->select_layers(xyz, n, axis, ranges, merge, out_a, out_b, capacity, counts, idx_a, idx_b); }
 int clm_map_lj(clm_handle* h, const void* p, int flags, void* e, void* f) { H_OR_FAIL; return h->e->map_lj(p, flags, e, f); }

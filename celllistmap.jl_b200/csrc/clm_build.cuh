@@ -6,12 +6,12 @@
 // counting sort into a cell-sorted packed record array:
 //   k_bin<count>  : wrap + rotate each particle, enumerate its 3^N-1 lattice images, keep those inside
 //                   the computing box, histogram real+image particles per cell (global atomics)
-//   k_row_starts  : one warp per ROW of device cells: prefix of the row's counts; the row's base comes from one
+//   k_rows        : one warp per ROW of device cells: prefix of the row's counts; the row's base comes from one
 //                   atomicAdd on the record counter, so rows are contiguous but placed in arbitrary order -- the
-//                   sweep only ever reads record ranges inside one row.  Replaces a 3-kernel global scan.
+//                   sweep only ever reads record ranges inside one row.  Replaces a 3-kernel global scan.  The same
+//                   warp cuts the row's active record range into tiles, appended to the tile array with one atomicAdd
+//                   per row (tile order is irrelevant: tiles are dealt out by a work counter)
 //   k_bin<scatter>: same traversal, records scattered to the per-cell atomic cursor; slot_of[particle] = its slot
-//   k_row_tiles   : one warp per row: the row's active record range cut into tiles, appended to the tile array with
-//                   one atomicAdd per row (tile order is irrelevant: tiles are dealt out by a work counter)
 //   k_twin        : (on request) the slot-tagged twin of the records for the Newton's-third-law force sweep, one
 //                   coalesced pass in record order
 // Round 2 also built the alternative the round-1 review asked for -- ONE wrapping pass that caches (position, cell) per
@@ -135,21 +135,23 @@ __device__ __forceinline__ bool cell_of(const GeomT<T>& g, const T p[3], bool re
 }
 
 // Count pass (SCATTER = false): per-cell histogram of real + image particles.  Scatter pass: records to the
-// atomic per-cell cursor.  cell_nact[c] flags cells holding a record that can act as particle i of a
-// pair: real particles, and images living in a REFERENCE cell that holds a real particle (the reference sweeps
-// exactly those cells, self.jl:56-57); ref_real[] flags reference cells with a real particle.
+// atomic per-cell cursor.  cell_nact[c] flags cells holding a record of a particle this rank owns (real or image);
+// ref_real[] flags reference cells with a real particle.  A record can act as particle i of a pair when it is owned and
+// lives in a REFERENCE cell that holds a real particle (the reference sweeps exactly those cells, self.jl:56-57):
+// k_rows combines the two flags once the count pass is complete.
 __device__ __forceinline__ float shfl_t(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ double shfl_t(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 template <class T, int DIM, bool SCATTER>
 __global__ void __launch_bounds__(256)
 k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __restrict__ fpos, int n, int n_own, int* __restrict__ cell_cursor,
-      int* __restrict__ cell_nact, int* __restrict__ ref_real, RecT<T>* __restrict__ rec, int* __restrict__ slot_of, int rec_cap, int* __restrict__ dscal) {
+      int* __restrict__ cell_nact, int* __restrict__ ref_real, RecT<T>* __restrict__ rec, int* __restrict__ slot_of, int rec_cap, int* __restrict__ dscal, const unsigned char* __restrict__ fmask) {
     typedef TagT<T> TG;
     const int ip = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
     constexpr int CENTER = (DIM == 3) ? 13 : 4;
     T p[3] = {T(0), T(0), T(0)};
     unsigned okmask = 0u;      // candidate images of this lane's particle (none for invalid / interior / non-periodic)
+    bool is_foreign = false;   // owned by another rank: the rows behind the owned ones, or flagged by clm_set_foreign_mask
     if (ip < n) {
         T x[DIM];
         bool bad = false;
@@ -172,7 +174,8 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
         if (!bad) {
             // cell_cursor: the per-cell histogram in the count pass; the per-cell write cursor (pre-loaded with the
             // exclusive starts) in the scatter pass
-            const typename TG::type foreign = (ip >= n_own) ? TG::FOREIGN : (typename TG::type)0;
+            is_foreign = (ip >= n_own) || (fmask && fmask[ip] != 0);
+            const typename TG::type foreign = is_foreign ? TG::FOREIGN : (typename TG::type)0;
             const int slot = atomicAdd(&cell_cursor[lin], 1);
             if (!SCATTER) {
                 if (!foreign) cell_nact[lin] = 1;   // flags: plain stores, every writer stores the same value
@@ -199,6 +202,22 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
                     const unsigned m0 = dimok[0] & 7u;
                     const unsigned m01 = ((dimok[1] & 1u) ? m0 : 0u) | ((dimok[1] & 2u) ? (m0 << 3) : 0u) | ((dimok[1] & 4u) ? (m0 << 6) : 0u);
                     okmask = (DIM == 2) ? m01 : (((dimok[2] & 1u) ? m01 : 0u) | ((dimok[2] & 2u) ? (m01 << 9) : 0u) | ((dimok[2] & 4u) ? (m01 << 18) : 0u));
+                } else {
+                    // triclinic / rotated cells: every lane tests its own 3^N - 1 shifts against the computing box (the same
+                    // additions and comparisons as below, so the same images survive): straight-line code, and the dealing
+                    // loop below then runs once per ~32 ACTUAL images instead of once per 32 candidates (26 trips per warp)
+                    unsigned m = 0u;
+#pragma unroll
+                    for (int img = 0; img < ((DIM == 3) ? 27 : 9); ++img) {
+                        bool in = true;
+#pragma unroll
+                        for (int k = 0; k < DIM; ++k) {
+                            const T qk = xadd(p[k], g.shift[img][k]);
+                            in = in && (g.cb_min[k] <= qk) && (qk < g.cb_max[k]);
+                        }
+                        if (in) m |= 1u << img;
+                    }
+                    okmask = m;
                 }
                 okmask &= ~(1u << CENTER);
             }
@@ -221,6 +240,7 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
         const int k_th = w - __shfl_sync(0xffffffffu, excl, s);
         const unsigned m = __shfl_sync(0xffffffffu, okmask, s);
         const int ips = __shfl_sync(0xffffffffu, ip, s);
+        const bool fsrc = __shfl_sync(0xffffffffu, is_foreign ? 1 : 0, s) != 0;
         const T px = shfl_t(p[0], s), py = shfl_t(p[1], s), pz = shfl_t(p[2], s);
         if (w >= total) continue;
         const int img = (int)__fns(m, 0u, k_th + 1);
@@ -235,44 +255,98 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
         if (!in) continue;
         int lq, rq;
         if (!cell_of<T, DIM>(g, q, false, lq, rq)) continue;
-        const typename TG::type foreign = (ips >= n_own) ? TG::FOREIGN : (typename TG::type)0;
+        const typename TG::type foreign = fsrc ? TG::FOREIGN : (typename TG::type)0;
         const int qslot = atomicAdd(&cell_cursor[lq], 1);
+        if (!SCATTER && !foreign) cell_nact[lq] = 1;
         if (SCATTER && qslot < rec_cap) {
             const bool home = ref_real[rq] != 0;
-            if (home && !foreign) cell_nact[lq] = 1;
             strec(&rec[qslot], q[0], q[1], q[2], (typename TG::type)ips | TG::GHOST | foreign | (home ? TG::HOME : (typename TG::type)0));
         }
     }
 }
 
-// ---- row starts ------------------------------------------------------------------------------------------
-// One warp per row of device cells.  cs = cell_start + 1 is the cursor array of the scatter pass: the cursor of cell x
-// of a row is cs[row * px + x], pre-loaded with the cell's first record; once every record is placed it holds the
-// cell's END, i.e. cell_start[row * px + x + 1] = start of cell x + 1, and cell_start[row * px] (never incremented)
-// stays the start of the row: no second counter array.
+// ---- rows: starts + tiles ----------------------------------------------------------------------------------
+// One warp per row of device cells, between the count pass and the scatter pass.
+//  * starts: cs = cell_start + 1 is the cursor array of the scatter pass: the cursor of cell x of a row is
+//    cs[row * px + x], pre-loaded with the cell's first record; once every record is placed it holds the cell's END, i.e.
+//    cell_start[row * px + x + 1] = start of cell x + 1, and cell_start[row * px] (never incremented) stays the start
+//    of the row: no second counter array.  The row's base comes from one atomicAdd on the record counter.
+//  * tiles (make_tiles): first / last cell holding a record that can act as particle i (owned record in a reference
+//    cell with a real particle) -> the record range [start(first), end(last)) cut into tiles of tile_i records, appended
+//    to the tile array with one atomicAdd per row.  Tiles only need the cell starts, not the records: building them here
+//    saves a launch and a pass over the per-cell arrays after the scatter.
+//  * the threads also count the reference cells holding a real particle (CellList.n_cells_with_real_particles).
+template <int DIM>
 static __global__ void __launch_bounds__(256)
-k_row_starts(const int* __restrict__ cell_count, int* __restrict__ cell_start, int nx, int nrows, int* __restrict__ ntot) {
-    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+k_rows(const int* __restrict__ cell_count, const int* __restrict__ cell_own, const int* __restrict__ ref_real, int* __restrict__ cell_start,
+       int nx, int ny, int nrows, int sub, int nc1, int nc2, int nref, int make_tiles, int tile_i, Tile* __restrict__ tiles, int tiles_cap,
+       int* __restrict__ dscal) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = gtid >> 5, lane = threadIdx.x & 31;
+    {
+        int c = 0;
+        for (int i = gtid; i < nref; i += gridDim.x * blockDim.x) c += (ref_real[i] != 0);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0 && c) atomicAdd(&dscal[DS_NCELLS_REAL], c);
+    }
     if (row >= nrows) return;
     const int px = nx + 1;
     const int* cnt = cell_count + (size_t)row * px;
+    const int* own = cell_own + (size_t)row * px;
     int* cs = cell_start + (size_t)row * px;
+    // reference cells of this row: reference linear index = (c0 * nc1 + c1) * nc2 + x / sub (cell_of), row = (c0, c1) sub-cells
+    const int rrow = (DIM == 3) ? ((row / ny) / sub) * nc1 + (row % ny) / sub : row / sub;
+    const int* rr = ref_real + (size_t)rrow * nc2;
     int total = 0;
     for (int c = lane; c < nx; c += 32) total += cnt[c];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
     int base = 0;
-    if (lane == 0) base = (total > 0) ? atomicAdd(ntot, total) : 0;
+    if (lane == 0) base = (total > 0) ? atomicAdd(&dscal[DS_NTOT], total) : 0;
     base = __shfl_sync(0xffffffffu, base, 0);
     if (lane == 0) cs[0] = base;
+    int first = IDX_NONE, last = -1, a = 0, b = 0, run = base;
     for (int c0 = 0; c0 < nx; c0 += 32) {
         const int c = c0 + lane;
         const int v = (c < nx) ? cnt[c] : 0;
         int inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        if (c < nx) cs[c + 1] = base + inc - v;    // cursor of cell c = its first record
-        base += __shfl_sync(0xffffffffu, inc, 31);
+        const int start = run + inc - v;
+        if (c < nx) {
+            cs[c + 1] = start;    // cursor of cell c = its first record
+            if (make_tiles && v > 0 && own[c] != 0 && rr[c / sub] != 0) {
+                if (c < first) { first = c; a = start; }
+                if (c > last) { last = c; b = start + v; }
+            }
+        }
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (!make_tiles) return;
+    // lanes hold ascending cells: the smallest first / largest last win, with their record bounds
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const int f2 = __shfl_xor_sync(0xffffffffu, first, o), a2 = __shfl_xor_sync(0xffffffffu, a, o);
+        const int l2 = __shfl_xor_sync(0xffffffffu, last, o), b2 = __shfl_xor_sync(0xffffffffu, b, o);
+        if (f2 < first) { first = f2; a = a2; }
+        if (l2 > last) { last = l2; b = b2; }
+    }
+    if (last < 0) return;
+    const int ntiles = (b - a + tile_i - 1) / tile_i;
+    int tbase = 0;
+    if (lane == 0 && ntiles > 0) tbase = atomicAdd(&dscal[DS_NTILES], ntiles);
+    tbase = __shfl_sync(0xffffffffu, tbase, 0);
+    __syncwarp();   // the starts this warp wrote are read back below
+    // cell of record k: the last cell c in [first, last] with start(c) = cs[c + 1] <= k
+    auto cell_x = [&](int k) { int lo = first, hi = last; while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (cs[mid + 1] <= k) lo = mid; else hi = mid - 1; } return lo; };
+    for (int t = lane; t < ntiles; t += 32) {
+        const int k0 = a + t * tile_i;
+        const int n = min(tile_i, b - k0);
+        Tile tl;
+        tl.k0 = k0; tl.cnt = n; tl.yz = (row % ny) | ((row / ny) << 16);
+        tl.cx = cell_x(k0) | (cell_x(k0 + n - 1) << 16);
+        if (tbase + t < tiles_cap) tiles[tbase + t] = tl;   // beyond the capacity only when the record capacity overflowed: the build is repeated
     }
 }
 
@@ -305,51 +379,6 @@ k_twin(const __grid_constant__ GeomT<T> g, const RecT<T>* __restrict__ rec, cons
                           ((unsigned)(c & 1) << 29);
     strec(&rec_n3[k], r.x, r.y, r.z, (tag_t)word);
     strec(reinterpret_cast<RecT<T>*>(facc) + k, T(0), T(0), T(0), (tag_t)0);
-}
-
-// ---- tiles ------------------------------------------------------------------------------------------------
-// One warp per row: first/last cell holding a record that can act as particle i -> the record range
-// [cell_start[first], cell_start[last + 1]) cut into tiles of tile_i records, appended to the tile array.  The threads
-// also count the reference cells holding a real particle (CellList.n_cells_with_real_particles).
-static __global__ void __launch_bounds__(256)
-k_row_tiles(const int* __restrict__ cell_nact, const int* __restrict__ cell_start, int nx, int ny, int nrows, int tile_i,
-            Tile* __restrict__ tiles, int tiles_cap, int* __restrict__ dscal, const int* __restrict__ ref_flags, int nref) {
-    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int row = gtid >> 5, lane = threadIdx.x & 31;
-    {
-        int c = 0;
-        for (int i = gtid; i < nref; i += gridDim.x * blockDim.x) c += (ref_flags[i] != 0);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (lane == 0 && c) atomicAdd(&dscal[DS_NCELLS_REAL], c);
-    }
-    if (row >= nrows) return;
-    const int px = nx + 1;
-    const int* act = cell_nact + (size_t)row * px;
-    const int* cs = cell_start + (size_t)row * px;   // cs[c] <= k < cs[c+1]  <=>  record k lives in cell c
-    int first = IDX_NONE, last = -1;
-    for (int c = lane; c < nx; c += 32)
-        if (act[c] > 0) { first = min(first, c); last = max(last, c); }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-        last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
-    }
-    if (last < 0) return;
-    const int a = cs[first], b = cs[last + 1];
-    const int ntiles = (b - a + tile_i - 1) / tile_i;
-    int base = 0;
-    if (lane == 0 && ntiles > 0) base = atomicAdd(&dscal[DS_NTILES], ntiles);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    auto cell_x = [&](int k) { int lo = first, hi = last; while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (cs[mid] <= k) lo = mid; else hi = mid - 1; } return lo; };
-    for (int t = lane; t < ntiles; t += 32) {
-        const int k0 = a + t * tile_i;
-        const int cnt = min(tile_i, b - k0);
-        Tile tl;
-        tl.k0 = k0; tl.cnt = cnt; tl.yz = (row % ny) | ((row / ny) << 16);
-        tl.cx = cell_x(k0) | (cell_x(k0 + cnt - 1) << 16);
-        if (base + t < tiles_cap) tiles[base + t] = tl;   // beyond the capacity only when the record capacity overflowed: the build is repeated
-    }
 }
 
 // reference-cell index of every particle along reference dimension `axis` (0-based, after wrapping and the

@@ -31,6 +31,7 @@ struct EngineBase {
     virtual int set_positions(int set, const void* xyz, int64_t n, int on_device) = 0;
     virtual int set_positions_async(int set, const void* xyz, int64_t n) = 0;
     virtual int set_foreign(int set, const void* xyz, int64_t n, int on_device) = 0;
+    virtual int set_foreign_mask(int set, const uint8_t* mask, int64_t n, int on_device) = 0;
     virtual int cell_coords(const void* xyz, int64_t n, int on_device, int axis, int32_t* out) = 0;
     virtual int comm_init(const void* id, int rank, int world) = 0;
     virtual int comm_destroy() = 0;
@@ -89,6 +90,8 @@ template <class T> struct DevSet {
     int64_t n = 0;
     DBuf<T> fpos;            // foreign particles of a slab-decomposed system (owned by other ranks), AoS
     int64_t n_foreign = 0;
+    DBuf<uint8_t> fmask;     // rows of pos that belong to other ranks (clm_set_foreign_mask: local numbering = global order)
+    int64_t n_mask = 0;      // 0: no mask
     DBuf<RecT<T>> rec;       // cell-sorted records, real + image particles
     int64_t n_tot = 0, n_cells_real = 0;
     DBuf<int> cell_start;    // row pitch nfast + 1: [row * pitch + x] = first record of cell x, entry nfast = end of the row (after the scatter pass)
@@ -156,6 +159,7 @@ template <class T> struct Engine : EngineBase {
     int set_positions(int set, const void* xyz, int64_t n, int on_device) override;
     int set_positions_async(int set, const void* xyz, int64_t n) override;
     int set_foreign(int set, const void* xyz, int64_t n, int on_device) override;
+    int set_foreign_mask(int set, const uint8_t* mask, int64_t n, int on_device) override;
     int cell_coords(const void* xyz, int64_t n, int on_device, int axis, int32_t* out) override;
     int select_layers(const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b, int64_t capacity, int32_t* counts, int32_t* idx_a, int32_t* idx_b) override;
     // slab decomposition over NCCL (clm_comm.cu)
@@ -236,7 +240,7 @@ template <class T> struct Engine : EngineBase {
     // reduction-type functors run in the reference's own exactly-once mode for the system type
     template <class F> int launch_reduce(const F& f, size_t smem) {
         if (sweep_mode() == MODE_TRI && (sets[0].n_foreign > 0))
-            return fail(CLM_ERR_UNSUPPORTED, "slab-decomposed triclinic self-set systems are not supported (the index_i < index_j rule needs global indices)");
+            return fail(CLM_ERR_UNSUPPORTED, "slab-decomposed triclinic self-set systems: the index_i < index_j rule needs the global numbering -- pass owned + halo particles as one array sorted by global index and flag the halo rows with clm_set_foreign_mask");
         switch (sweep_mode()) {
             case MODE_HALF: return launch<MODE_HALF>(f, smem);
             case MODE_TRI: return launch<MODE_TRI>(f, smem);
@@ -245,7 +249,7 @@ template <class T> struct Engine : EngineBase {
     }
     // Newton's-third-law force sweep of a self-set system (clm_sweep_n3.cuh): sweep into the record-ordered accumulator,
     // then gather into the caller's particle order
-    bool n3_usable() const { return (opt_n3 < 0 ? sizeof(T) == 4 : opt_n3 != 0) && !two_sets && sets[0].n_foreign == 0; }
+    bool n3_usable() const { return (opt_n3 < 0 ? sizeof(T) == 4 : opt_n3 != 0) && !two_sets && sets[0].n_foreign == 0 && sets[0].n_mask == 0; }
     int n3_request() { want_n3 = true; if (!have_n3) dirty = true; return CLM_OK; }   // the list in place has no slot-tagged records: rebuild
     template <int MODE, class F> int launch_n3(const F& f, T* out, int accumulate, T scale) {
         auto kern = k_sweep_n3<T, MODE, F>;

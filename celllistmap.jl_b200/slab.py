@@ -13,7 +13,15 @@ evaluation of the single-GPU sweep therefore happens on exactly one rank, on bit
   * neighbour lists stay per rank (indices mapped to the caller's global ids), concatenation is the caller's choice.
 
 The path has ONE exchange step (the halo); it is a neighbour send/recv, not a collective reduction, so it is issued
-as batched P2P ops.  Only orthorhombic cells are supported (triclinic lattice shifts move images across slabs).
+as batched P2P ops.
+
+Triclinic cells (unitcell = matrix): lattice shifts move images across slabs, so the halo of a rank is every particle
+with ANY periodic image inside the rank's slab +- lcell layers (computed here from the engine's own box record, with one
+layer of slack; extra halo particles are harmless -- they only ever act as partners), sent point to point to whichever
+ranks need it.  The reference's exactly-once rule for triclinic cells compares particle indices (index_i < index_j,
+src/internals/self.jl:164-184), so a rank hands owned + halo particles to the engine as ONE array sorted by GLOBAL id with
+the halo rows flagged (clm_set_foreign_mask): local order = global order, every pair is evaluated once, by the owner of
+its smaller-index particle, from the same periodic image as on one GPU.
 """
 import numpy as np
 import torch
@@ -105,6 +113,42 @@ def exchange_halo(payloads, to_lower, to_upper, plan, rank, group=None):
     return out
 
 
+def exchange_rows(payloads, sends, world, rank, group=None):
+    """General point-to-point row exchange: `sends` maps peer rank -> boolean mask over the rows of every payload.
+    Returns the received rows of every payload, concatenated in ascending peer order."""
+    if world == 1:
+        return [p[:0] for p in payloads]
+    stage = dist.get_backend(group) == "gloo"
+    dev = payloads[0].device
+    comm_dev = torch.device("cpu") if stage else dev
+    counts = torch.zeros(world, dtype=torch.int64)
+    for peer, m in sends.items():
+        counts[peer] = int(m.sum())
+    all_counts = [torch.zeros(world, dtype=torch.int64, device=comm_dev) for _ in range(world)]
+    dist.all_gather(all_counts, counts.to(comm_dev), group=group)
+    n_in = [int(all_counts[q][rank]) if q != rank else 0 for q in range(world)]
+    out = []
+    for p in payloads:
+        ops, keep, recv = [], [], {}
+        for peer, m in sends.items():
+            if int(counts[peer]) == 0:
+                continue
+            buf = p[m].contiguous()
+            buf = buf.cpu() if stage else buf
+            keep.append(buf)
+            ops.append(dist.P2POp(dist.isend, buf, peer, group))
+        for q in range(world):
+            if n_in[q]:
+                recv[q] = torch.empty((n_in[q],) + tuple(p.shape[1:]), dtype=p.dtype, device=comm_dev)
+                ops.append(dist.P2POp(dist.irecv, recv[q], q, group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        got = torch.cat([recv[q] for q in sorted(recv)], dim=0) if recv else torch.empty((0,) + tuple(p.shape[1:]), dtype=p.dtype, device=comm_dev)
+        out.append(got.to(dev) if stage else got)
+    return out
+
+
 class SlabSystem:
     """One rank's share of a slab-decomposed self-set particle system on its own B200.
 
@@ -121,14 +165,21 @@ class SlabSystem:
         self.tdtype = torch.float32 if self.dtype == np.float32 else torch.float64
         self.dim = dim
         uc = np.asarray(unitcell, dtype=self.dtype)
-        if uc.ndim != 1:
-            raise ValueError("slab decomposition supports orthorhombic cells (unitcell = sides) only")
+        self.triclinic = uc.ndim == 2
         self.h = Handle(dim, self.dtype, self.device.index or 0)
         # the engine enqueues on torch's current stream, so torch ops and collectives are ordered with its kernels
         # (0 is the legacy default stream: CUDA's cudaStreamLegacy handle is 1)
         self.h.set_stream(torch.cuda.current_stream(self.device).cuda_stream or 1)
-        self.h.set_box(_capi.ORTHORHOMBIC, uc, cutoff, lcell)
+        self.h.set_box(_capi.TRICLINIC if self.triclinic else _capi.ORTHORHOMBIC, uc, cutoff, lcell)
         b = self.h.get_box()
+        if self.triclinic:
+            # what the halo selection needs from the engine's box record (float64 copies; column-major, stride = dim)
+            g = lambda a: torch.tensor(np.array(a[:dim * dim], dtype=np.float64).reshape(dim, dim).T.copy(), dtype=torch.float64, device=self.device)
+            self._M, self._A = g(b.input_unit_cell), g(b.aligned_unit_cell)
+            self._cb0, self._cs0 = float(b.computing_box_min[0]), float(b.cell_size[0])
+            idx = torch.cartesian_prod(*([torch.tensor([-1.0, 0.0, 1.0], dtype=torch.float64, device=self.device)] * dim)).reshape(-1, dim)
+            self._shift0 = torch.unique(idx @ self._A[0])        # distinct displacements of the periodic images along dimension 1
+        self._own_rows = None         # triclinic: rows of the owned particles in the engine's (global-id ordered) array
         self.plan = SlabPlan(int(b.nc[0]) - 2 * lcell - 1, lcell, self.world)
         self._inner_cells = float(np.prod([max(1, int(b.nc[k]) - 2 * lcell - 1) for k in range(dim)]))
         self._lcell = lcell
@@ -163,6 +214,8 @@ class SlabSystem:
         self.n_owned = int(x.shape[0])
         if aux is not None:
             aux = torch.as_tensor(aux).to(self.device, self.tdtype).reshape(self.n_owned, -1).contiguous()
+        if self.triclinic:
+            return self._update_triclinic(x, ids, aux)
         if self._n_global is None:
             # the engine sizes its device grid from the particle density; a rank only sees its slab, so tell it the
             # global density (same rule as Engine::build: ~4 particles per device cell)
@@ -203,6 +256,70 @@ class SlabSystem:
         self.h.set_positions(0, x)
         self.h.set_foreign(0, self.x_foreign)
         return self
+
+    def _update_triclinic(self, x, ids, aux):
+        if ids is None:
+            raise ValueError("triclinic slabs need the global particle ids (partition() returns them): the index_i < index_j rule follows the global numbering")
+        ids_t = torch.as_tensor(ids).to(self.device, torch.int64)
+        if self._n_global is None:
+            n = torch.tensor([self.n_owned], dtype=torch.int64, device=self.device)
+            if self.world > 1:
+                n = n.cpu() if dist.get_backend(self.group) == "gloo" else n
+                dist.all_reduce(n, group=self.group)
+            self._n_global = int(n)
+            sub = int(np.floor(max(self._n_global / self._inner_cells / 4.0, 1.0) ** (1.0 / self.dim) + 0.35))
+            self.h.set_option("sub", max(1, min(sub, 7 // self._lcell)))
+        sends = {}
+        if self.world > 1 and self.n_owned:
+            # cell layer along dimension 1 of every periodic image of every owned particle (float64 restatement of the build's
+            # wrap; one layer of slack on either side absorbs the rounding differences to the engine's arithmetic)
+            xd = x.to(torch.float64)
+            frac = torch.linalg.solve(self._M, xd.T).T
+            frac = frac - torch.floor(frac)
+            p0 = frac @ self._A[0]
+            layer = torch.floor((p0[:, None] + self._shift0[None, :] - self._cb0) / self._cs0)
+            b, lc = self.plan.bounds, self._lcell
+            for r in range(self.world):
+                if r == self.rank:
+                    continue
+                lo, hi = b[r] - lc - 1, b[r + 1] + lc + 1 + (1 if r == self.world - 1 else 0)
+                m = ((layer >= lo) & (layer < hi)).any(dim=1)
+                if bool(m.any()):
+                    sends[r] = m
+        payloads = [x, ids_t] + ([] if aux is None else [aux])
+        res = exchange_rows(payloads, sends, self.world, self.rank, self.group)
+        xs, gs = torch.cat([x, res[0]], dim=0), torch.cat([ids_t, res[1]])
+        foreign = torch.cat([torch.zeros(self.n_owned, dtype=torch.uint8, device=self.device), torch.ones(res[0].shape[0], dtype=torch.uint8, device=self.device)])
+        order = torch.argsort(gs)
+        self.x_local = xs[order].contiguous()
+        self.ids_local = gs[order].contiguous()
+        self._mask = foreign[order].contiguous()
+        self._own_rows = torch.nonzero(self._mask == 0).flatten()        # owned particles, by ascending global id
+        inv = torch.empty_like(order)
+        inv[order] = torch.arange(order.shape[0], device=self.device)
+        self._own_pos = inv[:self.n_owned]                              # row of the k-th owned particle (caller's order)
+        self.aux = None if aux is None else torch.cat([aux, res[2]], dim=0)[order].contiguous()
+        self.ids, self.foreign_ids = ids_t, res[1]
+        self.n_foreign = int(res[0].shape[0])
+        self.h.set_positions(0, self.x_local)
+        self.h.set_foreign(0, None)
+        self.h.set_foreign_mask(0, self._mask)
+        return self
+
+    def _id_table(self):
+        """global id of every engine-side particle index (0-based rows)."""
+        return self.ids_local if self.triclinic else torch.cat([self.ids, self.foreign_ids])
+
+    def _forces_arg(self, forces):
+        """the per-particle output buffer the engine writes: the caller's (owned rows) or, for triclinic slabs, a local one
+        covering owned + halo rows in global-id order."""
+        if forces is None or not self.triclinic:
+            return forces
+        return torch.zeros((self.x_local.shape[0], forces.shape[1]), dtype=forces.dtype, device=self.device)
+
+    def _forces_back(self, forces, buf):
+        if forces is not None and self.triclinic:
+            forces.copy_(buf[self._own_pos])
 
     def _alloc_fast(self, cap):
         if self._cap is not None and cap <= self._cap:
@@ -284,7 +401,9 @@ class SlabSystem:
     def map_lj(self, c6, c12, forces=None, profile=False):
         """returns the GLOBAL energy (all_reduce) and fills `forces` (n_owned x N, device) for the owned particles."""
         e = torch.zeros(1, dtype=self.tdtype, device=self.device)
-        self.h.map_lj(c6, c12, e, forces, reset=True, profile=profile)
+        buf = self._forces_arg(forces)
+        self.h.map_lj(c6, c12, e, buf, reset=True, profile=profile)
+        self._forces_back(forces, buf)
         if self.world > 1:
             dist.all_reduce(e, group=self.group)
         return e
@@ -298,7 +417,9 @@ class SlabSystem:
         """k w_i w_j / d with the weights given as update(..., aux=w): GLOBAL energy, forces of the owned particles."""
         w = self._need_aux(1)
         e = torch.zeros(1, dtype=self.tdtype, device=self.device)
-        self.h.map_coulomb(k, w, None, e, forces, reset=True, profile=profile)
+        buf = self._forces_arg(forces)
+        self.h.map_coulomb(k, w, None, e, buf, reset=True, profile=profile)
+        self._forces_back(forces, buf)
         if self.world > 1:
             dist.all_reduce(e, group=self.group)
         return e
@@ -322,7 +443,7 @@ class SlabSystem:
         d = np.full(1, np.inf, self.dtype)
         self.h.map_mindist(i, j, d, reset=True)
         if self.ids is not None and i[0] > 0:
-            table = torch.cat([self.ids, self.foreign_ids]).cpu().numpy()
+            table = self._id_table().cpu().numpy()
             i[0], j[0] = table[i[0] - 1], table[j[0] - 1]
         cand = [(float(d[0]), int(i[0]), int(j[0]))]
         if self.world > 1:
@@ -344,7 +465,7 @@ class SlabSystem:
         fid, info = self._custom[key]
         aux = self._need_aux(info.naux) if info.naux else None
         sc = torch.zeros(info.nscalar, dtype=self.tdtype, device=self.device) if info.nscalar else None
-        pp = torch.zeros((self.n_owned, info.npart), dtype=self.tdtype, device=self.device) if info.npart else None
+        pp = torch.zeros((self.x_local.shape[0] if self.triclinic else self.n_owned, info.npart), dtype=self.tdtype, device=self.device) if info.npart else None
         hc = torch.zeros(nbins, dtype=torch.int64, device=self.device) if info.hist else None
         hs = torch.zeros(nbins, dtype=self.tdtype, device=self.device) if info.hist else None
         self.h.map_custom(fid, params, aux, None, sc, pp, hc, hs, reset=True)
@@ -352,6 +473,8 @@ class SlabSystem:
             for t in (sc, hc, hs):
                 if t is not None:
                     dist.all_reduce(t, group=self.group)
+        if pp is not None and self.triclinic:
+            pp = pp[self._own_pos].contiguous()
         return sc, pp, hc, hs
 
     def sum_d_d2(self):
@@ -377,7 +500,7 @@ class SlabSystem:
         if n:
             self.h.neighborlist_copy(rec)
         if self.ids is not None:
-            table = torch.cat([self.ids, self.foreign_ids]).cpu().numpy()
+            table = self._id_table().cpu().numpy()
             rec["i"] = table[rec["i"] - 1]
             rec["j"] = table[rec["j"] - 1]
         return rec

@@ -139,8 +139,13 @@ CLM_API int clm_set_positions_async(clm_handle* h, int set, const void* aos_xyz_
  * Indices: owned particles 1..n, foreign ones n+1..n+n_foreign; per-particle INPUT side arrays of a map (weights,
  * velocities, aux_x / aux_y) then have n + n_foreign rows in that order, per-particle OUTPUTS n rows.  clm_cell_coords returns the 0-based reference-cell
  * index along `axis` of arbitrary coordinates with exactly the arithmetic of the build (ownership / halo selection).
- * Supported for orthorhombic and non-periodic cells (triclinic self-set systems need global-index tie-breaks). */
+ * clm_set_foreign: orthorhombic and non-periodic cells.  Triclinic self-set systems evaluate a pair from the particle
+ * with the smaller index (index_i < index_j, src/internals/self.jl:164-184), so the LOCAL numbering of a rank must follow
+ * the global one: there the owned and the halo particles are passed as ONE array with clm_set_positions, sorted by
+ * global index, and clm_set_foreign_mask flags the rows that belong to other ranks (mask[k] != 0: partner only, never
+ * particle i; NULL removes the mask).  Works for every cell type; the mask is n bytes (n of clm_set_positions). */
 CLM_API int clm_set_foreign(clm_handle* h, int set, const void* aos_xyz, int64_t n, int on_device);
+CLM_API int clm_set_foreign_mask(clm_handle* h, int set, const uint8_t* mask, int64_t n, int on_device);
 CLM_API int clm_cell_coords(clm_handle* h, const void* aos_xyz, int64_t n, int on_device, int axis, int32_t* cell_out);
 /* one-pass face selection for the halo exchange; every pointer except `ranges` is a DEVICE pointer and the call only
  * enqueues.  Particles whose cell layer along `axis` is in [ranges[0], ranges[1]) are appended (AoS rows of T) to out_a,

@@ -50,7 +50,23 @@ def _worker(rank, world, port, case, q, fast=False, backend="gloo"):
     try:
         import celllistmap_b200  # noqa: F401
         from celllistmap_b200 import slab
-        dtype = np.float64 if case in ("list", "aux", "cross") else np.float32
+        dtype = np.float64 if case in ("list", "aux", "cross", "tri") else np.float32
+        if case in ("tri", "tri32"):
+            # triclinic self-set system: halo by periodic images, owned + halo rows in global-id order with a foreign mask
+            dt = np.float64 if case == "tri" else np.float32
+            w = W.c3_triclinic_cross(6000, 10, dt, cutoff=12.0)
+            s = slab.SlabSystem(w["unitcell"], w["cutoff"], dtype=dt)
+            xo, ids = s.partition(w["x"])
+            s.update(xo, ids)
+            rec = s.neighborlist()
+            sd, sd2, n = s.sum_d_d2()
+            mi, mj, md = s.mindist()
+            f = torch.zeros((s.n_owned, 3), dtype=torch.float64 if case == "tri" else torch.float32, device="cuda")
+            e = s.map_lj(4.0, 9.0e5, f)
+            q.put((rank, rec["i"].tolist(), rec["j"].tolist(), rec["d"].tolist(), n, (mi, mj, md), ids.cpu().numpy().tolist(),
+                   f.cpu().numpy().tolist(), float(e), s.n_foreign, s.n_owned))
+            s.close()
+            return
         if case == "cross":
             # two-set system: x particles sharded by slab, the y set (partners only) with its halo
             rng = np.random.default_rng(21)
@@ -306,3 +322,43 @@ def test_slab_two_set_system(oracle_mod, world):
         assert r[4] == len(wi)
         assert r[5][2] == wd[k] and (r[5][0], r[5][1]) == (int(wi[k]), int(wj[k]))
         assert r[6] > 0
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("case", ["tri", "tri32"])
+def test_slab_triclinic(oracle_mod, world, case):
+    """triclinic slabs (src/internals/self.jl:164-184: i real, index_i < index_j): owned + halo particles reach the engine in
+    GLOBAL-id order with the halo rows flagged (clm_set_foreign_mask), so every pair is evaluated by the owner of its
+    smaller-index particle from the same periodic image as on one GPU: the union of the per-rank lists equals the
+    reference list bit for bit (distances included), forces and energy within tolerance."""
+    dt = np.float64 if case == "tri" else np.float32
+    res = _run(world, case)
+    w = W.c3_triclinic_cross(6000, 10, dt, cutoff=12.0)
+    o = oracle_mod.Oracle(w["x"], w["cutoff"], unitcell=w["unitcell"], dtype=dt)
+    wi, wj, wd = o.neighborlist()
+    gi = np.concatenate([np.array(r[1], np.int64) for r in res])
+    gj = np.concatenate([np.array(r[2], np.int64) for r in res])
+    gd = np.concatenate([np.array(r[3], dt) for r in res])
+    key = lambda a, b, d: sorted(zip(np.minimum(a, b).tolist(), np.maximum(a, b).tolist(), d.tolist()))
+    assert key(gi, gj, gd) == key(wi, wj, wd), "union of the per-rank lists must equal the reference list bit for bit"
+    k = int(np.argmin(wd))
+    o64 = oracle_mod.Oracle(w["x"].astype(np.float64), w["cutoff"], unitcell=w["unitcell"].astype(np.float64))
+    we, wf = o64.lj(4.0, 9.0e5, forces=True)
+    f = np.zeros_like(wf)
+    seen = np.zeros(len(wf), bool)
+    n_halo = 0
+    esame, fsame = o.lj(4.0, 9.0e5, forces=True)     # same precision as the ranks: the bar (random close pairs amplify the
+    for r in res:                                    # Float32 coordinate rounding far beyond 1e-5 against Float64 arithmetic)
+        assert r[4] == len(wi)
+        assert r[5][2] == wd[k] and {r[5][0], r[5][1]} == {int(wi[k]), int(wj[k])}
+        ids = np.array(r[6]) - 1
+        assert not seen[ids].any()
+        seen[ids] = True
+        f[ids] = np.array(r[7])
+        assert abs(r[8] - esame) <= (1e-10 if dt == np.float64 else 1e-5) * abs(esame)
+        n_halo += r[9]
+        print(f"[slab] triclinic rank {r[0]}: {r[10]} owned, {r[9]} halo particles of {len(wf)}")   # (a box of 5 x 5 x 6 cells: most of it is halo)
+    assert seen.all() and n_halo > 0
+    from parity_util import force_report
+    err_same, _, _ = force_report(f"triclinic slab LJ {world} ranks {case}", f, fsame, wf)
+    assert err_same <= (1e-10 if dt == np.float64 else 1e-5)

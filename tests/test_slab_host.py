@@ -95,3 +95,40 @@ def test_plan_rejects_thin_slabs():
     p = slab.SlabPlan(30, 1, 8)
     assert p.bounds[0] == 1 and p.bounds[-1] == 31
     assert (np.diff(p.bounds) >= 3).all()
+
+
+def _rows_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import celllistmap_b200  # noqa: F401
+        from celllistmap_b200 import slab
+        # rank r owns ids r+1, r+1+world, ...; row k goes to every other rank q with (id + q) % 3 == 0: arbitrary peers,
+        # some rows to several ranks, some to none (the general point-to-point exchange of the triclinic slabs)
+        ids = torch.arange(rank + 1, 601, world)
+        x = torch.stack([ids.double(), ids.double() ** 2, -ids.double()], 1)
+        sends = {qq: ((ids + qq) % 3 == 0) for qq in range(world) if qq != rank}
+        sends = {qq: m for qq, m in sends.items() if bool(m.any())}
+        gx, gi = slab.exchange_rows([x, ids], sends, world, rank)
+        q.put((rank, gi.tolist(), bool(torch.equal(gx, torch.stack([gi.double(), gi.double() ** 2, -gi.double()], 1)))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_rows_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rows_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, got, same in res:
+        assert same, "rows must arrive bit-identical, every payload in the same order"
+        want = sorted(i for i in range(1, 601) if (i - 1) % world != rank and (i + rank) % 3 == 0)
+        assert sorted(got) == want and len(got) == len(set(got))
