@@ -26,6 +26,7 @@ template <class T> int Engine<T>::init(int dim_, int device_) {
     CLM_CK(cudaEventCreate(&ev1));
     CLM_CK(cudaEventCreate(&ev2));
     CLM_CK(cudaEventCreate(&ev3));
+    CLM_CK(cudaStreamCreateWithFlags(&pub_stream, cudaStreamNonBlocking));
     CLM_CK(cudaEventCreateWithFlags(&ev_built, cudaEventDisableTiming));
     CLM_CK(cudaEventCreate(&ev_b0));
     CLM_CK(cudaEventCreate(&ev_b1));
@@ -61,6 +62,7 @@ template <class T> Engine<T>::~Engine() {
     if (ev_built) cudaEventDestroy(ev_built);
     if (ev_b0) cudaEventDestroy(ev_b0);
     if (ev_b1) cudaEventDestroy(ev_b1);
+    if (pub_stream) { cudaStreamSynchronize(pub_stream); cudaStreamDestroy(pub_stream); }
     if (own_stream) cudaStreamDestroy(own_stream);
 }
 
@@ -247,6 +249,7 @@ template <class T> int Engine<T>::build_enqueue() {
         if (sets[s].n + sets[s].n_foreign > 0x7fffffffLL / 28 || sets[s].n + sets[s].n_foreign > (int64_t)TagT<float>::MASK) return fail(CLM_ERR_UNSUPPORTED, "too many particles for 32-bit record indices");
     if (pending_h2d) { if (!(dbg & 1)) CLM_CK(cudaStreamWaitEvent(stream, ev_h2d, 0)); pending_h2d = false; }
     CLM_CK(cudaEventRecord(ev_b0, stream));
+    if (published) CLM_CK(cudaStreamWaitEvent(stream, ev_built, 0));   // the side-stream publish of the previous build has read the scalars (long ago)
     // device scalars (a kernel, not a copy: see k_dscal_init)
     k_dscal_init<<<1, 32, 0, stream>>>(dscal.p);
     CLM_CK(cudaGetLastError());
@@ -439,10 +442,15 @@ template <class T> int Engine<T>::build_enqueue() {
         CLM_CK(cudaEventRecord(ev_b1, stream));
         if (ev_posfree) CLM_CK(cudaEventRecord(ev_posfree, stream));   // pipelined frames: the coordinate buffer has been read
         // the one host round trip of the build (validation flags, record counts, tile count) is only ENQUEUED here; the
-        // caller queues its map kernels behind it and then waits for this event, so the GPU never idles on the host
-        k_dscal_publish<<<1, 32, 0, stream>>>(dscal.p, h_dscal_dev);
+        // caller queues its map kernels behind it and then waits for this event, so the GPU never idles on the host.  The
+        // publish kernel runs on a SIDE stream: its write to mapped host memory travels the same PCIe direction as the
+        // force copy-out of the previous pipelined frame and completed only behind it, which held up the sweep queued
+        // behind the publish on the compute stream by ~0.09 ms per frame (tools/diag_e2e.py)
+        CLM_CK(cudaStreamWaitEvent(pub_stream, ev_b1, 0));
+        k_dscal_publish<<<1, 32, 0, pub_stream>>>(dscal.p, h_dscal_dev);
         CLM_CK(cudaGetLastError());
-        CLM_CK(cudaEventRecord(ev_built, stream));
+        CLM_CK(cudaEventRecord(ev_built, pub_stream));
+        published = true;
     }
     validate_pending = true;
     dirty = false;
@@ -503,6 +511,7 @@ template <class T> int Engine<T>::prepare_map(int flags) {
     // accumulating into caller-owned DEVICE buffers cannot be redone: validate the build before anything is added
     if ((flags & CLM_OUT_DEVICE) && !(flags & CLM_RESET)) { if (int rc = build()) return rc; }
     else if (int rc = build_enqueue()) return rc;
+    if (int rc = flush_pending_out(ev_b1)) return rc;   // outputs of the previous pipelined frame: copied out next to this frame's sweep
     profile_sweep = (flags & CLM_PROFILE) != 0;
     if (flags & CLM_PROFILE) CLM_CK(cudaEventRecord(ev0, stream));
     static_assert(sizeof(ResultBlock) % 8 == 0 && sizeof(ResultBlock) / 8 <= 32, "k_map_begin zeroes the result block with one warp");
@@ -513,13 +522,19 @@ template <class T> int Engine<T>::prepare_map(int flags) {
 template <class T> int Engine<T>::finish_map(int flags) {
     if (flags & CLM_PROFILE) {
         CLM_CK(cudaEventRecord(ev1, stream));
-        CLM_CK(cudaEventSynchronize(ev1));
-        float ms = 0;
-        CLM_CK(cudaEventElapsedTime(&ms, ev0, ev1));
-        stats.map_ms = ms;
-        CLM_CK(cudaEventElapsedTime(&ms, ev2, ev3));
-        stats.sweep_ms = ms;
+        if (flags & CLM_ASYNC) { profile_pending = true; return CLM_OK; }   // pipelined frame: the times are read by clm_get_stats
+        return profile_collect();
     }
+    return CLM_OK;
+}
+template <class T> int Engine<T>::profile_collect() {
+    profile_pending = false;
+    CLM_CK(cudaEventSynchronize(ev1));
+    float ms = 0;
+    CLM_CK(cudaEventElapsedTime(&ms, ev0, ev1));
+    stats.map_ms = ms;
+    CLM_CK(cudaEventElapsedTime(&ms, ev2, ev3));
+    stats.sweep_ms = ms;
     return CLM_OK;
 }
 template <class T> int Engine<T>::fetch_results() {
@@ -603,6 +618,7 @@ template <class T> int Engine<T>::part_end(void* forces_out, int flags, int ncom
 template <class T> int Engine<T>::get_stats(clm_stats* out) {
     if (!out) return fail(CLM_ERR_ARGUMENT, "output pointer is NULL");
     { const int v = build_validate(); if (v != CLM_OK && v != CLM_RETRY_INTERNAL) return v; }
+    if (profile_pending) { if (int rc = profile_collect()) return rc; }
     *out = stats;
     return CLM_OK;
 }

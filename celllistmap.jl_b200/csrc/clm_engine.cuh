@@ -101,11 +101,13 @@ template <class T> struct DevSet {
 };
 
 template <class T> struct Engine : EngineBase {
-    cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaStream_t stream = nullptr, own_stream = nullptr, pub_stream = nullptr;
+    bool published = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev_built = nullptr, ev_b0 = nullptr, ev_b1 = nullptr;
     bool validate_pending = false;
     int build_retries = 0;
-    bool profile_sweep = false;
+    bool profile_sweep = false, profile_pending = false;
+    int profile_collect();
     HostBox<T> box;
     GeomT<T> geom;
     bool box_set = false, nonperiodic = false, two_sets = false, dirty = true;
@@ -149,6 +151,7 @@ template <class T> struct Engine : EngineBase {
     int set_stream(void* s) override { stream = s ? (cudaStream_t)s : own_stream; return CLM_OK; }
     int synchronize() override {
         if (copy_in) CLM_CK(cudaStreamSynchronize(copy_in));
+        if (int rc = flush_pending_out(nullptr)) return rc;
         CLM_CK(cudaStreamSynchronize(stream));
         if (copy_out) { CLM_CK(cudaStreamSynchronize(copy_out)); out_pending[0] = out_pending[1] = false; }
         const int v = build_validate();
@@ -291,7 +294,7 @@ template <class T> struct Engine : EngineBase {
     cudaEvent_t ev_h2d = nullptr, ev_posfree = nullptr, ev_done = nullptr, ev_out[2] = {nullptr, nullptr};
     bool pending_h2d = false, out_pending[2] = {false, false};
     int frame = 0;
-    int dbg = 0;   // debugging switches of the pipelined path (clm_set_option "dbg"): 1 no wait for the copy-in, 2 no force copy-out, 4 no copy-in
+    int dbg = 0;   // debugging switches of the pipelined path (clm_set_option "dbg"): 1 no wait for the copy-in, 2 no force copy-out, 4 no copy-in, 8 copy out at once
     DBuf<T> d_forces_alt, d_eout;
     int pipeline_init() {
         if (copy_in) return CLM_OK;
@@ -327,11 +330,26 @@ template <class T> struct Engine : EngineBase {
         }
         CLM_CK(cudaEventRecord(ev_done, stream));
         CLM_CK(cudaStreamWaitEvent(copy_out, ev_done, 0));
-        if (f_host && force_count && !(dbg & 2)) CLM_CK(cudaMemcpyAsync(f_host, (p ? d_forces_alt.p : d_forces.p), force_count * sizeof(T), cudaMemcpyDeviceToHost, copy_out));
-        if (e_host) CLM_CK(cudaMemcpyAsync(e_host, d_eout.p + p, sizeof(T), cudaMemcpyDeviceToHost, copy_out));
+        // The copies themselves are enqueued by the NEXT map call, gated on the end of its cell-list build (or by
+        // clm_synchronize): a 12 MB device->host transfer that runs next to the build slows it by ~50 % -- the build is a
+        // chain of short kernels, and while the copy saturates the upstream PCIe direction every kernel launch waits longer
+        // for its commands (tools/diag_e2e.py: build 0.096 -> 0.145 ms, map tail +0.05 ms).  Next to the one long sweep
+        // kernel the copy is free.
+        pend_e = e_host; pend_f = (f_host && force_count && !(dbg & 2)) ? f_host : nullptr; pend_count = force_count; pend_p = p; pend_valid = true;
+        if (dbg & 8) { if (int rc = flush_pending_out(nullptr)) return rc; }   // debugging: copy out at once (the round-2 behaviour)
+        frame += 1;
+        return CLM_OK;
+    }
+    void* pend_e = nullptr; void* pend_f = nullptr; size_t pend_count = 0; int pend_p = 0; bool pend_valid = false;
+    int flush_pending_out(cudaEvent_t gate) {
+        if (!pend_valid) return CLM_OK;
+        pend_valid = false;
+        const int p = pend_p;
+        if (gate) CLM_CK(cudaStreamWaitEvent(copy_out, gate, 0));
+        if (pend_f) CLM_CK(cudaMemcpyAsync(pend_f, (p ? d_forces_alt.p : d_forces.p), pend_count * sizeof(T), cudaMemcpyDeviceToHost, copy_out));
+        if (pend_e) CLM_CK(cudaMemcpyAsync(pend_e, d_eout.p + p, sizeof(T), cudaMemcpyDeviceToHost, copy_out));
         CLM_CK(cudaEventRecord(ev_out[p], copy_out));
         out_pending[p] = true;
-        frame += 1;
         return CLM_OK;
     }
 };

@@ -59,7 +59,7 @@ template <class T> int Engine<T>::map_lj(const void* p, int flags, void* e, void
     if (v) return v;
     break;
     }
-    if (async) return async_end(e, f, f ? (size_t)sets[0].n * dim : 0, scale);
+    if (async) { if (flags & CLM_PROFILE) { if (int rc = finish_map(flags)) return rc; } return async_end(e, f, f ? (size_t)sets[0].n * dim : 0, scale); }
     if (!(flags & CLM_OUT_DEVICE)) { if (int rc = fetch_results()) return rc; }
     if (int rc = store_real(e, &d_res.p->f[RB_ENERGY], &h_res->f[RB_ENERGY], 1, scale, flags)) return rc;
     if (f) { if (int rc = forces_end(f, flags)) return rc; }

@@ -70,6 +70,19 @@ def c3_triclinic_cross(nx=1_000_000, ny=1_000_000, dtype=np.float64, cutoff=12.0
                 cutoff=cutoff)
 
 
+def triclinic_argon(nside=18, dtype=np.float64, cutoff=12.0):
+    """nside^3 jittered lattice sites (fractional coordinates) in the triclinic cell of C3 scaled to argon density: a
+    well-conditioned triclinic self-set system (no close pairs) for force parity, order shuffled."""
+    M0 = np.array([[80.0, 0.0, 30.0], [30.0, 80.0, 0.0], [0.0, 40.0, 80.0]])
+    n = nside ** 3
+    s = ((n / ARGON_RHO) / abs(np.linalg.det(M0))) ** (1.0 / 3.0)
+    M = s * M0
+    g = np.arange(nside, dtype=np.float64)
+    frac = (np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(n, 3) + 0.4 + 0.2 * uniform(SEED + 5, (n, 3))) / nside
+    x = (frac @ M.T)[shuffle_perm(SEED + 6, n)]
+    return dict(x=np.ascontiguousarray(x.astype(dtype)), unitcell=M.astype(dtype), cutoff=cutoff, c6=ARGON_C6, c12=ARGON_C12)
+
+
 def c4_galaxies(n=4_000_000, dim=3, dtype=np.float64):
     """C4: halotools-style pair-velocity input (test/examples/pairwise_velocities.jl:38-49): density 10^5/20.274^3
     per Mpc^3 (3-D) or its 2/3 power (2-D), velocities uniform in [0,1), r-bins 0..5, cutoff 5."""
