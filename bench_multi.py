@@ -153,8 +153,9 @@ def run(args, rank, world, local):
         # end-to-end arm: host buffers in (pinned), forces + energy back to the host, inside the timed region
         x_pin = torch.from_numpy(x_host).pin_memory()
         f_pin = torch.zeros((n_own, 3), dtype=torch.float32).pin_memory()
+        # (a) synchronous: copy in, step, copy out, one frame at a time (the latency of a dependent step)
         e2e = []
-        for it in range(3 + args.steps):
+        for it in range(2 + max(3, args.steps // 4)):
             flush_buf.zero_()
             torch.cuda.synchronize()
             dist.barrier()
@@ -166,10 +167,93 @@ def run(args, rank, world, local):
             e_host = e.cpu()
             b.record(stream)
             b.synchronize()
-            if it >= 3:
+            if it >= 2:
                 e2e.append(a.elapsed_time(b))
-        te = torch.tensor([sum(e2e) / len(e2e)], dtype=torch.float64, device=dev)
+        te_sync = torch.tensor([sum(e2e) / len(e2e)], dtype=torch.float64, device=dev)
+        dist.all_reduce(te_sync, op=dist.ReduceOp.MAX)
+        # (b) pipelined frames (independent frames of a trajectory): copy-in of frame k+1, exchange + build + sweep of frame k
+        # and copy-out of frame k-1 overlap on three streams, double-buffered by frame parity; EVERY frame's positions come
+        # from pinned host memory and its forces + energy go back to it inside the timed region; the L2 flush runs on the
+        # compute stream between frames (timed).  Wall clock over all frames between two barriers, max over ranks.
+        cin, cout = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        xb = [x_dev, torch.empty_like(x_dev)]
+        fb = [f_dev, torch.zeros_like(f_dev)]
+        xp = [x_pin, torch.from_numpy(x_host).pin_memory()]
+        fp = [f_pin, torch.zeros((n_own, 3), dtype=torch.float32).pin_memory()]
+        ep = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+        ev_h2d = [torch.cuda.Event() for _ in range(2)]
+        ev_xfree = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        used = [False, False]
+        keep = []
+        trace = []      # CLM_BENCH_VERBOSE: (frame, label, timing event) of the last frames, printed as a timeline
+        verbose = bool(os.environ.get("CLM_BENCH_VERBOSE"))
+
+        def mark(k, label, st):
+            if verbose and k >= args.steps - 3:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(st)
+                trace.append((k, label, ev))
+
+        def frame(k):
+            p = k & 1
+            with torch.cuda.stream(cin):
+                if used[p]:
+                    cin.wait_event(ev_xfree[p])              # the step that read this buffer two frames ago is done with it
+                mark(k, "h2d start", cin)
+                xb[p].copy_(xp[p], non_blocking=True)
+                ev_h2d[p].record(cin)
+                mark(k, "h2d end", cin)
+            stream.wait_event(ev_h2d[p])
+            if used[p]:
+                stream.wait_event(ev_out[p])                 # the copy-out of frame k-2 has drained this force buffer
+            mark(k, "compute start", stream)
+            flush_buf.zero_()
+            s.update(xb[p])
+            mark(k, "exchange end", stream)
+            copy_out_pending()                               # frame k-1's outputs travel next to this frame's build + sweep
+            e = s.map_lj(W.ARGON_C6, W.ARGON_C12, fb[p])
+            ev_xfree[p].record(stream)
+            ev_done[p].record(stream)
+            mark(k, "compute end", stream)
+            keep.append(e)
+            pending.append((k, p, e))
+            used[p] = True
+            if len(keep) > 4:
+                keep.pop(0)
+
+        pending = []
+
+        def copy_out_pending():
+            while pending:
+                k, p, e = pending.pop(0)
+                with torch.cuda.stream(cout):
+                    cout.wait_event(ev_done[p])
+                    mark(k, "d2h start", cout)
+                    fp[p].copy_(fb[p], non_blocking=True)
+                    ep[p].copy_(e, non_blocking=True)
+                    ev_out[p].record(cout)
+                    mark(k, "d2h end", cout)
+
+        for k in range(4):
+            frame(k)
+        copy_out_pending()
+        torch.cuda.synchronize()
+        dist.barrier()
+        import time as _time
+        t0 = _time.perf_counter()
+        for k in range(args.steps):
+            frame(k)
+        copy_out_pending()
+        torch.cuda.synchronize()
+        te = torch.tensor([1e3 * (_time.perf_counter() - t0) / args.steps], dtype=torch.float64, device=dev)
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e_pipe = float(ep[(args.steps - 1) & 1][0])
+        x_dev, f_dev = xb[0], fb[0]
+        if trace:
+            base = trace[0][2]
+            print(f"[rank {rank}] pipelined e2e timeline (ms): " + "; ".join(f"f{k} {lab} {base.elapsed_time(ev):.2f}" for k, lab, ev in trace), flush=True)
         # BASELINE metric 2 at N GPUs: neighbour-list build (halo exchange + cell-list build + emission, per-rank lists left
         # on the device), max over ranks
         nl_ms, nl_pairs = [], 0
@@ -217,7 +301,13 @@ def run(args, rank, world, local):
                        "l2": "flushed between timed steps (256 MiB memset, untimed); per-step CUDA events, max over ranks"},
             "clocks": clocks,
             "e2e": {"value": P_in / (float(te[0]) * 1e-3), "unit": bench.UNIT, "ms_per_step": float(te[0]),
-                    "h2d_bytes_per_step": int(x_host.nbytes) * world, "d2h_bytes_per_step": (int(f_pin.numel()) * 4 + 4) * world},
+                    "h2d_bytes_per_step": int(x_host.nbytes) * world, "d2h_bytes_per_step": (int(f_pin.numel()) * 4 + 4) * world,
+                    "mode": "pipelined frames: every frame's positions are copied from pinned host memory and its forces + energy copied back inside the "
+                            "timed region; copy-in of frame k+1, halo exchange + build + sweep of frame k and copy-out of frame k-1 overlap on three streams; "
+                            "L2 flush between frames on the compute stream, inside the timed region; wall clock over all frames, max over ranks",
+                    "energy": e_pipe},
+            "e2e_sync": {"value": P_in / (float(te_sync[0]) * 1e-3), "unit": bench.UNIT, "ms_per_step": float(te_sync[0]),
+                         "mode": "copy in, step, copy out, one frame at a time (barrier between frames): the latency of a dependent step"},
             "gpu_launches": launches * world,
             "breakdown_ms": {"step_max": ms, "sweep_kernel_max": float(tmax[1]), "build_max": float(tmax[4])},
             "energy": float(e_host),

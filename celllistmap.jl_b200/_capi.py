@@ -24,7 +24,7 @@ SYMBOLS = [
     "clm_create", "clm_destroy", "clm_last_error", "clm_set_stream", "clm_synchronize", "clm_set_box", "clm_get_box",
     "clm_set_positions", "clm_set_positions_async", "clm_build", "clm_map_lj", "clm_map_coulomb", "clm_map_dist_hist", "clm_map_pairvel",
     "clm_map_mindist", "clm_map_sum_d_d2", "clm_neighborlist", "clm_neighborlist_copy", "clm_get_stats",
-    "clm_set_option", "clm_version", "clm_measure_fma_peak", "clm_set_foreign", "clm_set_foreign_mask", "clm_cell_coords", "clm_select_layers",
+    "clm_set_option", "clm_version", "clm_measure_fma_peak", "clm_set_foreign", "clm_set_foreign_mask", "clm_read_ints", "clm_cell_coords", "clm_select_layers",
     "clm_custom_compile", "clm_custom_log", "clm_map_custom", "clm_custom_check",
     "clm_comm_unique_id", "clm_comm_init", "clm_comm_destroy", "clm_slab_range", "clm_slab_update", "clm_comm_allreduce_sum", "clm_slab_info",
 ]
@@ -118,6 +118,7 @@ def lib():
     L.clm_measure_fma_peak.argtypes = [ci, ci, C.POINTER(C.c_double)]
     L.clm_set_foreign.argtypes = [vp, ci, vp, i64, ci]
     L.clm_set_foreign_mask.argtypes = [vp, ci, vp, i64, ci]
+    L.clm_read_ints.argtypes = [vp, vp, C.c_int32, C.POINTER(C.c_int32)]
     L.clm_cell_coords.argtypes = [vp, vp, i64, ci, ci, vp]
     L.clm_select_layers.argtypes = [vp, vp, i64, ci, C.POINTER(C.c_int32), ci, vp, vp, i64, vp, vp, vp]
     L.clm_custom_compile.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(CustomInfo)]
@@ -274,6 +275,13 @@ class Handle:
         p, dev = _addr(mask)
         self._chk(self.L.clm_set_foreign_mask(self.h, int(which), p, int(mask.shape[0]), 1 if dev else 0))
         self._keep_mask = mask
+
+    def read_ints(self, t):
+        """a small int32 CUDA tensor (<= 64 entries) -> Python ints, without a DMA copy (clm_read_ints)."""
+        n = int(t.numel())
+        out = (C.c_int32 * max(n, 1))()
+        self._chk(self.L.clm_read_ints(self.h, _addr(t)[0], n, out))
+        return [int(out[k]) for k in range(n)]
 
     def cell_coords(self, x, axis, out=None):
         """0-based reference-cell index along `axis` of every row of x (numpy in -> numpy out, torch CUDA in -> torch out)."""

@@ -55,6 +55,11 @@ static __global__ void k_map_begin(unsigned long long* __restrict__ res_words, i
     if (threadIdx.x < nwords) res_words[threadIdx.x] = 0ull;
     if (threadIdx.x == 0) *work = 0;
 }
+// n device ints -> mapped pinned host memory (clm_read_ints: a read-back that does not queue on the DMA engines)
+static __global__ void k_publish_ints(const int* __restrict__ src, int n, volatile int* __restrict__ h_dst) {
+    for (int k = threadIdx.x; k < n; k += blockDim.x) h_dst[k] = src[k];
+    __threadfence_system();
+}
 static __global__ void k_dscal_publish(const int* __restrict__ dscal, volatile int* __restrict__ h_pub) {
     const int k = threadIdx.x;
     if (k < DS_COUNT) h_pub[k] = dscal[k];

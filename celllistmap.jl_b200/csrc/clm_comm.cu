@@ -186,8 +186,7 @@ template <class T> int Engine<T>::slab_update(const void* xyz, int64_t n, int on
         k_max2<<<1, 32, 0, stream>>>(c->cnt.p, c->cnt.p + 4);
         CLM_CK(cudaGetLastError());
         CLM_NCCL(g_nccl.AllReduce(c->cnt.p + 4, c->cnt.p + 4, 1, NCCL_INT32, NCCL_MAX, c->comm, stream));
-        CLM_CK(cudaMemcpyAsync(c->h_cnt, c->cnt.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream));
-        CLM_CK(cudaStreamSynchronize(stream));      // the one synchronisation
+        if (int rc = read_ints(c->cnt.p, 8, c->h_cnt)) return rc;      // the one synchronisation (mapped pinned memory, no DMA copy)
         stats.launches += 2;
         if ((int64_t)c->h_cnt[4] <= c->cap) break;
         if (attempt == 3) return fail(CLM_ERR_COMM, "halo messages did not converge on a capacity");

@@ -32,6 +32,7 @@ struct EngineBase {
     virtual int set_positions_async(int set, const void* xyz, int64_t n) = 0;
     virtual int set_foreign(int set, const void* xyz, int64_t n, int on_device) = 0;
     virtual int set_foreign_mask(int set, const uint8_t* mask, int64_t n, int on_device) = 0;
+    virtual int read_ints(const int32_t* dev, int32_t n, int32_t* host_out) = 0;
     virtual int cell_coords(const void* xyz, int64_t n, int on_device, int axis, int32_t* out) = 0;
     virtual int comm_init(const void* id, int rank, int world) = 0;
     virtual int comm_destroy() = 0;
@@ -121,6 +122,8 @@ template <class T> struct Engine : EngineBase {
     DBuf<int> dscal;
     DBuf<Tile> tiles;
     int* h_dscal = nullptr;          // pinned, mapped: written by k_dscal_publish
+    int* h_ints = nullptr; int* h_ints_dev = nullptr; cudaEvent_t ev_ints = nullptr;   // clm_read_ints: mapped pinned scratch (READ_INTS_MAX ints)
+    static constexpr int READ_INTS_MAX = 64;
     int* h_dscal_dev = nullptr;      // its device-side address
     DBuf<ResultBlock> d_res;
     ResultBlock* h_res = nullptr;    // pinned
@@ -163,6 +166,7 @@ template <class T> struct Engine : EngineBase {
     int set_positions_async(int set, const void* xyz, int64_t n) override;
     int set_foreign(int set, const void* xyz, int64_t n, int on_device) override;
     int set_foreign_mask(int set, const uint8_t* mask, int64_t n, int on_device) override;
+    int read_ints(const int32_t* dev, int32_t n, int32_t* host_out) override;
     int cell_coords(const void* xyz, int64_t n, int on_device, int axis, int32_t* out) override;
     int select_layers(const void* xyz, int64_t n, int axis, const int32_t* ranges, int merge, void* out_a, void* out_b, int64_t capacity, int32_t* counts, int32_t* idx_a, int32_t* idx_b) override;
     // slab decomposition over NCCL (clm_comm.cu)

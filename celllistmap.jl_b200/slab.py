@@ -379,7 +379,12 @@ class SlabSystem:
         flag = (allc.max() > cap).to(torch.int32).reshape(1)
         flag = flag.cpu() if stage else flag
         dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=g)
-        counts = torch.cat([allc, flag.to(allc.device)]).cpu().tolist()      # the one synchronisation
+        if stage:
+            counts = torch.cat([allc, flag.to(allc.device)]).cpu().tolist()  # the one synchronisation
+        else:
+            # the one synchronisation -- through mapped pinned memory, not a DMA copy: a 20-byte cudaMemcpy would queue behind
+            # the force copy-out of the previous pipelined frame on the device->host engine (clm_read_ints)
+            counts = self.h.read_ints(torch.cat([allc, flag.to(allc.device)]).to(torch.int32).contiguous())
         if counts[4]:
             return None
         n_up, n_lo = counts[2], (0 if merge else counts[3])

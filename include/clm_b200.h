@@ -146,6 +146,10 @@ CLM_API int clm_set_positions_async(clm_handle* h, int set, const void* aos_xyz_
  * particle i; NULL removes the mask).  Works for every cell type; the mask is n bytes (n of clm_set_positions). */
 CLM_API int clm_set_foreign(clm_handle* h, int set, const void* aos_xyz, int64_t n, int on_device);
 CLM_API int clm_set_foreign_mask(clm_handle* h, int set, const uint8_t* mask, int64_t n, int on_device);
+/* n <= 64 DEVICE ints back to the host, ordered behind everything enqueued on the handle's stream: written into mapped
+ * pinned memory by a one-warp kernel + an event wait.  For the fill counts of a halo exchange: a cudaMemcpy of the same
+ * bytes queues on the device->host DMA engine behind the bulk copy-out of the previous pipelined frame. */
+CLM_API int clm_read_ints(clm_handle* h, const int32_t* dev_ints, int32_t n, int32_t* host_out);
 CLM_API int clm_cell_coords(clm_handle* h, const void* aos_xyz, int64_t n, int on_device, int axis, int32_t* cell_out);
 /* one-pass face selection for the halo exchange; every pointer except `ranges` is a DEVICE pointer and the call only
  * enqueues.  Particles whose cell layer along `axis` is in [ranges[0], ranges[1]) are appended (AoS rows of T) to out_a,
