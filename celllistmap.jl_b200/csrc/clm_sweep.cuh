@@ -31,7 +31,11 @@
 namespace clm {
 
 enum { MODE_HALF = 0, MODE_TRI = 1, MODE_ALL = 2 };
-constexpr int SWEEP_THREADS = 128;
+#ifndef CLM_SWEEP_THREADS
+#define CLM_SWEEP_THREADS 128
+#endif
+constexpr int SWEEP_THREADS = CLM_SWEEP_THREADS;   // warps of a CTA work independently (own staging buffer, own mbarrier): the CTA size only sets the register / occupancy granularity
+static_assert(SWEEP_THREADS % 32 == 0 && SWEEP_THREADS >= 32 && SWEEP_THREADS <= 128, "block_sum scratch holds 4 warps");
 constexpr int NB_PRIV_MAX = 16;  // histograms with <= this many bins use per-thread private shared-memory bins
 constexpr int LF_MAX = 7;        // largest stencil reach in device cells (lcell * sub)
 constexpr int TILE_I = 8, LOG2_TILE_I = 3, NSLICE = 32 / TILE_I;   // particles i per warp tile; the other lanes split the partners into j-slices

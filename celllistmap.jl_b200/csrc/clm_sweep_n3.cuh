@@ -147,8 +147,13 @@ template <class T, bool AUX> struct N3MinBlocks { static constexpr int value = (
 // The key of a keyed partner (its reference cell along the row) is rbase + (parity bit of its record ^ parity of
 // rbase): no key array.  A tile that spans more than two reference cells (sparse rows only) is processed in several
 // trips of the rbase loop, each with the particles i of two reference cells.
+#ifdef CLM_N3_MAXNREG   // tuning builds: an explicit register cap instead of the occupancy target (tools/tune_n3_cta.sh)
+#define CLM_N3_BOUNDS __maxnreg__(CLM_N3_MAXNREG)
+#else
+#define CLM_N3_BOUNDS __launch_bounds__(SWEEP_THREADS, N3MinBlocks<T, F::AUX>::value)
+#endif
 template <class T, int MODE, class F>
-__global__ void __launch_bounds__(SWEEP_THREADS, N3MinBlocks<T, F::AUX>::value)
+__global__ void CLM_N3_BOUNDS
 k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, T* __restrict__ facc) {
     typedef TagT<T> TG;
     typedef typename TG::type tag_t;
