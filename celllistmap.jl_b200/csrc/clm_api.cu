@@ -336,7 +336,7 @@ template <class T> int Engine<T>::build_enqueue() {
     double nref_total = 1;
     for (int k = 0; k < dim; ++k) nref_total *= (double)box.nc[k];
     if (nref_total > 2.0e9) return fail(CLM_ERR_UNSUPPORTED, "more than 2e9 computing cells: increase the cutoff or use lcell = 1");
-    if (box.lcell > LF_MAX) return fail(CLM_ERR_UNSUPPORTED, "lcell > 7 is not supported by the device stencil table");
+    if (box.lcell > LF_MAX) return fail(CLM_ERR_UNSUPPORTED, "lcell > 15 is not supported by the device stencil table");
     nref = (int64_t)nref_total;
     // device grid: split every reference cell into sub^N sub-cells, aiming at ~4 particles per device cell
     {
@@ -344,7 +344,7 @@ template <class T> int Engine<T>::build_enqueue() {
         for (int k = 0; k < dim; ++k) inner *= (double)std::max<int64_t>(1, box.nc[k] - 2 * box.lcell - 1);
         const double per_cell = (double)std::max(sets[0].n, two_sets ? sets[1].n : (int64_t)0) / inner;
         int sub = opt_sub > 0 ? opt_sub : (int)std::floor(std::pow(std::max(per_cell / 4.0, 1.0), 1.0 / dim) + 0.35);
-        sub = std::max(1, std::min(sub, LF_MAX / box.lcell));
+        sub = std::max(1, std::min(sub, SUB_MAX / box.lcell));
         while (sub > 1) {
             double nd = nref_total * std::pow((double)sub, dim);
             bool ok = nd <= 4.0e8;
@@ -647,7 +647,7 @@ template <class T> int Engine<T>::get_stats(clm_stats* out) {
 template <class T> int Engine<T>::set_option(const char* name, int64_t v) {
     if (!name) return fail(CLM_ERR_ARGUMENT, "option name is NULL");
     const std::string s(name);
-    if (s == "sub") { if (v < 0 || v > LF_MAX) return fail(CLM_ERR_ARGUMENT, "sub must be in 0..7"); opt_sub = (int)v; dirty = true; return CLM_OK; }
+    if (s == "sub") { if (v < 0 || v > SUB_MAX) return fail(CLM_ERR_ARGUMENT, "sub must be in 0..7"); opt_sub = (int)v; dirty = true; return CLM_OK; }
     if (s == "dbg") { dbg = (int)v; return CLM_OK; }
     if (s == "n3") { opt_n3 = (v < 0) ? -1 : (v ? 1 : 0); return CLM_OK; }
     if (s == "blocks_per_sm") { if (v < 0) return fail(CLM_ERR_ARGUMENT, "blocks_per_sm must be >= 0"); opt_bps = (int)v; return CLM_OK; }

@@ -150,7 +150,7 @@ template <class T> int Engine<T>::slab_update(const void* xyz, int64_t n, int on
             double inner = 1;
             for (int k = 0; k < dim; ++k) inner *= (double)std::max<int64_t>(1, box.nc[k] - 2 * box.lcell - 1);
             const int sub = (int)std::floor(std::pow(std::max((double)hn / inner / 4.0, 1.0), 1.0 / dim) + 0.35);
-            opt_sub = std::max(1, std::min(sub, LF_MAX / box.lcell));
+            opt_sub = std::max(1, std::min(sub, SUB_MAX / box.lcell));
         }
         const int layers = std::max(1, ((int)box.nc[0] - 2 * lcell - 1) / world);
         const double frac = std::min(1.0, (double)lcell / layers * (merge ? 2.0 : 1.0));

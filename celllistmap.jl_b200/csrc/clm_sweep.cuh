@@ -37,7 +37,8 @@ enum { MODE_HALF = 0, MODE_TRI = 1, MODE_ALL = 2 };
 constexpr int SWEEP_THREADS = CLM_SWEEP_THREADS;   // warps of a CTA work independently (own staging buffer, own mbarrier): the CTA size only sets the register / occupancy granularity
 static_assert(SWEEP_THREADS % 32 == 0 && SWEEP_THREADS >= 32 && SWEEP_THREADS <= 128, "block_sum scratch holds 4 warps");
 constexpr int NB_PRIV_MAX = 16;  // histograms with <= this many bins use per-thread private shared-memory bins
-constexpr int LF_MAX = 7;        // largest stencil reach in device cells (lcell * sub)
+constexpr int LF_MAX = 15;       // largest stencil reach in device cells (lcell * sub): the stencil tables of SweepArgs hold (2 LF_MAX + 1)^2 rows
+constexpr int SUB_MAX = 7;       // largest sub-cell split chosen for a reference cell (lcell * sub <= SUB_MAX unless lcell itself is larger)
 constexpr int TILE_I = 8, LOG2_TILE_I = 3, NSLICE = 32 / TILE_I;   // particles i per warp tile; the other lanes split the partners into j-slices
 // per-warp staging buffer of partner records: small buffers keep 8 CTAs (32 warps) resident per SM, which hides the
 // latency of the tile fetch / cell_start loads / bulk copies better than fewer, larger chunks (tools/tune_stage.sh)

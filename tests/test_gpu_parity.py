@@ -81,6 +81,42 @@ def test_neighborlist_self_bit_exact(clm, oracle_mod, dtype, kind, dim, lcell):
     assert_lists_identical(got, want)
 
 
+@pytest.mark.parametrize("kind,dim,dtype,lcell", [("ortho", 3, np.float64, 9), ("triclinic", 3, np.float32, 8), ("nonperiodic", 2, np.float64, 12),
+                                                  ("triclinic", 2, np.float64, 15), ("ortho", 3, np.float32, 5)])
+def test_neighborlist_large_lcell_bit_exact(clm, oracle_mod, kind, dim, dtype, lcell):
+    """lcell beyond the usual 1-3 (the reference accepts any lcell >= 1, src/internals/Box.jl:192): cells of cutoff / lcell,
+    (2 lcell + 1)^(N-1) stencil rows per tile; no sub-cell split beyond lcell = 7."""
+    rng = np.random.default_rng(31 + lcell)
+    x, uc = random_system(rng, 2000 if dim == 3 else 1200, dim, kind, dtype)
+    cutoff = 1.2
+    got = clm.neighborlist(xpositions=x, cutoff=cutoff, unitcell=uc, lcell=lcell)
+    want = oracle_mod.Oracle(x, cutoff, unitcell=uc, lcell=lcell, dtype=dtype).neighborlist()
+    assert len(want[0]) > 100
+    assert_lists_identical(got, want)
+    if kind != "nonperiodic" and dim == 3 and dtype == np.float64:     # the force sweeps walk the same stencil tables
+        n = x.shape[0]
+        sys_ = clm.ParticleSystem(xpositions=x, unitcell=uc, cutoff=cutoff, lcell=lcell, output=clm.EnergyAndForces(0.0, np.zeros((n, 3), dtype)))
+        out = clm.pairwise(clm.LJEnergyAndForces(1.0e-3, 1.0e-6), sys_)
+        we, wf = oracle_mod.Oracle(x, cutoff, unitcell=uc, lcell=lcell, dtype=dtype).lj(1.0e-3, 1.0e-6, forces=True)
+        assert abs(out.energy - we) <= 1e-10 * abs(we)
+        assert np.abs(np.asarray(out.forces) - wf).max() <= 1e-10 * np.abs(wf).max()
+    if kind == "ortho" and dtype == np.float32:
+        # Float32 forces take the Newton's-third-law sweep, which walks the stencil tables with its own code: a missed or doubled
+        # pair would be an O(1) error; random close pairs make anything tighter than the pair-set check a conditioning question
+        n = x.shape[0]
+        sys_ = clm.ParticleSystem(xpositions=x, unitcell=uc, cutoff=cutoff, lcell=lcell, output=clm.EnergyAndForces(0.0, np.zeros((n, 3), dtype)))
+        out = clm.pairwise(clm.LJEnergyAndForces(1.0e-3, 1.0e-6), sys_)
+        we, wf = oracle_mod.Oracle(x.astype(np.float64), cutoff, unitcell=uc.astype(np.float64), lcell=lcell).lj(1.0e-3, 1.0e-6, forces=True)
+        assert abs(out.energy - we) <= 1e-3 * abs(we)
+        assert np.abs(np.asarray(out.forces) - wf).max() <= 1e-3 * np.abs(wf).max()
+
+
+def test_lcell_beyond_the_stencil_table_is_refused(clm):
+    x = np.random.default_rng(1).random((100, 3))
+    with pytest.raises(Exception, match="lcell"):
+        clm.neighborlist(xpositions=x, cutoff=0.1, unitcell=[1.0, 1.0, 1.0], lcell=16)
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("kind", ["ortho", "triclinic", "nonperiodic"])
 @pytest.mark.parametrize("dim", [2, 3])
