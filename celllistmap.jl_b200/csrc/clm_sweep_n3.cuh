@@ -131,9 +131,13 @@ enum { N3_PLAIN = 0, N3_KEYED = 1, N3_GENERAL = 2, N3_TRI = 3 };
 #ifndef CLM_N3_MINB_F32
 #define CLM_N3_MINB_F32 5
 #endif
-#ifndef CLM_N3_MINB_F64
-#define CLM_N3_MINB_F64 4
+#ifndef CLM_N3_HALVES_F64
+#define CLM_N3_HALVES_F64 1   // 2: measured slower (see the comment at the i-side accumulators)
 #endif
+#ifndef CLM_N3_MINB_F64
+#define CLM_N3_MINB_F64 ((CLM_N3_HALVES_F64 == 2) ? 5 : 4)
+#endif
+template <class T> struct N3Halves { static constexpr int value = (sizeof(T) == 8) ? CLM_N3_HALVES_F64 : 1; };
 template <class T, bool AUX> struct N3MinBlocks { static constexpr int value = (sizeof(T) == 4) ? (AUX ? 4 : CLM_N3_MINB_F32) : (AUX ? 3 : CLM_N3_MINB_F64); };
 
 // Per tile (TILE_I consecutive records of one row, particles i):
@@ -160,6 +164,7 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
     typedef N3Cap<T, F::AUX> CP;
     extern __shared__ __align__(128) unsigned char dsm_raw[];
     const int lane = threadIdx.x & 31;
+    constexpr int NH = N3Halves<T>::value, IH = TILE_I / NH;
     // one base address per warp; everything else sits at a compile-time offset from it
     unsigned char* const wb = dsm_raw + (threadIdx.x >> 5) * CP::WSTRIDE;
     // [TILE_I] i-side keys.  MODE_HALF: x = (reference cell - rbase) << 30 | own slot (an image particle: | 0x3fffffff, so that
@@ -208,10 +213,43 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
             rfx_i = div_sub(cx); rfa = div_sub(cxa); rfb = div_sub(cxb);
         }
         const int ry_i = div_sub(iy), rz_i = div_sub(iz);
-        T fi[TILE_I][3];
+        // i-side accumulators: NH == 1: all TILE_I particles of the tile, reduced once per tile.  NH == 2 (tuning builds,
+        // -DCLM_N3_HALVES_F64=2): the chunks of a pass are swept twice, once per HALF of the tile's particles, with IH x 3
+        // accumulators that are zeroed before and reduced after every half-sweep.  Built for Float64, where 8 x 3 doubles live
+        // through the pair loop cost 128 registers + spills (16 warps / SM, 5.8e8 warp instructions), and measured SLOWER:
+        // 0.984 ms (128 registers, no spills) / 1.047 ms (96 registers, 20 warps) against 0.920 ms of NH == 1 and 0.906 ms of the
+        // full shell -- every partner is loaded and its force flushed (three scalar f64 reductions) twice
+        // (tools/tune_n3_f64.sh, profiles/r2_tune_n3_f64.txt)
+        T fi[IH][3];
 #pragma unroll
-        for (int i = 0; i < TILE_I; ++i) fi[i][0] = fi[i][1] = fi[i][2] = T(0);
+        for (int i = 0; i < IH; ++i) fi[i][0] = fi[i][1] = fi[i][2] = T(0);
         T e_tile = T(0);
+        // f_i: reduce-scatter of the IH x 3 per-lane partial sums over the warp: after log2(IH) halving steps the 32 / IH lanes
+        // of group g hold the partial sums of particle i0 + g, butterfly steps finish them; the accumulators are zeroed
+        auto reduce_fi = [&](const int i0) {
+            T v[3 * IH];
+#pragma unroll
+            for (int i = 0; i < IH; ++i) { v[3 * i] = fi[i][0]; v[3 * i + 1] = fi[i][1]; v[3 * i + 2] = fi[i][2]; fi[i][0] = fi[i][1] = fi[i][2] = T(0); }
+#pragma unroll
+            for (int half = 3 * IH / 2, o = 16; half >= 3; half >>= 1, o >>= 1) {
+                const bool upper = (lane & o) != 0;
+#pragma unroll
+                for (int k = 0; k < half; ++k) {
+                    const T send = upper ? v[k] : v[k + half];
+                    const T keep = upper ? v[k + half] : v[k];
+                    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+            constexpr int GL = 32 / IH;       // lanes per particle
+#pragma unroll
+            for (int o = GL / 2; o >= 1; o >>= 1) {
+                v[0] += __shfl_xor_sync(0xffffffffu, v[0], o); v[1] += __shfl_xor_sync(0xffffffffu, v[1], o); v[2] += __shfl_xor_sync(0xffffffffu, v[2], o);
+            }
+            const int g = i0 + lane / GL;
+            const int slot_g = (int)(__shfl_sync(0xffffffffu, swi, g) & N3_SLOT);
+            const bool act_g = __shfl_sync(0xffffffffu, active0 ? 1 : 0, g) != 0;
+            if ((lane & (GL - 1)) == 0 && act_g && (v[0] != T(0) || v[1] != T(0) || v[2] != T(0))) red_add3(facc + (size_t)slot_g * 4, v[0], v[1], v[2]);
+        };
 
 #pragma unroll 1
         for (int rbase = rfa; rbase <= rfb; rbase += 2) {
@@ -238,8 +276,9 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
             int nl = 0, nk = 0;   // partners waiting at buf[0 .. nl); the first nk of them are keyed
 
             // ---- one chunk = 32 partners, one per lane; one warp step per particle i of the tile ------------------
-            auto chunk = [&](auto kind_tag, const int s) {
+            auto chunk = [&](auto kind_tag, auto half_tag, const int s) {
                 constexpr int KIND = decltype(kind_tag)::value;
+                constexpr int I0 = decltype(half_tag)::value * IH;
                 const RecT<T> rj = ldrec_s(buf + s);
                 T wj = T(0);
                 if constexpr (F::AUX) wj = ldrec_s(abuf + s).x;
@@ -253,7 +292,8 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
                     KJ = ((s < nk) ? ((((sw >> N3_PAR_SHIFT) & 1u) ^ rpar) << 30) : 0x80000000u) | (gj ? 0x3fffffffu : (unsigned)slot_j);
                 T fjx = T(0), fjy = T(0), fjz = T(0);
 #pragma unroll
-                for (int i = 0; i < TILE_I; ++i) {
+                for (int ii = 0; ii < IH; ++ii) {
+                    const int i = I0 + ii;
                     const Vec4S<T> pi = ldvec4_s(ipos + i);
                     const T dx = pi.x - rj.x, dy = pi.y - rj.y, dz = pi.z - rj.z;
                     const T d2 = xfma(dz, dz, xfma(dy, dy, dx * dx));
@@ -262,7 +302,7 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
                     else if (KIND == N3_GENERAL) { const int2 ik = ikey[i]; ok = (KJ > (unsigned)ik.x) && !(ik.y && gj); }
                     const bool hit = ok && (d2 <= rc2);
                     const T sc = f.fs(hit, d2, e_tile, pi.w, wj);
-                    fi[i][0] = xfma(sc, dx, fi[i][0]); fi[i][1] = xfma(sc, dy, fi[i][1]); fi[i][2] = xfma(sc, dz, fi[i][2]);
+                    fi[ii][0] = xfma(sc, dx, fi[ii][0]); fi[ii][1] = xfma(sc, dy, fi[ii][1]); fi[ii][2] = xfma(sc, dz, fi[ii][2]);
                     fjx = xfma(-sc, dx, fjx); fjy = xfma(-sc, dy, fjy); fjz = xfma(-sc, dz, fjz);
                 }
                 if (any_nonzero(fjx, fjy, fjz)) red_add3(facc + (size_t)slot_j * 4, fjx, fjy, fjz);
@@ -378,13 +418,21 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
                         ns = nfull * 32;
                     }
                     __syncwarp();
+                    auto sweep_chunks = [&](auto half_tag) {
 #pragma unroll 1
-                    for (int ch = 0; ch < nfull; ++ch) {
-                        const int s = ch * 32 + lane;
-                        if (MODE == MODE_TRI) chunk(std::integral_constant<int, N3_TRI>{}, s);
-                        else if (any_ghost_i) chunk(std::integral_constant<int, N3_GENERAL>{}, s);
-                        else if (ch * 32 < nk) chunk(std::integral_constant<int, N3_KEYED>{}, s);
-                        else chunk(std::integral_constant<int, N3_PLAIN>{}, s);
+                        for (int ch = 0; ch < nfull; ++ch) {
+                            const int s = ch * 32 + lane;
+                            if (MODE == MODE_TRI) chunk(std::integral_constant<int, N3_TRI>{}, half_tag, s);
+                            else if (any_ghost_i) chunk(std::integral_constant<int, N3_GENERAL>{}, half_tag, s);
+                            else if (ch * 32 < nk) chunk(std::integral_constant<int, N3_KEYED>{}, half_tag, s);
+                            else chunk(std::integral_constant<int, N3_PLAIN>{}, half_tag, s);
+                        }
+                    };
+                    sweep_chunks(std::integral_constant<int, 0>{});
+                    if constexpr (NH == 2) {
+                        if (nfull > 0) reduce_fi(0);
+                        sweep_chunks(std::integral_constant<int, 1>{});
+                        if (nfull > 0) reduce_fi(IH);
                     }
                     const int rem = ns & 31;
                     if (nfull > 0 && rem > 0) {
@@ -405,31 +453,7 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
             }
         }
 
-        // ---- f_i: reduce-scatter of the TILE_I x 3 per-lane partial sums over the warp: after three halving steps the
-        //      four lanes 4g .. 4g+3 hold the partial sums of particle g, two butterfly steps finish them ----
-        {
-            T v[24];
-#pragma unroll
-            for (int i = 0; i < TILE_I; ++i) { v[3 * i] = fi[i][0]; v[3 * i + 1] = fi[i][1]; v[3 * i + 2] = fi[i][2]; }
-#pragma unroll
-            for (int half = 12, o = 16; half >= 3; half >>= 1, o >>= 1) {
-                const bool upper = (lane & o) != 0;
-#pragma unroll
-                for (int k = 0; k < half; ++k) {
-                    const T send = upper ? v[k] : v[k + half];
-                    const T keep = upper ? v[k + half] : v[k];
-                    v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
-                }
-            }
-#pragma unroll
-            for (int o = 2; o >= 1; o >>= 1) {
-                v[0] += __shfl_xor_sync(0xffffffffu, v[0], o); v[1] += __shfl_xor_sync(0xffffffffu, v[1], o); v[2] += __shfl_xor_sync(0xffffffffu, v[2], o);
-            }
-            const int g = lane >> 2;
-            const int slot_g = (int)(__shfl_sync(0xffffffffu, swi, g) & N3_SLOT);
-            const bool act_g = __shfl_sync(0xffffffffu, active0 ? 1 : 0, g) != 0;
-            if ((lane & 3) == 0 && act_g && (v[0] != T(0) || v[1] != T(0) || v[2] != T(0))) red_add3(facc + (size_t)slot_g * 4, v[0], v[1], v[2]);
-        }
+        if constexpr (NH == 1) reduce_fi(0);   // Float32: once per tile
         e_acc += (double)e_tile;
     }
     {

@@ -23,6 +23,8 @@ e_dev = torch.zeros(1, dtype=tdt, device="cuda")
 f_dev = torch.zeros((n, 3), dtype=tdt, device="cuda")
 h = clm.Handle(3, dtype)
 h.set_box(clm._capi.ORTHORHOMBIC, w["unitcell"], w["cutoff"], 1)
+if os.environ.get("CLM_N3"):
+    h.set_option("n3", int(os.environ["CLM_N3"]))   # 1: Newton's-third-law sweep (default for Float32 only), 0: full shell
 for it in range(steps):
     h.set_positions(0, x_dev)
     h.build()
