@@ -24,7 +24,7 @@ SYMBOLS = [
     "clm_create", "clm_destroy", "clm_last_error", "clm_set_stream", "clm_synchronize", "clm_set_box", "clm_get_box",
     "clm_set_positions", "clm_set_positions_async", "clm_build", "clm_map_lj", "clm_map_coulomb", "clm_map_dist_hist", "clm_map_pairvel",
     "clm_map_mindist", "clm_map_sum_d_d2", "clm_neighborlist", "clm_neighborlist_copy", "clm_get_stats",
-    "clm_set_option", "clm_version", "clm_measure_fma_peak", "clm_set_foreign", "clm_set_foreign_mask", "clm_read_ints", "clm_cell_coords", "clm_select_layers",
+    "clm_set_option", "clm_version", "clm_measure_fma_peak", "clm_host_register", "clm_host_unregister", "clm_set_foreign", "clm_set_foreign_mask", "clm_read_ints", "clm_cell_coords", "clm_select_layers",
     "clm_custom_compile", "clm_custom_log", "clm_map_custom", "clm_custom_check",
     "clm_comm_unique_id", "clm_comm_init", "clm_comm_destroy", "clm_slab_range", "clm_slab_update", "clm_comm_allreduce_sum", "clm_slab_info",
 ]
@@ -116,6 +116,8 @@ def lib():
     L.clm_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.clm_set_option.argtypes = [vp, C.c_char_p, i64]
     L.clm_measure_fma_peak.argtypes = [ci, ci, C.POINTER(C.c_double)]
+    L.clm_host_register.argtypes = [vp, i64]
+    L.clm_host_unregister.argtypes = [vp]
     L.clm_set_foreign.argtypes = [vp, ci, vp, i64, ci]
     L.clm_set_foreign_mask.argtypes = [vp, ci, vp, i64, ci]
     L.clm_read_ints.argtypes = [vp, vp, C.c_int32, C.POINTER(C.c_int32)]
@@ -153,6 +155,15 @@ def _addr(a):
     if not a.flags["C_CONTIGUOUS"]:
         raise ValueError("arrays must be C-contiguous")
     return a.ctypes.data_as(C.c_void_p), False
+
+
+def host_register(a):
+    """page-lock the memory of a numpy array the caller reuses across calls (clm_host_register); False when the driver refuses."""
+    return lib().clm_host_register(a.ctypes.data_as(C.c_void_p), int(a.nbytes)) == 0
+
+
+def host_unregister(a):
+    lib().clm_host_unregister(a.ctypes.data_as(C.c_void_p))
 
 
 def measure_fma_peak(dtype, device=0):

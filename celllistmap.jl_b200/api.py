@@ -609,8 +609,20 @@ class InPlaceNeighborList:
                                   output_name="nb", parallel=parallel, nbatches=nbatches, lcell=lcell, device=device)
         self.show_progress = show_progress
         self._list = np.zeros(0, dtype=nl_dtype(self.sys.dtype))
+        self._pinned, self._reused = False, 0
         self.n = 0
         self.n_cutoff_band = 0   # pairs of the last list whose d2 lies within 1 ulp of cutoff^2 (north_star: reported separately)
+
+    def _unpin(self):
+        if self._pinned:
+            _capi.host_unregister(self._list)
+            self._pinned = False
+
+    def __del__(self):
+        try:
+            self._unpin()
+        except Exception:
+            pass
 
     def update(self, x=None, y=None, *, cutoff=None, unitcell=None, parallel=None):
         """update!(system, x, [y]; cutoff, unitcell, parallel) (src/API/neighborlist.jl:159-169)."""
@@ -624,7 +636,14 @@ class InPlaceNeighborList:
         try:
             n = s._h.neighborlist_count()
             if self._list.shape[0] < n:
+                self._unpin()
                 self._list = np.zeros(max(n, int(1.2 * self._list.shape[0])), dtype=nl_dtype(s.dtype))
+                self._reused = 0
+            elif n and not self._pinned and self._reused >= 1:
+                # the record array is being reused in place: page-lock it once, so that the copy-out of every later list is a
+                # direct DMA transfer (clm_host_register; a one-shot list never pays the registration)
+                self._pinned = _capi.host_register(self._list)
+            self._reused += 1
             if n:
                 s._h.neighborlist_copy(self._list)
         except ClmError as e:

@@ -707,6 +707,18 @@ struct clm_handle { EngineBase* e; };
 
 extern "C" {
 int clm_version(void) { return 100; }
+int clm_host_register(void* ptr, int64_t bytes) {
+    if (!ptr || bytes <= 0) { clm::g_create_error = "clm_host_register: NULL pointer or empty range"; return CLM_ERR_ARGUMENT; }
+    const cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); clm::g_create_error = std::string("cudaHostRegister: ") + cudaGetErrorString(e); return CLM_ERR_CUDA; }
+    return CLM_OK;
+}
+int clm_host_unregister(void* ptr) {
+    if (!ptr) { clm::g_create_error = "clm_host_unregister: NULL pointer"; return CLM_ERR_ARGUMENT; }
+    const cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) { (void)cudaGetLastError(); clm::g_create_error = std::string("cudaHostUnregister: ") + cudaGetErrorString(e); return CLM_ERR_CUDA; }
+    return CLM_OK;
+}
 int clm_measure_fma_peak(int device, int dtype, double* tflops) {
     if (!tflops) return CLM_ERR_ARGUMENT;
     return dtype == CLM_F32 ? clm::fma_peak<float>(device, tflops) : clm::fma_peak<double>(device, tflops);

@@ -143,6 +143,28 @@ def test_c1_neighborlist_config(clm, oracle_mod):
     assert len(np.unique(np.stack([a, b], 1), axis=0)) == len(a)
 
 
+def test_inplace_neighborlist_reuses_a_page_locked_buffer(clm, oracle_mod):
+    """InPlaceNeighborList (src/API/neighborlist.jl:84-111) overwrites its record array in place; from the second list on the
+    array is page-locked (clm_host_register) so that the copy-out is a direct DMA transfer.  Lists stay bit-identical across
+    the switch, across position updates, and across a regrowth of the array (which unpins the old one)."""
+    w = W.c1_neighborlist(4000)
+    nb = clm.InPlaceNeighborList(x=w["x"], cutoff=w["cutoff"], unitcell=w["unitcell"])
+    want = oracle_mod.Oracle(w["x"], w["cutoff"], unitcell=w["unitcell"]).neighborlist()
+    for k in range(3):
+        clm.update(nb, xpositions=w["x"])
+        assert_lists_identical(nb.neighborlist().copy(), want)
+        assert nb._pinned == (k >= 1)
+    x2 = np.mod(w["x"] + 0.013, 1.0)
+    clm.update(nb, xpositions=x2)
+    assert_lists_identical(nb.neighborlist().copy(), oracle_mod.Oracle(x2, w["cutoff"], unitcell=w["unitcell"]).neighborlist())
+    assert nb._pinned
+    clm.update(nb, xpositions=x2, cutoff=1.5 * w["cutoff"])          # ~3.4x the pairs: the array regrows, unpinned until reused again
+    assert_lists_identical(nb.neighborlist().copy(), oracle_mod.Oracle(x2, 1.5 * w["cutoff"], unitcell=w["unitcell"]).neighborlist())
+    assert not nb._pinned
+    assert_lists_identical(nb.neighborlist().copy(), oracle_mod.Oracle(x2, 1.5 * w["cutoff"], unitcell=w["unitcell"]).neighborlist())
+    assert nb._pinned
+
+
 # ---------------------------------------------------------------------------------------------------------
 # reductions
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
