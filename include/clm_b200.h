@@ -72,7 +72,11 @@ enum clm_flags {
     CLM_ASYNC = 8       /* pipelined frames (clm_map_lj; needs CLM_RESET and PINNED host outputs): the call only enqueues; the
                            outputs are written by a device->host copy on a separate stream and are valid after
                            clm_synchronize().  With clm_set_positions_async the copy-in of frame k+1, the compute of frame
-                           k and the copy-out of frame k-1 overlap (frames of a trajectory are independent) */
+                           k and the copy-out of frame k-1 overlap (frames of a trajectory are independent).  The copy-out of
+                           a frame is issued by the NEXT map call (behind that frame's cell-list build, so that it travels next
+                           to the long sweep kernel instead of slowing the build's chain of short kernels) or by
+                           clm_synchronize(), whichever comes first: the outputs of frame k are complete after
+                           clm_synchronize(), never merely because later frames were enqueued */
 };
 
 /* Box record (src/internals/Box.jl:84-96); values widened to double (exact for float). */
