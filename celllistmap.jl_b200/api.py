@@ -29,7 +29,7 @@ __all__ = [
     "InPlaceNeighborList", "neighborlist_", "get_computing_box", "Box", "NeighborPair", "DimensionMismatch",
     "LJEnergy", "LJForces", "LJEnergyAndForces", "CoulombEnergy", "CoulombForces", "CoulombEnergyAndForces",
     "DistanceHistogram", "PairwiseVelocities", "MinimumDistanceMap", "SumDistances", "MinimumDistance",
-    "EnergyAndForces", "wrap_relative_to", "CustomPairFunction", "CustomOutput",
+    "EnergyAndForces", "wrap_relative_to", "CustomPairFunction", "CustomOutput", "FramePipeline",
 ]
 
 
@@ -670,3 +670,70 @@ def neighborlist(*, xpositions=None, ypositions=None, positions=None, cutoff, un
     nb = InPlaceNeighborList(x=x, y=ypositions, cutoff=cutoff, unitcell=unitcell, parallel=parallel,
                              show_progress=show_progress, nbatches=nbatches, lcell=lcell, device=device)
     return nb.neighborlist().copy()
+
+
+class FramePipeline:
+    """Independent frames of a trajectory -- the reference's `sys.xpositions .= frame; pairwise!(f, sys)` loop
+    (docs/src/ParticleSystem/updating.md) -- through `handles` particle systems that take the frames in turn.
+
+    Every handle has its own copy-in, compute and copy-out streams (clm_set_positions_async + CLM_ASYNC maps), so within a
+    handle the copy-in of its next frame, the compute of the current one and the copy-out of the previous one overlap; across
+    handles the cell-list build of frame k+1 (a chain of short, latency-bound kernels) runs NEXT TO the pair sweep of frame k,
+    which `blocks_per_sm` keeps from filling the SMs' register files (-1: one resident sweep CTA per SM fewer than fit, i.e. 4
+    instead of 5 for the Float32 force sweep on B200: the sweep alone gets ~5 % slower, the pair of frames ~15 % faster: 0.658 -> 0.558 ms per 1M-particle LJ frame, L2 flushed
+    between frames, tools/diag_e2e_two.py).  Positions and outputs are PINNED host arrays that must stay untouched until
+    `synchronize()`; a buffer may be reused once `handles * 2` later frames have been submitted and synchronised or -- simpler
+    -- after `synchronize()`.  Self-set LJ energy + forces (the headline map); other maps run through `Handle` directly."""
+
+    def __init__(self, dim, dtype, unitcell, cutoff, lcell=1, handles=2, device=0, blocks_per_sm=-1, streams=None):
+        self.dtype = np.dtype(dtype)
+        uc = None if unitcell is None else np.asarray(unitcell, dtype=self.dtype)
+        cell_type = _capi.NONPERIODIC if uc is None else (_capi.TRICLINIC if uc.ndim == 2 else _capi.ORTHORHOMBIC)
+        self.handles = []
+        for k in range(int(handles)):
+            h = Handle(dim, self.dtype, device)
+            if streams is not None:
+                h.set_stream(streams[k])
+            h.set_box(cell_type, uc, cutoff, lcell)
+            if blocks_per_sm and handles > 1:
+                h.set_option("blocks_per_sm", int(blocks_per_sm))
+            self.handles.append(h)
+        self.frames = 0
+        self._last = [None] * len(self.handles)
+
+    def next_handle(self):
+        """index of the handle (and of the stream passed in `streams`) the next submitted frame runs on."""
+        return self.frames % len(self.handles)
+
+    def submit_lj(self, c6, c12, x_pinned, energy_pinned, forces_pinned):
+        """enqueue one frame: positions in, LJ energy and forces out (pinned host arrays of the pipeline's dtype)."""
+        a = self.next_handle()
+        h = self.handles[a]
+        cur = (c6, c12, x_pinned, energy_pinned, forces_pinned)
+        try:
+            try:
+                h.set_positions_async(0, x_pinned)
+                h.map_lj(c6, c12, energy_pinned, forces_pinned, async_=True)
+            except ClmError as e:
+                if e.code != 6 or self._last[a] is None:      # CLM_ERR_CAPACITY: the record capacity of this handle's PREVIOUS frame was
+                    raise                                     # too small (first frames only); it has been grown: repeat that frame, then this one
+                for (p6, p12, px, pe, pf) in (self._last[a], cur):
+                    h.set_positions_async(0, px)
+                    h.map_lj(p6, p12, pe, pf, async_=True)
+        except ClmError as e:
+            _raise(e)
+        self._last[a] = cur
+        self.frames += 1
+
+    def synchronize(self):
+        """every submitted frame's outputs are in host memory on return."""
+        try:
+            for h in self.handles:
+                h.synchronize()
+        except ClmError as e:
+            _raise(e)
+
+    def close(self):
+        for h in self.handles:
+            h.close()
+        self.handles = []

@@ -650,7 +650,7 @@ template <class T> int Engine<T>::set_option(const char* name, int64_t v) {
     if (s == "sub") { if (v < 0 || v > SUB_MAX) return fail(CLM_ERR_ARGUMENT, "sub must be in 0..7"); opt_sub = (int)v; dirty = true; return CLM_OK; }
     if (s == "dbg") { dbg = (int)v; return CLM_OK; }
     if (s == "n3") { opt_n3 = (v < 0) ? -1 : (v ? 1 : 0); return CLM_OK; }
-    if (s == "blocks_per_sm") { if (v < 0) return fail(CLM_ERR_ARGUMENT, "blocks_per_sm must be >= 0"); opt_bps = (int)v; return CLM_OK; }
+    if (s == "blocks_per_sm") { if (v < -8) return fail(CLM_ERR_ARGUMENT, "blocks_per_sm must be >= -8"); opt_bps = (int)v; return CLM_OK; }   // > 0: cap of resident sweep CTAs per SM; < 0: that many below the occupancy maximum; 0: maximum
     return fail(CLM_ERR_ARGUMENT, "unknown option " + s);
 }
 

@@ -234,6 +234,7 @@ template <class T> struct Engine : EngineBase {
         CLM_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SWEEP_THREADS, smem));
         if (bps < 1) return fail(CLM_ERR_CUDA, "sweep kernel does not fit on an SM");
         if (opt_bps > 0) bps = std::min(bps, opt_bps);
+        else if (opt_bps < 0) bps = std::max(1, bps + opt_bps);   // relative: leave room for |opt_bps| CTAs per SM (FramePipeline)
         int64_t grid = (int64_t)n_sm * bps;
         grid = std::max<int64_t>(1, std::min<int64_t>(grid, (tiles_upper + (SWEEP_THREADS / 32) - 1) / (SWEEP_THREADS / 32)));
         if (profile_sweep) CLM_CK(cudaEventRecord(ev2, stream));
@@ -268,6 +269,7 @@ template <class T> struct Engine : EngineBase {
         CLM_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SWEEP_THREADS, smem));
         if (bps < 1) return fail(CLM_ERR_CUDA, "sweep kernel does not fit on an SM");
         if (opt_bps > 0) bps = std::min(bps, opt_bps);
+        else if (opt_bps < 0) bps = std::max(1, bps + opt_bps);   // relative: leave room for |opt_bps| CTAs per SM (FramePipeline)
         int64_t grid = (int64_t)n_sm * bps;
         grid = std::max<int64_t>(1, std::min<int64_t>(grid, (tiles_upper + (SWEEP_THREADS / 32) - 1) / (SWEEP_THREADS / 32)));
         DevSet<T>& S = sets[0];

@@ -262,7 +262,10 @@ CLM_API int clm_neighborlist_copy(clm_handle* h, void* records24, int64_t capaci
 CLM_API int clm_get_stats(clm_handle* h, clm_stats* out);
 /* tuning knobs (do not change results):
  * "sub" = sub-cells per reference cell and dimension of the device grid (1..7, 0 = from the density),
- * "blocks_per_sm" (0 = auto). */
+ * "blocks_per_sm" = resident CTAs per SM of the persistent sweep kernels (0 = as many as fit; k > 0 = at most k; k < 0 = |k| fewer than
+ *   fit: two handles that process independent frames in turn leave each other room this way, so that the cell-list build of one
+ *   frame runs next to the sweep of the other -- celllistmap.jl_b200/api.py FramePipeline),
+ * "n3" = Newton's-third-law force sweep for self-set force maps (1 / 0; -1 = default: Float32 yes, Float64 no). */
 CLM_API int clm_set_option(clm_handle* h, const char* name, int64_t value);
 CLM_API int clm_version(void);
 /* measurement helper: best-of-4 TFLOP/s of a register-resident FMA loop (8 independent chains per thread, all SMs

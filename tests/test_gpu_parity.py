@@ -669,6 +669,41 @@ def test_pipelined_frames_equal_synchronous(clm, dtype):
     h.close()
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("handles", [1, 2, 3])
+def test_frame_pipeline_equals_synchronous(clm, dtype, handles):
+    """clm.FramePipeline: independent frames through several handles in turn (the build of one frame next to the sweep of the
+    previous one): every frame's energy and forces are those of a synchronous call."""
+    import torch
+    w = W.c2_argon(24, dtype)
+    n = w["x"].shape[0]
+    rng = np.random.default_rng(13)
+    frames = [(w["x"] + (0.05 * k * rng.standard_normal(w["x"].shape)).astype(dtype)) for k in range(9)]
+    frames[4] = frames[4][: n - 777]
+    want = []
+    hs = clm.Handle(3, dtype)
+    hs.set_box(clm._capi.ORTHORHOMBIC, w["unitcell"], w["cutoff"], 1)
+    for x in frames:
+        hs.set_positions(0, x)
+        e, f = np.zeros(1, dtype), np.zeros((x.shape[0], 3), dtype)
+        hs.map_lj(w["c6"], w["c12"], e, f)
+        want.append((e.copy(), f.copy()))
+    hs.close()
+    tdt = torch.float32 if dtype == np.float32 else torch.float64
+    xs = [torch.from_numpy(x).pin_memory() for x in frames]
+    es = [torch.zeros(1, dtype=tdt).pin_memory() for _ in frames]
+    fs = [torch.zeros((x.shape[0], 3), dtype=tdt).pin_memory() for x in frames]
+    pipe = clm.FramePipeline(3, dtype, w["unitcell"], w["cutoff"], handles=handles)
+    for k in range(len(frames)):
+        pipe.submit_lj(w["c6"], w["c12"], xs[k].numpy(), es[k].numpy(), fs[k].numpy())
+    pipe.synchronize()
+    for k, (we, wf) in enumerate(want):
+        tol = 1e-6 if dtype == np.float32 else 1e-13
+        assert abs(float(es[k][0]) - float(we[0])) <= tol * abs(float(we[0])), k
+        assert np.abs(fs[k].numpy() - wf).max() <= tol * np.abs(wf).max(), k
+    pipe.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # non-periodic systems reuse the box of the previous build while the new coordinates stay inside the limits it was made
 # from (_limits_fit_in_box, src/internals/ParticleSystem.jl:165-174; checked on the device, no host round trip) and get
