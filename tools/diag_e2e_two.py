@@ -43,3 +43,28 @@ for nh in (1, 2):
             torch.cuda.synchronize()
             print("handles=%d blocks_per_sm=%d flush=%d: wall/frame %.3f ms  E=%.7e" % (nh, bps, fl, 1e3 * (time.perf_counter() - t0) / steps, float(es[0][0])), flush=True)
         for h in hs: h.close()
+
+# device-resident: the same alternation with positions and outputs on the device (no copies): throughput of independent steps
+xd = torch.from_numpy(w["x"]).cuda()
+for nh, bps in ((1, 0), (2, 0), (2, -1)):
+    hs, sts, fd, ed = [], [], [], []
+    for k in range(nh):
+        h = clm.Handle(3, dtype); st = torch.cuda.Stream(); h.set_stream(st.cuda_stream)
+        h.set_box(clm._capi.ORTHORHOMBIC, w["unitcell"], w["cutoff"], 1)
+        if bps: h.set_option("blocks_per_sm", bps)
+        hs.append(h); sts.append(st)
+        fd.append(torch.zeros((n, 3), dtype=tdt, device="cuda")); ed.append(torch.zeros(1, dtype=tdt, device="cuda"))
+    def step(k, fl):
+        a = k % nh
+        with torch.cuda.stream(sts[a]):
+            if fl: flush.zero_()
+            hs[a].set_positions(0, xd)
+            hs[a].map_lj(w["c6"], w["c12"], ed[a], fd[a])
+    for k in range(8): step(k, 0)
+    torch.cuda.synchronize()
+    for fl in (0, 1):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for k in range(steps): step(k, fl)
+        torch.cuda.synchronize()
+        print("device-resident handles=%d blocks_per_sm=%d flush=%d: wall/step %.3f ms  E=%.7e" % (nh, bps, fl, 1e3 * (time.perf_counter() - t0) / steps, float(ed[0][0])), flush=True)
+    for h in hs: h.close()
