@@ -14,8 +14,8 @@ w = W.c2_argon(100, dtype); n = w["x"].shape[0]
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 flush.zero_()
 steps = 60
-for nh in (1, 2):
-    for bps in (0, -1, 4):
+for nh in (1, 2, 3):
+    for bps in ((0,) if nh == 1 else (0, -1, -2)):
         hs, sts = [], []
         for k in range(nh):
             h = clm.Handle(3, dtype)
@@ -46,7 +46,7 @@ for nh in (1, 2):
 
 # device-resident: the same alternation with positions and outputs on the device (no copies): throughput of independent steps
 xd = torch.from_numpy(w["x"]).cuda()
-for nh, bps in ((1, 0), (2, 0), (2, -1)):
+for nh, bps in ((1, 0), (2, 0), (2, -1), (3, -1), (3, -2)):
     hs, sts, fd, ed = [], [], [], []
     for k in range(nh):
         h = clm.Handle(3, dtype); st = torch.cuda.Stream(); h.set_stream(st.cuda_stream)
