@@ -728,8 +728,18 @@ class FramePipeline:
     def synchronize(self):
         """every submitted frame's outputs are in host memory on return."""
         try:
-            for h in self.handles:
-                h.synchronize()
+            for a, h in enumerate(self.handles):
+                for attempt in range(4):
+                    try:
+                        h.synchronize()
+                        break
+                    except ClmError as e:
+                        if e.code != 6 or self._last[a] is None or attempt == 3:
+                            raise
+                        # the record capacity of this handle's LAST frame was too small (it has been grown): repeat that frame
+                        p6, p12, px, pe, pf = self._last[a]
+                        h.set_positions_async(0, px)
+                        h.map_lj(p6, p12, pe, pf, async_=True)
         except ClmError as e:
             _raise(e)
 

@@ -704,6 +704,42 @@ def test_frame_pipeline_equals_synchronous(clm, dtype, handles):
     pipe.close()
 
 
+@pytest.mark.parametrize("handles", [1, 2])
+def test_frame_pipeline_repeats_a_frame_whose_record_capacity_was_too_small(clm, handles):
+    """The record capacity of a build is estimated without a host round trip (uniform density); a frame with many more
+    periodic images than that -- here every particle sits in a corner of the cell, 7 images each -- overflows it.  The overflow
+    of a pipelined frame is only seen when the next frame of that handle is submitted (or at synchronize()): FramePipeline
+    repeats the frame.  Results: those of synchronous calls."""
+    import torch
+    dtype = np.float64
+    rng = np.random.default_rng(3)
+    L, n, cutoff = 10.0, 6000, 1.0
+    uniform = (L * rng.random((n, 3))).astype(dtype)
+    corner = (0.8 * cutoff * rng.random((n, 3))).astype(dtype)      # every image index in {-1,0,1}^3 lands in the computing box
+    frames = [uniform, corner, uniform + 0.01, corner + 0.01, corner + 0.02]
+    uc = np.full(3, L, dtype)
+    want = []
+    hs = clm.Handle(3, dtype)
+    hs.set_box(clm._capi.ORTHORHOMBIC, uc, cutoff, 1)
+    for x in frames:
+        hs.set_positions(0, x)
+        e, f = np.zeros(1, dtype), np.zeros((n, 3), dtype)
+        hs.map_lj(1.0e-3, 1.0e-6, e, f)
+        want.append((e.copy(), f.copy()))
+    hs.close()
+    xs = [torch.from_numpy(x).pin_memory() for x in frames]
+    es = [torch.zeros(1, dtype=torch.float64).pin_memory() for _ in frames]
+    fs = [torch.zeros((n, 3), dtype=torch.float64).pin_memory() for _ in frames]
+    pipe = clm.FramePipeline(3, dtype, uc, cutoff, handles=handles)
+    for k in range(len(frames)):
+        pipe.submit_lj(1.0e-3, 1.0e-6, xs[k].numpy(), es[k].numpy(), fs[k].numpy())
+    pipe.synchronize()
+    for k, (we, wf) in enumerate(want):
+        assert abs(float(es[k][0]) - float(we[0])) <= 1e-12 * abs(float(we[0])), k
+        assert np.abs(fs[k].numpy() - wf).max() <= 1e-12 * np.abs(wf).max(), k
+    pipe.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # non-periodic systems reuse the box of the previous build while the new coordinates stay inside the limits it was made
 # from (_limits_fit_in_box, src/internals/ParticleSystem.jl:165-174; checked on the device, no host round trip) and get
