@@ -187,7 +187,23 @@ def run_reference_arm(args):
         o.lj(w["c6"], w["c12"], forces=True, nbatches=nt)
         return o
 
-    for _ in range(args.warmup):
+    # bounded: the whole --steps K --warmup W run should end within a few minutes.  One probe step on the full sample; when the
+    # projected total exceeds ~3 minutes the sample shrinks (same generator, density and cutoff; the metric is a throughput)
+    t0 = time.perf_counter()
+    step()
+    t1 = time.perf_counter() - t0
+    budget = 180.0
+    total_steps = args.steps + max(args.warmup - 1, 0)
+    if t1 * total_steps > budget:
+        shrink = (budget / (t1 * total_steps)) ** (1.0 / 3.0)
+        nside = max(48, int(nside * shrink))
+        if args.gpus > 1:
+            x, uc = bench_multi.slab_lattice(0, 1, nside, nside, dtype)
+        else:
+            wz = W.c2_argon(nside, dtype)
+            x, uc = wz["x"], wz["unitcell"]
+            workload += f" -- CPU arm bounded to {nside}^3 particles of the same generator (K + W = {args.steps + args.warmup} steps within ~3 minutes)"
+    for _ in range(max(args.warmup - 1, 0)):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
