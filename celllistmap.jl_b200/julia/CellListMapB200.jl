@@ -14,7 +14,7 @@ module CellListMapB200
 using StaticArrays
 using LinearAlgebra: Diagonal
 
-export ParticleSystem, pairwise!, update!, resize_output!, neighborlist, neighborlist!, InPlaceNeighborList,
+export ParticleSystem, ParticleSystemPositions, pairwise!, update!, resize_output!, neighborlist, neighborlist!, InPlaceNeighborList,
        NeighborPair, get_computing_box, LJEnergy, LJForces, LJEnergyAndForces, CoulombEnergy, CoulombEnergyAndForces,
        DistanceHistogram, PairwiseVelocities, MinimumDistanceMap, MinimumDistance, EnergyAndForces,
        CustomPairFunction, CustomOutput
@@ -63,18 +63,42 @@ struct MinimumDistanceMap <: CatalogueFunction end
 struct MinimumDistance{T}; i::Int; j::Int; d::T; end
 mutable struct EnergyAndForces{T,V}; energy::T; forces::V; end
 
+# ---- ParticleSystemPositions (src/API/ParticleSystemPositions.jl:14-101) -------------------------------------------
+"""Positions of one particle set: an owning `Vector{SVector{N,T}}` plus a flag that every mutation raises, so that
+`sys.xpositions[i] = v`, `sys.xpositions .= frame`, `push!`, `resize!` ... are followed by a rebuild of the cell list at the
+next `pairwise!` / `neighborlist!` without an explicit `update!`.  Views share the flag (they write through `setindex!`)."""
+struct ParticleSystemPositions{N,T} <: AbstractVector{SVector{N,T}}
+    x::Vector{SVector{N,T}}
+    updated::Base.RefValue{Bool}
+end
+ParticleSystemPositions{N,T}(x) where {N,T} = ParticleSystemPositions{N,T}([SVector{N,T}(v) for v in x], Ref(true))
+Base.size(p::ParticleSystemPositions) = size(p.x)
+Base.IndexStyle(::Type{<:ParticleSystemPositions}) = IndexLinear()
+Base.@propagate_inbounds Base.getindex(p::ParticleSystemPositions, i::Int) = p.x[i]
+Base.@propagate_inbounds function Base.setindex!(p::ParticleSystemPositions{N,T}, v, i::Int) where {N,T}
+    p.updated[] = true
+    p.x[i] = SVector{N,T}(v)
+    return p
+end
+Base.resize!(p::ParticleSystemPositions, n::Integer) = (p.updated[] = true; resize!(p.x, n); p)
+Base.push!(p::ParticleSystemPositions{N,T}, v) where {N,T} = (p.updated[] = true; push!(p.x, SVector{N,T}(v)); p)
+Base.append!(p::ParticleSystemPositions{N,T}, vs) where {N,T} = (p.updated[] = true; append!(p.x, [SVector{N,T}(v) for v in vs]); p)
+Base.empty!(p::ParticleSystemPositions) = (p.updated[] = true; empty!(p.x); p)
+# ccall: the AoS n x N memory of the owning vector is what the ABI takes (no conversion); the Vector is rooted by ccall
+Base.cconvert(::Type{Ptr{SVector{N,T}}}, p::ParticleSystemPositions{N,T}) where {N,T} = p.x
+
 # ---- ParticleSystem (src/API/ParticleSystem.jl:142-202, AbstractParticleSystem.jl:32-60) -------------------------
 mutable struct ParticleSystem{N,T,O}
     handle::Ptr{Cvoid}
-    xpositions::Vector{SVector{N,T}}        # owning copy (ParticleSystemPositions, src/API/ParticleSystemPositions.jl:19-22)
-    ypositions::Union{Vector{SVector{N,T}},Nothing}
+    xpositions::ParticleSystemPositions{N,T}        # owning copy + mutation flag
+    ypositions::Union{ParticleSystemPositions{N,T},Nothing}
     unitcell::Union{SVector{N,T},SMatrix{N,N,T},Nothing}
     cutoff::T
     lcell::Int
     output::O
     output_name::Symbol
     parallel::Bool
-    xupdated::Bool; yupdated::Bool; boxdirty::Bool
+    boxdirty::Bool
 end
 
 function ParticleSystem(; positions=nothing, xpositions=nothing, ypositions=nothing, unitcell=nothing, cutoff,
@@ -85,13 +109,13 @@ function ParticleSystem(; positions=nothing, xpositions=nothing, ypositions=noth
     x0 = isnothing(positions) ? xpositions : positions
     N = isnothing(unitcell) ? length(first(x0)) : size(unitcell, 1)
     T = eltype(first(x0)) == Float32 ? Float32 : Float64
-    x = [SVector{N,T}(v) for v in x0]
-    y = isnothing(ypositions) ? nothing : [SVector{N,T}(v) for v in ypositions]
+    x = ParticleSystemPositions{N,T}(x0)
+    y = isnothing(ypositions) ? nothing : ParticleSystemPositions{N,T}(ypositions)
     uc = isnothing(unitcell) ? nothing : (unitcell isa AbstractVector ? SVector{N,T}(unitcell) : SMatrix{N,N,T}(unitcell))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     code = ccall((:clm_create, libclm), Cint, (Ref{Ptr{Cvoid}}, Cint, Cint, Cint, Cint), h, N, T == Float32 ? CLM_F32 : CLM_F64, device, 1)
     code == 0 || error(unsafe_string(ccall((:clm_last_error, libclm), Cstring, (Ptr{Cvoid},), C_NULL)))
-    sys = ParticleSystem{N,T,typeof(output)}(h[], x, y, uc, T(cutoff), lcell, output, output_name, parallel, true, !isnothing(y), true)
+    sys = ParticleSystem{N,T,typeof(output)}(h[], x, y, uc, T(cutoff), lcell, output, output_name, parallel, true)
     finalizer(s -> ccall((:clm_destroy, libclm), Cint, (Ptr{Cvoid},), s.handle), sys)
     _sync!(sys)                              # the reference builds the cell list at construction
     return sys
@@ -110,17 +134,20 @@ function _sync!(sys::ParticleSystem{N,T}) where {N,T}
             GC.@preserve uc _check(h, ccall((:clm_set_box, libclm), Cint, (Ptr{Cvoid}, Cint, Ptr{T}, Cint, Ref{T}, Cint),
                                             h, is_matrix == 1 ? CLM_TRICLINIC : CLM_ORTHORHOMBIC, uc, is_matrix, rc, sys.lcell))
         end
-        sys.boxdirty = false; sys.xupdated = true
+        sys.boxdirty = false; sys.xpositions.updated[] = true
     end
-    if sys.xupdated     # Vector{SVector{N,T}} is the AoS n x N memory the ABI takes: no conversion, one H2D copy
+    xup = sys.xpositions.updated[]
+    yup = !isnothing(sys.ypositions) && sys.ypositions.updated[]
+    if xup              # Vector{SVector{N,T}} is the AoS n x N memory the ABI takes: no conversion, one H2D copy
         _check(h, ccall((:clm_set_positions, libclm), Cint, (Ptr{Cvoid}, Cint, Ptr{SVector{N,T}}, Int64, Cint), h, 0, sys.xpositions, length(sys.xpositions), 0))
     end
-    if !isnothing(sys.ypositions) && sys.yupdated
+    if yup
         _check(h, ccall((:clm_set_positions, libclm), Cint, (Ptr{Cvoid}, Cint, Ptr{SVector{N,T}}, Int64, Cint), h, 1, sys.ypositions, length(sys.ypositions), 0))
     end
-    if sys.xupdated || sys.yupdated
+    if xup || yup
         _check(h, ccall((:clm_build, libclm), Cint, (Ptr{Cvoid},), h))      # UpdateCellList!
-        sys.xupdated = false; sys.yupdated = false
+        sys.xpositions.updated[] = false
+        isnothing(sys.ypositions) || (sys.ypositions.updated[] = false)
     end
     return sys
 end
@@ -131,8 +158,8 @@ function update!(sys::ParticleSystem{N,T}; positions=nothing, xpositions=nothing
     (!isnothing(positions) && !isnothing(xpositions)) && throw(ArgumentError("Either `positions` OR `xpositions` must be provided, not both."))
     x = isnothing(positions) ? xpositions : positions
     (!isnothing(ypositions) && isnothing(sys.ypositions)) && throw(ArgumentError("ypositions can only be set for a two-set particle system"))
-    if !isnothing(x); resize!(sys.xpositions, length(x)); sys.xpositions .= SVector{N,T}.(x); sys.xupdated = true; end
-    if !isnothing(ypositions); resize!(sys.ypositions, length(ypositions)); sys.ypositions .= SVector{N,T}.(ypositions); sys.yupdated = true; end
+    if !isnothing(x); resize!(sys.xpositions, length(x)); sys.xpositions .= x; end                      # every write raises the flag
+    if !isnothing(ypositions); resize!(sys.ypositions, length(ypositions)); sys.ypositions .= ypositions; end
     if !isnothing(cutoff); sys.cutoff = T(cutoff); sys.boxdirty = true; end
     if !isnothing(unitcell)
         isnothing(sys.unitcell) && throw(ArgumentError("Manual updating of the unit cell of non-periodic systems is not allowed."))
