@@ -418,14 +418,20 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
                         ns = nfull * 32;
                     }
                     __syncwarp();
+                    // one loop per chunk kind (each kind is inlined exactly once): no per-chunk dispatch
                     auto sweep_chunks = [&](auto half_tag) {
+                        if (MODE == MODE_TRI) {
 #pragma unroll 1
-                        for (int ch = 0; ch < nfull; ++ch) {
-                            const int s = ch * 32 + lane;
-                            if (MODE == MODE_TRI) chunk(std::integral_constant<int, N3_TRI>{}, half_tag, s);
-                            else if (any_ghost_i) chunk(std::integral_constant<int, N3_GENERAL>{}, half_tag, s);
-                            else if (ch * 32 < nk) chunk(std::integral_constant<int, N3_KEYED>{}, half_tag, s);
-                            else chunk(std::integral_constant<int, N3_PLAIN>{}, half_tag, s);
+                            for (int ch = 0; ch < nfull; ++ch) chunk(std::integral_constant<int, N3_TRI>{}, half_tag, ch * 32 + lane);
+                        } else if (any_ghost_i) {
+#pragma unroll 1
+                            for (int ch = 0; ch < nfull; ++ch) chunk(std::integral_constant<int, N3_GENERAL>{}, half_tag, ch * 32 + lane);
+                        } else {
+                            const int nkc = min(nfull, (nk + 31) >> 5);     // chunks that hold keyed partners come first
+#pragma unroll 1
+                            for (int ch = 0; ch < nkc; ++ch) chunk(std::integral_constant<int, N3_KEYED>{}, half_tag, ch * 32 + lane);
+#pragma unroll 1
+                            for (int ch = nkc; ch < nfull; ++ch) chunk(std::integral_constant<int, N3_PLAIN>{}, half_tag, ch * 32 + lane);
                         }
                     };
                     sweep_chunks(std::integral_constant<int, 0>{});
