@@ -272,11 +272,12 @@ template <class T> int Engine<T>::build_enqueue() {
     if (pending_h2d) { if (!(dbg & 1)) CLM_CK(cudaStreamWaitEvent(stream, ev_h2d, 0)); pending_h2d = false; }
     CLM_CK(cudaEventRecord(ev_b0, stream));
     if (published) CLM_CK(cudaStreamWaitEvent(stream, ev_built, 0));   // the side-stream publish of the previous build has read the scalars (long ago)
-    // device scalars (a kernel, not a copy: see k_dscal_init)
-    k_dscal_init<<<1, 32, 0, stream>>>(dscal.p);
-    CLM_CK(cudaGetLastError());
+    // device scalars (a kernel, not a copy: see k_dscal_init).  Only the limits pass of a non-periodic system needs them
+    // before the counters are zeroed; otherwise the zero fill of set 0 initialises them in passing (one launch less)
     const bool np_reuse = nonperiodic && box_set && np_have_limits && !np_force_limits;
     if (nonperiodic && !np_reuse) {
+        k_dscal_init<<<1, 32, 0, stream>>>(dscal.p);
+        CLM_CK(cudaGetLastError());
         // Box(limits(x[,y]), cutoff): sides = extent + 2.1*cutoff, origin = minimum coordinates
         // (CellOperations.jl:290-324, Box.jl:38, :374-377); limits by a device reduction, ONE host round trip for both
         // sets and the NaN flags
@@ -324,8 +325,7 @@ template <class T> int Engine<T>::build_enqueue() {
         for (int k = 0; k < 3; ++k) { np_lo[k] = (k < dim) ? lo[k] : T(0); np_hi[k] = (k < dim) ? hi[k] : T(0); }
         np_have_limits = true;
         np_force_limits = false;
-        k_dscal_init<<<1, 32, 0, stream>>>(dscal.p);    // the limits pass used the flags
-        CLM_CK(cudaGetLastError());
+        // (the limits pass used the flags: the zero fill of set 0 below resets them)
     }
     if (!box_set) return fail(CLM_ERR_STATE, "clm_set_box must be called before clm_build");
     fill_geom(box, geom);
@@ -418,12 +418,12 @@ template <class T> int Engine<T>::build_enqueue() {
             S.cell_count = S.counters.p; S.cell_nact = S.counters.p + ncp; S.ref_real = S.counters.p + 2 * ncp;
             {   // one zero fill of [cell_count | cell_nact | ref_real] (a kernel: see k_dscal_init)
                 const long long nz = 2 * ncp + nref;
-                k_zero_ints<<<(int)std::min<long long>((nz / 4 + 255) / 256 + 1, (long long)n_sm * 8), 256, 0, stream>>>(S.counters.p, nz);
+                k_zero_ints<<<(int)std::min<long long>((nz / 4 + 255) / 256 + 1, (long long)n_sm * 8), 256, 0, stream>>>(S.counters.p, nz, s == 0 ? dscal.p : nullptr);
                 CLM_CK(cudaGetLastError());
             }
             int* ds = dscal.p + s * DS_SET_STRIDE;
             const int64_t nall = S.n + S.n_foreign;
-            const int nb = (int)((nall + 255) / 256);
+            const int nb = (int)std::min<int64_t>((nall + 255) / 256, bin_blocks_per_sm > 0 ? (int64_t)n_sm * bin_blocks_per_sm : (int64_t)0x7fffffff);   // k_bin strides over the rest
             const int rec_cap = (int)std::min<size_t>(S.rec.cap, 0x7fffffff);
             if (S.n_mask != 0 && S.n_mask != S.n) return fail(CLM_ERR_ARGUMENT, "clm_set_foreign_mask: the mask must have one byte per row of clm_set_positions");
             const uint8_t* fm = S.n_mask ? S.fmask.p : nullptr;
@@ -649,6 +649,7 @@ template <class T> int Engine<T>::set_option(const char* name, int64_t v) {
     const std::string s(name);
     if (s == "sub") { if (v < 0 || v > SUB_MAX) return fail(CLM_ERR_ARGUMENT, "sub must be in 0..7"); opt_sub = (int)v; dirty = true; return CLM_OK; }
     if (s == "dbg") { dbg = (int)v; return CLM_OK; }
+    if (s == "bin_blocks_per_sm") { if (v < 0 || v > 64) return fail(CLM_ERR_ARGUMENT, "bin_blocks_per_sm must be in 0..64"); bin_blocks_per_sm = (int)v; return CLM_OK; }
     if (s == "n3") { opt_n3 = (v < 0) ? -1 : (v ? 1 : 0); return CLM_OK; }
     if (s == "blocks_per_sm") { if (v < -8) return fail(CLM_ERR_ARGUMENT, "blocks_per_sm must be >= -8"); opt_bps = (int)v; return CLM_OK; }   // > 0: cap of resident sweep CTAs per SM; < 0: that many below the occupancy maximum; 0: maximum
     return fail(CLM_ERR_ARGUMENT, "unknown option " + s);

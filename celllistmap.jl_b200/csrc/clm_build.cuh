@@ -41,7 +41,12 @@ static __global__ void k_dscal_init(int* __restrict__ dscal) {
     if (k < DS_COUNT) dscal[k] = (k == DS_NAN || k == DS_OOB || k == DS_SET_STRIDE_DEV + DS_NAN || k == DS_SET_STRIDE_DEV + DS_OOB) ? IDX_NONE : 0;
 }
 // zero fills as kernels for the same reason (cudaMemsetAsync may be served by a DMA engine)
-static __global__ void __launch_bounds__(256) k_zero_ints(int* __restrict__ p, long long n) {
+// (dscal != nullptr: block 0 also initialises the device scalar block, which saves the k_dscal_init launch of a build)
+static __global__ void __launch_bounds__(256) k_zero_ints(int* __restrict__ p, long long n, int* __restrict__ dscal = nullptr) {
+    if (dscal && blockIdx.x == 0 && threadIdx.x < DS_COUNT) {
+        const int k = threadIdx.x;
+        dscal[k] = (k == DS_NAN || k == DS_OOB || k == DS_SET_STRIDE_DEV + DS_NAN || k == DS_SET_STRIDE_DEV + DS_OOB) ? IDX_NONE : 0;
+    }
     const long long n4 = n >> 2;
     int4* p4 = reinterpret_cast<int4*>(p);
     for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n4; k += (long long)gridDim.x * blockDim.x) p4[k] = make_int4(0, 0, 0, 0);
@@ -148,12 +153,16 @@ __device__ __forceinline__ float shfl_t(float v, int src) { return __shfl_sync(0
 __device__ __forceinline__ double shfl_t(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 template <class T, int DIM, bool SCATTER>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 8 : 4)
 k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __restrict__ fpos, int n, int n_own, int* __restrict__ cell_cursor,
       int* __restrict__ cell_nact, int* __restrict__ ref_real, RecT<T>* __restrict__ rec, int* __restrict__ slot_of, int rec_cap, int* __restrict__ dscal, const unsigned char* __restrict__ fmask) {
     typedef TagT<T> TG;
-    const int ip = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31;
     constexpr int CENTER = (DIM == 3) ? 13 : 4;
+    // grid-stride over blocks of 256 particles: the grid can be capped (clm_set_option "bin_blocks_per_sm"); the default is one
+    // block per 256 particles, which the hardware block scheduler balances better than a capped persistent grid (measured)
+    for (int ip0 = blockIdx.x * blockDim.x; ip0 < n; ip0 += gridDim.x * blockDim.x) {
+    const int ip = ip0 + threadIdx.x;
     T p[3] = {T(0), T(0), T(0)};
     unsigned okmask = 0u;      // candidate images of this lane's particle (none for invalid / interior / non-periodic)
     bool is_foreign = false;   // owned by another rank: the rows behind the owned ones, or flagged by clm_set_foreign_mask
@@ -267,6 +276,7 @@ k_bin(const __grid_constant__ GeomT<T> g, const T* __restrict__ pos, const T* __
             const bool home = ref_real[rq] != 0;
             strec(&rec[qslot], q[0], q[1], q[2], (typename TG::type)ips | TG::GHOST | foreign | (home ? TG::HOME : (typename TG::type)0));
         }
+    }
     }
 }
 

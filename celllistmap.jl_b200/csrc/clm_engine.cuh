@@ -140,6 +140,7 @@ template <class T> struct Engine : EngineBase {
     signed char row_hw[(2 * LF_MAX + 1) * (2 * LF_MAX + 1)];   // per stencil row: half-width along the row in device cells, -1 = skip
     int opt_sub = 0;                      // 0 = choose the sub-cell split from the particle density
     int tile_i = TILE_I, opt_bps = 0;
+    int bin_blocks_per_sm = 0;    // grid cap of k_bin in blocks per SM (it strides over the particles); clm_set_option "bin_blocks_per_sm", 0 = one block per 256 particles (measured fastest: profiles/r2_tune_bin_grid.txt)
     // self-set force maps: 1 = Newton's-third-law sweep (k_sweep_n3: every pair once, from the same periodic images as the
     // reference, so Float32 forces match the reference's Float32 arithmetic to ~1e-6), 0 = full-shell k_sweep<MODE_ALL>
     // (faster, but a pair that crosses the periodic boundary is evaluated from two different image pairs: 5.6e-5 in
