@@ -64,6 +64,13 @@ __device__ __forceinline__ void red_add3(double* p, double x, double y, double z
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p + 1), "d"(y) : "memory");
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p + 2), "d"(z) : "memory");
 }
+// accumulator row of a record slot: facc + slot * 4 elements as ONE 32 x 32 -> 64-bit multiply-add (the compiler's own
+// 64-bit address arithmetic for a masked 29-bit slot is seven instructions per flush)
+template <class T> __device__ __forceinline__ T* facc_row(T* facc, uint32_t slot) {
+    unsigned long long p;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(p) : "r"(slot), "r"((uint32_t)(4 * sizeof(T))), "l"(facc));
+    return reinterpret_cast<T*>(p);
+}
 // true unless all three are +0 (a lane that saw no pair holds exact +0s; -0 only costs a redundant reduction)
 __device__ __forceinline__ bool any_nonzero(float x, float y, float z) { return (__float_as_uint(x) | __float_as_uint(y) | __float_as_uint(z)) != 0u; }
 __device__ __forceinline__ bool any_nonzero(double x, double y, double z) { return x != 0.0 || y != 0.0 || z != 0.0; }
@@ -248,7 +255,7 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
             const int g = i0 + lane / GL;
             const int slot_g = (int)(__shfl_sync(0xffffffffu, swi, g) & N3_SLOT);
             const bool act_g = __shfl_sync(0xffffffffu, active0 ? 1 : 0, g) != 0;
-            if ((lane & (GL - 1)) == 0 && act_g && (v[0] != T(0) || v[1] != T(0) || v[2] != T(0))) red_add3(facc + (size_t)slot_g * 4, v[0], v[1], v[2]);
+            if ((lane & (GL - 1)) == 0 && act_g && (v[0] != T(0) || v[1] != T(0) || v[2] != T(0))) red_add3(facc_row(facc, (uint32_t)slot_g), v[0], v[1], v[2]);
         };
 
 #pragma unroll 1
@@ -305,7 +312,7 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
                     fi[ii][0] = xfma(sc, dx, fi[ii][0]); fi[ii][1] = xfma(sc, dy, fi[ii][1]); fi[ii][2] = xfma(sc, dz, fi[ii][2]);
                     fjx = xfma(-sc, dx, fjx); fjy = xfma(-sc, dy, fjy); fjz = xfma(-sc, dz, fjz);
                 }
-                if (any_nonzero(fjx, fjy, fjz)) red_add3(facc + (size_t)slot_j * 4, fjx, fjy, fjz);
+                if (any_nonzero(fjx, fjy, fjz)) red_add3(facc_row(facc, (uint32_t)slot_j), fjx, fjy, fjz);
             };
             // one cull step: 32 staged records, survivors compacted in place behind buf[ns)
             auto cull_step = [&](const RecT<T>* q, int& ns) -> unsigned {

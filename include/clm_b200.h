@@ -265,7 +265,9 @@ CLM_API int clm_get_stats(clm_handle* h, clm_stats* out);
  * "blocks_per_sm" = resident CTAs per SM of the persistent sweep kernels (0 = as many as fit; k > 0 = at most k; k < 0 = |k| fewer than
  *   fit: two handles that process independent frames in turn leave each other room this way, so that the cell-list build of one
  *   frame runs next to the sweep of the other -- celllistmap.jl_b200/api.py FramePipeline),
- * "n3" = Newton's-third-law force sweep for self-set force maps (1 / 0; -1 = default: Float32 yes, Float64 no). */
+ * "n3" = Newton's-third-law force sweep for self-set force maps (1 / 0; -1 = default: Float32 yes, Float64 no),
+ * "bin_blocks_per_sm" = grid cap of the binning kernel of the cell-list build in blocks per SM (0 = default: one block per 256
+ *   particles; k > 0: at most k blocks per SM striding over the particles). */
 CLM_API int clm_set_option(clm_handle* h, const char* name, int64_t value);
 CLM_API int clm_version(void);
 /* measurement helper: best-of-4 TFLOP/s of a register-resident FMA loop (8 independent chains per thread, all SMs

@@ -502,6 +502,20 @@ def test_inplace_neighborlist_reuse(clm, oracle_mod):
     assert_lists_identical(clm.neighborlist_(nb).copy(), oracle_mod.Oracle(x2, 0.12, unitcell=[1.0, 1, 1]).neighborlist())
 
 
+@pytest.mark.parametrize("kind", ["ortho", "triclinic", "nonperiodic"])
+@pytest.mark.parametrize("cap", [1, 3])
+def test_capped_bin_grid_gives_the_same_list(clm, oracle_mod, kind, cap):
+    """clm_set_option "bin_blocks_per_sm": the binning kernel strides over the particles with a capped grid (120 000 particles on
+    148 x cap blocks of 256: several trips per block, a partial last one); a tuning knob must not change the result."""
+    rng = np.random.default_rng(97)
+    x, uc = random_system(rng, 120000, 3, kind, np.float64, scale=30.0)
+    nb = clm.InPlaceNeighborList(x=x, cutoff=1.0, unitcell=uc)
+    nb.sys._h.set_option("bin_blocks_per_sm", cap)
+    clm.update(nb, xpositions=x)
+    got = clm.neighborlist_(nb).copy()
+    assert_lists_identical(got, oracle_mod.Oracle(x, 1.0, unitcell=uc).neighborlist())
+
+
 # ---------------------------------------------------------------------------------------------------------
 # full-size property checks (BASELINE.json configs[1]): what the domain offers independent of size
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])

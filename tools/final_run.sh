@@ -1,3 +1,4 @@
+# final single-GPU record of a round: smoke, GPU tests, reference arm, bench, ncu launch list, ncu --set full capture of one step
 set -x
 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE OK')" 2>&1 | tail -3
 (time python -m pytest tests -m gpu -x -q 2>&1 | tail -5) 2>&1 | tee gpurun_out/pytest_r2_final.txt
