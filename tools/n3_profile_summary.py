@@ -17,6 +17,9 @@ L_PAIR0, L_PAIR1 = line_of("for (int ii = 0; ii < IH; ++ii)"), line_of("if (any_
 L_CULLLOOP, L_SWEEP = line_of("far-away dummies round the staged records"), line_of("auto sweep_chunks = [&]")
 L_TILE, L_REDUCE, L_RBASE = line_of("const Tile tl = a.tiles[t];"), line_of("auto reduce_fi = [&]"), line_of("for (int rbase = rfa;")
 L_END = line_of("if constexpr (NH == 1) reduce_fi(0);")
+# helper blocks in front of the kernel: reduction / slot helpers, the pair-force functors, the vector load of particle i
+L_RED0, L_FUNC0, L_FUNC1 = line_of("__device__ __forceinline__ void red_add3(float* p"), line_of("// ---- pair-force functors"), line_of("template <class T> struct Vec4S;")
+L_VEC0, L_VEC1 = L_FUNC1, line_of("enum { N3_PLAIN = 0")
 keys = ["pair loop (8 i-steps per 32-partner chunk)", "cull + in-place compaction", "staging: bulk-copy issue + mbarrier", "chunk loop: partner load, key, RED flush, carry",
         "row classification, prefixes, pass control", "tile setup (tile fetch, cells of the tile, keys, bounding box)", "f_i reduce-scatter + RED, energy fold",
         "other (shuffle / vote intrinsics, address arithmetic)"]
@@ -32,10 +35,10 @@ def cat(f, l):
     if f == "cmath": return 1
     if f == "device_atomic_functions.hpp": return 5
     if f != "clm_sweep_n3.cuh": return 7
-    if 76 <= l <= 102 or l in range(119, 128) or L_PAIR0 <= l < L_PAIR1: return 0
+    if L_FUNC0 <= l < L_FUNC1 or L_VEC0 <= l < L_VEC1 or L_PAIR0 <= l < L_PAIR1: return 0
     if L_CULL <= l < L_ROWS or L_CULLLOOP <= l < L_SWEEP - 12: return 1
     if L_PASS <= l < L_CULLLOOP: return 2
-    if L_CHUNK <= l < L_PAIR0 or L_PAIR1 <= l < L_CULL or L_SWEEP - 12 <= l < L_END or l in range(59, 73): return 3
+    if L_CHUNK <= l < L_PAIR0 or L_PAIR1 <= l < L_CULL or L_SWEEP - 12 <= l < L_END or L_RED0 <= l < L_FUNC0: return 3
     if L_ROWS <= l < L_PASS: return 4
     if L_REDUCE <= l < L_RBASE or l >= L_END: return 6
     if l < L_REDUCE or L_RBASE <= l < L_CHUNK: return 5
@@ -55,7 +58,7 @@ ntiles = 126384
 L = ["# Newton's-third-law force sweep k_sweep_n3<float, MODE_HALF, N3LJ<float,true,true>> on the C2 workload (1 M argon-density",
      "# particles, cutoff 12 A), FINAL round-2 kernel (sources %s).  Source: %s" % (bench.src_hash(), rep),
      "# (ncu --set full --clock-control none --import-source on -k regex:... python tools/prof_c2.py 100 f32 4), joined with",
-     "# nvdisasm -g line info by tools/sass_lines.py; written by tools/n3_profile_summary.py.  Warm CUDA-event time of the same kernel: 0.464-0.467 ms.",
+     "# nvdisasm -g line info by tools/sass_lines.py; written by tools/n3_profile_summary.py.  Warm CUDA-event time of the same kernel: 0.458-0.462 ms.",
      "#",
      "# gpu__time_duration %s us (cold, under ncu); smsp__inst_executed %.4g; issue active %.1f %%; %s registers, 20 warps / SM;" % (g("gpu__time_duration.sum"), float(g("smsp__inst_executed.sum")), float(g("smsp__issue_active.avg.pct_of_peak_sustained_active")), g("launch__registers_per_thread")),
      "# dram__bytes_read %s + write %s (units of the report) per launch (profiles/r2_traffic.json); thread instructions per warp instruction %s." % (g("dram__bytes_read.sum"), g("dram__bytes_write.sum"), g("smsp__thread_inst_executed_per_inst_executed.ratio")),
