@@ -293,6 +293,34 @@ template <class T> struct Engine : EngineBase {
         last_grid = (int)grid;
         return CLM_OK;
     }
+    // energy-only functors (F::FORCES == false) on the same lean sweep: every pair once from the reference's own image, no
+    // accumulator rows, nothing to gather afterwards.  Default for Float32 only, like the force maps: in Float64 the FP64 pipe
+    // bounds the pair loop and the half shell's looser cull (31 % against 39 % lane hit rate) makes the lean sweep slower
+    bool n3_scalar_usable() const { return n3_usable(); }
+    template <int MODE, class F> int launch_n3_scalar(const F& f) {
+        static_assert(!F::FORCES, "launch_n3_scalar is for functors without force outputs");
+        auto kern = k_sweep_n3<T, MODE, F>;
+        const size_t smem = (size_t)N3Smem<T, F::AUX, true>::value;
+        static size_t smem_set[64] = {0};
+        size_t& set = smem_set[device & 63];
+        if (smem > set) { CLM_CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set = smem; }
+        int bps = 0;
+        CLM_CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SWEEP_THREADS, smem));
+        if (bps < 1) return fail(CLM_ERR_CUDA, "sweep kernel does not fit on an SM");
+        if (opt_bps > 0) bps = std::min(bps, opt_bps);
+        else if (opt_bps < 0) bps = std::max(1, bps + opt_bps);
+        int64_t grid = (int64_t)n_sm * bps;
+        grid = std::max<int64_t>(1, std::min<int64_t>(grid, (tiles_upper + (SWEEP_THREADS / 32) - 1) / (SWEEP_THREADS / 32)));
+        SweepArgs<T> a = make_args();
+        a.rec_j = sets[0].rec_n3.p;
+        if (profile_sweep) CLM_CK(cudaEventRecord(ev2, stream));
+        kern<<<(unsigned)grid, SWEEP_THREADS, smem, stream>>>(a, f, (T*)nullptr);
+        CLM_CK(cudaGetLastError());
+        if (profile_sweep) CLM_CK(cudaEventRecord(ev3, stream));
+        stats.launches += 1;
+        last_grid = (int)grid;
+        return CLM_OK;
+    }
     int last_grid = 0;
 
     // ---- pipelined frames (clm_set_positions_async + CLM_ASYNC maps): independent frames of a trajectory overlap their

@@ -10,10 +10,11 @@ template <class T> int Engine<T>::map_lj(const void* p, int flags, void* e, void
     double scale = 1.0;
     const bool norm = FLJ<T, true, true>::can_normalise(c[0], c[1]);
     const bool n3 = f && n3_usable();
+    const bool n3e = !f && n3_scalar_usable();    // energy only: the same lean sweep without force accumulators
     const bool async = (flags & CLM_ASYNC) != 0;
     if (async) { if (int rc = async_begin(flags)) return rc; }
     for (;;) {   // repeated only when the build's record-capacity estimate was too small (build_validate)
-    if (n3) n3_request();
+    if (n3 || n3e) n3_request();
     if (int rc = prepare_map(flags)) return rc;
     if (n3) {
         // self-set forces: every pair once, both particles updated (clm_sweep_n3.cuh)
@@ -46,6 +47,13 @@ template <class T> int Engine<T>::map_lj(const void* p, int flags, void* e, void
             if (int rc = launch<MODE_ALL>(fn, 0)) return rc;
         }
         scale = two_sets ? 1.0 : 0.5;
+    } else if (n3e) {
+        // energy only, self-set: the reference's exactly-once pair set with the direct form r6 (c12 r6 - c6), on the lean
+        // partner-per-lane sweep (clm_sweep_n3.cuh) -- no force accumulators, so more warps are resident
+        N3LJ<T, false, true, false> fn;
+        fn.set(c[0], c[1]);
+        const int rc = (sweep_mode() == MODE_TRI) ? launch_n3_scalar<MODE_TRI>(fn) : launch_n3_scalar<MODE_HALF>(fn);
+        if (rc) return rc;
     } else {
         // energy only: the reference's exactly-once sweep with the direct form (same pair set and arithmetic as the oracle)
         FLJ<T, false, false> fn;

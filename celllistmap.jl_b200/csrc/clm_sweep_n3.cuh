@@ -46,15 +46,26 @@ constexpr int N3_PAR_SHIFT = 29;
 #ifndef CLM_N3_STAGE_BYTES_F64
 #define CLM_N3_STAGE_BYTES_F64 8192
 #endif
-template <class T, bool AUX> struct N3Cap {
-    static constexpr int SB = AUX ? 6144 : ((sizeof(T) == 4) ? CLM_N3_STAGE_BYTES_F32 : CLM_N3_STAGE_BYTES_F64);
+// (LEAN = a functor without force outputs -- energy only.  Measured on the C2 workload, Float32, tools/tune_n3_energy.sh,
+//  profiles/r2_tune_n3_energy.txt: the kernel wants ~116 registers spill-free even without the accumulators; 5 resident CTAs
+//  at 96 registers with the 8 KB buffer are fastest -- 0.329 ms against 0.361 ms of k_sweep<MODE_HALF>; 8 CTAs at 64 registers
+//  spill and take 0.409 ms.  Float64 stays on k_sweep<MODE_HALF>: 0.66 ms here against 0.574 ms.)
+#ifndef CLM_N3E_STAGE_BYTES_F32
+#define CLM_N3E_STAGE_BYTES_F32 8192
+#endif
+#ifndef CLM_N3E_STAGE_BYTES_F64
+#define CLM_N3E_STAGE_BYTES_F64 8192
+#endif
+template <class T, bool AUX, bool LEAN = false> struct N3Cap {
+    static constexpr int SB = AUX ? 6144 : (LEAN ? ((sizeof(T) == 4) ? CLM_N3E_STAGE_BYTES_F32 : CLM_N3E_STAGE_BYTES_F64)
+                                                 : ((sizeof(T) == 4) ? CLM_N3_STAGE_BYTES_F32 : CLM_N3_STAGE_BYTES_F64));
     static constexpr int REC = (int)sizeof(RecT<T>);
     static constexpr int SLOTS = SB / REC;
     static constexpr int CAPP = SLOTS - 64;      // staged per pass: the carried partial chunk (< 32) and the padding (< 32) share the buffer
     static constexpr int IKEY_OFF = 128, IPOS_OFF = 256, BUF_OFF = 512, ABUF_OFF = BUF_OFF + SB;
     static constexpr int WSTRIDE = BUF_OFF + SB * (AUX ? 2 : 1);
 };
-template <class T, bool AUX> struct N3Smem { static constexpr int value = (SWEEP_THREADS / 32) * N3Cap<T, AUX>::WSTRIDE; };
+template <class T, bool AUX, bool LEAN = false> struct N3Smem { static constexpr int value = (SWEEP_THREADS / 32) * N3Cap<T, AUX, LEAN>::WSTRIDE; };
 
 __device__ __forceinline__ void red_add3(float* p, float x, float y, float z) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(x), "f"(y), "f"(z), "f"(0.f) : "memory");
@@ -80,9 +91,10 @@ __device__ __forceinline__ uint32_t slotword(const RecT<double>& r) { return (ui
 
 // ---- pair-force functors: fs(hit, d2, e, wi, wj) returns the scalar s with F_i += s (x_i - x_j), F_j -= s (x_i - x_j);
 //      e accumulates the (unscaled) pair energy of the tile ----
-template <class T, bool NORM, bool ENERGY> struct N3LJ {
+template <class T, bool NORM, bool ENERGY, bool FORCES_ = true> struct N3LJ {
     T c6, c12, s2, escale, fscale;      // see FLJ (clm_sweep.cuh): q = (c12/c6)/d2^3 form when both constants are positive
     static constexpr bool AUX = false;
+    static constexpr bool FORCES = FORCES_;   // false: energy only (the exactly-once energy map rides the same lean sweep)
     __device__ __forceinline__ const RecT<T>* aux_j() const { return nullptr; }
     __device__ __forceinline__ T wi(int) const { return T(0); }
     __device__ __forceinline__ T fs(bool hit, T d2, T& e, T, T) const {
@@ -96,6 +108,7 @@ template <class T, bool NORM, bool ENERGY> struct N3LJ {
         } else {
             const T r6 = inv * inv * inv;
             if (ENERGY) e = xfma(r6, xfma(c12, r6, -c6), e);
+            if (!FORCES) return T(0);
             return inv * r6 * xfma(T(12) * c12, r6, T(-6) * c6);
         }
     }
@@ -112,6 +125,7 @@ template <class T, bool ENERGY> struct N3Coul {
     const T* w_rec;   // weights gathered into record order, one record-sized slot (w, 0, 0, 0) per record (Engine::gather_aux)
     T fscale;         // 1
     static constexpr bool AUX = true;
+    static constexpr bool FORCES = true;
     __device__ __forceinline__ const RecT<T>* aux_j() const { return reinterpret_cast<const RecT<T>*>(w_rec); }
     __device__ __forceinline__ T wi(int ki) const { return k * w_rec[(size_t)ki * 4]; }
     __device__ __forceinline__ T fs(bool hit, T d2, T& e, T wi_, T wj) const {
@@ -145,7 +159,16 @@ enum { N3_PLAIN = 0, N3_KEYED = 1, N3_GENERAL = 2, N3_TRI = 3 };
 #define CLM_N3_MINB_F64 ((CLM_N3_HALVES_F64 == 2) ? 5 : 4)
 #endif
 template <class T> struct N3Halves { static constexpr int value = (sizeof(T) == 8) ? CLM_N3_HALVES_F64 : 1; };
-template <class T, bool AUX> struct N3MinBlocks { static constexpr int value = (sizeof(T) == 4) ? (AUX ? 4 : CLM_N3_MINB_F32) : (AUX ? 3 : CLM_N3_MINB_F64); };
+#ifndef CLM_N3E_MINB_F32
+#define CLM_N3E_MINB_F32 5
+#endif
+#ifndef CLM_N3E_MINB_F64
+#define CLM_N3E_MINB_F64 3
+#endif
+template <class T, bool AUX, bool LEAN = false> struct N3MinBlocks {
+    static constexpr int value = (LEAN && !AUX) ? ((sizeof(T) == 4) ? CLM_N3E_MINB_F32 : CLM_N3E_MINB_F64)
+                                                : ((sizeof(T) == 4) ? (AUX ? 4 : CLM_N3_MINB_F32) : (AUX ? 3 : CLM_N3_MINB_F64));
+};
 
 // Per tile (TILE_I consecutive records of one row, particles i):
 //   1. lane r classifies stencil row r and fetches its record range; rows of the tile's own REFERENCE row split into
@@ -161,14 +184,15 @@ template <class T, bool AUX> struct N3MinBlocks { static constexpr int value = (
 #ifdef CLM_N3_MAXNREG   // tuning builds: an explicit register cap instead of the occupancy target (tools/tune_n3_cta.sh)
 #define CLM_N3_BOUNDS __maxnreg__(CLM_N3_MAXNREG)
 #else
-#define CLM_N3_BOUNDS __launch_bounds__(SWEEP_THREADS, N3MinBlocks<T, F::AUX>::value)
+#define CLM_N3_BOUNDS __launch_bounds__(SWEEP_THREADS, N3MinBlocks<T, F::AUX, !F::FORCES>::value)
 #endif
 template <class T, int MODE, class F>
 __global__ void CLM_N3_BOUNDS
 k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, T* __restrict__ facc) {
     typedef TagT<T> TG;
     typedef typename TG::type tag_t;
-    typedef N3Cap<T, F::AUX> CP;
+    typedef N3Cap<T, F::AUX, !F::FORCES> CP;
+    constexpr bool FORCES = F::FORCES;
     extern __shared__ __align__(128) unsigned char dsm_raw[];
     const int lane = threadIdx.x & 31;
     constexpr int NH = N3Halves<T>::value, IH = TILE_I / NH;
@@ -227,16 +251,17 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
         // 0.984 ms (128 registers, no spills) / 1.047 ms (96 registers, 20 warps) against 0.920 ms of NH == 1 and 0.906 ms of the
         // full shell -- every partner is loaded and its force flushed (three scalar f64 reductions) twice
         // (tools/tune_n3_f64.sh, profiles/r2_tune_n3_f64.txt)
-        T fi[IH][3];
+        T fi[FORCES ? IH : 1][3];
 #pragma unroll
-        for (int i = 0; i < IH; ++i) fi[i][0] = fi[i][1] = fi[i][2] = T(0);
+        for (int i = 0; i < (FORCES ? IH : 1); ++i) fi[i][0] = fi[i][1] = fi[i][2] = T(0);
         T e_tile = T(0);
         // f_i: reduce-scatter of the IH x 3 per-lane partial sums over the warp: after log2(IH) halving steps the 32 / IH lanes
         // of group g hold the partial sums of particle i0 + g, butterfly steps finish them; the accumulators are zeroed
         auto reduce_fi = [&](const int i0) {
+            if constexpr (!FORCES) return;
             T v[3 * IH];
 #pragma unroll
-            for (int i = 0; i < IH; ++i) { v[3 * i] = fi[i][0]; v[3 * i + 1] = fi[i][1]; v[3 * i + 2] = fi[i][2]; fi[i][0] = fi[i][1] = fi[i][2] = T(0); }
+            for (int i = 0; i < IH; ++i) { const int ia = FORCES ? i : 0; v[3 * i] = fi[ia][0]; v[3 * i + 1] = fi[ia][1]; v[3 * i + 2] = fi[ia][2]; fi[ia][0] = fi[ia][1] = fi[ia][2] = T(0); }
 #pragma unroll
             for (int half = 3 * IH / 2, o = 16; half >= 3; half >>= 1, o >>= 1) {
                 const bool upper = (lane & o) != 0;
@@ -309,10 +334,12 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
                     else if (KIND == N3_GENERAL) { const int2 ik = ikey[i]; ok = (KJ > (unsigned)ik.x) && !(ik.y && gj); }
                     const bool hit = ok && (d2 <= rc2);
                     const T sc = f.fs(hit, d2, e_tile, pi.w, wj);
-                    fi[ii][0] = xfma(sc, dx, fi[ii][0]); fi[ii][1] = xfma(sc, dy, fi[ii][1]); fi[ii][2] = xfma(sc, dz, fi[ii][2]);
-                    fjx = xfma(-sc, dx, fjx); fjy = xfma(-sc, dy, fjy); fjz = xfma(-sc, dz, fjz);
+                    if constexpr (FORCES) {
+                        fi[ii][0] = xfma(sc, dx, fi[ii][0]); fi[ii][1] = xfma(sc, dy, fi[ii][1]); fi[ii][2] = xfma(sc, dz, fi[ii][2]);
+                        fjx = xfma(-sc, dx, fjx); fjy = xfma(-sc, dy, fjy); fjz = xfma(-sc, dz, fjz);
+                    }
                 }
-                if (any_nonzero(fjx, fjy, fjz)) red_add3(facc_row(facc, (uint32_t)slot_j), fjx, fjy, fjz);
+                if constexpr (FORCES) { if (any_nonzero(fjx, fjy, fjz)) red_add3(facc_row(facc, (uint32_t)slot_j), fjx, fjy, fjz); }
             };
             // one cull step: 32 staged records, survivors compacted in place behind buf[ns)
             auto cull_step = [&](const RecT<T>* q, int& ns) -> unsigned {
