@@ -220,6 +220,14 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
     const T rc2 = a.rc2;
     const unsigned lt = (1u << lane) - 1u;
     const RecT<T>* const rec = a.rec_j;           // slot-tagged records (rec_n3)
+    // stencil row of this lane (row offset, half width along the row), looked up ONCE when the stencil has at most 32 rows
+    // (lcell * sub <= 2): the two dependent indexed constant loads leave the per-tile path
+    int rowpack = 0;
+    const bool rows_fit = nrows_st <= 32;
+    if (rows_fit && lane < nrows_st) {
+        const int dz = a.rdz[lane], dy = a.rdy[lane];
+        rowpack = (a.hw[(dz + lf) * hww + dy + lf] & 0xff) | ((dy & 0xff) << 8) | ((dz & 0xff) << 16);
+    }
     int t_next = 0;
     if (lane == 0) t_next = atomicAdd(&a.dscal[DS_WORK], 1);
     for (;;) {
@@ -239,8 +247,14 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
         int rfx_i = 0, rfa = 0, rfb = 0;
         if (MODE == MODE_HALF) {
             const int* cs = a.cell_start_i + (size_t)(iz * a.ny + iy) * (a.nx + 1);
+            // device cell of record ki: cxa + the number of cells of the tile that end at or before ki (cell ends are monotone).
+            // The ends are loaded by the lanes in parallel and compared through shuffles: one memory round trip instead of a
+            // chain of dependent loads
             int cx = cxa;
-            while (cx < cxb && cs[cx + 1] <= ki) ++cx;
+            const int ncs = min(cxb - cxa, 32);
+            const int vend = (lane < ncs) ? cs[cxa + 1 + lane] : 0x7fffffff;
+            for (int k = 0; k < ncs; ++k) cx += (__shfl_sync(0xffffffffu, vend, k) <= ki) ? 1 : 0;
+            if (cxb - cxa > 32) { while (cx >= cxa + 32 && cx < cxb && cs[cx + 1] <= ki) ++cx; }
             rfx_i = div_sub(cx); rfa = div_sub(cxa); rfb = div_sub(cxb);
         }
         const int ry_i = div_sub(iy), rz_i = div_sub(iz);
@@ -366,9 +380,10 @@ k_sweep_n3(const __grid_constant__ SweepArgs<T> a, const __grid_constant__ F f, 
                 const int r = rb + lane;
                 int j0 = 0, j1 = 0, d0 = 0, d1 = 0;
                 if (r < nrows_st) {
-                    const int dz = a.rdz[r], dy = a.rdy[r];
+                    int dz, dy, w;
+                    if (rows_fit) { w = (int)(signed char)(rowpack & 0xff); dy = (int)(signed char)((rowpack >> 8) & 0xff); dz = (int)(signed char)((rowpack >> 16) & 0xff); }
+                    else { dz = a.rdz[r]; dy = a.rdy[r]; w = a.hw[(dz + lf) * hww + dy + lf]; }
                     const int z2 = iz + dz, y2 = iy + dy;
-                    const int w = a.hw[(dz + lf) * hww + dy + lf];
                     bool use = ((unsigned)z2 < (unsigned)a.nz) && ((unsigned)y2 < (unsigned)a.ny) && (w >= 0);
                     int rel = 1;
                     if (MODE == MODE_HALF && use) {
