@@ -58,7 +58,7 @@ ntiles = 126384
 L = ["# Newton's-third-law force sweep k_sweep_n3<float, MODE_HALF, N3LJ<float,true,true>> on the C2 workload (1 M argon-density",
      "# particles, cutoff 12 A), FINAL round-2 kernel (sources %s).  Source: %s" % (bench.src_hash(), rep),
      "# (ncu --set full --clock-control none --import-source on -k regex:... python tools/prof_c2.py 100 f32 4), joined with",
-     "# nvdisasm -g line info by tools/sass_lines.py; written by tools/n3_profile_summary.py.  Warm CUDA-event time of the same kernel: 0.458-0.462 ms.",
+     "# nvdisasm -g line info by tools/sass_lines.py; written by tools/n3_profile_summary.py.  Warm CUDA-event time of the same kernel: 0.449-0.452 ms.",
      "#",
      "# gpu__time_duration %s us (cold, under ncu); smsp__inst_executed %.4g; issue active %.1f %%; %s registers, 20 warps / SM;" % (g("gpu__time_duration.sum"), float(g("smsp__inst_executed.sum")), float(g("smsp__issue_active.avg.pct_of_peak_sustained_active")), g("launch__registers_per_thread")),
      "# dram__bytes_read %s + write %s (units of the report) per launch (profiles/r2_traffic.json); thread instructions per warp instruction %s." % (g("dram__bytes_read.sum"), g("dram__bytes_write.sum"), g("smsp__thread_inst_executed_per_inst_executed.ratio")),
