@@ -502,6 +502,36 @@ def test_inplace_neighborlist_reuse(clm, oracle_mod):
     assert_lists_identical(clm.neighborlist_(nb).copy(), oracle_mod.Oracle(x2, 0.12, unitcell=[1.0, 1, 1]).neighborlist())
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("kind", ["ortho", "triclinic", "nonperiodic"])
+def test_energy_only_lean_sweep_equals_mode_half(clm, oracle_mod, dtype, kind):
+    """LJ energy without forces: the lean partner-per-lane sweep (option "n3" = 1; the Float32 default) visits the pair set of
+    k_sweep<MODE_HALF / MODE_TRI> (option "n3" = 0; the Float64 default), so the two energies agree to the rounding of the
+    order-free sums, and both meet the north_star bar against the oracle in Float64 (scale: the sum of the term magnitudes, as
+    in test_lj_energy_forces)."""
+    rng = np.random.default_rng(5)
+    x, uc = random_system(rng, 6000, 3, kind, dtype, scale=12.6)
+    cutoff, c6, c12 = 2.7, 4.0, 4.0
+    uc64 = None if uc is None else uc.astype(np.float64)
+    want = float(oracle_mod.Oracle(x.astype(np.float64), cutoff, unitcell=uc64).lj(c6, c12, forces=False))
+    escale = abs(float(oracle_mod.Oracle(x.astype(np.float64), cutoff, unitcell=uc64).lj(c6, -c12, forces=False)))
+    got = {}
+    for n3 in (1, 0):
+        sys_ = clm.ParticleSystem(xpositions=x, unitcell=uc, cutoff=cutoff, output=0.0)
+        sys_._h.set_option("n3", n3)
+        got[n3] = float(clm.pairwise(clm.LJEnergy(c6, c12), sys_))
+    scale = max(abs(want), escale)
+    tol = RTOL[np.dtype(dtype)]
+    # distance to Float64 arithmetic: bounded by the conditioning of the wrapped Float32 coordinates at the closest pair, which
+    # dominates a random system's energy (tests/parity_util.py); the bar proper is the agreement of the two sweeps
+    dmin = float(oracle_mod.Oracle(x.astype(np.float64), cutoff, unitcell=uc64).neighborlist()[2].min())
+    bar64 = max(tol, conditioning_bound(dtype, 1.3 * 12.6, dmin, 12))
+    print(f"[parity] energy-only {kind} {np.dtype(dtype).name}: lean vs MODE_HALF {abs(got[1] - got[0]) / scale:.2e}; lean {abs(got[1] - want) / scale:.2e}, "
+          f"MODE_HALF {abs(got[0] - want) / scale:.2e} of the Float64 oracle (closest pair {dmin:.3g}, conditioning bound {bar64:.1e})")
+    assert abs(got[1] - got[0]) <= tol * scale
+    assert abs(got[1] - want) <= bar64 * scale and abs(got[0] - want) <= bar64 * scale
+
+
 @pytest.mark.parametrize("kind", ["ortho", "triclinic", "nonperiodic"])
 @pytest.mark.parametrize("cap", [1, 3])
 def test_capped_bin_grid_gives_the_same_list(clm, oracle_mod, kind, cap):
