@@ -28,7 +28,7 @@ if os.environ.get("CLM_N3"):
 for it in range(steps):
     h.set_positions(0, x_dev)
     h.build()
-    h.map_lj(w["c6"], w["c12"], e_dev, f_dev, reset=True, profile=True)
+    h.map_lj(w["c6"], w["c12"], e_dev, None if os.environ.get("CLM_ENERGY_ONLY") else f_dev, reset=True, profile=True)   # CLM_ENERGY_ONLY=1: the energy map
     st = h.stats()
     print(f"step {it}: sweep {st.sweep_ms:.4f} ms build {st.build_ms:.4f} ms tiles {st.n_tiles} E={float(e_dev[0]):.6e}", flush=True)
 h.close()
